@@ -1,0 +1,218 @@
+/*
+ * nmb200.h -- C ABI of libnmb200.so, the B200 (sm_100a) data plane for nanomotif's
+ * motif-scoring hot path.
+ *
+ * The reference (MicrobialDarkMatter/nanomotif 1.1.2) is pure Python and has no FFI of its
+ * own; the operator boundary is a set of Python callables.  Each entry
+ * point below names the reference callable(s) whose arithmetic it replaces.  The Python mirror
+ * of the reference API (nanomotif_b200/api.py) binds these with ctypes; INTEGRATION.md shows
+ * the stub a nanomotif maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative nmb_status; it never throws and never
+ *     aborts.  nmb_last_error() returns a thread-local message for the last failure.
+ *   - all pointers are DEVICE pointers unless the parameter name ends in _h.
+ *   - the caller owns every buffer; nothing is allocated behind the caller's back except the
+ *     small per-call scratch documented at the function.
+ *   - functions enqueue work on `stream` (a cudaStream_t passed as void*) and return without
+ *     synchronising; they keep no global state, so N host threads/processes can drive N GPUs.
+ *   - no torch / C++ types cross the boundary.
+ *
+ * Packed layout ("tile records", described in DESIGN.md section 3)
+ *   The assembly lives in one global position space.  Contig c occupies positions
+ *   [start_c, start_c + len_c), start_c a multiple of NMB_CHUNK_BP (256); consecutive contigs are
+ *   separated by >= NMB_MIN_GAP_BP positions flagged non-ACGT.  The space is cut into tiles of
+ *   NMB_TILE_BP (65536) positions.  Per tile t:
+ *     seq record  : uint32 x[NMB_TILE_WORDS+8], y[NMB_TILE_WORDS+8], int32 chunk_info[256]
+ *                   x = high code bit, y = low code bit (A=0 T=1 G=2 C=3, nanomotif/constants.py:1);
+ *                   4 halo words of the neighbouring tiles are duplicated on each side so that one
+ *                   bulk copy (TMA) brings a self-contained tile into shared memory.
+ *                   chunk_info[q] = contig id of 256-bp chunk q, bit 30 set when the chunk (or its
+ *                   halo) touches a non-ACGT letter, -1 for an empty chunk.
+ *     class record: uint32 plane[4][NMB_TILE_WORDS] per mod type:
+ *                   0 = methylated '+', 1 = unmethylated '+', 2 = methylated '-', 3 = unmethylated '-'
+ *                   (fraction_mod >= high / <= low, nanomotif/find_motifs_bin.py:1308-1314).
+ *   The non-ACGT plane is a flat uint32 array with 4 leading pad words.
+ */
+#ifndef NMB200_H
+#define NMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NMB_API __attribute__((visibility("default")))
+#else
+#define NMB_API
+#endif
+
+#define NMB_CHUNK_WORDS 8
+#define NMB_CHUNK_BP 256
+#define NMB_TILE_WORDS 2048
+#define NMB_TILE_BP 65536
+#define NMB_TILE_CHUNKS 256
+#define NMB_HALO_WORDS 4
+#define NMB_SEQ_PLANE_WORDS (NMB_TILE_WORDS + 2 * NMB_HALO_WORDS)           /* 2056 */
+#define NMB_SEQ_REC_WORDS (2 * NMB_SEQ_PLANE_WORDS + NMB_TILE_CHUNKS)       /* 4368 */
+#define NMB_CLS_REC_WORDS (4 * NMB_TILE_WORDS)                              /* 8192 */
+#define NMB_MIN_GAP_BP 64
+#define NMB_MAX_MOTIF_LEN 62
+#define NMB_MAX_WINDOW 63
+#define NMB_MAX_MOTIFS_PER_ITEM 32
+
+typedef enum nmb_status {
+    NMB_OK = 0,
+    NMB_ERR_INVALID = -1, /* bad argument */
+    NMB_ERR_CUDA = -2,    /* CUDA runtime error, see nmb_last_error() */
+    NMB_ERR_NO_DEVICE = -3,
+    NMB_ERR_CAPACITY = -4 /* caller-provided output too small */
+} nmb_status;
+
+/* One motif, already stripped of flanking wildcards (nanomotif/motif.py:213-224).
+ * allowed[j] is the set of bases accepted at motif position j: bit0=A bit1=T bit2=G bit3=C
+ * (order of nanomotif/constants.py:21-28); 0xF is the regex wildcard '.', which is the only
+ * thing a non-ACGT contig letter matches (regex-literal semantics, nanomotif/utils.py:61-66). */
+typedef struct nmb_motif {
+    uint8_t allowed[NMB_MAX_MOTIF_LEN];
+    uint8_t len;     /* 1..NMB_MAX_MOTIF_LEN */
+    uint8_t mod_pos; /* 0..len-1 */
+} nmb_motif; /* 64 bytes */
+
+/* Device view of a packed assembly (all device pointers). */
+typedef struct nmb_assembly {
+    const uint32_t *seq_records;   /* [n_tiles][NMB_SEQ_REC_WORDS] */
+    const uint32_t *nonacgt;       /* [NMB_HALO_WORDS + n_tiles*NMB_TILE_WORDS + NMB_HALO_WORDS] */
+    const int64_t *contig_start;   /* [n_contigs] global start position (multiple of 256) */
+    const int64_t *contig_len;     /* [n_contigs] */
+    int32_t n_contigs;
+    int32_t n_tiles;
+} nmb_assembly;
+
+/* One homogeneous unit of scan work: motifs [motif_begin, motif_begin+motif_count) of one
+ * mod type against tiles [tile_begin, tile_begin+tile_count), counting only contigs
+ * [contig_begin, contig_end).  Output row of (motif m, group g) is
+ *     out[(out_base + (m - motif_begin) * n_groups + g) * 4 + {0: n_mod '+', 1: n_nomod '+',
+ *                                                           2: n_mod '-', 3: n_nomod '-'}]
+ * group_mode 0: g = 0 (one posterior per motif: motif_model_bin, find_motifs_bin.py:1265-1283)
+ *            1: g = contig - contig_begin (one row per contig: motif_model_contig / the table)
+ *            2: g = contig_group[contig], negative = contig skipped. */
+typedef struct nmb_job {
+    int32_t motif_begin;
+    int32_t motif_count;
+    int32_t modtype;
+    int32_t tile_begin;
+    int32_t tile_count;
+    int32_t contig_begin;
+    int32_t contig_end;
+    int32_t group_mode;
+    int32_t n_groups;
+    int32_t item_offset; /* exclusive prefix sum of tile_count*ceil(motif_count/motifs_per_item) */
+    int64_t out_base;
+} nmb_job; /* 48 bytes */
+
+NMB_API int nmb_abi_version(void);
+NMB_API const char *nmb_last_error(void);
+/* Number of SMs of the current device (grid sizing), or negative status. */
+NMB_API int nmb_device_sm_count(void);
+
+/* ---- K1: loaders (replaces nanomotif/fasta.py:35-49 + nanomotif/seq.py:53-55 string storage,
+ *      and the per-call polars splits of nanomotif/find_motifs_bin.py:1308-1314) ---- */
+
+/* ASCII contigs (concatenated in `ascii`, contig c at byte offset ascii_off[c], length
+ * contig_len[c], any case) -> tile records + non-ACGT plane.  Buffers must be sized as in
+ * nmb_assembly; they are fully overwritten. */
+NMB_API int nmb_pack_sequence(const uint8_t *ascii, const int64_t *ascii_off, const int64_t *contig_start,
+                      const int64_t *contig_len, int32_t n_contigs, int32_t n_tiles,
+                      uint32_t *seq_records, uint32_t *nonacgt, void *stream);
+
+/* Pileup rows -> class records.  Row r belongs to contig contig_id[r] (negative = ignored),
+ * 0-based forward-strand position pos[r], strand[r] (0 '+', 1 '-'), mod type index modtype[r]
+ * (NULL = all rows are type 0), fraction_mod[r] (= column 11 / 100, nanomotif/dataload.py:85).
+ * A row is methylated iff fraction >= high and unmethylated iff fraction <= low, compared in
+ * float64 exactly like the reference.  class_records [n_modtypes][n_tiles][4][NMB_TILE_WORDS] is
+ * zeroed first.  Rows must be unique per (contig, pos, strand, modtype) -- the reference's
+ * np.isin(assume_unique=True) makes the same assumption (find_motifs_bin.py:1258-1261). */
+NMB_API int nmb_build_class_planes(const int32_t *contig_id, const int64_t *pos, const uint8_t *strand,
+                           const uint8_t *modtype, const double *fraction_mod, int64_t n_rows,
+                           double low, double high, const nmb_assembly *assembly_h,
+                           int32_t n_modtypes, uint32_t *class_records, void *stream);
+
+/* ---- K2: scan + gather-join + segmented reduce (replaces utils.subseq_indices utils.py:44-67,
+ *      methylated_motif_occourances find_motifs_bin.py:1234-1263, the count step of
+ *      motif_model_contig :1285-1331 and the per-bin sum of motif_model_bin :1265-1283) ---- */
+
+/* Compile motifs into per-strand scan programs (forward motif and its reverse complement,
+ * nanomotif/motif.py:260-266).  programs: n_motifs * nmb_program_bytes() bytes. */
+NMB_API int nmb_program_bytes(void);
+NMB_API int nmb_compile_motifs(const nmb_motif *motifs, int32_t n_motifs, void *programs, void *stream);
+
+/* Count methylated / unmethylated motif occurrences.  jobs: device array of n_jobs nmb_job with
+ * item_offset filled for `motifs_per_item` (1..32); n_items = total items.  out (int64) is
+ * ACCUMULATED into (zero it to get counts).  contig_group may be NULL unless a job uses
+ * group_mode 2.  max_motif_len = longest motif in the batch (selects the halo width). */
+NMB_API int nmb_scan_count(const nmb_assembly *assembly_h, const uint32_t *class_records,
+                   const void *programs, const nmb_job *jobs, int32_t n_jobs, int32_t n_items,
+                   int32_t motifs_per_item, int32_t max_motif_len, const int32_t *contig_group,
+                   int64_t *out, int32_t grid_ctas /* 0 = auto */, void *stream);
+
+/* ---- K3: occurrence positions (subseq_indices output and the save_motif_positions=True lists
+ *      of motif_model_contig, find_motifs_bin.py:1322-1329) ---- */
+
+/* Match bit-plane of ONE program strand over tiles [tile_begin, tile_begin+tile_count):
+ * bit p of match_plane (flat, word index = global_pos/32, no pad, n_tiles*NMB_TILE_WORDS words) is
+ * set iff the motif occurs with its mod_pos at global position p.  Compile the motif with
+ * mod_pos = 0 to get start positions (utils.subseq_indices); strand 0 = forward program, 1 = its
+ * reverse complement.  motif_len selects the halo width. */
+NMB_API int nmb_match_plane(const nmb_assembly *assembly_h, const void *programs, int32_t motif_index,
+                    int32_t strand, int32_t motif_len, int32_t tile_begin, int32_t tile_count,
+                    uint32_t *match_plane, void *stream);
+
+/* Ascending positions of the set bits of plane & (mask or all-ones) within the global position
+ * range [pos_begin, pos_end).  Two passes on the same stream: tile_counts is scratch of
+ * ceil((pos_end-pos_begin)/NMB_TILE_BP)+2 int64.  Positions are written relative to pos_begin.
+ * *n_out (device int64) receives the total; at most capacity positions are written. */
+NMB_API int nmb_compact_positions(const uint32_t *plane, const uint32_t *mask /* may be NULL */,
+                          int64_t pos_begin, int64_t pos_end, int64_t *tile_counts,
+                          int64_t *out_pos, int64_t capacity, int64_t *n_out, void *stream);
+
+/* Gather-join in pileup order: flag[r] = bit (base + pos[r]) of plane (0 when out of
+ * [0, limit)).  This is np.isin(positions, motif_index) of find_motifs_bin.py:1258-1261. */
+NMB_API int nmb_test_positions(const uint32_t *plane, int64_t base, int64_t limit, const int64_t *pos,
+                       int64_t n, uint8_t *flag, void *stream);
+
+/* ---- K4: motif-growth step (replaces DNAsequence.sample_at_indices seq.py:170-189,
+ *      EqualLengthDNASet.reverse_compliment :387-389, convert_to_DNAarray :474-478,
+ *      DNAarray.filter_sequence_matches :499-524, DNAarray.pssm :526-537 and the KL/argmax part of
+ *      MotifSearcher._motif_child_nodes_kl_dist_max find_motifs_bin.py:957-1000) ---- */
+
+/* Windows of width 2*padding+1 <= NMB_MAX_WINDOW around global positions gpos[i] (strand[i] 1 =
+ * reverse-complement the window).  Window i is stored as three uint64: x bits, y bits, N bits
+ * (bit j = window column j).  The caller has already applied the reference's strict bound
+ * padding < i < len - padding (seq.py:186). */
+NMB_API int nmb_extract_windows(const nmb_assembly *assembly_h, const int64_t *gpos, const uint8_t *strand,
+                        int64_t n, int32_t padding, uint64_t *windows /* [n][3] */, void *stream);
+
+/* For each of n_motifs full-width masks (allowed[j] per window column, len = window width):
+ * rows kept by filter_sequence_matches(keep_matches=True), i.e. one-hot(row) <= mask everywhere,
+ * restricted to rows with alive[i] != 0 (alive may be NULL); hist[m][j][b] = column sums of the
+ * kept one-hot rows (N adds 1 to all four), n_active[m] = kept rows. hist/n_active are
+ * overwritten.  keep[m*n + i] (may be NULL) receives the per-row decision. */
+NMB_API int nmb_window_hist(const uint64_t *windows, const uint8_t *alive, int64_t n, int32_t width,
+                    const nmb_motif *masks, int32_t n_motifs, int32_t *hist /* [n_motifs][width][4] */,
+                    int64_t *n_active, uint8_t *keep, void *stream);
+
+/* PSSM + KL(meth || background) per column in float64: pssm[m][b][j] = hist/n_active (4 x width,
+ * rows A,T,G,C), kl[m][j] = sum_b p ln(p/q) after per-column renormalisation of both (scipy.stats.
+ * entropy semantics: 0 ln 0 = 0, p>0 & q=0 -> inf).  bg_pssm is [4][width] float64. */
+NMB_API int nmb_pssm_kl(const int32_t *hist, const int64_t *n_active, int32_t n_motifs, int32_t width,
+                const double *bg_pssm, double *pssm, double *kl, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMB200_H */

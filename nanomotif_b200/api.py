@@ -1,0 +1,315 @@
+"""Drop-in replacements for the reference's scoring operators, backed by libnmb200 (CUDA, sm_100a).
+
+Same names, argument meaning, return types and error behaviour as the reference callables
+(SURVEY.md section 8a/8b):
+
+    subseq_indices                 nanomotif/utils.py:44-67
+    methylated_motif_occourances   nanomotif/find_motifs_bin.py:1234-1263
+    motif_model_contig             nanomotif/find_motifs_bin.py:1285-1331
+    motif_model_bin                nanomotif/find_motifs_bin.py:1265-1283
+    get_parent_scores              nanomotif/find_motifs_bin.py:1382-1433
+
+plus the batched forms the GPU needs to be kept busy (`motif_model_bin_many`, `BinScorer`).
+There is no CPU fallback: without a CUDA device every function raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr
+from .device import DeviceAssembly, DevicePileup, MotifPrograms, _stream, make_jobs, scan_count, sequence_of
+from .model import BetaBernoulliModel, predictive_evaluation_score
+from .motif import Motif, as_motif, tokenize
+from .pileup import PileupTable, strand_codes
+
+# ---------------------------------------------------------------------------------------------
+# small identity-keyed caches so that repeated calls with the same Python objects (what the
+# reference's search loop does) do not re-pack / re-upload
+# ---------------------------------------------------------------------------------------------
+
+
+class _IdCache:
+    def __init__(self, capacity: int):
+        self.capacity = capacity
+        self._d: OrderedDict = OrderedDict()
+
+    def get(self, key, refs, build):
+        hit = self._d.get(key)
+        if hit is not None and all(a is b for a, b in zip(hit[0], refs)):
+            self._d.move_to_end(key)
+            return hit[1]
+        val = build()
+        self._d[key] = (refs, val)  # holding refs keeps the ids stable while cached
+        while len(self._d) > self.capacity:
+            self._d.popitem(last=False)
+        return val
+
+    def clear(self):
+        self._d.clear()
+
+
+_seq_cache = _IdCache(8)
+_bin_cache = _IdCache(8)
+
+
+def clear_caches() -> None:
+    _seq_cache.clear()
+    _bin_cache.clear()
+
+
+def _single_contig_assembly(seq: str) -> DeviceAssembly:
+    return _seq_cache.get(("seq", id(seq), len(seq)), (seq,), lambda: DeviceAssembly.from_sequences({"_": seq}))
+
+
+# ---------------------------------------------------------------------------------------------
+# K3-backed position functions
+# ---------------------------------------------------------------------------------------------
+
+
+def _match_plane(asm: DeviceAssembly, motif: Motif, align: int, strand: int = 0) -> tuple[torch.Tensor, int, int]:
+    """Device bit-plane of the occurrences of `motif` (regex as given, flanking wildcards allowed).
+
+    Returns (plane, delta, length): bit p of `plane` is set iff the stripped motif occurs with motif
+    position `align - delta` at p.  delta is 0 unless `align` points into the flanking wildcards.
+    The caller restores the whole-motif-inside-contig rule with `length`.
+    """
+    toks = tokenize(motif.string)
+    length = len(toks)
+    lead = 0
+    while lead < length and toks[lead] == ".":
+        lead += 1
+    core = Motif(motif.string.strip("."), 0)
+    core_len = len(tokenize(core.string))
+    a = min(max(align - lead, 0), core_len - 1)
+    delta = (align - lead) - a
+    progs = MotifPrograms([core], asm.device, strip=False, mod_pos_override=a)
+    plane = torch.empty(asm.n_words, dtype=torch.int32, device=asm.device)
+    view = asm.view()
+    check(lib.nmb_match_plane(C.byref(view), ptr(progs.programs), 0, strand, progs.max_len, 0, asm.n_tiles,
+                              ptr(plane), _stream()), "nmb_match_plane")
+    return plane, delta, length
+
+
+def subseq_indices(subseq: str, seq: str) -> np.ndarray:
+    """All (overlapping) 0-based start positions of the regex motif `subseq` in `seq`, ascending int64.
+
+    Supports the motif alphabet the reference generates: A C G T, '.', and bracket classes.
+    """
+    seq = sequence_of(seq)
+    toks = tokenize(subseq)
+    length, L = len(toks), len(seq)
+    if length == 0:
+        raise ValueError("empty motif")
+    if all(t == "." for t in toks):  # closed form: every start where the motif fits
+        return np.arange(0, max(0, L - length + 1), dtype=np.int64)
+    asm = _single_contig_assembly(seq)
+    lead = next(i for i, t in enumerate(toks) if t != ".")
+    # align at the first constrained position: the stripped motif's position 0
+    plane, _, length = _match_plane(asm, Motif(subseq, 0), align=lead)
+    pos = _compact(plane, 0, L)
+    # whole (unstripped) motif inside the contig: 0 <= start and start + length <= L
+    pos = pos - lead
+    pos = pos[(pos >= 0) & (pos <= L - length)]
+    return pos.cpu().numpy()
+
+
+def _compact(plane: torch.Tensor, pos_begin: int, pos_end: int, mask: torch.Tensor | None = None) -> torch.Tensor:
+    d = plane.device
+    n_blocks = -(-(pos_end - pos_begin) // _lib.TILE_BP)
+    scratch = torch.empty(n_blocks + 2, dtype=torch.int64, device=d)
+    n_out = torch.zeros(1, dtype=torch.int64, device=d)
+    # pass 1 sizes the output, pass 2 writes it (both inside nmb_compact_positions when capacity > 0)
+    check(lib.nmb_compact_positions(ptr(plane), ptr(mask), pos_begin, pos_end, ptr(scratch), None, 0, ptr(n_out),
+                                    _stream()), "nmb_compact_positions")
+    n = int(n_out.item())
+    out = torch.empty(n, dtype=torch.int64, device=d)
+    if n:
+        check(lib.nmb_compact_positions(ptr(plane), ptr(mask), pos_begin, pos_end, ptr(scratch), ptr(out), n,
+                                        ptr(n_out), _stream()), "nmb_compact_positions")
+    return out
+
+
+def _test(plane: torch.Tensor, base: int, limit: int, positions: np.ndarray) -> np.ndarray:
+    """np.isin(positions, occurrences) evaluated on the device, in the order given."""
+    pos = np.ascontiguousarray(positions, dtype=np.int64)
+    if pos.size == 0:
+        return np.zeros(0, dtype=bool)
+    d = plane.device
+    pos_d = torch.from_numpy(pos).to(d)
+    flag = torch.empty(pos.size, dtype=torch.uint8, device=d)
+    check(lib.nmb_test_positions(ptr(plane), base, limit, ptr(pos_d), pos.size, ptr(flag), _stream()),
+          "nmb_test_positions")
+    return flag.cpu().numpy().astype(bool)
+
+
+def methylated_motif_occourances(motif, sequence, methylated_positions, non_methylated_positions) -> tuple:
+    """Subsets of the two position arrays that coincide with the modified base of a motif occurrence,
+    in the order given (find_motifs_bin.py:1234-1263)."""
+    assert len(motif) > 0, "Motif is empty"
+    assert len(sequence) > 0, "Sequence is empty"
+    assert hasattr(motif, "mod_position") and isinstance(motif, str), "Motif is not a Motif type"
+    m = as_motif(motif)
+    sequence = sequence_of(sequence)
+    meth = np.asarray(methylated_positions)
+    nonmeth = np.asarray(non_methylated_positions)
+    toks = tokenize(m.string)
+    length, L, mp = len(toks), len(sequence), int(m.mod_position)
+    if all(t == "." for t in toks):
+        ok = lambda p: (p - mp >= 0) & (p - mp <= L - length)
+        return meth[ok(meth)] if meth.size else meth, nonmeth[ok(nonmeth)] if nonmeth.size else nonmeth
+    asm = _single_contig_assembly(sequence)
+    plane, delta, length = _match_plane(asm, m, align=mp)
+
+    def pick(p):
+        if p.size == 0:
+            return p
+        pi = p.astype(np.int64)
+        keep = _test(plane, 0, L, pi - delta)
+        keep &= (pi - mp >= 0) & (pi - mp <= L - length)  # whole motif inside the contig
+        return p[keep]
+
+    return pick(meth), pick(nonmeth)
+
+
+# ---------------------------------------------------------------------------------------------
+# K2-backed scoring
+# ---------------------------------------------------------------------------------------------
+
+
+class BinScorer:
+    """Device context of one (bin, mod_type): the bin's contigs packed once, its pileup as class planes.
+
+    `score(motifs)` evaluates any number of motifs in ONE launch and returns int64 counts
+    [n_motifs, 2] = (n_mod, n_nomod) summed over both strands and all contigs -- exactly what
+    motif_model_bin adds to the Beta(5,5) prior.
+    """
+
+    def __init__(self, pileup, contigs, low_meth_threshold: float, high_meth_threshold: float, device=None):
+        table = PileupTable.from_frame(pileup)
+        self.assembly = DeviceAssembly.from_sequences(contigs, device)
+        asm = self.assembly
+        if table.contig is None:
+            if asm.n_contigs != 1:
+                raise KeyError("pileup has no 'contig' column but several contigs were given")
+            cid = np.zeros(len(table), dtype=np.int32)
+        else:
+            names = np.asarray(table.contig)
+            uniq, inv = np.unique(names, return_inverse=True)
+            lut = np.fromiter((asm.index.get(str(u), -1) for u in uniq), dtype=np.int32, count=len(uniq))
+            cid = lut[inv] if len(uniq) else np.zeros(0, dtype=np.int32)
+        self.table = table
+        self.contig_id = cid
+        self.pileup = DevicePileup.from_columns(asm, cid, table.position, strand_codes(table.strand),
+                                                table.fraction_mod, low_meth_threshold, high_meth_threshold)
+
+    def _jobs(self, n_motifs: int, per_contig: bool) -> tuple[np.ndarray, int]:
+        asm = self.assembly
+        jobs = make_jobs(1)
+        jobs["motif_begin"], jobs["motif_count"] = 0, n_motifs
+        jobs["tile_begin"], jobs["tile_count"] = 0, asm.n_tiles
+        jobs["contig_begin"], jobs["contig_end"] = 0, asm.n_contigs
+        jobs["group_mode"] = 1 if per_contig else 0
+        groups = asm.n_contigs if per_contig else 1
+        jobs["n_groups"] = groups
+        return jobs, n_motifs * groups
+
+    def counts_by_strand(self, motifs, per_contig: bool = False, motifs_per_item=None) -> torch.Tensor:
+        """int64 device tensor [n_motifs, (n_contigs,) 4]: n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'."""
+        motifs = list(motifs)
+        if not motifs:
+            shape = (0, self.assembly.n_contigs, 4) if per_contig else (0, 4)
+            return torch.zeros(shape, dtype=torch.int64, device=self.assembly.device)
+        progs = MotifPrograms(motifs, self.assembly.device, strip=True)
+        jobs, rows = self._jobs(len(motifs), per_contig)
+        out = scan_count(self.assembly, self.pileup, progs, jobs, rows, motifs_per_item)
+        return out.view(len(motifs), self.assembly.n_contigs, 4) if per_contig else out
+
+    def score(self, motifs) -> np.ndarray:
+        c = self.counts_by_strand(motifs).cpu().numpy()
+        return np.stack([c[:, 0] + c[:, 2], c[:, 1] + c[:, 3]], axis=1)
+
+
+def _scorer_for(pileup, contigs, low, high) -> BinScorer:
+    key = ("bin", id(pileup), id(contigs), float(low), float(high))
+    return _bin_cache.get(key, (pileup, contigs), lambda: BinScorer(pileup, contigs, low, high))
+
+
+def motif_model_bin(pileup, contigs, motif, model, low_meth_threshold, high_meth_threshold):
+    """Posterior of one motif over all contigs of a bin; mutates and returns `model`
+    (find_motifs_bin.py:1265-1283)."""
+    if len(contigs) == 0:
+        return model
+    n_mod, n_nomod = _scorer_for(pileup, contigs, low_meth_threshold, high_meth_threshold).score([motif])[0]
+    model.update(int(n_mod), int(n_nomod))
+    return model
+
+
+def motif_model_bin_many(pileup, contigs, motifs, low_meth_threshold, high_meth_threshold, model_factory=BetaBernoulliModel):
+    """Batched motif_model_bin: one launch for all motifs, one fresh model per motif."""
+    motifs = list(motifs)
+    if len(contigs) == 0 or not motifs:
+        return [model_factory() for _ in motifs]
+    counts = _scorer_for(pileup, contigs, low_meth_threshold, high_meth_threshold).score(motifs)
+    models = []
+    for n_mod, n_nomod in counts:
+        mdl = model_factory()
+        mdl.update(int(n_mod), int(n_nomod))
+        models.append(mdl)
+    return models
+
+
+def motif_model_contig(pileup, contig: str, prior, motif, low_meth_threshold=0.3, high_meth_threshold=0.7,
+                       save_motif_positions=False):
+    """Posterior update of one motif on one contig; `pileup` holds that contig's rows
+    (find_motifs_bin.py:1285-1331).  Mutates and returns `prior`."""
+    contig = sequence_of(contig)
+    table = PileupTable.from_frame(pileup)
+    m = as_motif(motif).new_stripped_motif()
+    key = ("contig", id(pileup), id(contig), float(low_meth_threshold), float(high_meth_threshold))
+
+    def build():
+        t = PileupTable(None, table.position, table.strand, table.fraction_mod)
+        return BinScorer(t, {"_": contig}, low_meth_threshold, high_meth_threshold)
+
+    scorer = _bin_cache.get(key, (pileup, contig), build)
+    c = scorer.counts_by_strand([m]).cpu().numpy()[0]
+    prior.update(int(c[0] + c[2]), int(c[1] + c[3]))
+    if not save_motif_positions:
+        return prior
+    # position lists in pileup order (find_motifs_bin.py:1308-1329)
+    strand = strand_codes(table.strand)
+    high = table.fraction_mod >= high_meth_threshold
+    low = table.fraction_mod <= low_meth_threshold
+    pos = table.position
+    fwd = methylated_motif_occourances(m, contig, pos[high & (strand == 0)], pos[low & (strand == 0)])
+    rev = methylated_motif_occourances(m.reverse_compliment(), contig, pos[high & (strand == 1)],
+                                       pos[low & (strand == 1)])
+    return prior, {"index_meth_fwd": fwd[0], "index_nonmeth_fwd": fwd[1],
+                   "index_meth_rev": rev[0], "index_nonmeth_rev": rev[1]}
+
+
+def get_parent_scores(motif, pileup, contigs, low_meth_threshold, high_meth_threshold):
+    """Score a motif against every parent (one constrained position reset to '.');
+    one batched launch instead of 1 + K sequential scans (find_motifs_bin.py:1382-1433)."""
+    m = as_motif(motif)
+    split = m.split()
+    parents, positions = [], []
+    for i, base in enumerate(split):
+        if i == m.mod_position or base in (".", "N"):
+            continue
+        toks = list(split)
+        toks[i] = "."
+        parents.append(Motif("".join(toks), m.mod_position))
+        positions.append(i)
+    models = motif_model_bin_many(pileup, contigs, [m] + parents, low_meth_threshold, high_meth_threshold)
+    child = models[0]
+    out = {}
+    for parent, i, pm in zip(parents, positions, models[1:]):
+        out[parent] = dict(motif_position=i, parent_model=pm, child_model=child,
+                           score=predictive_evaluation_score(child, pm))
+    return out

@@ -1,0 +1,189 @@
+// K1 -- loaders: ASCII contigs -> 2-bit tile records (+ non-ACGT plane), pileup rows -> class
+// bit-planes.  Reference behaviour being replaced: nanomotif/fasta.py:35-49 (contig strings),
+// nanomotif/seq.py:53-55 (upper-casing), nanomotif/find_motifs_bin.py:1308-1314 (per-call split
+// of the pileup into methylated / unmethylated x strand position arrays).
+#include "common.cuh"
+
+namespace nmb {
+
+// One warp per 256-bp chunk.  Lane l reads base l of each of the chunk's 8 words (coalesced
+// 32-byte reads) and three ballots build the word of each plane.
+__global__ void __launch_bounds__(256) pack_sequence_kernel(
+    const uint8_t *__restrict__ ascii, const int64_t *__restrict__ ascii_off,
+    const int64_t *__restrict__ contig_start, const int64_t *__restrict__ contig_len,
+    int n_contigs, int n_tiles, uint32_t *__restrict__ seq_records, uint32_t *__restrict__ nonacgt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_chunks = (int64_t)n_tiles * kTileChunks;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); q < n_chunks;
+         q += warps_total) {
+        const int64_t chunk_pos = q * NMB_CHUNK_BP;
+        // largest c with contig_start[c] <= chunk_pos (uniform binary search)
+        int lo = 0, hi = n_contigs;  // invariant: start[lo-1] <= chunk_pos < start[hi]
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(contig_start + mid) <= chunk_pos) lo = mid + 1; else hi = mid;
+        }
+        int c = lo - 1;
+        int64_t local0 = 0, len = 0, aoff = 0;
+        if (c >= 0) {
+            local0 = chunk_pos - __ldg(contig_start + c);
+            len = __ldg(contig_len + c);
+            aoff = __ldg(ascii_off + c);
+            if (local0 >= len) c = -1;
+        }
+        uint32_t my_x = 0, my_y = 0, my_n = 0xFFFFFFFFu;
+#pragma unroll
+        for (int w = 0; w < kChunkWords; ++w) {
+            int code = 4;
+            if (c >= 0) {
+                int64_t local = local0 + w * 32 + lane;
+                if (local < len) {
+                    int ch = ascii[aoff + local] & 0xDF;  // upper-case (seq.py:55)
+                    code = ch == 'A' ? 0 : ch == 'T' ? 1 : ch == 'G' ? 2 : ch == 'C' ? 3 : 4;
+                }
+            }
+            uint32_t xb = __ballot_sync(0xFFFFFFFFu, (code & 2) && code < 4);
+            uint32_t yb = __ballot_sync(0xFFFFFFFFu, (code & 1) && code < 4);
+            uint32_t nb = __ballot_sync(0xFFFFFFFFu, code == 4);
+            if (lane == w) { my_x = xb; my_y = yb; my_n = nb; }
+        }
+        if (lane < kChunkWords) {
+            const int64_t gw = q * kChunkWords + lane;  // global word
+            const int64_t tile = gw / kTileWords;
+            const int wt = (int)(gw % kTileWords);
+            uint32_t *rec = seq_records + tile * kSeqRecWords;
+            rec[kHalo + wt] = my_x;
+            rec[kSeqPlaneWords + kHalo + wt] = my_y;
+            if (wt < kHalo) {  // also the right halo of the previous tile / zero left edge
+                if (tile > 0) {
+                    uint32_t *prev = rec - kSeqRecWords;
+                    prev[kHalo + kTileWords + wt] = my_x;
+                    prev[kSeqPlaneWords + kHalo + kTileWords + wt] = my_y;
+                } else {
+                    rec[wt] = 0;
+                    rec[kSeqPlaneWords + wt] = 0;
+                }
+            }
+            if (wt >= kTileWords - kHalo) {  // also the left halo of the next tile / zero right edge
+                const int h = wt - (kTileWords - kHalo);
+                if (tile + 1 < n_tiles) {
+                    uint32_t *next = rec + kSeqRecWords;
+                    next[h] = my_x;
+                    next[kSeqPlaneWords + h] = my_y;
+                } else {
+                    rec[kHalo + kTileWords + h] = 0;
+                    rec[kSeqPlaneWords + kHalo + kTileWords + h] = 0;
+                }
+            }
+            nonacgt[kHalo + gw] = my_n;
+        }
+        if (lane == 0) {
+            const int64_t tile = q / kTileChunks;
+            seq_records[tile * kSeqRecWords + 2 * kSeqPlaneWords + (int)(q % kTileChunks)] =
+                (uint32_t)c;
+        }
+    }
+}
+
+// Second pass: a chunk needs the non-ACGT path when any flagged letter lies within its words or
+// the two halo words on either side (motif length <= 62 < 64).
+__global__ void __launch_bounds__(256) chunk_flags_kernel(int n_tiles,
+                                                          uint32_t *__restrict__ seq_records,
+                                                          uint32_t *__restrict__ nonacgt) {
+    const int64_t n_chunks = (int64_t)n_tiles * kTileChunks;
+    const int64_t n_words = (int64_t)n_tiles * kTileWords;
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) {
+        for (int i = 0; i < kHalo; ++i) {
+            nonacgt[i] = 0xFFFFFFFFu;
+            nonacgt[kHalo + n_words + i] = 0xFFFFFFFFu;
+        }
+    }
+    if (q >= n_chunks) return;
+    uint32_t any = 0;
+    const uint32_t *p = nonacgt + kHalo + q * kChunkWords;
+    for (int i = -2; i < kChunkWords + 2; ++i) {
+        // pad words are written by thread 0 concurrently: treat the array ends as flagged
+        int64_t gw = q * kChunkWords + i;
+        any |= (gw < 0 || gw >= n_words) ? 0xFFFFFFFFu : p[i];
+    }
+    uint32_t *info = seq_records + (q / kTileChunks) * kSeqRecWords + 2 * kSeqPlaneWords +
+                     (int)(q % kTileChunks);
+    int c = (int)*info;
+    if (c >= 0 && any) *info = (uint32_t)(c | kChunkFlagN);
+}
+
+__global__ void __launch_bounds__(256) class_planes_kernel(
+    const int32_t *__restrict__ contig_id, const int64_t *__restrict__ pos,
+    const uint8_t *__restrict__ strand, const uint8_t *__restrict__ modtype,
+    const double *__restrict__ fraction, int64_t n_rows, double low, double high,
+    const int64_t *__restrict__ contig_start, const int64_t *__restrict__ contig_len, int n_contigs,
+    int n_tiles, int n_modtypes, uint32_t *__restrict__ cls) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const int c = contig_id[r];
+        if (c < 0 || c >= n_contigs) continue;
+        const int64_t p = pos[r];
+        if (p < 0 || p >= __ldg(contig_len + c)) continue;
+        const int mt = modtype ? modtype[r] : 0;
+        if (mt >= n_modtypes) continue;
+        const double f = fraction[r];
+        const bool is_mod = f >= high;   // find_motifs_bin.py:1308
+        const bool is_non = f <= low;    // find_motifs_bin.py:1309
+        if (!is_mod && !is_non) continue;
+        const int64_t g = __ldg(contig_start + c) + p;
+        const int64_t tile = g >> 16;
+        const int w = (int)((g >> 5) & (kTileWords - 1));
+        const uint32_t bit = 1u << (g & 31);
+        uint32_t *rec = cls + ((int64_t)mt * n_tiles + tile) * kClsRecWords +
+                        (strand[r] ? 2 : 0) * kTileWords + w;
+        if (is_mod) atomicOr(rec, bit);
+        if (is_non) atomicOr(rec + kTileWords, bit);
+    }
+}
+
+}  // namespace nmb
+
+extern "C" {
+
+int nmb_pack_sequence(const uint8_t *ascii, const int64_t *ascii_off, const int64_t *contig_start,
+                      const int64_t *contig_len, int32_t n_contigs, int32_t n_tiles,
+                      uint32_t *seq_records, uint32_t *nonacgt, void *stream) {
+    NMB_REQUIRE(n_contigs >= 0 && n_tiles > 0, "nmb_pack_sequence: n_contigs=%d n_tiles=%d", n_contigs,
+                n_tiles);
+    NMB_REQUIRE(seq_records && nonacgt, "nmb_pack_sequence: null output");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n_chunks = (int64_t)n_tiles * nmb::kTileChunks;
+    int64_t blocks = (n_chunks + 7) / 8;  // 8 warps per block
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    nmb::pack_sequence_kernel<<<(unsigned)blocks, 256, 0, s>>>(ascii, ascii_off, contig_start,
+                                                              contig_len, n_contigs, n_tiles,
+                                                              seq_records, nonacgt);
+    NMB_CUDA(cudaGetLastError());
+    nmb::chunk_flags_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, s>>>(n_tiles, seq_records,
+                                                                              nonacgt);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_build_class_planes(const int32_t *contig_id, const int64_t *pos, const uint8_t *strand,
+                           const uint8_t *modtype, const double *fraction_mod, int64_t n_rows,
+                           double low, double high, const nmb_assembly *a, int32_t n_modtypes,
+                           uint32_t *class_records, void *stream) {
+    NMB_REQUIRE(a && class_records, "nmb_build_class_planes: null argument");
+    NMB_REQUIRE(n_rows >= 0 && n_modtypes > 0 && a->n_tiles > 0, "nmb_build_class_planes: bad sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = (size_t)n_modtypes * a->n_tiles * nmb::kClsRecBytes;
+    NMB_CUDA(cudaMemsetAsync(class_records, 0, bytes, s));
+    if (n_rows == 0) return NMB_OK;
+    int64_t blocks = (n_rows + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    nmb::class_planes_kernel<<<(unsigned)blocks, 256, 0, s>>>(
+        contig_id, pos, strand, modtype, fraction_mod, n_rows, low, high, a->contig_start,
+        a->contig_len, a->n_contigs, a->n_tiles, n_modtypes, class_records);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+}  // extern "C"

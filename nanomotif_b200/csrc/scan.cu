@@ -1,0 +1,302 @@
+// K2 -- fused motif scan + gather-join + segmented reduce, and the motif compiler.
+//
+// Replaces, for a whole batch of (motif, contig-set) pairs in one launch:
+//   utils.subseq_indices                      nanomotif/utils.py:44-67        (regex scan)
+//   methylated_motif_occourances              nanomotif/find_motifs_bin.py:1234-1263 (np.isin join)
+//   motif_model_contig (count step)           nanomotif/find_motifs_bin.py:1285-1331
+//   motif_model_bin (sum over contigs)        nanomotif/find_motifs_bin.py:1265-1283
+//
+// Persistent CTAs walk a list of work items (tile, block of <=32 motifs).  A tile is one
+// self-contained 17.5 KB sequence record + one 32 KB class record, brought into shared memory by two
+// cp.async.bulk (TMA) copies that complete on an mbarrier; a 2-stage ring overlaps the copy of the
+// next item with the bit-parallel evaluation of the current one.  Counts are popcounts of
+// match & class-plane, reduced with warp REDUX, accumulated per CTA in shared memory and flushed
+// with one 64-bit atomic per (motif, counter) per item.
+#include "scan.cuh"
+
+namespace nmb {
+
+constexpr int kStages = 2;
+constexpr int kStageBytes = ((kSeqRecBytes + kClsRecBytes + 127) / 128) * 128;  // 50304
+constexpr int kScanThreads = kTileChunks;                                       // 256
+constexpr int kMaxMpi = NMB_MAX_MOTIFS_PER_ITEM;
+
+struct ScanParams {
+    const uint32_t *seq_records;
+    const uint32_t *nonacgt;
+    const uint32_t *cls;
+    const Program *programs;
+    const nmb_job *jobs;
+    const int32_t *contig_group;
+    unsigned long long *out;
+    int n_jobs, n_items, mpi, n_tiles;
+};
+
+struct ItemMeta {
+    int job, tile, mblk, pad;
+};
+
+__device__ __forceinline__ ItemMeta decode_item(const ScanParams &p, int item) {
+    int lo = 0, hi = p.n_jobs;  // largest j with item_offset[j] <= item
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&p.jobs[mid].item_offset) <= item) lo = mid; else hi = mid;
+    }
+    const int local = item - __ldg(&p.jobs[lo].item_offset);
+    const int nblk = (__ldg(&p.jobs[lo].motif_count) + p.mpi - 1) / p.mpi;
+    ItemMeta m;
+    m.job = lo;
+    m.tile = __ldg(&p.jobs[lo].tile_begin) + local / nblk;  // tile-major: concurrent CTAs share a tile in L2
+    m.mblk = local % nblk;
+    m.pad = 0;
+    return m;
+}
+
+__device__ __forceinline__ int group_of(const nmb_job &job, int contig, const int32_t *contig_group) {
+    if (contig < job.contig_begin || contig >= job.contig_end) return -1;
+    if (job.group_mode == 0) return 0;
+    if (job.group_mode == 1) return contig - job.contig_begin;
+    return __ldg(contig_group + contig);
+}
+
+template <bool HASN, int H>
+__device__ __forceinline__ void count_strand(const ProgramView &pv, const LaneSeq<H> &q,
+                                             const uint32_t *cls_mod, const uint32_t *cls_non,
+                                             uint32_t &n_mod, uint32_t &n_non) {
+    uint32_t m[NW];
+    match_words<HASN, H>(pv, q, m);
+    const uint4 a0 = *reinterpret_cast<const uint4 *>(cls_mod);
+    const uint4 a1 = *reinterpret_cast<const uint4 *>(cls_mod + 4);
+    const uint4 b0 = *reinterpret_cast<const uint4 *>(cls_non);
+    const uint4 b1 = *reinterpret_cast<const uint4 *>(cls_non + 4);
+    n_mod = __popc(m[0] & a0.x) + __popc(m[1] & a0.y) + __popc(m[2] & a0.z) + __popc(m[3] & a0.w) +
+            __popc(m[4] & a1.x) + __popc(m[5] & a1.y) + __popc(m[6] & a1.z) + __popc(m[7] & a1.w);
+    n_non = __popc(m[0] & b0.x) + __popc(m[1] & b0.y) + __popc(m[2] & b0.z) + __popc(m[3] & b0.w) +
+            __popc(m[4] & b1.x) + __popc(m[5] & b1.y) + __popc(m[6] & b1.z) + __popc(m[7] & b1.w);
+}
+
+template <int H>
+__global__ void __launch_bounds__(kScanThreads, 2) scan_count_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ ItemMeta s_meta[kStages];
+    __shared__ uint32_t s_acc[2][kMaxMpi][4];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int n_my = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < 2 * kMaxMpi * 4; i += kScanThreads) (&s_acc[0][0][0])[i] = 0;
+    __syncthreads();
+
+    auto issue = [&](int k) {  // thread 0 only
+        const int stage = k % kStages;
+        const ItemMeta m = decode_item(p, (int)blockIdx.x + k * (int)gridDim.x);
+        s_meta[stage] = m;
+        uint8_t *dst = smem + (size_t)stage * kStageBytes;
+        const int modtype = __ldg(&p.jobs[m.job].modtype);
+        fence_proxy_async();  // order earlier generic reads of this stage before the async writes
+        mbar_expect_tx(&full_bar[stage], kSeqRecBytes + kClsRecBytes);
+        bulk_g2s(dst, p.seq_records + (size_t)m.tile * kSeqRecWords, kSeqRecBytes, &full_bar[stage]);
+        bulk_g2s(dst + kSeqRecBytes,
+                 p.cls + ((size_t)modtype * p.n_tiles + m.tile) * kClsRecWords, kClsRecBytes,
+                 &full_bar[stage]);
+    };
+
+    if (tid == 0)
+        for (int k = 0; k < kStages - 1 && k < n_my; ++k) issue(k);
+
+    for (int k = 0; k < n_my; ++k) {
+        const int stage = k % kStages;
+        if (tid == 0 && k + kStages - 1 < n_my) issue(k + kStages - 1);
+        mbar_wait(&full_bar[stage], (uint32_t)((k / kStages) & 1));
+
+        const ItemMeta meta = s_meta[stage];
+        const nmb_job job = p.jobs[meta.job];
+        const uint32_t *sx = reinterpret_cast<const uint32_t *>(smem + (size_t)stage * kStageBytes);
+        const uint32_t *sy = sx + kSeqPlaneWords;
+        const int32_t *sinfo = reinterpret_cast<const int32_t *>(sy + kSeqPlaneWords);
+        const uint32_t *scls = sx + kSeqRecWords;
+        const int par = k & 1;
+
+        const int info = sinfo[tid];
+        const int contig = info < 0 ? -1 : (info & kChunkIdMask);
+        const int g = contig < 0 ? -1 : group_of(job, contig, p.contig_group);
+        const bool valid = g >= 0;
+        // group whose counts go through the CTA's shared accumulators: the one of the tile's first chunk
+        const int info0 = sinfo[0];
+        const int primary = info0 < 0 ? -1 : group_of(job, info0 & kChunkIdMask, p.contig_group);
+
+        if (__any_sync(0xFFFFFFFFu, valid)) {
+            const int g0 = __shfl_sync(0xFFFFFFFFu, g, 0);
+            const bool uniform = __all_sync(0xFFFFFFFFu, g == g0);
+            const bool warp_n = __any_sync(0xFFFFFFFFu, valid && (info & kChunkFlagN));
+
+            LaneSeq<H> q;
+            load_plane<H>(sx + kHalo + tid * NW, q.x);
+            load_plane<H>(sy + kHalo + tid * NW, q.y);
+            if (warp_n) {
+                const uint32_t *gn = p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H;
+#pragma unroll
+                for (int i = 0; i < NW + 2 * H; ++i) q.n[i] = __ldg(gn + i);
+            }
+            const uint32_t *cl = scls + tid * NW;
+            const int m_begin = job.motif_begin + meta.mblk * p.mpi;
+            const int m_count = min(p.mpi, job.motif_count - meta.mblk * p.mpi);
+
+#pragma unroll 1
+            for (int mi = 0; mi < m_count; ++mi) {
+                const Program *prog = p.programs + (size_t)(m_begin + mi) * 2;
+                uint32_t cnt[4];  // n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'
+#pragma unroll 1
+                for (int st = 0; st < 2; ++st) {  // forward motif, then its reverse complement
+                    const ProgramView pv = load_program(prog + st);
+                    const uint32_t *c0 = cl + 2 * st * kTileWords;
+                    uint32_t a, b;
+                    if (warp_n)
+                        count_strand<true, H>(pv, q, c0, c0 + kTileWords, a, b);
+                    else
+                        count_strand<false, H>(pv, q, c0, c0 + kTileWords, a, b);
+                    if (st == 0) { cnt[0] = a; cnt[1] = b; } else { cnt[2] = a; cnt[3] = b; }
+                }
+                const uint32_t mod_f = cnt[0], non_f = cnt[1], mod_r = cnt[2], non_r = cnt[3];
+                // per-lane counts are <= 256: two 16-bit fields per word survive a 32-lane sum
+                uint32_t pk_f = valid ? (mod_f | (non_f << 16)) : 0u;
+                uint32_t pk_r = valid ? (mod_r | (non_r << 16)) : 0u;
+                const long long row =
+                    job.out_base + (long long)(meta.mblk * p.mpi + mi) * job.n_groups;
+                if (uniform) {
+                    pk_f = __reduce_add_sync(0xFFFFFFFFu, pk_f);
+                    pk_r = __reduce_add_sync(0xFFFFFFFFu, pk_r);
+                    if (lane == 0 && (pk_f | pk_r)) {
+                        const uint32_t v[4] = {pk_f & 0xFFFFu, pk_f >> 16, pk_r & 0xFFFFu, pk_r >> 16};
+                        if (g0 == primary) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                if (v[c]) atomicAdd(&s_acc[par][mi][c], v[c]);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                if (v[c]) atomicAdd(p.out + (row + g0) * 4 + c, (unsigned long long)v[c]);
+                        }
+                    }
+                } else if (pk_f | pk_r) {
+                    const uint32_t v[4] = {pk_f & 0xFFFFu, pk_f >> 16, pk_r & 0xFFFFu, pk_r >> 16};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (v[c]) atomicAdd(p.out + (row + g) * 4 + c, (unsigned long long)v[c]);
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with this stage and with s_acc[par]
+        if (tid < kMaxMpi * 4) {
+            const int mi = tid >> 2, c = tid & 3;
+            const uint32_t v = s_acc[par][mi][c];
+            if (v) {
+                s_acc[par][mi][c] = 0;
+                const long long row =
+                    job.out_base + (long long)(meta.mblk * p.mpi + mi) * job.n_groups + primary;
+                atomicAdd(p.out + row * 4 + c, (unsigned long long)v);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// motif compiler: nmb_motif -> forward and reverse-complement Programs
+// ---------------------------------------------------------------------------------------------
+__global__ void compile_motifs_kernel(const nmb_motif *__restrict__ motifs, int n_motifs,
+                                      Program *__restrict__ programs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n_motifs) return;
+    const nmb_motif mt = motifs[t >> 1];
+    const bool rc = t & 1;
+    Program pr;
+    uint16_t *ent = pr.ent;
+    for (int i = 0; i < kMaxLen; ++i) ent[i] = 0;
+    int len = mt.len, mp = mt.mod_pos;
+    if (len < 1 || len > kMaxLen || mp >= len) {  // invalid: compile to "never matches"
+        pr.n = 1; pr.n_left = 1; pr.mod_pos = 0; pr.len = 1;
+        ent[0] = 0;
+        programs[t] = pr;
+        return;
+    }
+    if (rc) mp = len - 1 - mp;  // motif.py:264
+    int n = 0, n_left = 0;
+    for (int j = 0; j < len; ++j) {
+        int a = mt.allowed[rc ? (len - 1 - j) : j] & 0xF;
+        if (rc) a = ((a & 5) << 1) | ((a & 10) >> 1);  // A<->T, G<->C (constants.py:14-20)
+        if (a == 0xF) continue;
+        ent[n++] = (uint16_t)(a | (j << 8));
+        if (j <= mp) n_left = n;
+    }
+    pr.n = (uint8_t)n; pr.n_left = (uint8_t)n_left; pr.mod_pos = (uint8_t)mp; pr.len = (uint8_t)len;
+    programs[t] = pr;
+}
+
+}  // namespace nmb
+
+extern "C" {
+
+int nmb_compile_motifs(const nmb_motif *motifs, int32_t n_motifs, void *programs, void *stream) {
+    NMB_REQUIRE(n_motifs >= 0, "nmb_compile_motifs: n_motifs=%d", n_motifs);
+    if (n_motifs == 0) return NMB_OK;
+    NMB_REQUIRE(motifs && programs, "nmb_compile_motifs: null argument");
+    nmb::compile_motifs_kernel<<<(2 * n_motifs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        motifs, n_motifs, (nmb::Program *)programs);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_scan_count(const nmb_assembly *a, const uint32_t *class_records, const void *programs,
+                   const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
+                   int32_t max_motif_len, const int32_t *contig_group, int64_t *out,
+                   int32_t grid_ctas, void *stream) {
+    NMB_REQUIRE(a && class_records && programs && jobs && out, "nmb_scan_count: null argument");
+    NMB_REQUIRE(n_jobs > 0 && n_items >= 0, "nmb_scan_count: n_jobs=%d n_items=%d", n_jobs, n_items);
+    NMB_REQUIRE(motifs_per_item >= 1 && motifs_per_item <= NMB_MAX_MOTIFS_PER_ITEM,
+                "nmb_scan_count: motifs_per_item=%d not in 1..%d", motifs_per_item,
+                NMB_MAX_MOTIFS_PER_ITEM);
+    NMB_REQUIRE(max_motif_len >= 1 && max_motif_len <= NMB_MAX_MOTIF_LEN,
+                "nmb_scan_count: max_motif_len=%d not in 1..%d", max_motif_len, NMB_MAX_MOTIF_LEN);
+    if (n_items == 0) return NMB_OK;
+    nmb::ScanParams p;
+    p.seq_records = a->seq_records;
+    p.nonacgt = a->nonacgt;
+    p.cls = class_records;
+    p.programs = (const nmb::Program *)programs;
+    p.jobs = jobs;
+    p.contig_group = contig_group;
+    p.out = (unsigned long long *)out;
+    p.n_jobs = n_jobs;
+    p.n_items = n_items;
+    p.mpi = motifs_per_item;
+    p.n_tiles = a->n_tiles;
+
+    int grid = grid_ctas;
+    if (grid <= 0) {
+        int sms = nmb_device_sm_count();
+        if (sms < 0) return sms;
+        grid = 2 * sms;
+    }
+    if (grid > n_items) grid = n_items;
+    const int smem = nmb::kStages * nmb::kStageBytes;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (max_motif_len <= 33) {
+        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<1>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nmb::scan_count_kernel<1><<<grid, nmb::kScanThreads, smem, s>>>(p);
+    } else {
+        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<2>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nmb::scan_count_kernel<2><<<grid, nmb::kScanThreads, smem, s>>>(p);
+    }
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+"""Device-resident data model of the scoring path: packed assembly, pileup class planes, scan launches.
+
+torch is used for device memory, streams and H2D/D2H copies only; every byte of arithmetic on the
+path happens in libnmb200's CUDA kernels (nanomotif_b200/csrc).  Layout: DESIGN.md section 3.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Mapping, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NmbAssembly, check, lib, ptr
+from .motif import pack_motifs
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("nanomotif_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"nanomotif_b200 runs on CUDA devices only, got {dev}")
+    return dev
+
+
+_NP_OF = {torch.int32: np.int32, torch.int64: np.int64, torch.uint8: np.uint8, torch.float64: np.float64}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _to_device(arr: np.ndarray, device: torch.device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=True)
+
+
+def sequence_of(obj) -> str:
+    """Contig text of a str or of a reference ``DNAsequence`` (nanomotif/seq.py:21-60)."""
+    return obj if isinstance(obj, str) else obj.sequence
+
+
+def plan_layout(lengths: Sequence[int]) -> tuple[np.ndarray, int]:
+    """Global start position of every contig (256-bp aligned, >= 64 flagged positions apart) and
+    the number of 65536-bp tiles."""
+    starts = np.zeros(len(lengths), dtype=np.int64)
+    cur = 0
+    for i, n in enumerate(lengths):
+        starts[i] = cur
+        cur = -(-(cur + int(n) + _lib.MIN_GAP_BP) // _lib.CHUNK_BP) * _lib.CHUNK_BP
+    n_tiles = max(1, -(-cur // _lib.TILE_BP))
+    return starts, n_tiles
+
+
+class DeviceAssembly:
+    """Contigs packed as 2-bit planes in tile records on one GPU (replaces the ``dict[str, DNAsequence]``
+    of Python strings the reference scans, nanomotif/seq.py:11-19)."""
+
+    def __init__(self, names, lengths, ascii_u8, ascii_off, device=None):
+        self.device = _require_cuda(device)
+        self.names = list(names)
+        self.index = {n: i for i, n in enumerate(self.names)}
+        self.lengths = np.asarray(lengths, dtype=np.int64)
+        self.starts, self.n_tiles = plan_layout(self.lengths)
+        self.n_contigs = len(self.names)
+        self.n_words = self.n_tiles * _lib.TILE_WORDS
+        with torch.cuda.device(self.device):
+            d = self.device
+            self.seq_records = torch.empty(self.n_tiles * _lib.SEQ_REC_WORDS, dtype=torch.int32, device=d)
+            self.nonacgt = torch.empty(self.n_words + 2 * _lib.HALO_WORDS, dtype=torch.int32, device=d)
+            self.contig_start = _to_device(self.starts, d)
+            self.contig_len = _to_device(self.lengths, d)
+            ascii_d = ascii_u8 if isinstance(ascii_u8, torch.Tensor) else _to_device(ascii_u8, d)
+            off_d = _to_device(np.asarray(ascii_off, dtype=np.int64), d)
+            check(
+                lib.nmb_pack_sequence(ptr(ascii_d), ptr(off_d), ptr(self.contig_start), ptr(self.contig_len),
+                                      self.n_contigs, self.n_tiles, ptr(self.seq_records), ptr(self.nonacgt),
+                                      _stream()),
+                "nmb_pack_sequence",
+            )
+            # ascii_d / off_d may be released once the kernels have run
+            torch.cuda.current_stream().synchronize()
+        self._view = NmbAssembly(ptr(self.seq_records), ptr(self.nonacgt), ptr(self.contig_start),
+                                 ptr(self.contig_len), self.n_contigs, self.n_tiles)
+
+    @classmethod
+    def from_sequences(cls, contigs: Mapping[str, object], device=None) -> "DeviceAssembly":
+        names = list(contigs.keys())
+        seqs = [sequence_of(contigs[n]) for n in names]
+        lengths = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
+        off = np.zeros(len(seqs), dtype=np.int64)
+        if len(seqs):
+            off[1:] = np.cumsum(lengths)[:-1]
+        buf = np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8) if len(seqs) else np.zeros(0, np.uint8)
+        if buf.size == 0:
+            buf = np.zeros(1, dtype=np.uint8)
+        return cls(names, lengths, buf, off, device)
+
+    def view(self) -> NmbAssembly:
+        return self._view
+
+    def tile_span(self, contig_begin: int, contig_end: int) -> tuple[int, int]:
+        """Tiles [begin, begin+count) that cover contigs [contig_begin, contig_end)."""
+        if contig_end <= contig_begin:
+            return 0, 0
+        first = int(self.starts[contig_begin]) // _lib.TILE_BP
+        last_pos = int(self.starts[contig_end - 1] + self.lengths[contig_end - 1]) - 1
+        last = max(first, last_pos // _lib.TILE_BP)
+        return first, last - first + 1
+
+    @property
+    def total_bp(self) -> int:
+        return int(self.lengths.sum())
+
+
+class DevicePileup:
+    """Methylated / unmethylated x strand bit-planes per mod type (class records)."""
+
+    def __init__(self, assembly: DeviceAssembly, n_modtypes: int, low: float, high: float):
+        self.assembly = assembly
+        self.n_modtypes = int(n_modtypes)
+        self.low, self.high = float(low), float(high)
+        self.class_records = torch.empty(self.n_modtypes * assembly.n_tiles * _lib.CLS_REC_WORDS,
+                                         dtype=torch.int32, device=assembly.device)
+
+    @classmethod
+    def from_columns(cls, assembly: DeviceAssembly, contig_id, position, strand, fraction_mod, low, high,
+                     mod_type=None, n_modtypes: int = 1) -> "DevicePileup":
+        """contig_id int32 (index into the assembly, negative = ignore), position int64, strand uint8
+        (0 '+', 1 '-'), fraction_mod float64, mod_type uint8 or None.  numpy arrays or device tensors."""
+        self = cls(assembly, n_modtypes, low, high)
+        d = assembly.device
+
+        def dev(a, dt):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                return a.to(device=d, dtype=dt).contiguous()
+            return _to_device(np.asarray(a).astype(_NP_OF[dt], copy=False), d)
+
+        with torch.cuda.device(d):
+            cid, pos = dev(contig_id, torch.int32), dev(position, torch.int64)
+            st, fr, mt = dev(strand, torch.uint8), dev(fraction_mod, torch.float64), dev(mod_type, torch.uint8)
+            n = int(cid.numel())
+            for t in (pos, st, fr) + ((mt,) if mt is not None else ()):
+                if int(t.numel()) != n:
+                    raise ValueError("pileup columns differ in length")
+            view = assembly.view()
+            check(
+                lib.nmb_build_class_planes(ptr(cid), ptr(pos), ptr(st), ptr(mt), ptr(fr), n, self.low, self.high,
+                                           C.byref(view), self.n_modtypes, ptr(self.class_records), _stream()),
+                "nmb_build_class_planes",
+            )
+            torch.cuda.current_stream().synchronize()
+        return self
+
+
+def make_jobs(n: int) -> np.ndarray:
+    return np.zeros(n, dtype=_lib.JOB_DTYPE)
+
+
+def choose_motifs_per_item(jobs: np.ndarray, sm_count: int) -> int:
+    motif_tiles = int((jobs["motif_count"].astype(np.int64) * jobs["tile_count"]).sum())
+    target_items = 16 * sm_count  # ~8 items per resident CTA keeps the tail short
+    mpi = motif_tiles // max(1, target_items)
+    return int(min(_lib.MAX_MOTIFS_PER_ITEM, max(1, mpi)))
+
+
+_SM_COUNT: dict[int, int] = {}
+
+
+def sm_count(device: torch.device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+class MotifPrograms:
+    """Motifs compiled on the device into forward / reverse-complement scan programs."""
+
+    def __init__(self, motifs: Iterable, device: torch.device, strip: bool = True, mod_pos_override=None):
+        packed = motifs if isinstance(motifs, np.ndarray) else pack_motifs(list(motifs), strip, mod_pos_override)
+        self.packed = packed
+        self.n = len(packed)
+        self.max_len = int(packed["len"].max()) if self.n else 1
+        self.device = device
+        with torch.cuda.device(device):
+            self.motifs_d = _to_device(packed.view(np.uint8).reshape(-1), device)
+            self.programs = torch.empty(max(1, self.n) * lib.nmb_program_bytes(), dtype=torch.uint8, device=device)
+            check(lib.nmb_compile_motifs(ptr(self.motifs_d), self.n, ptr(self.programs), _stream()),
+                  "nmb_compile_motifs")
+
+
+def scan_count(assembly: DeviceAssembly, pileup: DevicePileup, programs: MotifPrograms, jobs: np.ndarray,
+               n_out_rows: int, motifs_per_item: int | None = None, contig_group: torch.Tensor | None = None,
+               grid_ctas: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Launch K2 for a batch of jobs.  Returns the int64 device tensor [n_out_rows, 4]
+    (n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'); nothing is synchronised."""
+    d = assembly.device
+    with torch.cuda.device(d):
+        mpi = motifs_per_item or choose_motifs_per_item(jobs, sm_count(d))
+        jobs = jobs.copy()
+        items = jobs["tile_count"].astype(np.int64) * (-(-jobs["motif_count"].astype(np.int64) // mpi))
+        offs = np.zeros(len(jobs), dtype=np.int64)
+        offs[1:] = np.cumsum(items)[:-1]
+        n_items = int(items.sum())
+        if n_items >= 2**31:
+            raise ValueError("too many work items for one launch")
+        jobs["item_offset"] = offs.astype(np.int32)
+        jobs_d = _to_device(jobs.view(np.uint8).reshape(-1), d)
+        if out is None:
+            out = torch.zeros((n_out_rows, 4), dtype=torch.int64, device=d)
+        view = assembly.view()
+        check(
+            lib.nmb_scan_count(C.byref(view), ptr(pileup.class_records), ptr(programs.programs), ptr(jobs_d),
+                               len(jobs), n_items, mpi, programs.max_len, ptr(contig_group), ptr(out), grid_ctas,
+                               _stream()),
+            "nmb_scan_count",
+        )
+        # jobs_d goes back to torch's caching allocator; reuse is ordered on this same stream
+    return out

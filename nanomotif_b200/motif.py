@@ -1,0 +1,196 @@
+"""Motif value type of the scoring path and its compilation to device masks.
+
+Mirrors the part of the reference's ``nanomotif.motif.Motif`` (nanomotif/motif.py:18-359) that the
+hot path consumes: a regex-subset string over ``A C G T . [..]`` plus the 0-based index of the
+modified base.  The string algebra stays on the host; what the GPU sees is one 4-bit allowed-set per
+motif position (bit0=A bit1=T bit2=G bit3=C, the order of nanomotif/constants.py:21-28).
+
+Any object with ``str(obj)`` = motif string and an integer ``mod_position`` attribute (e.g. the
+reference's own ``Motif``) is accepted wherever this module takes a motif.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+BASES = ("A", "T", "G", "C")  # nanomotif/constants.py:1 -- PSSM row order and bit order
+_BIT = {"A": 1, "T": 2, "G": 4, "C": 8}
+_WILD = 0xF
+_COMP_BASE = {"A": "T", "T": "A", "G": "C", "C": "G", ".": ".", "N": "N"}
+_IUPAC_SETS = {
+    "A": "A", "C": "C", "G": "G", "T": "T", "R": "AG", "Y": "CT", "S": "CG", "W": "AT", "K": "GT",
+    "M": "AC", "B": "CGT", "D": "AGT", "H": "ACT", "V": "ACG", "N": "ACGT",
+}
+_SET_TO_IUPAC = {frozenset(v): k for k, v in _IUPAC_SETS.items()}
+
+
+def tokenize(motif_string: str) -> list[str]:
+    """Split into per-position tokens, keeping bracket classes together (motif.py:226-245)."""
+    out, i, n = [], 0, len(motif_string)
+    while i < n:
+        ch = motif_string[i]
+        if ch == "[":
+            j = motif_string.find("]", i)
+            if j < 0:
+                raise ValueError("Unmatched bracket")
+            out.append(motif_string[i : j + 1])
+            i = j + 1
+        else:
+            out.append(ch)
+            i += 1
+    return out
+
+
+def token_mask(token: str) -> int:
+    """Allowed-set of one token under *regex* semantics (what utils.subseq_indices matches)."""
+    if token == ".":
+        return _WILD
+    letters = token[1:-1] if token.startswith("[") else token
+    m = 0
+    for ch in letters:
+        if ch not in _BIT:
+            raise ValueError(f"motif token {token!r}: only A, C, G, T, '.' and [..] classes are supported")
+        m |= _BIT[ch]
+    if m == 0:
+        raise ValueError(f"empty motif token {token!r}")
+    return m
+
+
+class Motif(str):
+    """``Motif("G[AG].GAAG[CT]", 5)`` -- same constructor and attributes as the reference type."""
+
+    def __new__(cls, motif_string, *args, **kwargs):
+        return str.__new__(cls, motif_string)
+
+    def __init__(self, _motif_string, mod_position):
+        self.mod_position = mod_position
+        self.string = str.__str__(self)
+
+    # value semantics identical to motif.py:26-36
+    def __eq__(self, other):
+        return (
+            hasattr(other, "mod_position")
+            and isinstance(other, str)
+            and str.__str__(self) == str.__str__(other)
+            and self.mod_position == other.mod_position
+        )
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash((self.string, self.mod_position))
+
+    def __repr__(self):
+        return f"Motif({self.string!r}, pos={self.mod_position})"
+
+    def split(self) -> list[str]:  # type: ignore[override]
+        return tokenize(self.string)
+
+    def length(self) -> int:
+        return len(self.split())
+
+    def new_stripped_motif(self, character: str = ".") -> "Motif":
+        """Drop flanking wildcards and re-base mod_position (motif.py:213-224)."""
+        s = self.string
+        lead = len(s) - len(s.lstrip(character))
+        if lead == len(s):  # nothing but wildcards: returned unchanged, like the reference
+            return self
+        return Motif(s.strip(character), self.mod_position - lead)
+
+    def reverse_compliment(self) -> "Motif":
+        """Reverse complement; bracket classes stay well formed (motif.py:260-266)."""
+        toks = self.split()
+        out = []
+        for tok in reversed(toks):
+            if tok.startswith("["):
+                out.append("[" + "".join(_COMP_BASE[c] for c in reversed(tok[1:-1])) + "]")
+            else:
+                out.append(_COMP_BASE[tok])
+        return Motif("".join(out), len(toks) - self.mod_position - 1)
+
+    def one_hot(self) -> np.ndarray:
+        """(length, 4) 0/1 matrix in A,T,G,C column order (motif.py:247-258)."""
+        toks = self.split()
+        arr = np.zeros((len(toks), 4), dtype=int)
+        for i, tok in enumerate(toks):
+            m = _WILD if tok in (".", "N") else token_mask(tok)
+            for b in range(4):
+                arr[i, b] = (m >> b) & 1
+        return arr
+
+    def iupac(self) -> str:
+        out = []
+        for tok in self.split():
+            if tok == ".":
+                out.append("N")
+            else:
+                letters = tok[1:-1] if tok.startswith("[") else tok
+                out.append(_SET_TO_IUPAC.get(frozenset(letters), ""))
+        return "".join(out)
+
+    def from_iupac(self) -> "Motif":
+        out = []
+        for ch in self.string:
+            s = _IUPAC_SETS[ch]
+            out.append("." if len(s) == 4 else (s if len(s) == 1 else "[" + s + "]"))
+        return Motif("".join(out), self.mod_position)
+
+
+def as_motif(motif) -> Motif:
+    if isinstance(motif, Motif):
+        return motif
+    if not hasattr(motif, "mod_position"):
+        raise TypeError("Motif is not a Motif type")  # same message as find_motifs_bin.py:1253
+    return Motif(str.__str__(motif), int(motif.mod_position))
+
+
+def motif_masks(motif) -> tuple[np.ndarray, int]:
+    """(allowed-set per position as uint8 array, mod_position) of the motif as given (not stripped)."""
+    m = as_motif(motif)
+    toks = m.split()
+    return np.fromiter((token_mask(t) for t in toks), dtype=np.uint8, count=len(toks)), int(m.mod_position)
+
+
+def pack_motifs(motifs, strip: bool = True, mod_pos_override: int | None = None) -> np.ndarray:
+    """Compile motifs to an array of ``nmb_motif`` records (include/nmb200.h).
+
+    strip=True applies new_stripped_motif first, as motif_model_contig does
+    (find_motifs_bin.py:1307).  Raises ValueError for motifs the device path cannot represent.
+    """
+    out = np.zeros(len(motifs), dtype=_lib.MOTIF_DTYPE)
+    for i, mo in enumerate(motifs):
+        m = as_motif(mo)
+        if strip:
+            m = m.new_stripped_motif()
+        masks, mp = motif_masks(m)
+        n = len(masks)
+        if n == 0:
+            raise ValueError("Motif is empty")
+        if n > _lib.MAX_MOTIF_LEN:
+            raise ValueError(f"motif {m!r}: stripped length {n} exceeds {_lib.MAX_MOTIF_LEN}")
+        if np.all(masks == _WILD):
+            raise ValueError(f"motif {m!r} has no constrained position")
+        if mod_pos_override is not None:
+            mp = mod_pos_override
+        if not (0 <= mp < n):
+            raise ValueError(f"motif {m!r}: mod_position {mp} outside the stripped motif")
+        out["allowed"][i, :n] = masks
+        out["len"][i] = n
+        out["mod_pos"][i] = mp
+    return out
+
+
+def window_masks(motifs, width: int) -> np.ndarray:
+    """Full-width (not stripped) masks for the window filter (DNAarray.filter_sequence_matches)."""
+    out = np.zeros(len(motifs), dtype=_lib.MOTIF_DTYPE)
+    for i, mo in enumerate(motifs):
+        toks = as_motif(mo).split()
+        if len(toks) != width:
+            raise AssertionError("Sequence must have the same length as sequences in the array")  # seq.py:516
+        # one_hot semantics (motif.py:247-258): 'N' and '.' are all-ones
+        out["allowed"][i, :width] = [(_WILD if t in (".", "N") else token_mask(t)) for t in toks]
+        out["len"][i] = width
+        out["mod_pos"][i] = min(int(getattr(mo, "mod_position", 0)), width - 1)
+    return out

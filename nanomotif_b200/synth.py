@@ -1,0 +1,127 @@
+"""Seeded synthetic assemblies and modkit-style pileups (SURVEY.md section 8d generators).
+
+Used by bench.py and the tests; there is no network for real datasets and the reference's bundled
+pileups are absent from the mount.  Everything is numpy ``Generator(PCG64(seed))``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .motif import tokenize, token_mask
+
+MOD_TYPES = ("a", "m", "21839")
+CANONICAL = {"a": "A", "m": "C", "21839": "C"}  # nanomotif/constants.py:31-35
+_COMP = {"A": "T", "T": "A", "G": "C", "C": "G"}
+_CODE_OF = np.full(256, 4, dtype=np.uint8)
+for _i, _b in enumerate("ATGC"):
+    _CODE_OF[ord(_b)] = _i
+
+# planted motifs in the style of nanomotif/datasets/e_coli_bin-motifs.tsv:2-4 (+ a 4mC motif)
+DEFAULT_PLANTED = (("GATC", 1, "a"), ("CC[AT]GG", 1, "m"), ("GCAC......GTT", 2, "a"), ("AAC......GTGC", 1, "a"),
+                   ("CCGG", 0, "21839"))
+
+
+def random_sequence(rng: np.random.Generator, length: int, gc: float = 0.5, n_run_rate: float = 0.0) -> np.ndarray:
+    """ASCII (uint8) i.i.d. sequence with GC fraction `gc`; optional runs of N (rate per bp, length 10-100)."""
+    p = np.array([(1 - gc) / 2, (1 - gc) / 2, gc / 2, gc / 2])
+    seq = np.frombuffer(b"ATGC", dtype=np.uint8)[rng.choice(4, size=length, p=p)].copy()
+    if n_run_rate > 0 and length > 200:
+        for s in rng.choice(length - 100, size=rng.poisson(n_run_rate * length), replace=False):
+            seq[s : s + int(rng.integers(10, 101))] = ord("N")
+    return seq
+
+
+def find_occurrences(seq: np.ndarray, motif: str) -> np.ndarray:
+    """Start positions of a regex-subset motif in an ASCII array (generator-side helper)."""
+    toks = tokenize(motif)
+    n = len(seq) - len(toks) + 1
+    if n <= 0:
+        return np.zeros(0, dtype=np.int64)
+    codes = _CODE_OF[seq]
+    ok = np.ones(n, dtype=bool)
+    for j, t in enumerate(toks):
+        m = token_mask(t)
+        if m == 0xF:
+            continue
+        allowed = np.array([(m >> c) & 1 for c in range(4)] + [0], dtype=bool)
+        ok &= allowed[codes[j : j + n]]
+    return np.flatnonzero(ok).astype(np.int64)
+
+
+def reverse_complement_motif(motif: str, mod_pos: int) -> tuple[str, int]:
+    toks = tokenize(motif)
+    out = []
+    for t in reversed(toks):
+        if t.startswith("["):
+            out.append("[" + "".join(_COMP[c] for c in reversed(t[1:-1])) + "]")
+        else:
+            out.append(_COMP.get(t, t))
+    return "".join(out), len(toks) - mod_pos - 1
+
+
+def synth_pileup(seq: np.ndarray, rng: np.random.Generator, planted=DEFAULT_PLANTED, depth: int = 100,
+                 mod_types=MOD_TYPES, p_meth: float = 0.95, p_unmeth: float = 0.02, false_high: float = 0.003,
+                 with_counts: bool = False) -> dict:
+    """Pileup columns for one contig: one row per canonical base on '+' and per complementary base on
+    '-' for every mod type; rows are unique per (position, strand, mod_type) and sorted by position."""
+    cols = {k: [] for k in ("position", "strand", "mod_type", "fraction_mod", "Nvalid_cov", "n_mod", "n_diff")}
+    for mt in mod_types:
+        base = CANONICAL[mt]
+        truth_plus = np.zeros(len(seq), dtype=bool)
+        truth_minus = np.zeros(len(seq), dtype=bool)
+        for motif, mp, mtype in planted:
+            if mtype != mt:
+                continue
+            truth_plus[find_occurrences(seq, motif) + mp] = True
+            rc, rmp = reverse_complement_motif(motif, mp)
+            truth_minus[find_occurrences(seq, rc) + rmp] = True
+        for strand, letter, truth in ((0, base, truth_plus), (1, _COMP[base], truth_minus)):
+            pos = np.flatnonzero(seq == ord(letter)).astype(np.int64)
+            n = len(pos)
+            cov = np.maximum(1, rng.poisson(depth, size=n)).astype(np.int64)
+            is_meth = truth[pos] | (rng.random(n) < false_high)
+            n_mod = rng.binomial(cov, np.where(is_meth, p_meth, p_unmeth)).astype(np.int64)
+            percent = np.round(100.0 * n_mod / cov, 2)  # modkit prints two decimals
+            cols["position"].append(pos)
+            cols["strand"].append(np.full(n, strand, dtype=np.uint8))
+            cols["mod_type"].append(np.full(n, mod_types.index(mt), dtype=np.uint8))
+            cols["fraction_mod"].append(percent / 100.0)  # dataload.py:85
+            cols["Nvalid_cov"].append(cov)
+            cols["n_mod"].append(n_mod)
+            cols["n_diff"].append(rng.poisson(depth * 0.02, size=n).astype(np.int64))
+    out = {k: np.concatenate(v) for k, v in cols.items()}
+    order = np.lexsort((out["mod_type"], out["strand"], out["position"]))
+    out = {k: v[order] for k, v in out.items()}
+    if not with_counts:
+        out.pop("n_mod")
+        out.pop("n_diff")
+    return out
+
+
+def random_motifs(rng: np.random.Generator, n: int, canonical: str = "A") -> list[tuple[str, int]]:
+    """Fixed work list of SURVEY 8d cfg 2: length 4-13, 0-2 degenerate positions, 0-1 gap of 4-8; the
+    modified base is a position holding `canonical`."""
+    out = []
+    while len(out) < n:
+        length = int(rng.integers(4, 14))
+        toks = [str(b) for b in rng.choice(list("ATGC"), size=length)]
+        for _ in range(int(rng.integers(0, 3))):
+            j = int(rng.integers(1, length - 1))
+            k = int(rng.integers(2, 4))
+            toks[j] = "[" + "".join(sorted(rng.choice(list("ACGT"), size=k, replace=False))) + "]"
+        if rng.random() < 0.5 and length >= 6:
+            gap = int(rng.integers(4, 9))
+            at = int(rng.integers(2, length - 2))
+            toks = toks[:at] + ["."] * gap + toks[at:]
+        cands = [i for i, t in enumerate(toks) if t == canonical]
+        if not cands:
+            j = int(rng.integers(0, len(toks)))
+            if toks[j] == "." or j in (0, len(toks) - 1) and False:
+                continue
+            toks[j] = canonical
+            cands = [j]
+        mp = int(rng.choice(cands))
+        if toks[0] == "." or toks[-1] == ".":
+            continue
+        out.append(("".join(toks), mp))
+    return out

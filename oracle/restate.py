@@ -1,0 +1,324 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of nanomotif's motif-scoring hot path.
+
+This module is the parity oracle for the CUDA path in ``nanomotif_b200/``.  It may be imported by
+``tests/``, by ``__graft_entry__.smoke()`` and by ``bench.py``'s cpu_baseline / ``--impl reference``
+legs, and by nothing else; the product never routes through it.
+
+Every function restates one reference function with numpy / ``regex`` / scipy (the same third-party
+calls the reference makes), citing the file:line it follows in MicrobialDarkMatter/nanomotif 1.1.2.
+Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks it against (a) the reference's own
+known-answer tests (tests/test_fasta.py:95-109, tests/test_motif_find.py:14-39,
+tests/test_dataload.py:37-69, tests/test_candidate.py:42-58) and (b) golden vectors produced by
+running the real reference functions through ``oracle/ref_shim.py``
+(``tests/golden/generate_golden.py`` -> ``tests/golden/*.json``).  The polars-dependent glue
+(motif_model_contig's row split, the three pileup filters) cannot run here (polars is not
+installed), so those restatements follow the cited lines and are pinned only through the pure
+functions they call plus the reference's adjacency-filter known answers.
+"""
+from __future__ import annotations
+
+import math
+import random
+
+import numpy as np
+import regex
+from scipy.special import psi
+from scipy.stats import entropy
+
+BASES = ["A", "T", "G", "C"]  # nanomotif/constants.py:1
+COMPLEMENT = {"A": "T", "T": "A", "G": "C", "C": "G", "N": "N", ".": ".", "[": "]", "]": "[",
+              "R": "Y", "Y": "R", "S": "S", "W": "W", "K": "M", "M": "K", "B": "V", "D": "H", "H": "D",
+              "V": "B"}  # nanomotif/constants.py:14-20
+MOD_TYPE_TO_CANONICAL = {"m": "C", "a": "A", "21839": "C"}  # nanomotif/constants.py:31-35
+BASE_TO_VECTOR = {"A": [1, 0, 0, 0], "T": [0, 1, 0, 0], "G": [0, 0, 1, 0], "C": [0, 0, 0, 1],
+                  "N": [1, 1, 1, 1], ".": [1, 1, 1, 1]}  # nanomotif/seq.py:41-48
+
+
+# ---------------------------------------------------------------------------------------------
+# motif string helpers (nanomotif/motif.py)
+# ---------------------------------------------------------------------------------------------
+def split_motif(s: str) -> list[str]:
+    """motif.py:226-245."""
+    return regex.findall(r"\[[^\]]*\]|.", s)
+
+
+def strip_motif(s: str, mod_pos: int) -> tuple[str, int]:
+    """new_stripped_motif, motif.py:213-224."""
+    m = regex.search(r"[^.]", s)
+    if m is None:
+        return s, mod_pos
+    return s.lstrip(".").rstrip("."), mod_pos - m.start()
+
+
+def reverse_complement_motif(s: str, mod_pos: int) -> tuple[str, int]:
+    """reverse_compliment, motif.py:260-266."""
+    return "".join(COMPLEMENT[c] for c in reversed(s)), len(split_motif(s)) - mod_pos - 1
+
+
+def motif_one_hot(s: str) -> np.ndarray:
+    """one_hot, motif.py:247-258."""
+    toks = split_motif(s)
+    arr = np.zeros((len(toks), 4), dtype=int)
+    for i, tok in enumerate(toks):
+        for ch in tok:
+            if ch in BASE_TO_VECTOR:
+                arr[i, :] += BASE_TO_VECTOR[ch]
+    return arr
+
+
+# ---------------------------------------------------------------------------------------------
+# a1 / a2: scan and gather-join
+# ---------------------------------------------------------------------------------------------
+def subseq_indices(subseq: str, seq: str) -> np.ndarray:
+    """utils.py:44-67 -- overlapping regex matches, start positions, int64."""
+    pattern = regex.compile(subseq)
+    return np.fromiter((m.start() for m in pattern.finditer(seq, overlapped=True)), dtype=np.int64)
+
+
+def subseq_indices_np(subseq: str, seq_bytes: np.ndarray) -> np.ndarray:
+    """Same result as subseq_indices, vectorised for large contigs: a position matches when every
+    non-'.' token contains the contig letter (regex-literal semantics: N only matches '.')."""
+    toks = split_motif(subseq)
+    n = len(seq_bytes) - len(toks) + 1
+    if n <= 0:
+        return np.zeros(0, dtype=np.int64)
+    ok = np.ones(n, dtype=bool)
+    for j, tok in enumerate(toks):
+        if tok == ".":
+            continue
+        letters = tok.strip("[]").encode()
+        ok &= np.isin(seq_bytes[j : j + n], np.frombuffer(letters, dtype=np.uint8))
+    return np.flatnonzero(ok).astype(np.int64)
+
+
+def methylated_motif_occourances(motif: str, mod_pos: int, sequence, meth: np.ndarray, nonmeth: np.ndarray,
+                                 fast: bool = False):
+    """find_motifs_bin.py:1234-1263."""
+    assert len(motif) > 0, "Motif is empty"
+    assert len(sequence) > 0, "Sequence is empty"
+    if fast:
+        idx = subseq_indices_np(motif, sequence) + mod_pos
+    else:
+        idx = subseq_indices(motif, sequence) + mod_pos
+    meth_occ = meth[np.isin(meth, idx, assume_unique=True)]
+    nonmeth_occ = nonmeth[np.isin(nonmeth, idx, assume_unique=True)]
+    return meth_occ, nonmeth_occ
+
+
+# ---------------------------------------------------------------------------------------------
+# a3 / a4: per-contig and per-bin counts
+# ---------------------------------------------------------------------------------------------
+def motif_model_contig(position, strand, fraction_mod, contig, motif: str, mod_pos: int, low=0.3, high=0.7,
+                       fast: bool = False):
+    """find_motifs_bin.py:1285-1331 with the polars frame replaced by its columns.
+    strand: array of '+'/'-'.  Returns (n_mod, n_nomod, positions dict)."""
+    position = np.asarray(position, dtype=np.int64)
+    strand = np.asarray(strand)
+    fraction_mod = np.asarray(fraction_mod, dtype=np.float64)
+    s_motif, s_pos = strip_motif(motif, mod_pos)  # :1307
+    is_high = fraction_mod >= high  # :1308
+    is_low = fraction_mod <= low  # :1309
+    plus, minus = strand == "+", strand == "-"
+    meth_fwd, non_fwd = position[is_high & plus], position[is_low & plus]  # :1311-1312
+    meth_rev, non_rev = position[is_high & minus], position[is_low & minus]  # :1313-1314
+    seq = np.frombuffer(contig.encode(), dtype=np.uint8) if fast else contig
+    i_mf, i_nf = methylated_motif_occourances(s_motif, s_pos, seq, meth_fwd, non_fwd, fast)  # :1316
+    rc_motif, rc_pos = reverse_complement_motif(s_motif, s_pos)
+    i_mr, i_nr = methylated_motif_occourances(rc_motif, rc_pos, seq, meth_rev, non_rev, fast)  # :1317
+    n_mod = len(i_mf) + len(i_mr)  # :1320
+    n_nomod = len(i_nf) + len(i_nr)
+    return n_mod, n_nomod, dict(index_meth_fwd=i_mf, index_nonmeth_fwd=i_nf, index_meth_rev=i_mr,
+                                index_nonmeth_rev=i_nr)
+
+
+def motif_model_bin(contig_col, position, strand, fraction_mod, contigs: dict, motif: str, mod_pos: int,
+                    low=0.3, high=0.7, fast: bool = False):
+    """find_motifs_bin.py:1265-1283: the same model threaded through every contig = plain sums.
+    Returns (n_mod, n_nomod) to be added to the Beta(5,5) prior."""
+    contig_col = np.asarray(contig_col)
+    n_mod = n_nomod = 0
+    for name, seq in contigs.items():
+        sel = contig_col == name  # :1274
+        a, b, _ = motif_model_contig(np.asarray(position)[sel], np.asarray(strand)[sel],
+                                     np.asarray(fraction_mod)[sel], seq, motif, mod_pos, low, high, fast)
+        n_mod += a
+        n_nomod += b
+    return n_mod, n_nomod
+
+
+# ---------------------------------------------------------------------------------------------
+# a5 - a7: posterior and scores (nanomotif/model.py, find_motifs_bin.py:1360-1379, :901-924)
+# ---------------------------------------------------------------------------------------------
+PRIOR_ALPHA = PRIOR_BETA = 5  # model.py:8-9
+
+
+def posterior(n_mod: int, n_nomod: int) -> tuple[int, int]:
+    return PRIOR_ALPHA + n_mod, PRIOR_BETA + n_nomod  # model.py:37-39
+
+
+def beta_mean(alpha, beta) -> float:
+    return alpha / (alpha + beta)  # model.py:48-49
+
+
+def _ppc_per_obs(alpha, beta, n_pos, n_neg) -> float:
+    """posterior_predictive_per_obs, model.py:78-92."""
+    n_new = n_pos + n_neg
+    if n_new == 0:
+        return 0.0
+    e_log_p = psi(alpha) - psi(alpha + beta)
+    e_log_1mp = psi(beta) - psi(alpha + beta)
+    return (n_pos * e_log_p + n_neg * e_log_1mp) / n_new
+
+
+def predictive_evaluation_score(next_ab, cur_ab) -> float:
+    """find_motifs_bin.py:1360-1379; arguments are (alpha, beta) INCLUDING the priors."""
+    a_n, b_n = next_ab
+    a_c, b_c = cur_ab
+    extra_pos, extra_neg = a_c - a_n, b_c - b_n
+    ppcp_next = _ppc_per_obs(a_n, b_n, a_n, b_n)
+    ppcp_extra = _ppc_per_obs(a_n, b_n, extra_pos, extra_neg)
+    return (beta_mean(a_n, b_n) / beta_mean(a_c, b_c)) * (ppcp_next - ppcp_extra)
+
+
+def priority_function(next_ab, root_ab) -> float:
+    """find_motifs_bin.py:915-923."""
+    return (1 - next_ab[0] / root_ab[0]) * (next_ab[1] / root_ab[1])
+
+
+# ---------------------------------------------------------------------------------------------
+# a9 - a12: motif-growth step
+# ---------------------------------------------------------------------------------------------
+def reverse_complement_seq(s: str) -> str:
+    return "".join(COMPLEMENT[c] for c in reversed(s))  # seq.py:297-299
+
+
+def sample_at_indices(seq: str, indices, padding: int) -> list[str]:
+    """seq.py:170-189 (strict bounds) + sample_at_index :148-168."""
+    keep = [i for i in indices if (i > padding) and (i < (len(seq) - padding))]
+    return [seq[i - padding : i + padding + 1] for i in keep]
+
+
+def methylation_windows(seq: str, index_plus, index_minus, padding: int) -> list[str]:
+    """find_motifs_bin.py:652-662: '+' windows, then reverse-complemented '-' windows."""
+    out = list(sample_at_indices(seq, index_plus, padding))
+    out += [reverse_complement_seq(w) for w in sample_at_indices(seq, index_minus, padding)]
+    return out
+
+
+def one_hot_windows(windows: list[str]) -> np.ndarray:
+    """convert_to_DNAarray, seq.py:474-478 -> (N, W, 4) int64."""
+    return np.array([[BASE_TO_VECTOR[b] for b in w] for w in windows], dtype=np.int64)
+
+
+def filter_sequence_matches(arr: np.ndarray, mask: np.ndarray, keep_matches: bool = True):
+    """seq.py:499-524; returns the boolean row selector and the filtered array (None when empty)."""
+    if keep_matches:
+        sel = np.all(arr <= mask, axis=(1, 2))
+    else:
+        sel = np.any(arr > mask, axis=(1, 2))
+    out = arr[sel, :]
+    return sel, (None if out.shape[0] == 0 else out)
+
+
+def pssm(arr: np.ndarray) -> np.ndarray:
+    """DNAarray.pssm, seq.py:526-537 -> (4, W) float64."""
+    return arr.sum(axis=0).transpose() / arr.shape[0]
+
+
+def background_pssm(windows: list[str]) -> np.ndarray:
+    """EqualLengthDNASet.pssm, seq.py:391-422 (exact-letter counts; N adds nothing)."""
+    n = len(windows)
+    width = len(windows[0])
+    out = np.zeros((4, width))
+    for b, nuc in enumerate(BASES):
+        for i in range(width):
+            out[b, i] = sum(1 for w in windows if w[i] == nuc) / n
+    return out
+
+
+def sample_background(seq: str, length: int, n: int, base: str, rng: random.Random) -> list[str]:
+    """sample_n_subsequences_unique, seq.py:202-225 (the reference uses the module-level `random`)."""
+    max_start = len(seq) - length + 1
+    mid = length // 2
+    valid = [s for s in range(max_start) if seq[s + mid] == base]
+    starts = rng.sample(valid, n)
+    return [seq[s : s + length] for s in starts]
+
+
+def n_background_samples(contig_length: int, frequency: float = 0.01) -> int:
+    return int(max(math.ceil(contig_length * frequency), 50))  # find_motifs_bin.py:633
+
+
+def kl_children(motif: str, mod_pos: int, meth_pssm: np.ndarray, bin_pssm: np.ndarray, min_kl: float = 0.05,
+                freq_threshold: float = 0.15):
+    """_motif_child_nodes_kl_dist_max, find_motifs_bin.py:957-1023.
+    Returns (kl vector, list of (child motif string, mod_pos))."""
+    kl = entropy(meth_pssm, bin_pssm)  # :974
+    toks = split_motif(motif)
+    evaluated = np.array([i for i, b in enumerate(toks) if b == "."])  # :978
+    if evaluated.size == 0:
+        return kl, []
+    masked = kl.copy()
+    masked[~np.isin(np.arange(len(toks)), evaluated)] = 0  # :983
+    if np.max(masked) < min_kl:  # :985-987
+        return kl, []
+    pos = int(np.argmax(masked))  # :989
+    higher = meth_pssm[:, pos] > bin_pssm[:, pos] * 0.5  # :992
+    above = meth_pssm[:, pos] > freq_threshold  # :995
+    bases = [BASES[int(i)] for i in np.argwhere(np.logical_and(higher, above)).reshape(-1)]
+    children = []
+    for base in bases:  # :1019-1023
+        t = list(toks)
+        t[pos] = base
+        children.append(("".join(t), mod_pos))
+    return kl, children
+
+
+# ---------------------------------------------------------------------------------------------
+# a13: pileup filters (nanomotif/dataload.py:191-247), columns instead of a polars frame
+# ---------------------------------------------------------------------------------------------
+def filter_pileup(nvalid_cov, min_coverage: int = 5) -> np.ndarray:
+    """dataload.py:191-200 -> boolean keep mask."""
+    return np.asarray(nvalid_cov) > min_coverage
+
+
+def filter_pileup_minimummod_frequency(contig, mod_type, fraction_mod, methylation_threshold=0.7,
+                                       min_mod_frequency=0.0001, min_mods_pr_contig=50) -> np.ndarray:
+    """dataload.py:202-226 -> boolean keep mask."""
+    contig, mod_type = np.asarray(contig), np.asarray(mod_type)
+    fraction_mod = np.asarray(fraction_mod, dtype=np.float64)
+    key = np.char.add(np.char.add(contig.astype(str), "_"), mod_type.astype(str))
+    uniq, inv = np.unique(key, return_inverse=True)
+    n_pos = np.bincount(inv, minlength=len(uniq))
+    n_mod = np.bincount(inv, weights=(fraction_mod > methylation_threshold).astype(np.float64),
+                        minlength=len(uniq)).astype(np.int64)
+    ok = ((n_mod / n_pos) > min_mod_frequency) & (n_mod > min_mods_pr_contig)
+    return ok[inv]
+
+
+def filter_pileup_adjacency_filter(contig, strand, position, fraction_mod, methylation_threshold=0.7,
+                                   adjacency_distance=8) -> np.ndarray:
+    """dataload.py:228-247 -> boolean keep mask (row order of the input; the reference returns rows
+    sorted by position within (contig, strand) groups).
+
+    polars rolling(index_column=position, period=window, offset=-(window//2+1)) looks at rows with
+    position in (p - window//2 - 1, p - window//2 - 1 + window] = [p - d, p + d] for window = 2d+1,
+    over ALL mod types of the (contig, strand) group.  A row is kept when its fraction equals the
+    window maximum or is below the threshold."""
+    contig, strand = np.asarray(contig), np.asarray(strand)
+    position = np.asarray(position, dtype=np.int64)
+    fraction_mod = np.asarray(fraction_mod, dtype=np.float64)
+    window = adjacency_distance * 2 + 1
+    lo_off = -(window // 2 + 1)
+    keep = np.zeros(len(position), dtype=bool)
+    key = np.char.add(np.char.add(contig.astype(str), "\t"), strand.astype(str))
+    for g in np.unique(key):
+        rows = np.flatnonzero(key == g)
+        order = rows[np.argsort(position[rows], kind="stable")]
+        p, f = position[order], fraction_mod[order]
+        left = np.searchsorted(p, p + lo_off, side="right")  # first index with pos > p + lo_off
+        right = np.searchsorted(p, p + lo_off + window, side="right")  # one past last pos <= upper
+        for k in range(len(order)):
+            roll_max = f[left[k] : right[k]].max()
+            keep[order[k]] = (f[k] == roll_max) or (f[k] < methylation_threshold)
+    return keep

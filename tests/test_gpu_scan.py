@@ -1,0 +1,117 @@
+"""Parity of the CUDA scan / join / reduce path (K1-K3) against the CPU oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import restate as O  # the checker, never the thing under test
+
+
+@pytest.fixture(scope="module")
+def nmb():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import nanomotif_b200 as nmb
+
+    return nmb
+
+
+def _strand_str(codes):
+    return np.where(np.asarray(codes) == 0, "+", "-")
+
+
+MOTIFS = [("GATC", 1), ("A", 0), ("CC[AT]GG", 1), ("G[AG].GAAG[CT]", 5), ("GCAC......GTT", 2), ("AAC......GTGC", 1),
+          ("[ACG]A[CT]", 1), ("C", 0), ("TTAA", 3), ("A..............................T", 0),
+          ("A........................................................C", 0), ("ACGT", 0), ("ACG[AT]", 2)]
+
+
+def test_subseq_indices_reference_kat(nmb):
+    # /root/reference/tests/test_fasta.py:95-109
+    seq = "AATTAAATTAAGTAAAT"
+    assert nmb.subseq_indices("AATT", seq).tolist() == [0, 5]
+    assert nmb.subseq_indices("AA.T", seq).tolist() == [0, 4, 5, 9, 13]
+    # SURVEY 8c golden (regex-literal semantics on non-ACGT letters)
+    seq = "ACGTNACGTRACGTACNT"
+    assert nmb.subseq_indices("ACGT", seq).tolist() == [0, 5, 10]
+    assert nmb.subseq_indices("AC.T", seq).tolist() == [0, 5, 10, 14]
+    assert nmb.subseq_indices("A[CG]GT", seq).tolist() == [0, 5, 10]
+
+
+def test_methylated_motif_occourances_reference_kat(nmb):
+    # /root/reference/tests/test_motif_find.py:14-39
+    m = nmb.Motif("ACG", 0)
+    seq = "TACGGACGCCACG"
+    a, b = nmb.methylated_motif_occourances(m, seq, np.array([1, 5]), np.array([10]))
+    assert a.tolist() == [1, 5] and b.tolist() == [10]
+    a, b = nmb.methylated_motif_occourances(m, seq, np.array([]), np.array([1, 10]))
+    assert a.tolist() == [] and b.tolist() == [1, 10]
+
+
+@pytest.mark.parametrize("length,n_rate", [(1000, 0.0), (70000, 0.0), (200001, 2e-5), (65536 - 64, 0.0), (65536, 1e-4)])
+def test_subseq_indices_random(nmb, length, n_rate):
+    from nanomotif_b200 import synth
+
+    rng = np.random.default_rng(length)
+    seq = synth.random_sequence(rng, length, 0.5, n_rate).tobytes().decode()
+    for motif, _ in MOTIFS + [(".A.", 0), ("..GATC...", 0), ("A.", 0)]:
+        got = nmb.subseq_indices(motif, seq)
+        want = O.subseq_indices(motif, seq)
+        assert got.dtype == np.int64
+        np.testing.assert_array_equal(got, want, err_msg=motif)
+
+
+def test_motif_model_bin_counts(nmb):
+    from nanomotif_b200 import synth
+
+    rng = np.random.default_rng(11)
+    lengths = [300, 5000, 65536 * 2 + 17, 256, 40000, 65472, 100000]
+    contigs, cols = {}, {k: [] for k in ("contig", "position", "strand", "fraction_mod")}
+    for i, L in enumerate(lengths):
+        seq = synth.random_sequence(rng, L, 0.45, 1e-4 if i % 2 else 0.0)
+        name = f"contig_{i}"
+        contigs[name] = seq.tobytes().decode()
+        p = synth.synth_pileup(seq, rng, depth=20, mod_types=("a",))
+        cols["contig"].append(np.full(len(p["position"]), name, dtype=object))
+        cols["position"].append(p["position"])
+        cols["strand"].append(_strand_str(p["strand"]))
+        cols["fraction_mod"].append(p["fraction_mod"])
+    pile = {k: np.concatenate(v) for k, v in cols.items()}
+    motifs = [nmb.Motif(s, p) for s, p in MOTIFS] + [nmb.Motif("....GATC....", 5)]
+    models = nmb.motif_model_bin_many(pile, contigs, motifs, 0.3, 0.7)
+    for m, mdl in zip(motifs, models):
+        want = O.motif_model_bin(pile["contig"], pile["position"], pile["strand"], pile["fraction_mod"], contigs,
+                                 m.string, m.mod_position, 0.3, 0.7, fast=True)
+        assert (mdl._alpha - 5, mdl._beta - 5) == want, (m, mdl, want)
+    # single-motif entry point mutates and returns the model it was given
+    mdl = nmb.BetaBernoulliModel()
+    out = nmb.motif_model_bin(pile, contigs, motifs[0], mdl, 0.3, 0.7)
+    assert out is mdl and (mdl._alpha, mdl._beta) == (models[0]._alpha, models[0]._beta)
+    # per-contig rows agree with the per-contig oracle
+    scorer = nmb.BinScorer(pile, contigs, 0.3, 0.7)
+    per = scorer.counts_by_strand(motifs[:4], per_contig=True).cpu().numpy()
+    for mi, m in enumerate(motifs[:4]):
+        for ci, (name, seq) in enumerate(contigs.items()):
+            sel = pile["contig"] == name
+            a, b, d = O.motif_model_contig(pile["position"][sel], pile["strand"][sel], pile["fraction_mod"][sel], seq,
+                                           m.string, m.mod_position, 0.3, 0.7, fast=True)
+            assert per[mi, ci].tolist() == [len(d["index_meth_fwd"]), len(d["index_nonmeth_fwd"]),
+                                            len(d["index_meth_rev"]), len(d["index_nonmeth_rev"])]
+
+
+def test_motif_model_contig_positions(nmb):
+    from nanomotif_b200 import synth
+
+    rng = np.random.default_rng(5)
+    seq = synth.random_sequence(rng, 30000, 0.5, 1e-4)
+    p = synth.synth_pileup(seq, rng, depth=15, mod_types=("a",))
+    pile = dict(position=p["position"], strand=_strand_str(p["strand"]), fraction_mod=p["fraction_mod"])
+    contig = seq.tobytes().decode()
+    for s, mp in MOTIFS[:6]:
+        mdl, data = nmb.motif_model_contig(pile, contig, nmb.BetaBernoulliModel(), nmb.Motif(s, mp), 0.3, 0.7,
+                                           save_motif_positions=True)
+        a, b, want = O.motif_model_contig(pile["position"], pile["strand"], pile["fraction_mod"], contig, s, mp)
+        assert (mdl._alpha - 5, mdl._beta - 5) == (a, b)
+        for k in want:
+            np.testing.assert_array_equal(data[k], want[k], err_msg=f"{s} {k}")
