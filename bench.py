@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py -- motif x contig-bp scored / second on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|stream]
+
+Workload at N=1 (config.workload = "cfg2"): BASELINE.json configs[1], the E. coli-sized monoculture --
+one 4.6 Mbp synthetic contig (GC 0.508), a depth-100 synthetic modkit pileup for 6mA / 5mC / 4mC with
+planted motifs, and a fixed seeded work list of 1000 random motifs per mod type.
+One STEP = one pass of the hot path over that batch: compile the 3000 motifs, scan both strands of the
+contig for every motif, join to the methylated / unmethylated pileup positions and reduce to the
+per-motif Beta-Bernoulli counts (= 3000 x 4.6e6 motif*bp units).
+
+  value   device-timed throughput, inputs already resident in HBM (packed contig + class planes)
+  e2e     same metric through the public API from HOST buffers: H2D of the ASCII contig + pileup columns
+          (pinned), pack, class planes, scan, D2H of the counts -- all inside the timed region
+  roofline  the scan kernel against the measured HBM copy bandwidth, ALGORITHMIC bytes = 0.75 B per
+          motif*bp.  With M motifs per launch the tile is re-used from L2 / shared memory, so
+          the actual DRAM traffic is far below the algorithmic bytes and `frac` can exceed 1; the
+          `stream` object is the M = 1 pass over an assembly larger than L2 where the same kernel is
+          genuinely HBM-bound.
+  cpu_baseline  the reference's own regex + np.isin path (oracle/cpu_baseline.py) on the host cores,
+          on a bounded sample of the same work list.
+
+N > 1 (torchrun): weak scaling -- every rank owns one 4.6 Mbp contig of the same bin (contig-sharded,
+SURVEY 8e) and the per-motif counts are summed with one NCCL all-reduce per step inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "motif x contig-bp scored/sec"
+UNIT = "motif*bp/s"
+ALG_BYTES_PER_UNIT = 0.75  # 2-bit sequence L/4 B + four 1-bit class planes L/2 B
+CFG2_LEN = 4_600_000
+CFG2_GC = 0.508
+CFG2_DEPTH = 100
+MOTIFS_PER_MODTYPE = 1000
+MOD_TYPES = ("a", "m", "21839")
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def recorded_traffic(kernel: str):
+    """Per-launch dram bytes of the dominant kernel from the committed ncu --set full summary, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def build_cfg2(seed: int, length: int = CFG2_LEN, n_motifs: int = MOTIFS_PER_MODTYPE):
+    from nanomotif_b200 import synth
+
+    rng = np.random.default_rng(seed)
+    seq = synth.random_sequence(rng, length, CFG2_GC, 1e-6)
+    pile = synth.synth_pileup(seq, rng, depth=CFG2_DEPTH, mod_types=MOD_TYPES)
+    work = []  # (motif string, mod_pos, mod type index)
+    mrng = np.random.default_rng(1000 + seed)
+    for mt, name in enumerate(MOD_TYPES):
+        for s, p in synth.random_motifs(mrng, n_motifs, synth.CANONICAL[name]):
+            work.append((s, p, mt))
+    return seq, pile, work
+
+
+class Cfg2Device:
+    """Resident state of the value leg: packed contig, class planes of the three mod types, job table."""
+
+    def __init__(self, seq, pile, work, device):
+        import torch
+
+        import nanomotif_b200 as nmb
+        from nanomotif_b200.device import DeviceAssembly, DevicePileup, make_jobs
+        from nanomotif_b200.motif import pack_motifs
+
+        self.torch = torch
+        self.device = device
+        self.asm = DeviceAssembly(["contig_0"], [len(seq)], seq, [0], device)
+        self.pile = DevicePileup.from_columns(self.asm, np.zeros(len(pile["position"]), np.int32), pile["position"],
+                                              pile["strand"], pile["fraction_mod"], 0.3, 0.7, pile["mod_type"],
+                                              n_modtypes=len(MOD_TYPES))
+        self.motifs = [nmb.Motif(s, p) for s, p, _ in work]
+        self.packed = pack_motifs(self.motifs)
+        self.jobs = make_jobs(len(MOD_TYPES))
+        mts = np.array([w[2] for w in work])
+        for mt in range(len(MOD_TYPES)):
+            idx = np.flatnonzero(mts == mt)
+            j = self.jobs[mt]
+            j["motif_begin"], j["motif_count"], j["modtype"] = idx[0], len(idx), mt
+            j["tile_begin"], j["tile_count"] = 0, self.asm.n_tiles
+            j["contig_begin"], j["contig_end"] = 0, 1
+            j["group_mode"], j["n_groups"], j["out_base"] = 0, 1, idx[0]
+        self.units = len(work) * len(seq)
+        self.out = torch.zeros((len(work), 4), dtype=torch.int64, device=device)
+        self.ev = None
+
+    def step(self, scan_events=None):
+        from nanomotif_b200.device import MotifPrograms, scan_count
+
+        progs = MotifPrograms(self.packed, self.device)  # upload 64 B per motif + compile kernel
+        self.out.zero_()
+        if scan_events is not None:
+            scan_events[0].record()
+        scan_count(self.asm, self.pile, progs, self.jobs, len(self.motifs), out=self.out)
+        if scan_events is not None:
+            scan_events[1].record()
+        return self.out
+
+
+def e2e_step(host, device):
+    """Public-API pass from pinned host buffers: returns the counts as a host array."""
+    from nanomotif_b200.device import DeviceAssembly, DevicePileup, MotifPrograms, make_jobs, scan_count
+
+    asm = DeviceAssembly(["contig_0"], [host["length"]], host["ascii"], [0], device)
+    pile = DevicePileup.from_columns(asm, host["contig_id"], host["position"], host["strand"], host["fraction_mod"],
+                                     0.3, 0.7, host["mod_type"], n_modtypes=len(MOD_TYPES))
+    progs = MotifPrograms(host["packed"], device)
+    jobs = host["jobs"].copy()
+    jobs["tile_count"] = asm.n_tiles
+    out = scan_count(asm, pile, progs, jobs, len(host["packed"]))
+    return out.cpu()
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
+                 str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# streaming leg: M = 1 over an assembly larger than L2 (cfg3-shaped), same kernel
+# ---------------------------------------------------------------------------------------------
+def stream_leg(device, total_bp: int = 1_500_000_000, n_contigs: int = 17000, reps: int = 5):
+    import torch
+
+    import nanomotif_b200 as nmb
+    from nanomotif_b200 import _lib
+    from nanomotif_b200.device import DeviceAssembly, DevicePileup, MotifPrograms, make_jobs, scan_count
+
+    g = torch.Generator(device=device)
+    g.manual_seed(3)
+    rng = np.random.default_rng(3)
+    lens = rng.lognormal(mean=0.0, sigma=1.0, size=n_contigs)
+    lens = np.maximum(2500, (lens / lens.sum() * total_bp).astype(np.int64))
+    off = np.zeros(n_contigs, dtype=np.int64)
+    off[1:] = np.cumsum(lens)[:-1]
+    codes = torch.randint(0, 4, (int(lens.sum()),), dtype=torch.uint8, device=device, generator=g)
+    # A=65 T=84 G=71 C=67 for codes 0..3 (order of nanomotif/constants.py:1)
+    ascii_d = 65 + (codes == 1).to(torch.uint8) * 19 + (codes == 2).to(torch.uint8) * 6 + (codes == 3).to(torch.uint8) * 2
+    del codes
+    asm = DeviceAssembly([f"c{i}" for i in range(n_contigs)], lens, ascii_d, off, device)
+    del ascii_d
+    # class planes straight from the packed planes: a random ~25 % / ~60 % of the A ('+') and T ('-') positions
+    pile = DevicePileup(asm, 1, 0.3, 0.7)
+    rec = asm.seq_records.view(asm.n_tiles, _lib.SEQ_REC_WORDS)
+    x = rec[:, _lib.HALO_WORDS:_lib.HALO_WORDS + _lib.TILE_WORDS]
+    y = rec[:, _lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS:_lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS + _lib.TILE_WORDS]
+    nn = asm.nonacgt[_lib.HALO_WORDS:_lib.HALO_WORDS + asm.n_words].view(asm.n_tiles, _lib.TILE_WORDS)
+    is_a, is_t = ~x & ~y & ~nn, ~x & y & ~nn
+    cls = pile.class_records.view(asm.n_tiles, 4, _lib.TILE_WORDS)
+
+    def rnd():
+        return torch.randint(-2**31, 2**31 - 1, x.shape, dtype=torch.int32, device=device, generator=g)
+
+    r1, r2 = rnd(), rnd()
+    cls[:, 0] = is_a & r1 & r2
+    cls[:, 1] = is_a & ~r1
+    r1, r2 = rnd(), rnd()
+    cls[:, 2] = is_t & r1 & r2
+    cls[:, 3] = is_t & ~r1
+    del r1, r2, is_a, is_t
+    out = {}
+    for name, motif in (("GATC", nmb.Motif("GATC", 1)), ("GRNGAAGY", nmb.Motif("G[AG].GAAG[CT]", 5))):
+        progs = MotifPrograms([motif], device)
+        jobs = make_jobs(1)
+        jobs["motif_count"], jobs["tile_count"], jobs["contig_end"], jobs["n_groups"] = 1, asm.n_tiles, n_contigs, 1
+        res = torch.zeros((1, 4), dtype=torch.int64, device=device)
+        for _ in range(2):
+            scan_count(asm, pile, progs, jobs, 1, out=res)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in evs:
+            a.record()
+            scan_count(asm, pile, progs, jobs, 1, out=res)
+            b.record()
+        torch.cuda.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        bp = asm.total_bp
+        out[name] = {"ms": ms, "motif_bp_per_s": bp / (ms * 1e-3), "alg_gbs": ALG_BYTES_PER_UNIT * bp / (ms * 1e-3) / 1e9,
+                     "record_gbs": asm.n_tiles * (_lib.SEQ_REC_WORDS + _lib.CLS_REC_WORDS) * 4 / (ms * 1e-3) / 1e9}
+    out["assembly_bp"] = asm.total_bp
+    out["contigs"] = n_contigs
+    out["tiles"] = asm.n_tiles
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs
+# ---------------------------------------------------------------------------------------------
+def cpu_leg(seq, pile, work, target_s: float, workers: int | None = None):
+    from oracle.cpu_baseline import CpuPool, presplit
+
+    seq_str = seq.tobytes().decode()
+    split = presplit(pile["position"], pile["strand"], pile["mod_type"], pile["fraction_mod"], len(MOD_TYPES))
+    pool = CpuPool(seq_str, split, workers)
+    try:
+        # interleave mod types so that the sample has the work list's mix
+        order = [work[i] for i in np.random.default_rng(7).permutation(len(work))]
+        _, t_probe = pool.run(order[:pool.workers])
+        n = int(max(pool.workers, min(len(order), pool.workers * max(1.0, target_s / max(t_probe, 1e-3)))))
+        _, secs = pool.run(order[:n])
+    finally:
+        pool.close()
+    return {"value": n * len(seq) / secs, "unit": UNIT, "cores": pool.workers, "kind": "port",
+            "sample": f"{n} of {len(work)} (motif, mod type) pairs x {len(seq)} bp, both strands, {secs:.1f} s; "
+                      "regex.finditer(overlapped) + np.isin exactly as nanomotif/utils.py:44-67 and "
+                      "find_motifs_bin.py:1234-1331, pileup pre-split once (favours the CPU)",
+            "seconds": secs}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    seq, pile, work = build_cfg2(1)
+    from oracle.cpu_baseline import CpuPool, presplit
+
+    seq_str = seq.tobytes().decode()
+    split = presplit(pile["position"], pile["strand"], pile["mod_type"], pile["fraction_mod"], len(MOD_TYPES))
+    pool = CpuPool(seq_str, split)
+    order = [work[i] for i in np.random.default_rng(7).permutation(len(work))]
+    per_step = 2 * pool.workers  # bounded sample per step
+    try:
+        k = 0
+        for _ in range(args.warmup):
+            pool.run(order[k:k + per_step])
+            k = (k + per_step) % (len(order) - per_step)
+        total = 0.0
+        for _ in range(args.steps):
+            _, s = pool.run(order[k:k + per_step])
+            total += s
+            k = (k + per_step) % (len(order) - per_step)
+    finally:
+        pool.close()
+    value = args.steps * per_step * len(seq) / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes / int64 counts",
+            "data": "synthetic", "config": config_dict(len(seq), len(work)),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": pool.workers, "kind": "port",
+                             "sample": f"{per_step} (motif, mod type) pairs x {len(seq)} bp per step, both strands"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_dict(length, n_work):
+    return {"workload": "cfg2: E. coli-sized monoculture (BASELINE.json configs[1])", "contig_bp": length,
+            "mod_types": list(MOD_TYPES), "pileup_depth": CFG2_DEPTH, "motifs": n_work,
+            "motif_list": "seeded random, len 4-13, 0-2 degenerate positions, 0-1 gap of 4-8 (SURVEY 8d)",
+            "thresholds": [0.3, 0.7], "l2": "256 MiB L2 flush between timed steps"}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--only-stream", action="store_true", help="run just the M=1 streaming leg (profiling)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--length", type=int, default=CFG2_LEN, help="contig length (debug)")
+    ap.add_argument("--motifs", type=int, default=MOTIFS_PER_MODTYPE, help="motifs per mod type (debug)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    import nanomotif_b200  # noqa: F401  (fails loudly without the CUDA library)
+
+    if args.only_stream:
+        print(json.dumps(stream_leg(device)))
+        return
+
+    seq, pile, work = build_cfg2(1 + rank, args.length, args.motifs)
+    state = Cfg2Device(seq, pile, work, device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def full_step(scan_events=None):
+        out = state.step(scan_events)
+        if world > 1:
+            dist.all_reduce(out)  # bin-level posterior counts over the contig shards (NCCL, int64 sum)
+        return out
+
+    for _ in range(args.warmup):
+        full_step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    scan_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()  # evict the working set from L2 between timed steps
+        step_ev[i][0].record()
+        full_step(scan_ev[i])
+        step_ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if sampler else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in step_ev)
+    scan_ms = sum(a.elapsed_time(b) for a, b in scan_ev) / args.steps
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    units_per_step = state.units * world
+    value = units_per_step * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e through the public API from pinned host buffers ----
+    n_rows = len(pile["position"])
+    host = {
+        "length": len(seq),
+        "ascii": torch.from_numpy(seq.copy()).pin_memory(),
+        "contig_id": torch.zeros(n_rows, dtype=torch.int32).pin_memory(),
+        "position": torch.from_numpy(pile["position"]).pin_memory(),
+        "strand": torch.from_numpy(pile["strand"]).pin_memory(),
+        "mod_type": torch.from_numpy(pile["mod_type"]).pin_memory(),
+        "fraction_mod": torch.from_numpy(pile["fraction_mod"]).pin_memory(),
+        "packed": state.packed,
+        "jobs": state.jobs,
+    }
+    h2d = len(seq) + n_rows * (4 + 8 + 1 + 1 + 8) + state.packed.nbytes + state.jobs.nbytes
+    d2h = len(work) * 4 * 8
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        res = e2e_step(host, device)
+    assert torch.equal(res, state.step().cpu()), "e2e counts differ from the resident path"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step(host, device)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = units_per_step * e2e_steps / float(t.item())
+
+    if rank == 0:
+        peak, peak_kind = measured_peak_gbs()
+        alg_bytes = ALG_BYTES_PER_UNIT * state.units  # one scan launch per step on this rank
+        achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+        kernel = "scan_count_kernel<1>"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 bit-planes / int64 counts", "data": "synthetic",
+            "config": config_dict(len(seq), len(work)),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+            "gpu_launches": args.steps * 2,  # compile_motifs_kernel + scan_count_kernel per step
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                         "traffic": recorded_traffic("cfg2"), "launch_ms": scan_ms,
+                         "alg_bytes_per_launch": alg_bytes, "motifs_per_launch": len(work),
+                         "note": "M-batched launch: tiles are re-used from L2/shared memory, so DRAM traffic << "
+                                 "algorithmic bytes; see `stream` for the M=1 HBM-bound regime of the same kernel"},
+            "clocks": clocks,
+            "wall_s": t_wall,
+        }
+        if not args.no_stream and world == 1:
+            st = stream_leg(device)
+            best = st["GATC"]
+            line["stream"] = {"workload": "cfg3-shaped: 1.5 Gbp / 17k contigs, one mod type, M = 1 motif per launch",
+                              "bound": "hbm", "achieved": best["alg_gbs"], "peak": peak, "unit": "GB/s",
+                              "frac": best["alg_gbs"] / peak, "traffic": recorded_traffic("stream"), "detail": st}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_leg(seq, pile, work, args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,15 +56,16 @@ constexpr int kChunkIdMask = (1 << 30) - 1;
 static_assert(kTileWords == kTileChunks * kChunkWords, "tile = 256 lane chunks");
 static_assert(kSeqRecBytes % 16 == 0 && kClsRecBytes % 16 == 0, "bulk copies need 16-byte sizes");
 
-// Compiled scan program of one motif strand (device representation, 128 bytes).
-// Constrained positions only, ascending; entries [0, n_left) have pos <= mod_pos and form the
-// left chain, entries [n_left, n) form the right chain.
+// Compiled scan program of one motif strand (device representation, 128 bytes).  Only constrained
+// positions appear.  Entries are in processing order: first the left chain (positions <= mod_pos,
+// ascending), then the right chain (positions > mod_pos, descending).  entry = allowed-set code
+// (1..14; 0 = never matches) | (distance to the previously processed position of its chain) << 8.
 struct Program {
-    uint8_t n;        // number of constrained positions
-    uint8_t n_left;   // how many of them are at or left of mod_pos
-    uint8_t mod_pos;
-    uint8_t len;
-    uint16_t ent[kMaxLen];  // allowed-set code (1..14; 0 = never matches) | motif position << 8
+    uint8_t n_left;   // entries of the left chain
+    uint8_t n_right;  // entries of the right chain
+    uint8_t sl;       // mod_pos - last left position (0 unless the modified base is a wildcard)
+    uint8_t sr;       // last processed right position - mod_pos
+    uint16_t ent[kMaxLen];
 };
 static_assert(sizeof(Program) == 128, "Program must be 128 bytes");
 constexpr int kProgramBytesPerMotif = 2 * sizeof(Program);  // forward + reverse complement

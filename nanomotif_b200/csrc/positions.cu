@@ -22,17 +22,16 @@ __global__ void __launch_bounds__(kTileChunks) match_plane_kernel(
     const bool warp_any = __any_sync(0xFFFFFFFFu, info >= 0);
     if (warp_any) {
         const bool warp_n = __any_sync(0xFFFFFFFFu, info >= 0 && (info & kChunkFlagN));
-        LaneSeq<H> q;
-        load_plane<H>(rec + kHalo + tid * NW, q.x);
-        load_plane<H>(rec + kSeqPlaneWords + kHalo + tid * NW, q.y);
         const ProgramView pv = load_program(program);
+        const uint32_t *lx = rec + kHalo + tid * NW, *ly = rec + kSeqPlaneWords + kHalo + tid * NW;
         if (warp_n) {
-            const uint32_t *gn = nonacgt + kHalo + (size_t)tile * kTileWords + tid * NW - H;
-#pragma unroll
-            for (int i = 0; i < NW + 2 * H; ++i) q.n[i] = __ldg(gn + i);
-            match_words<true, H>(pv, q, m);
+            LaneSeq<H, true> q;
+            load_planes<H>(lx, ly, nonacgt + kHalo + (size_t)tile * kTileWords + tid * NW - H, q);
+            match_words<H, true>(pv, q, m);
         } else {
-            match_words<false, H>(pv, q, m);
+            LaneSeq<H, false> q;
+            load_xy<H>(lx, ly, q);
+            match_words<H, false>(pv, q, m);
         }
         if (info < 0) {
 #pragma unroll

@@ -59,20 +59,60 @@ __device__ __forceinline__ int group_of(const nmb_job &job, int contig, const in
     return __ldg(contig_group + contig);
 }
 
-template <bool HASN, int H>
-__device__ __forceinline__ void count_strand(const ProgramView &pv, const LaneSeq<H> &q,
-                                             const uint32_t *cls_mod, const uint32_t *cls_non,
-                                             uint32_t &n_mod, uint32_t &n_non) {
-    uint32_t m[NW];
-    match_words<HASN, H>(pv, q, m);
-    const uint4 a0 = *reinterpret_cast<const uint4 *>(cls_mod);
-    const uint4 a1 = *reinterpret_cast<const uint4 *>(cls_mod + 4);
-    const uint4 b0 = *reinterpret_cast<const uint4 *>(cls_non);
-    const uint4 b1 = *reinterpret_cast<const uint4 *>(cls_non + 4);
-    n_mod = __popc(m[0] & a0.x) + __popc(m[1] & a0.y) + __popc(m[2] & a0.z) + __popc(m[3] & a0.w) +
-            __popc(m[4] & a1.x) + __popc(m[5] & a1.y) + __popc(m[6] & a1.z) + __popc(m[7] & a1.w);
-    n_non = __popc(m[0] & b0.x) + __popc(m[1] & b0.y) + __popc(m[2] & b0.z) + __popc(m[3] & b0.w) +
-            __popc(m[4] & b1.x) + __popc(m[5] & b1.y) + __popc(m[6] & b1.z) + __popc(m[7] & b1.w);
+// Evaluate the item's motifs on this lane's chunk and accumulate the four counters.
+template <int H, bool PLANES>
+__device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job &job, const ItemMeta &meta,
+                                             const LaneSeq<H, PLANES> &q, const uint32_t *cl, bool valid,
+                                             bool uniform, int g, int g0, int primary, int lane,
+                                             uint32_t (*acc)[4]) {
+    const int m_begin = job.motif_begin + meta.mblk * p.mpi;
+    const int m_count = min(p.mpi, job.motif_count - meta.mblk * p.mpi);
+#pragma unroll 1
+    for (int mi = 0; mi < m_count; ++mi) {
+        const Program *prog = p.programs + (size_t)(m_begin + mi) * 2;
+        uint32_t pk[2];  // [strand]: n_mod | n_nomod << 16  (per-lane counts are <= 256)
+#pragma unroll 1
+        for (int st = 0; st < 2; ++st) {  // forward motif, then its reverse complement
+            const ProgramView pv = load_program(prog + st);
+            uint32_t m[NW];
+            match_words<H, PLANES>(pv, q, m);
+            const uint32_t *c0 = cl + 2 * st * kTileWords;
+            const uint4 a0 = *reinterpret_cast<const uint4 *>(c0);
+            const uint4 a1 = *reinterpret_cast<const uint4 *>(c0 + 4);
+            const uint4 b0 = *reinterpret_cast<const uint4 *>(c0 + kTileWords);
+            const uint4 b1 = *reinterpret_cast<const uint4 *>(c0 + kTileWords + 4);
+            const uint32_t n_mod = __popc(m[0] & a0.x) + __popc(m[1] & a0.y) + __popc(m[2] & a0.z) +
+                                   __popc(m[3] & a0.w) + __popc(m[4] & a1.x) + __popc(m[5] & a1.y) +
+                                   __popc(m[6] & a1.z) + __popc(m[7] & a1.w);
+            const uint32_t n_non = __popc(m[0] & b0.x) + __popc(m[1] & b0.y) + __popc(m[2] & b0.z) +
+                                   __popc(m[3] & b0.w) + __popc(m[4] & b1.x) + __popc(m[5] & b1.y) +
+                                   __popc(m[6] & b1.z) + __popc(m[7] & b1.w);
+            pk[st] = valid ? (n_mod | (n_non << 16)) : 0u;
+        }
+        uint32_t pk_f = pk[0], pk_r = pk[1];
+        const long long row = job.out_base + (long long)(meta.mblk * p.mpi + mi) * job.n_groups;
+        if (uniform) {  // two 16-bit fields per word survive a 32-lane sum (<= 8192)
+            pk_f = __reduce_add_sync(0xFFFFFFFFu, pk_f);
+            pk_r = __reduce_add_sync(0xFFFFFFFFu, pk_r);
+            if (lane == 0 && (pk_f | pk_r)) {
+                const uint32_t v[4] = {pk_f & 0xFFFFu, pk_f >> 16, pk_r & 0xFFFFu, pk_r >> 16};
+                if (g0 == primary) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (v[c]) atomicAdd(&acc[mi][c], v[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (v[c]) atomicAdd(p.out + (row + g0) * 4 + c, (unsigned long long)v[c]);
+                }
+            }
+        } else if (pk_f | pk_r) {
+            const uint32_t v[4] = {pk_f & 0xFFFFu, pk_f >> 16, pk_r & 0xFFFFu, pk_r >> 16};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (v[c]) atomicAdd(p.out + (row + g) * 4 + c, (unsigned long long)v[c]);
+        }
+    }
 }
 
 template <int H>
@@ -136,60 +176,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_count_kernel(const ScanP
             const bool uniform = __all_sync(0xFFFFFFFFu, g == g0);
             const bool warp_n = __any_sync(0xFFFFFFFFu, valid && (info & kChunkFlagN));
 
-            LaneSeq<H> q;
-            load_plane<H>(sx + kHalo + tid * NW, q.x);
-            load_plane<H>(sy + kHalo + tid * NW, q.y);
-            if (warp_n) {
-                const uint32_t *gn = p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H;
-#pragma unroll
-                for (int i = 0; i < NW + 2 * H; ++i) q.n[i] = __ldg(gn + i);
-            }
+            const uint32_t *lx = sx + kHalo + tid * NW, *ly = sy + kHalo + tid * NW;
             const uint32_t *cl = scls + tid * NW;
-            const int m_begin = job.motif_begin + meta.mblk * p.mpi;
-            const int m_count = min(p.mpi, job.motif_count - meta.mblk * p.mpi);
-
-#pragma unroll 1
-            for (int mi = 0; mi < m_count; ++mi) {
-                const Program *prog = p.programs + (size_t)(m_begin + mi) * 2;
-                uint32_t cnt[4];  // n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'
-#pragma unroll 1
-                for (int st = 0; st < 2; ++st) {  // forward motif, then its reverse complement
-                    const ProgramView pv = load_program(prog + st);
-                    const uint32_t *c0 = cl + 2 * st * kTileWords;
-                    uint32_t a, b;
-                    if (warp_n)
-                        count_strand<true, H>(pv, q, c0, c0 + kTileWords, a, b);
-                    else
-                        count_strand<false, H>(pv, q, c0, c0 + kTileWords, a, b);
-                    if (st == 0) { cnt[0] = a; cnt[1] = b; } else { cnt[2] = a; cnt[3] = b; }
-                }
-                const uint32_t mod_f = cnt[0], non_f = cnt[1], mod_r = cnt[2], non_r = cnt[3];
-                // per-lane counts are <= 256: two 16-bit fields per word survive a 32-lane sum
-                uint32_t pk_f = valid ? (mod_f | (non_f << 16)) : 0u;
-                uint32_t pk_r = valid ? (mod_r | (non_r << 16)) : 0u;
-                const long long row =
-                    job.out_base + (long long)(meta.mblk * p.mpi + mi) * job.n_groups;
-                if (uniform) {
-                    pk_f = __reduce_add_sync(0xFFFFFFFFu, pk_f);
-                    pk_r = __reduce_add_sync(0xFFFFFFFFu, pk_r);
-                    if (lane == 0 && (pk_f | pk_r)) {
-                        const uint32_t v[4] = {pk_f & 0xFFFFu, pk_f >> 16, pk_r & 0xFFFFu, pk_r >> 16};
-                        if (g0 == primary) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (v[c]) atomicAdd(&s_acc[par][mi][c], v[c]);
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (v[c]) atomicAdd(p.out + (row + g0) * 4 + c, (unsigned long long)v[c]);
-                        }
-                    }
-                } else if (pk_f | pk_r) {
-                    const uint32_t v[4] = {pk_f & 0xFFFFu, pk_f >> 16, pk_r & 0xFFFFu, pk_r >> 16};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (v[c]) atomicAdd(p.out + (row + g) * 4 + c, (unsigned long long)v[c]);
-                }
+            if (warp_n) {  // chunk (or halo) touches non-ACGT letters / contig padding
+                LaneSeq<H, true> q;
+                load_planes<H>(lx, ly, p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H, q);
+                score_motifs<H, true>(p, job, meta, q, cl, valid, uniform, g, g0, primary, lane, s_acc[par]);
+            } else {
+                LaneSeq<H, false> q;
+                load_xy<H>(lx, ly, q);
+                score_motifs<H, false>(p, job, meta, q, cl, valid, uniform, g, g0, primary, lane, s_acc[par]);
             }
         }
         __syncthreads();  // everyone is done with this stage and with s_acc[par]
@@ -216,25 +212,36 @@ __global__ void compile_motifs_kernel(const nmb_motif *__restrict__ motifs, int 
     const nmb_motif mt = motifs[t >> 1];
     const bool rc = t & 1;
     Program pr;
-    uint16_t *ent = pr.ent;
-    for (int i = 0; i < kMaxLen; ++i) ent[i] = 0;
+    for (int i = 0; i < kMaxLen; ++i) pr.ent[i] = 0;
     int len = mt.len, mp = mt.mod_pos;
     if (len < 1 || len > kMaxLen || mp >= len) {  // invalid: compile to "never matches"
-        pr.n = 1; pr.n_left = 1; pr.mod_pos = 0; pr.len = 1;
-        ent[0] = 0;
+        pr.n_left = 1; pr.n_right = 0; pr.sl = 0; pr.sr = 0;
         programs[t] = pr;
         return;
     }
     if (rc) mp = len - 1 - mp;  // motif.py:264
-    int n = 0, n_left = 0;
+    uint8_t code[kMaxLen];
     for (int j = 0; j < len; ++j) {
         int a = mt.allowed[rc ? (len - 1 - j) : j] & 0xF;
         if (rc) a = ((a & 5) << 1) | ((a & 10) >> 1);  // A<->T, G<->C (constants.py:14-20)
-        if (a == 0xF) continue;
-        ent[n++] = (uint16_t)(a | (j << 8));
-        if (j <= mp) n_left = n;
+        code[j] = (uint8_t)a;
     }
-    pr.n = (uint8_t)n; pr.n_left = (uint8_t)n_left; pr.mod_pos = (uint8_t)mp; pr.len = (uint8_t)len;
+    int n = 0, prev = -1;
+    for (int j = 0; j <= mp; ++j) {  // left chain, ascending
+        if (code[j] == 0xF) continue;
+        pr.ent[n++] = (uint16_t)(code[j] | ((prev < 0 ? 0 : j - prev) << 8));
+        prev = j;
+    }
+    pr.n_left = (uint8_t)n;
+    pr.sl = (uint8_t)(prev < 0 ? 0 : mp - prev);
+    prev = -1;
+    for (int j = len - 1; j > mp; --j) {  // right chain, descending
+        if (code[j] == 0xF) continue;
+        pr.ent[n++] = (uint16_t)(code[j] | ((prev < 0 ? 0 : prev - j) << 8));
+        prev = j;
+    }
+    pr.n_right = (uint8_t)(n - pr.n_left);
+    pr.sr = (uint8_t)(prev < 0 ? 0 : prev - mp);
     programs[t] = pr;
 }
 

@@ -6,14 +6,17 @@
 // at the modified base is
 //     M[p] = AND_i  ind_{j_i}( base[p + j_i - mp] )
 // evaluated as two Horner chains so that every constrained position costs one funnel shift of the
-// running plane plus ONE lop3 per word:
-//     left  chain (j_i <= mp, ascending):  L <- ind_j(x, y) & (L << (j - j_prev))
-//     right chain (j_i >  mp, descending): R <- ind_j(x, y) & (R >> (j_prev - j))
+// running plane plus ONE logic op per word:
+//     left  chain (j_i <= mp, ascending):  L <- ind_j & (L << (j - j_prev))
+//     right chain (j_i >  mp, descending): R <- ind_j & (R >> (j_prev - j))
 //     M = (L << (mp - j_last_left)) & (R >> (j_first_right - mp))
-// ind_j is one of 14 two-variable boolean functions, so the allowed-set is folded into the lop3
-// immediate; the switch on the set code is uniform across the CTA.  Non-ACGT letters (and the
-// padding between contigs) must fail every constrained position: warps that touch a flagged chunk
-// take the HASN variant, which spends one more lop3 per word.
+// Two register representations of the sequence:
+//   XY     the raw planes; a single-base indicator is folded into the lop3 immediate
+//          (R <- lop3<base>(x, y, shifted R)).  Used by warps whose chunks are pure ACGT.
+//   PLANES four one-hot planes A,T,G,C with non-ACGT letters (and inter-contig padding) cleared, so
+//          such letters fail every constrained position and only match '.', which is the regex
+//          semantics of the reference.  Used by flagged warps.
+// The branch on the base is uniform across the CTA (it depends on the motif only).
 #pragma once
 #include "common.cuh"
 
@@ -21,53 +24,57 @@ namespace nmb {
 
 constexpr int NW = kChunkWords;  // words per lane
 
+template <int H, bool PLANES>
+struct LaneSeq;
+
 template <int H>
-struct LaneSeq {
+struct LaneSeq<H, false> {
     static constexpr int XW = NW + 2 * H;  // words held per plane: [-H, NW + H)
-    uint32_t x[XW], y[XW], n[XW];
+    uint32_t x[XW], y[XW];
+    template <int C>  // indicator of single base C (0=A 1=T 2=G 3=C) at plane word i, ANDed with s
+    __device__ __forceinline__ uint32_t and_base(int i, uint32_t s) const {
+        constexpr int T = (C == 0 ? 0x03 : C == 1 ? 0x0C : C == 2 ? 0x30 : 0xC0) & 0xAA;
+        return lop3<T>(x[i], y[i], s);
+    }
+    // indicator of an arbitrary set given as four uniform masks (0 / ~0), ANDed with s
+    __device__ __forceinline__ uint32_t and_set(int i, uint32_t mA, uint32_t mT, uint32_t mG,
+                                                uint32_t mC, uint32_t s) const {
+        const uint32_t g0 = (y[i] & mT) | (~y[i] & mA);  // x = 0: A or T
+        const uint32_t g1 = (y[i] & mC) | (~y[i] & mG);  // x = 1: G or C
+        return ((x[i] & g1) | (~x[i] & g0)) & s;
+    }
 };
 
-// Entry of a Program: allowed-set code | motif position << 8.
+template <int H>
+struct LaneSeq<H, true> {
+    static constexpr int XW = NW + 2 * H;
+    uint32_t p[4][XW];  // one-hot planes, non-ACGT cleared
+    template <int C>
+    __device__ __forceinline__ uint32_t and_base(int i, uint32_t s) const {
+        return p[C][i] & s;
+    }
+    __device__ __forceinline__ uint32_t and_set(int i, uint32_t mA, uint32_t mT, uint32_t mG,
+                                                uint32_t mC, uint32_t s) const {
+        return ((p[0][i] & mA) | (p[1][i] & mT) | (p[2][i] & mG) | (p[3][i] & mC)) & s;
+    }
+};
+
+// Program header and entries (see common.cuh::Program): entries are stored in processing order,
+// left chain first; entry = set code | (shift from the previously processed entry) << 8.
 struct ProgramView {
     const uint16_t *ent;
-    int n, n_left, mod_pos;
+    int n_left, n_right, sl, sr;
 };
 
 __device__ __forceinline__ ProgramView load_program(const Program *p) {
     const uint32_t hdr = __ldg(reinterpret_cast<const uint32_t *>(p));
     ProgramView v;
-    v.n = hdr & 0xFF;
-    v.n_left = (hdr >> 8) & 0xFF;
-    v.mod_pos = (hdr >> 16) & 0xFF;
-    v.ent = reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(p) + 4);
+    v.n_left = hdr & 0xFF;
+    v.n_right = (hdr >> 8) & 0xFF;
+    v.sl = (hdr >> 16) & 0xFF;
+    v.sr = (hdr >> 24) & 0xFF;
+    v.ent = p->ent;
     return v;
-}
-
-template <int M, bool HASN, bool LEFT, int H>
-__device__ __forceinline__ void chain_step(uint32_t (&c)[NW + H], const LaneSeq<H> &q, int s) {
-    constexpr int CW = NW + H;
-    constexpr int T = set_truth(M);
-    if (!LEFT) {  // word i of the chain is lane word i; planes are indexed from -H
-#pragma unroll
-        for (int i = 0; i < CW; ++i) {
-            const uint32_t hi = (i + 1 < CW) ? c[i + 1] : 0u;
-            const uint32_t sh = __funnelshift_r(c[i], hi, s);
-            if (HASN)
-                c[i] = lop3<(T & 0x55)>(q.x[i + H], q.y[i + H], q.n[i + H]) & sh;
-            else
-                c[i] = lop3<(T & 0xAA)>(q.x[i + H], q.y[i + H], sh);
-        }
-    } else {  // word i of the chain is lane word i - H
-#pragma unroll
-        for (int i = CW - 1; i >= 0; --i) {
-            const uint32_t lo = (i > 0) ? c[i - 1] : 0u;
-            const uint32_t sh = __funnelshift_l(lo, c[i], s);
-            if (HASN)
-                c[i] = lop3<(T & 0x55)>(q.x[i], q.y[i], q.n[i]) & sh;
-            else
-                c[i] = lop3<(T & 0xAA)>(q.x[i], q.y[i], sh);
-        }
-    }
 }
 
 template <bool LEFT, int H>
@@ -82,47 +89,80 @@ __device__ __forceinline__ void chain_shift_words(uint32_t (&c)[NW + H]) {  // s
     }
 }
 
+// word i of the right chain is lane word i (plane index i + H); word i of the left chain is lane
+// word i - H (plane index i).
+template <bool LEFT, int H>
+__device__ __forceinline__ uint32_t shifted(const uint32_t (&c)[NW + H], int i, int s) {
+    constexpr int CW = NW + H;
+    if (!LEFT) return __funnelshift_r(c[i], (i + 1 < CW) ? c[i + 1] : 0u, s);
+    return __funnelshift_l((i > 0) ? c[i - 1] : 0u, c[i], s);
+}
+
 template <bool LEFT, int H>
 __device__ __forceinline__ void chain_shift_bits(uint32_t (&c)[NW + H], int s) {  // 0 < s < 32
     constexpr int CW = NW + H;
     if (!LEFT) {
 #pragma unroll
-        for (int i = 0; i < CW; ++i) c[i] = __funnelshift_r(c[i], (i + 1 < CW) ? c[i + 1] : 0u, s);
+        for (int i = 0; i < CW; ++i) c[i] = shifted<LEFT, H>(c, i, s);
     } else {
 #pragma unroll
-        for (int i = CW - 1; i >= 0; --i) c[i] = __funnelshift_l((i > 0) ? c[i - 1] : 0u, c[i], s);
+        for (int i = CW - 1; i >= 0; --i) c[i] = shifted<LEFT, H>(c, i, s);
     }
 }
 
-#define NMB_SET_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
-
-template <bool HASN, bool LEFT, int H>
-__device__ __forceinline__ void chain_apply(uint32_t (&c)[NW + H], const LaneSeq<H> &q, int code,
-                                            int s) {
-    while (s >= 32) {
-        chain_shift_words<LEFT, H>(c);
-        s -= 32;
-    }
-    switch (code) {
-#define NMB_CASE(m)                           \
-    case m:                                   \
-        chain_step<m, HASN, LEFT, H>(c, q, s); \
-        break;
-        NMB_SET_CASES(NMB_CASE)
-#undef NMB_CASE
-        case 15:  // wildcard entries are never compiled into a program; keep it a pure shift
-            if (s) chain_shift_bits<LEFT, H>(c, s);
-            break;
-        default:  // empty set: nothing matches
+template <int C, bool LEFT, int H, bool PLANES>
+__device__ __forceinline__ void step_base(uint32_t (&c)[NW + H], const LaneSeq<H, PLANES> &q, int s) {
+    constexpr int CW = NW + H;
+    if (!LEFT) {
 #pragma unroll
-            for (int i = 0; i < NW + H; ++i) c[i] = 0u;
-            break;
+        for (int i = 0; i < CW; ++i) c[i] = q.template and_base<C>(i + H, shifted<LEFT, H>(c, i, s));
+    } else {
+#pragma unroll
+        for (int i = CW - 1; i >= 0; --i) c[i] = q.template and_base<C>(i, shifted<LEFT, H>(c, i, s));
+    }
+}
+
+template <bool LEFT, int H, bool PLANES>
+__device__ __forceinline__ void step_set(uint32_t (&c)[NW + H], const LaneSeq<H, PLANES> &q, int code,
+                                         int s) {
+    constexpr int CW = NW + H;
+    const uint32_t mA = (code & 1) ? 0xFFFFFFFFu : 0u, mT = (code & 2) ? 0xFFFFFFFFu : 0u;
+    const uint32_t mG = (code & 4) ? 0xFFFFFFFFu : 0u, mC = (code & 8) ? 0xFFFFFFFFu : 0u;
+    if (!LEFT) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) c[i] = q.and_set(i + H, mA, mT, mG, mC, shifted<LEFT, H>(c, i, s));
+    } else {
+#pragma unroll
+        for (int i = CW - 1; i >= 0; --i) c[i] = q.and_set(i, mA, mT, mG, mC, shifted<LEFT, H>(c, i, s));
+    }
+}
+
+// Run `n` program entries starting at ent[0] over chain c.
+template <bool LEFT, int H, bool PLANES>
+__device__ __forceinline__ void run_chain(uint32_t (&c)[NW + H], const LaneSeq<H, PLANES> &q,
+                                          const uint16_t *ent, int n) {
+    uint32_t e = __ldg(ent);
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const uint32_t cur = e;
+        if (i + 1 < n) e = __ldg(ent + i + 1);  // prefetch the next entry
+        int s = cur >> 8;
+        const int code = cur & 0xFF;
+        while (s >= 32) {
+            chain_shift_words<LEFT, H>(c);
+            s -= 32;
+        }
+        if (code == 1) step_base<0, LEFT, H, PLANES>(c, q, s);
+        else if (code == 2) step_base<1, LEFT, H, PLANES>(c, q, s);
+        else if (code == 4) step_base<2, LEFT, H, PLANES>(c, q, s);
+        else if (code == 8) step_base<3, LEFT, H, PLANES>(c, q, s);
+        else step_set<LEFT, H, PLANES>(c, q, code, s);  // degenerate position (or empty set: code 0)
     }
 }
 
 // Match words of the lane's NW words, aligned at the program's mod_pos.
-template <bool HASN, int H>
-__device__ __forceinline__ void match_words(const ProgramView &pv, const LaneSeq<H> &q,
+template <int H, bool PLANES>
+__device__ __forceinline__ void match_words(const ProgramView &pv, const LaneSeq<H, PLANES> &q,
                                             uint32_t (&m)[NW]) {
     constexpr int CW = NW + H;
     uint32_t L[CW], R[CW];
@@ -131,49 +171,26 @@ __device__ __forceinline__ void match_words(const ProgramView &pv, const LaneSeq
         L[i] = 0xFFFFFFFFu;
         R[i] = 0xFFFFFFFFu;
     }
-    // left chain: entries [0, n_left) ascending
-    int prev = 0;
     if (pv.n_left > 0) {
-        uint32_t e = __ldg(pv.ent);
-        prev = e >> 8;
-        int s = 0;
-#pragma unroll 1
-        for (int i = 0; i < pv.n_left; ++i) {
-            const uint32_t cur = e;
-            if (i + 1 < pv.n_left) e = __ldg(pv.ent + i + 1);  // prefetch next entry
-            chain_apply<HASN, true, H>(L, q, cur & 0xFF, s);
-            s = (int)(e >> 8) - (int)(cur >> 8);
-            prev = cur >> 8;
-        }
-        int sl = pv.mod_pos - prev;  // modified base itself is a wildcard: pure shift
+        run_chain<true, H, PLANES>(L, q, pv.ent, pv.n_left);
+        int sl = pv.sl;  // only non-zero when the modified base itself is a wildcard
         while (sl >= 32) {
             chain_shift_words<true, H>(L);
             sl -= 32;
         }
         if (sl) chain_shift_bits<true, H>(L, sl);
     }
-    // right chain: entries (n_left, n] descending
     int sr = 0;
-    if (pv.n > pv.n_left) {
-        uint32_t e = __ldg(pv.ent + pv.n - 1);
-        int s = 0;
-#pragma unroll 1
-        for (int i = pv.n - 1; i >= pv.n_left; --i) {
-            const uint32_t cur = e;
-            if (i - 1 >= pv.n_left) e = __ldg(pv.ent + i - 1);
-            chain_apply<HASN, false, H>(R, q, cur & 0xFF, s);
-            s = (int)(cur >> 8) - (int)(e >> 8);
-            prev = cur >> 8;
-        }
-        sr = prev - pv.mod_pos;
+    if (pv.n_right > 0) {
+        run_chain<false, H, PLANES>(R, q, pv.ent + pv.n_left, pv.n_right);
+        sr = pv.sr;
         while (sr >= 32) {
             chain_shift_words<false, H>(R);
             sr -= 32;
         }
     }
 #pragma unroll
-    for (int k = 0; k < NW; ++k)
-        m[k] = L[k + H] & __funnelshift_r(R[k], R[k + 1], sr);
+    for (int k = 0; k < NW; ++k) m[k] = L[k + H] & __funnelshift_r(R[k], R[k + 1], sr);
 }
 
 // Load the lane's words [-H, NW+H) of one plane; `base` points at lane word 0 and is 16-byte
@@ -188,6 +205,29 @@ __device__ __forceinline__ void load_plane(const uint32_t *base, uint32_t (&w)[N
     for (int i = 0; i < H; ++i) {
         w[i] = base[i - H];
         w[NW + H + i] = base[NW + i];
+    }
+}
+
+// Build both representations of the lane's sequence words.  sx / sy point at lane word 0 of the x
+// and y planes (shared or global); gn at word -H of the non-ACGT plane (global).
+template <int H>
+__device__ __forceinline__ void load_xy(const uint32_t *sx, const uint32_t *sy, LaneSeq<H, false> &q) {
+    load_plane<H>(sx, q.x);
+    load_plane<H>(sy, q.y);
+}
+template <int H>
+__device__ __forceinline__ void load_planes(const uint32_t *sx, const uint32_t *sy, const uint32_t *gn,
+                                            LaneSeq<H, true> &q) {
+    uint32_t x[NW + 2 * H], y[NW + 2 * H];
+    load_plane<H>(sx, x);
+    load_plane<H>(sy, y);
+#pragma unroll
+    for (int i = 0; i < NW + 2 * H; ++i) {
+        const uint32_t ok = ~__ldg(gn + i);
+        q.p[0][i] = ~x[i] & ~y[i] & ok;
+        q.p[1][i] = ~x[i] & y[i] & ok;
+        q.p[2][i] = x[i] & ~y[i] & ok;
+        q.p[3][i] = x[i] & y[i] & ok;
     }
 }
 

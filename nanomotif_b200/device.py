@@ -33,7 +33,10 @@ def _stream() -> int:
 
 
 def _to_device(arr: np.ndarray, device: torch.device) -> torch.Tensor:
-    return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=True)
+    arr = np.ascontiguousarray(arr)
+    if not arr.flags.writeable:  # e.g. np.frombuffer over a bytes object; torch wants writable memory
+        arr = arr.copy()
+    return torch.from_numpy(arr).to(device, non_blocking=True)
 
 
 def sequence_of(obj) -> str:
@@ -71,7 +74,10 @@ class DeviceAssembly:
             self.nonacgt = torch.empty(self.n_words + 2 * _lib.HALO_WORDS, dtype=torch.int32, device=d)
             self.contig_start = _to_device(self.starts, d)
             self.contig_len = _to_device(self.lengths, d)
-            ascii_d = ascii_u8 if isinstance(ascii_u8, torch.Tensor) else _to_device(ascii_u8, d)
+            if isinstance(ascii_u8, torch.Tensor):  # device tensor, or (pinned) host tensor
+                ascii_d = ascii_u8.to(d, non_blocking=True)
+            else:
+                ascii_d = _to_device(ascii_u8, d)
             off_d = _to_device(np.asarray(ascii_off, dtype=np.int64), d)
             check(
                 lib.nmb_pack_sequence(ptr(ascii_d), ptr(off_d), ptr(self.contig_start), ptr(self.contig_len),
@@ -136,7 +142,7 @@ class DevicePileup:
             if a is None:
                 return None
             if isinstance(a, torch.Tensor):
-                return a.to(device=d, dtype=dt).contiguous()
+                return a.to(device=d, dtype=dt, non_blocking=True).contiguous()
             return _to_device(np.asarray(a).astype(_NP_OF[dt], copy=False), d)
 
         with torch.cuda.device(d):

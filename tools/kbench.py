@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmark for scan_count (development tool; not the judged bench).
+
+    python tools/kbench.py [--bp 1500000000] [--contigs 17000] [--reps 20] [--grid 0] [--mpi 1]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nanomotif_b200 as nmb  # noqa: E402
+from nanomotif_b200 import _lib  # noqa: E402
+from nanomotif_b200.device import DeviceAssembly, DevicePileup, MotifPrograms, make_jobs, scan_count  # noqa: E402
+
+MOTIFS = {"A": ("A", 0), "GATC": ("GATC", 1), "CCWGG": ("CC[AT]GG", 1), "GRNGAAGY": ("G[AG].GAAG[CT]", 5),
+          "GCACN6GTT": ("GCAC......GTT", 2), "L13": ("ACGTTGCAAGCTA", 3)}
+
+
+def build(device, total_bp, n_contigs, seed=3):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    lens = rng.lognormal(mean=0.0, sigma=1.0, size=n_contigs)
+    lens = np.maximum(2500, (lens / lens.sum() * total_bp).astype(np.int64))
+    off = np.zeros(n_contigs, dtype=np.int64)
+    off[1:] = np.cumsum(lens)[:-1]
+    codes = torch.randint(0, 4, (int(lens.sum()),), dtype=torch.uint8, device=device, generator=g)
+    ascii_d = 65 + (codes == 1).to(torch.uint8) * 19 + (codes == 2).to(torch.uint8) * 6 + (codes == 3).to(torch.uint8) * 2
+    del codes
+    asm = DeviceAssembly([f"c{i}" for i in range(n_contigs)], lens, ascii_d, off, device)
+    del ascii_d
+    pile = DevicePileup(asm, 1, 0.3, 0.7)
+    rec = asm.seq_records.view(asm.n_tiles, _lib.SEQ_REC_WORDS)
+    x = rec[:, _lib.HALO_WORDS:_lib.HALO_WORDS + _lib.TILE_WORDS]
+    y = rec[:, _lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS:_lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS + _lib.TILE_WORDS]
+    nn = asm.nonacgt[_lib.HALO_WORDS:_lib.HALO_WORDS + asm.n_words].view(asm.n_tiles, _lib.TILE_WORDS)
+    is_a, is_t = ~x & ~y & ~nn, ~x & y & ~nn
+    cls = pile.class_records.view(asm.n_tiles, 4, _lib.TILE_WORDS)
+    rnd = lambda: torch.randint(-2**31, 2**31 - 1, x.shape, dtype=torch.int32, device=device, generator=g)
+    r1, r2 = rnd(), rnd()
+    cls[:, 0] = is_a & r1 & r2
+    cls[:, 1] = is_a & ~r1
+    r1, r2 = rnd(), rnd()
+    cls[:, 2] = is_t & r1 & r2
+    cls[:, 3] = is_t & ~r1
+    return asm, pile
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bp", type=int, default=1_500_000_000)
+    ap.add_argument("--contigs", type=int, default=17000)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--grid", type=int, nargs="*", default=[0])
+    ap.add_argument("--mpi", type=int, nargs="*", default=[1])
+    ap.add_argument("--motifs", nargs="*", default=["GATC", "GRNGAAGY", "A", "L13"])
+    ap.add_argument("--batch", type=int, default=1, help="replicate each motif this many times in the launch")
+    args = ap.parse_args()
+    device = torch.device("cuda", 0)
+    asm, pile = build(device, args.bp, args.contigs)
+    rec_bytes = asm.n_tiles * (_lib.SEQ_REC_WORDS + _lib.CLS_REC_WORDS) * 4
+    print(json.dumps({"bp": asm.total_bp, "tiles": asm.n_tiles, "record_bytes": rec_bytes}))
+    for name in args.motifs:
+        s, p = MOTIFS[name]
+        progs = MotifPrograms([nmb.Motif(s, p)] * args.batch, device)
+        jobs = make_jobs(1)
+        jobs["motif_count"], jobs["tile_count"] = args.batch, asm.n_tiles
+        jobs["contig_end"], jobs["n_groups"] = asm.n_contigs, 1
+        res = torch.zeros((args.batch, 4), dtype=torch.int64, device=device)
+        for grid in args.grid:
+            for mpi in args.mpi:
+                for _ in range(3):
+                    scan_count(asm, pile, progs, jobs, args.batch, motifs_per_item=mpi, grid_ctas=grid, out=res)
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.reps)]
+                for a, b in evs:
+                    a.record()
+                    scan_count(asm, pile, progs, jobs, args.batch, motifs_per_item=mpi, grid_ctas=grid, out=res)
+                    b.record()
+                torch.cuda.synchronize()
+                ts = np.array([a.elapsed_time(b) for a, b in evs])
+                ms = float(np.median(ts))
+                units = asm.total_bp * args.batch
+                print(json.dumps({"motif": name, "grid": grid, "mpi": mpi, "batch": args.batch, "ms_med": round(ms, 4),
+                                  "ms_min": round(float(ts.min()), 4), "Tunits_s": round(units / ms / 1e9, 3),
+                                  "alg_GBs": round(0.75 * units / ms / 1e6, 1),
+                                  "rec_GBs": round(rec_bytes / ms / 1e6, 1) if args.batch == 1 else None}))
+
+
+if __name__ == "__main__":
+    main()
