@@ -63,54 +63,56 @@ __device__ __forceinline__ int group_of(const nmb_job &job, int contig, const in
 template <int H, bool PLANES>
 __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job &job, const ItemMeta &meta,
                                              const LaneSeq<H, PLANES> &q, const uint32_t *cl, bool valid,
-                                             bool uniform, int g, int g0, int primary, int lane,
+                                             bool uniform, unsigned peers, bool leader, int g, int primary,
                                              uint32_t (*acc)[4]) {
     const int m_begin = job.motif_begin + meta.mblk * p.mpi;
     const int m_count = min(p.mpi, job.motif_count - meta.mblk * p.mpi);
 #pragma unroll 1
     for (int mi = 0; mi < m_count; ++mi) {
         const Program *prog = p.programs + (size_t)(m_begin + mi) * 2;
-        uint32_t pk[2];  // [strand]: n_mod | n_nomod << 16  (per-lane counts are <= 256)
+        uint32_t pk_f = 0, pk_r = 0;  // n_mod | n_nomod << 16 per strand (per-lane counts are <= 256)
 #pragma unroll 1
         for (int st = 0; st < 2; ++st) {  // forward motif, then its reverse complement
             const ProgramView pv = load_program(prog + st);
-            uint32_t m[NW];
-            match_words<H, PLANES>(pv, q, m);
+            uint32_t L[NW + H], R[NW + H];
+            const int sr = eval_program<H, PLANES>(pv, q, L, R);
             const uint32_t *c0 = cl + 2 * st * kTileWords;
-            const uint4 a0 = *reinterpret_cast<const uint4 *>(c0);
-            const uint4 a1 = *reinterpret_cast<const uint4 *>(c0 + 4);
-            const uint4 b0 = *reinterpret_cast<const uint4 *>(c0 + kTileWords);
-            const uint4 b1 = *reinterpret_cast<const uint4 *>(c0 + kTileWords + 4);
-            const uint32_t n_mod = __popc(m[0] & a0.x) + __popc(m[1] & a0.y) + __popc(m[2] & a0.z) +
-                                   __popc(m[3] & a0.w) + __popc(m[4] & a1.x) + __popc(m[5] & a1.y) +
-                                   __popc(m[6] & a1.z) + __popc(m[7] & a1.w);
-            const uint32_t n_non = __popc(m[0] & b0.x) + __popc(m[1] & b0.y) + __popc(m[2] & b0.z) +
-                                   __popc(m[3] & b0.w) + __popc(m[4] & b1.x) + __popc(m[5] & b1.y) +
-                                   __popc(m[6] & b1.z) + __popc(m[7] & b1.w);
-            pk[st] = valid ? (n_mod | (n_non << 16)) : 0u;
-        }
-        uint32_t pk_f = pk[0], pk_r = pk[1];
-        const long long row = job.out_base + (long long)(meta.mblk * p.mpi + mi) * job.n_groups;
-        if (uniform) {  // two 16-bit fields per word survive a 32-lane sum (<= 8192)
-            pk_f = __reduce_add_sync(0xFFFFFFFFu, pk_f);
-            pk_r = __reduce_add_sync(0xFFFFFFFFu, pk_r);
-            if (lane == 0 && (pk_f | pk_r)) {
-                const uint32_t v[4] = {pk_f & 0xFFFFu, pk_f >> 16, pk_r & 0xFFFFu, pk_r >> 16};
-                if (g0 == primary) {
+            uint32_t n_mod = 0, n_non = 0;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (v[c]) atomicAdd(&acc[mi][c], v[c]);
-                } else {
+            for (int h = 0; h < NW; h += 4) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(c0 + h);
+                const uint4 b = *reinterpret_cast<const uint4 *>(c0 + kTileWords + h);
+                const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (v[c]) atomicAdd(p.out + (row + g0) * 4 + c, (unsigned long long)v[c]);
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t rs = __funnelshift_r(R[h + k], R[h + k + 1], sr);
+                    n_mod += __popc(lop3<0x80>(L[h + k + H], rs, av[k]));  // L & R>>sr & methylated
+                    n_non += __popc(lop3<0x80>(L[h + k + H], rs, bv[k]));  // L & R>>sr & unmethylated
                 }
             }
-        } else if (pk_f | pk_r) {
+            const uint32_t pk = valid ? (n_mod | (n_non << 16)) : 0u;
+            if (st == 0) pk_f = pk; else pk_r = pk;
+        }
+        const long long row = job.out_base + (long long)(meta.mblk * p.mpi + mi) * job.n_groups;
+        // two 16-bit fields per word survive a 32-lane sum (<= 8192)
+        if (uniform) {  // all counted lanes of the warp feed the same output row (the common case)
+            pk_f = __reduce_add_sync(0xFFFFFFFFu, pk_f);
+            pk_r = __reduce_add_sync(0xFFFFFFFFu, pk_r);
+        } else {  // contig / group boundary inside the warp: segmented sums over equal-group lanes
+            pk_f = __reduce_add_sync(peers, pk_f);
+            pk_r = __reduce_add_sync(peers, pk_r);
+        }
+        if (leader && (pk_f | pk_r)) {
             const uint32_t v[4] = {pk_f & 0xFFFFu, pk_f >> 16, pk_r & 0xFFFFu, pk_r >> 16};
+            if (g == primary) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (v[c]) atomicAdd(p.out + (row + g) * 4 + c, (unsigned long long)v[c]);
+                for (int c = 0; c < 4; ++c)
+                    if (v[c]) atomicAdd(&acc[mi][c], v[c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (v[c]) atomicAdd(p.out + (row + g) * 4 + c, (unsigned long long)v[c]);
+            }
         }
     }
 }
@@ -171,9 +173,19 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_count_kernel(const ScanP
         const int info0 = sinfo[0];
         const int primary = info0 < 0 ? -1 : group_of(job, info0 & kChunkIdMask, p.contig_group);
 
-        if (__any_sync(0xFFFFFFFFu, valid)) {
-            const int g0 = __shfl_sync(0xFFFFFFFFu, g, 0);
-            const bool uniform = __all_sync(0xFFFFFFFFu, g == g0);
+        const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (vmask) {
+            // lanes that are not counted (padding, contigs outside the job) contribute zeros, so the warp
+            // is uniform when all COUNTED lanes share one group
+            const int first = __ffs(vmask) - 1;
+            const int g0 = __shfl_sync(0xFFFFFFFFu, g, first);
+            const bool uniform = __all_sync(0xFFFFFFFFu, !valid || g == g0);
+            unsigned peers = 0xFFFFFFFFu;
+            bool leader = lane == first;
+            if (!uniform) {
+                peers = __match_any_sync(0xFFFFFFFFu, g);
+                leader = valid && lane == __ffs(peers) - 1;
+            }
             const bool warp_n = __any_sync(0xFFFFFFFFu, valid && (info & kChunkFlagN));
 
             const uint32_t *lx = sx + kHalo + tid * NW, *ly = sy + kHalo + tid * NW;
@@ -181,11 +193,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_count_kernel(const ScanP
             if (warp_n) {  // chunk (or halo) touches non-ACGT letters / contig padding
                 LaneSeq<H, true> q;
                 load_planes<H>(lx, ly, p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H, q);
-                score_motifs<H, true>(p, job, meta, q, cl, valid, uniform, g, g0, primary, lane, s_acc[par]);
+                score_motifs<H, true>(p, job, meta, q, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
             } else {
                 LaneSeq<H, false> q;
                 load_xy<H>(lx, ly, q);
-                score_motifs<H, false>(p, job, meta, q, cl, valid, uniform, g, g0, primary, lane, s_acc[par]);
+                score_motifs<H, false>(p, job, meta, q, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
             }
         }
         __syncthreads();  // everyone is done with this stage and with s_acc[par]
@@ -226,22 +238,36 @@ __global__ void compile_motifs_kernel(const nmb_motif *__restrict__ motifs, int 
         if (rc) a = ((a & 5) << 1) | ((a & 10) >> 1);  // A<->T, G<->C (constants.py:14-20)
         code[j] = (uint8_t)a;
     }
+    // Gaps of 32 or more positions become "shift one word" pseudo entries so that every real entry
+    // (and the final alignment shifts sl / sr) carries a shift < 32.
     int n = 0, prev = -1;
     for (int j = 0; j <= mp; ++j) {  // left chain, ascending
         if (code[j] == 0xF) continue;
-        pr.ent[n++] = (uint16_t)(code[j] | ((prev < 0 ? 0 : j - prev) << 8));
+        int d = prev < 0 ? 0 : j - prev;
+        for (; d >= 32; d -= 32) pr.ent[n++] = kEntShift32;
+        pr.ent[n++] = (uint16_t)(code[j] | (d << 8));
         prev = j;
     }
+    {
+        int d = prev < 0 ? 0 : mp - prev;
+        for (; d >= 32; d -= 32) pr.ent[n++] = kEntShift32;
+        pr.sl = (uint8_t)d;
+    }
     pr.n_left = (uint8_t)n;
-    pr.sl = (uint8_t)(prev < 0 ? 0 : mp - prev);
     prev = -1;
     for (int j = len - 1; j > mp; --j) {  // right chain, descending
         if (code[j] == 0xF) continue;
-        pr.ent[n++] = (uint16_t)(code[j] | ((prev < 0 ? 0 : prev - j) << 8));
+        int d = prev < 0 ? 0 : prev - j;
+        for (; d >= 32; d -= 32) pr.ent[n++] = kEntShift32;
+        pr.ent[n++] = (uint16_t)(code[j] | (d << 8));
         prev = j;
     }
+    {
+        int d = prev < 0 ? 0 : prev - mp;
+        for (; d >= 32; d -= 32) pr.ent[n++] = kEntShift32;
+        pr.sr = (uint8_t)d;
+    }
     pr.n_right = (uint8_t)(n - pr.n_left);
-    pr.sr = (uint8_t)(prev < 0 ? 0 : prev - mp);
     programs[t] = pr;
 }
 

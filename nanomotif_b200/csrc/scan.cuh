@@ -137,58 +137,83 @@ __device__ __forceinline__ void step_set(uint32_t (&c)[NW + H], const LaneSeq<H,
     }
 }
 
-// Run `n` program entries starting at ent[0] over chain c.
+// First entry of a chain: the running plane is the indicator itself (no shift, no AND).
+template <int C, bool LEFT, int H, bool PLANES>
+__device__ __forceinline__ void init_base(uint32_t (&c)[NW + H], const LaneSeq<H, PLANES> &q) {
+#pragma unroll
+    for (int i = 0; i < NW + H; ++i) c[i] = q.template and_base<C>(LEFT ? i : i + H, 0xFFFFFFFFu);
+}
+template <bool LEFT, int H, bool PLANES>
+__device__ __forceinline__ void init_set(uint32_t (&c)[NW + H], const LaneSeq<H, PLANES> &q, int code) {
+    const uint32_t mA = (code & 1) ? 0xFFFFFFFFu : 0u, mT = (code & 2) ? 0xFFFFFFFFu : 0u;
+    const uint32_t mG = (code & 4) ? 0xFFFFFFFFu : 0u, mC = (code & 8) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+    for (int i = 0; i < NW + H; ++i) c[i] = q.and_set(LEFT ? i : i + H, mA, mT, mG, mC, 0xFFFFFFFFu);
+}
+
+// Run the n >= 1 program entries at ent[0..n) over chain c.  Entry codes: 1/2/4/8 single base,
+// kEntShift32 = "shift the chain by one word" (emitted by the compiler for gaps >= 32), anything
+// else a degenerate set (0 = empty set).  All shifts are < 32 and the first entry's shift is 0.
+constexpr int kEntShift32 = 0x10;
+
 template <bool LEFT, int H, bool PLANES>
 __device__ __forceinline__ void run_chain(uint32_t (&c)[NW + H], const LaneSeq<H, PLANES> &q,
                                           const uint16_t *ent, int n) {
     uint32_t e = __ldg(ent);
+    {
+        const int code = e & 0xFF;
+        if (n > 1) e = __ldg(ent + 1);
+        if (code == 1) init_base<0, LEFT, H, PLANES>(c, q);
+        else if (code == 2) init_base<1, LEFT, H, PLANES>(c, q);
+        else if (code == 4) init_base<2, LEFT, H, PLANES>(c, q);
+        else if (code == 8) init_base<3, LEFT, H, PLANES>(c, q);
+        else init_set<LEFT, H, PLANES>(c, q, code);
+    }
 #pragma unroll 1
-    for (int i = 0; i < n; ++i) {
+    for (int i = 1; i < n; ++i) {
         const uint32_t cur = e;
         if (i + 1 < n) e = __ldg(ent + i + 1);  // prefetch the next entry
-        int s = cur >> 8;
+        const int s = cur >> 8;
         const int code = cur & 0xFF;
-        while (s >= 32) {
-            chain_shift_words<LEFT, H>(c);
-            s -= 32;
-        }
         if (code == 1) step_base<0, LEFT, H, PLANES>(c, q, s);
         else if (code == 2) step_base<1, LEFT, H, PLANES>(c, q, s);
         else if (code == 4) step_base<2, LEFT, H, PLANES>(c, q, s);
         else if (code == 8) step_base<3, LEFT, H, PLANES>(c, q, s);
-        else step_set<LEFT, H, PLANES>(c, q, code, s);  // degenerate position (or empty set: code 0)
+        else if (code == kEntShift32) chain_shift_words<LEFT, H>(c);
+        else step_set<LEFT, H, PLANES>(c, q, code, s);
     }
 }
 
-// Match words of the lane's NW words, aligned at the program's mod_pos.
+// Evaluate one program on the lane's words.  On return the match plane aligned at mod_pos is
+//     M[k] = L[k + H] & funnel_r(R[k], R[k + 1], sr)        for k in [0, NW)
+// (left chain empty -> L = ~0; right chain empty -> R = ~0, sr = 0).
+template <int H, bool PLANES>
+__device__ __forceinline__ int eval_program(const ProgramView &pv, const LaneSeq<H, PLANES> &q,
+                                            uint32_t (&L)[NW + H], uint32_t (&R)[NW + H]) {
+    constexpr int CW = NW + H;
+    if (pv.n_left > 0) {
+        run_chain<true, H, PLANES>(L, q, pv.ent, pv.n_left);
+        if (pv.sl) {  // only when the modified base itself is a wildcard (sl < 32 by construction)
+            chain_shift_bits<true, H>(L, pv.sl);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) L[i] = 0xFFFFFFFFu;
+    }
+    if (pv.n_right > 0) {
+        run_chain<false, H, PLANES>(R, q, pv.ent + pv.n_left, pv.n_right);
+        return pv.sr;
+    }
+#pragma unroll
+    for (int i = 0; i < CW; ++i) R[i] = 0xFFFFFFFFu;
+    return 0;
+}
+
 template <int H, bool PLANES>
 __device__ __forceinline__ void match_words(const ProgramView &pv, const LaneSeq<H, PLANES> &q,
                                             uint32_t (&m)[NW]) {
-    constexpr int CW = NW + H;
-    uint32_t L[CW], R[CW];
-#pragma unroll
-    for (int i = 0; i < CW; ++i) {
-        L[i] = 0xFFFFFFFFu;
-        R[i] = 0xFFFFFFFFu;
-    }
-    if (pv.n_left > 0) {
-        run_chain<true, H, PLANES>(L, q, pv.ent, pv.n_left);
-        int sl = pv.sl;  // only non-zero when the modified base itself is a wildcard
-        while (sl >= 32) {
-            chain_shift_words<true, H>(L);
-            sl -= 32;
-        }
-        if (sl) chain_shift_bits<true, H>(L, sl);
-    }
-    int sr = 0;
-    if (pv.n_right > 0) {
-        run_chain<false, H, PLANES>(R, q, pv.ent + pv.n_left, pv.n_right);
-        sr = pv.sr;
-        while (sr >= 32) {
-            chain_shift_words<false, H>(R);
-            sr -= 32;
-        }
-    }
+    uint32_t L[NW + H], R[NW + H];
+    const int sr = eval_program<H, PLANES>(pv, q, L, R);
 #pragma unroll
     for (int k = 0; k < NW; ++k) m[k] = L[k + H] & __funnelshift_r(R[k], R[k + 1], sr);
 }
