@@ -20,14 +20,14 @@
  *
  * Packed layout ("tile records", described in DESIGN.md section 3)
  *   The assembly lives in one global position space.  Contig c occupies positions
- *   [start_c, start_c + len_c), start_c a multiple of NMB_CHUNK_BP (256); consecutive contigs are
+ *   [start_c, start_c + len_c), start_c a multiple of NMB_CHUNK_BP (512); consecutive contigs are
  *   separated by >= NMB_MIN_GAP_BP positions flagged non-ACGT.  The space is cut into tiles of
  *   NMB_TILE_BP (65536) positions.  Per tile t:
- *     seq record  : uint32 x[NMB_TILE_WORDS+8], y[NMB_TILE_WORDS+8], int32 chunk_info[256]
+ *     seq record  : uint32 x[NMB_TILE_WORDS+8], y[NMB_TILE_WORDS+8], int32 chunk_info[128]
  *                   x = high code bit, y = low code bit (A=0 T=1 G=2 C=3, nanomotif/constants.py:1);
  *                   4 halo words of the neighbouring tiles are duplicated on each side so that one
  *                   bulk copy (TMA) brings a self-contained tile into shared memory.
- *                   chunk_info[q] = contig id of 256-bp chunk q, bit 30 set when the chunk (or its
+ *                   chunk_info[q] = contig id of 512-bp chunk q, bit 30 set when the chunk (or its
  *                   halo) touches a non-ACGT letter, -1 for an empty chunk.
  *     class record: uint32 plane[4][NMB_TILE_WORDS] per mod type:
  *                   0 = methylated '+', 1 = unmethylated '+', 2 = methylated '-', 3 = unmethylated '-'
@@ -51,14 +51,14 @@ extern "C" {
 #define NMB_API
 #endif
 
-#define NMB_CHUNK_WORDS 8
-#define NMB_CHUNK_BP 256
+#define NMB_CHUNK_WORDS 16
+#define NMB_CHUNK_BP 512
 #define NMB_TILE_WORDS 2048
 #define NMB_TILE_BP 65536
-#define NMB_TILE_CHUNKS 256
+#define NMB_TILE_CHUNKS 128
 #define NMB_HALO_WORDS 4
 #define NMB_SEQ_PLANE_WORDS (NMB_TILE_WORDS + 2 * NMB_HALO_WORDS)           /* 2056 */
-#define NMB_SEQ_REC_WORDS (2 * NMB_SEQ_PLANE_WORDS + NMB_TILE_CHUNKS)       /* 4368 */
+#define NMB_SEQ_REC_WORDS (2 * NMB_SEQ_PLANE_WORDS + NMB_TILE_CHUNKS)       /* 4240 */
 #define NMB_CLS_REC_WORDS (4 * NMB_TILE_WORDS)                              /* 8192 */
 #define NMB_MIN_GAP_BP 64
 #define NMB_MAX_MOTIF_LEN 62
@@ -87,7 +87,7 @@ typedef struct nmb_motif {
 typedef struct nmb_assembly {
     const uint32_t *seq_records;   /* [n_tiles][NMB_SEQ_REC_WORDS] */
     const uint32_t *nonacgt;       /* [NMB_HALO_WORDS + n_tiles*NMB_TILE_WORDS + NMB_HALO_WORDS] */
-    const int64_t *contig_start;   /* [n_contigs] global start position (multiple of 256) */
+    const int64_t *contig_start;   /* [n_contigs] global start position (multiple of 512) */
     const int64_t *contig_len;     /* [n_contigs] */
     int32_t n_contigs;
     int32_t n_tiles;

@@ -15,11 +15,11 @@ LIB_PATH = os.path.join(_HERE, "libnmb200.so")
 
 # ---- constants mirrored from include/nmb200.h -------------------------------------------------
 ABI_VERSION = 1
-CHUNK_WORDS = 8
-CHUNK_BP = 256
+CHUNK_WORDS = 16
+CHUNK_BP = 512
 TILE_WORDS = 2048
 TILE_BP = 65536
-TILE_CHUNKS = 256
+TILE_CHUNKS = 128
 HALO_WORDS = 4
 SEQ_PLANE_WORDS = TILE_WORDS + 2 * HALO_WORDS
 SEQ_REC_WORDS = 2 * SEQ_PLANE_WORDS + TILE_CHUNKS

@@ -40,31 +40,32 @@ char *last_error_buffer();  // thread-local, 512 bytes (api.cu)
 // ---------------------------------------------------------------------------------------------
 // layout constants (mirrors of nmb200.h)
 // ---------------------------------------------------------------------------------------------
-constexpr int kChunkWords = NMB_CHUNK_WORDS;       // words per lane chunk (256 bp)
+constexpr int kChunkWords = NMB_CHUNK_WORDS;       // words per lane chunk (512 bp)
 constexpr int kTileWords = NMB_TILE_WORDS;         // words per tile (65536 bp)
-constexpr int kTileChunks = NMB_TILE_CHUNKS;       // 256 chunks = 256 threads
+constexpr int kTileChunks = NMB_TILE_CHUNKS;       // 128 chunks = 128 threads
 constexpr int kHalo = NMB_HALO_WORDS;              // duplicated halo words per side
 constexpr int kSeqPlaneWords = NMB_SEQ_PLANE_WORDS;
 constexpr int kSeqRecWords = NMB_SEQ_REC_WORDS;
 constexpr int kClsRecWords = NMB_CLS_REC_WORDS;
-constexpr int kSeqRecBytes = kSeqRecWords * 4;     // 17472
+constexpr int kSeqRecBytes = kSeqRecWords * 4;     // 16960
 constexpr int kClsRecBytes = kClsRecWords * 4;     // 32768
 constexpr int kMaxLen = NMB_MAX_MOTIF_LEN;
 constexpr int kChunkFlagN = 1 << 30;
 constexpr int kChunkIdMask = (1 << 30) - 1;
 
-static_assert(kTileWords == kTileChunks * kChunkWords, "tile = 256 lane chunks");
+static_assert(kTileWords == kTileChunks * kChunkWords, "tile = 128 lane chunks");
+static_assert(kChunkWords % 4 == 0 && kChunkWords <= 32, "lane chunk is a whole number of uint4");
 static_assert(kSeqRecBytes % 16 == 0 && kClsRecBytes % 16 == 0, "bulk copies need 16-byte sizes");
 
 // Compiled scan program of one motif strand (device representation, 128 bytes).  Only constrained
-// positions appear.  Entries are in processing order: first the left chain (positions <= mod_pos,
-// ascending), then the right chain (positions > mod_pos, descending).  entry = allowed-set code
-// (1..14; 0 = never matches) | (distance to the previously processed position of its chain) << 8.
+// positions appear, in processing order (LAST position first).  entry = allowed-set code (1..14;
+// 0 = never matches) | (distance to the previously processed position) << 8; gaps >= 32 are split
+// off as "shift one word" pseudo entries (code 0x10), so every shift is < 32.
 struct Program {
-    uint8_t n_left;   // entries of the left chain
-    uint8_t n_right;  // entries of the right chain
-    uint8_t sl;       // mod_pos - last left position (0 unless the modified base is a wildcard)
-    uint8_t sr;       // last processed right position - mod_pos
+    uint8_t n;        // entries (pseudo entries included)
+    uint8_t mod_pos;  // modified-base position within the stripped motif
+    uint8_t len;
+    uint8_t reserved;
     uint16_t ent[kMaxLen];
 };
 static_assert(sizeof(Program) == 128, "Program must be 128 bytes");

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(kTileChunks) match_plane_kernel(
         const uint32_t *lx = rec + kHalo + tid * NW, *ly = rec + kSeqPlaneWords + kHalo + tid * NW;
         if (warp_n) {
             LaneSeq<H, true> q;
-            load_planes<H>(lx, ly, nonacgt + kHalo + (size_t)tile * kTileWords + tid * NW - H, q);
+            load_xyn<H>(lx, ly, nonacgt + kHalo + (size_t)tile * kTileWords + tid * NW - H, q);
             match_words<H, true>(pv, q, m);
         } else {
             LaneSeq<H, false> q;
@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(kTileChunks) match_plane_kernel(
         }
     }
     uint4 *dst = reinterpret_cast<uint4 *>(match_plane + (size_t)tile * kTileWords + tid * NW);
-    dst[0] = make_uint4(m[0], m[1], m[2], m[3]);
-    dst[1] = make_uint4(m[4], m[5], m[6], m[7]);
+#pragma unroll
+    for (int v = 0; v < NW / 4; ++v) dst[v] = make_uint4(m[4 * v], m[4 * v + 1], m[4 * v + 2], m[4 * v + 3]);
 }
 
 // ---- compaction ---------------------------------------------------------------------------------

@@ -7,18 +7,18 @@
 //   motif_model_bin (sum over contigs)        nanomotif/find_motifs_bin.py:1265-1283
 //
 // Persistent CTAs walk a list of work items (tile, block of <=32 motifs).  A tile is one
-// self-contained 17.5 KB sequence record + one 32 KB class record, brought into shared memory by two
-// cp.async.bulk (TMA) copies that complete on an mbarrier; a 2-stage ring overlaps the copy of the
-// next item with the bit-parallel evaluation of the current one.  Counts are popcounts of
+// self-contained 17 KB sequence record + one 32 KB class record, brought into shared memory by two
+// cp.async.bulk (TMA) copies that complete on an mbarrier.  Four CTAs of 128 threads are resident per
+// SM, so copy latency is hidden by the other CTAs' bit-parallel evaluation.  Counts are popcounts of
 // match & class-plane, reduced with warp REDUX, accumulated per CTA in shared memory and flushed
 // with one 64-bit atomic per (motif, counter) per item.
+#include <stdlib.h>
+
 #include "scan.cuh"
 
 namespace nmb {
 
-constexpr int kStages = 2;
-constexpr int kStageBytes = ((kSeqRecBytes + kClsRecBytes + 127) / 128) * 128;  // 50304
-constexpr int kScanThreads = kTileChunks;                                       // 256
+constexpr int kScanThreads = kTileChunks;                                       // 128
 constexpr int kMaxMpi = NMB_MAX_MOTIFS_PER_ITEM;
 
 struct ScanParams {
@@ -74,8 +74,10 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
 #pragma unroll 1
         for (int st = 0; st < 2; ++st) {  // forward motif, then its reverse complement
             const ProgramView pv = load_program(prog + st);
-            uint32_t L[NW + H], R[NW + H];
-            const int sr = eval_program<H, PLANES>(pv, q, L, R);
+            uint32_t c[NW + 2 * H];
+            run_chain<H, PLANES>(pv, q, c);
+            const bool far = pv.mod_pos >= 32;  // only possible when H == 2
+            const int sh = pv.mod_pos & 31;
             const uint32_t *c0 = cl + 2 * st * kTileWords;
             uint32_t n_mod = 0, n_non = 0;
 #pragma unroll
@@ -85,9 +87,9 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
                 const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t rs = __funnelshift_r(R[h + k], R[h + k + 1], sr);
-                    n_mod += __popc(lop3<0x80>(L[h + k + H], rs, av[k]));  // L & R>>sr & methylated
-                    n_non += __popc(lop3<0x80>(L[h + k + H], rs, bv[k]));  // L & R>>sr & unmethylated
+                    const uint32_t m = aligned_word<H>(c, h + k, sh, far);
+                    n_mod += __popc(m & av[k]);  // occurrences whose modified base is methylated
+                    n_non += __popc(m & bv[k]);  // ... unmethylated
                 }
             }
             const uint32_t pk = valid ? (n_mod | (n_non << 16)) : 0u;
@@ -117,11 +119,17 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
     }
 }
 
+// One tile (sequence record + class record = 49.7 KB) per CTA in shared memory; four CTAs of four warps
+// are resident per SM, so while one CTA waits for its bulk copies the other three keep the ALUs busy and
+// up to ~200 KB of copies are in flight per SM.  (Measured alternatives on B200: a 2-stage ring with two
+// resident CTAs, and a split ring with three, were both slower -- profiles/r01_notes.md.)
+constexpr int kScanSmemBytes = kSeqRecBytes + kClsRecBytes;
+
 template <int H>
-__global__ void __launch_bounds__(kScanThreads, 2) scan_count_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 4) scan_count_kernel(const ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    __shared__ ItemMeta s_meta[kStages];
+    __shared__ __align__(8) uint64_t full_bar;
+    __shared__ ItemMeta s_meta;
     __shared__ uint32_t s_acc[2][kMaxMpi][4];
 
     const int tid = threadIdx.x;
@@ -129,37 +137,28 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_count_kernel(const ScanP
     const int n_my = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_init(&full_bar, 1);
         fence_barrier_init();
     }
     for (int i = tid; i < 2 * kMaxMpi * 4; i += kScanThreads) (&s_acc[0][0][0])[i] = 0;
     __syncthreads();
 
-    auto issue = [&](int k) {  // thread 0 only
-        const int stage = k % kStages;
-        const ItemMeta m = decode_item(p, (int)blockIdx.x + k * (int)gridDim.x);
-        s_meta[stage] = m;
-        uint8_t *dst = smem + (size_t)stage * kStageBytes;
-        const int modtype = __ldg(&p.jobs[m.job].modtype);
-        fence_proxy_async();  // order earlier generic reads of this stage before the async writes
-        mbar_expect_tx(&full_bar[stage], kSeqRecBytes + kClsRecBytes);
-        bulk_g2s(dst, p.seq_records + (size_t)m.tile * kSeqRecWords, kSeqRecBytes, &full_bar[stage]);
-        bulk_g2s(dst + kSeqRecBytes,
-                 p.cls + ((size_t)modtype * p.n_tiles + m.tile) * kClsRecWords, kClsRecBytes,
-                 &full_bar[stage]);
-    };
-
-    if (tid == 0)
-        for (int k = 0; k < kStages - 1 && k < n_my; ++k) issue(k);
-
     for (int k = 0; k < n_my; ++k) {
-        const int stage = k % kStages;
-        if (tid == 0 && k + kStages - 1 < n_my) issue(k + kStages - 1);
-        mbar_wait(&full_bar[stage], (uint32_t)((k / kStages) & 1));
+        if (tid == 0) {  // two bulk copies (TMA) bring the self-contained tile; completion on the mbarrier
+            const ItemMeta m = decode_item(p, (int)blockIdx.x + k * (int)gridDim.x);
+            s_meta = m;
+            const int modtype = __ldg(&p.jobs[m.job].modtype);
+            fence_proxy_async();  // order the previous item's generic reads before the async writes
+            mbar_expect_tx(&full_bar, kSeqRecBytes + kClsRecBytes);
+            bulk_g2s(smem, p.seq_records + (size_t)m.tile * kSeqRecWords, kSeqRecBytes, &full_bar);
+            bulk_g2s(smem + kSeqRecBytes, p.cls + ((size_t)modtype * p.n_tiles + m.tile) * kClsRecWords,
+                     kClsRecBytes, &full_bar);
+        }
+        mbar_wait(&full_bar, (uint32_t)(k & 1));
 
-        const ItemMeta meta = s_meta[stage];
+        const ItemMeta meta = s_meta;
         const nmb_job job = p.jobs[meta.job];
-        const uint32_t *sx = reinterpret_cast<const uint32_t *>(smem + (size_t)stage * kStageBytes);
+        const uint32_t *sx = reinterpret_cast<const uint32_t *>(smem);
         const uint32_t *sy = sx + kSeqPlaneWords;
         const int32_t *sinfo = reinterpret_cast<const int32_t *>(sy + kSeqPlaneWords);
         const uint32_t *scls = sx + kSeqRecWords;
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_count_kernel(const ScanP
             const uint32_t *cl = scls + tid * NW;
             if (warp_n) {  // chunk (or halo) touches non-ACGT letters / contig padding
                 LaneSeq<H, true> q;
-                load_planes<H>(lx, ly, p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H, q);
+                load_xyn<H>(lx, ly, p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H, q);
                 score_motifs<H, true>(p, job, meta, q, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
             } else {
                 LaneSeq<H, false> q;
@@ -200,7 +199,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_count_kernel(const ScanP
                 score_motifs<H, false>(p, job, meta, q, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
             }
         }
-        __syncthreads();  // everyone is done with this stage and with s_acc[par]
+        __syncthreads();  // everyone is done with the tile and with s_acc[par]
         if (tid < kMaxMpi * 4) {
             const int mi = tid >> 2, c = tid & 3;
             const uint32_t v = s_acc[par][mi][c];
@@ -226,48 +225,27 @@ __global__ void compile_motifs_kernel(const nmb_motif *__restrict__ motifs, int 
     Program pr;
     for (int i = 0; i < kMaxLen; ++i) pr.ent[i] = 0;
     int len = mt.len, mp = mt.mod_pos;
+    pr.reserved = 0;
     if (len < 1 || len > kMaxLen || mp >= len) {  // invalid: compile to "never matches"
-        pr.n_left = 1; pr.n_right = 0; pr.sl = 0; pr.sr = 0;
+        pr.n = 1; pr.mod_pos = 0; pr.len = 1;
         programs[t] = pr;
         return;
     }
     if (rc) mp = len - 1 - mp;  // motif.py:264
-    uint8_t code[kMaxLen];
-    for (int j = 0; j < len; ++j) {
+    // Gaps of 32 or more positions become "shift one word" pseudo entries so that every real entry
+    // carries a shift < 32.  The first processed entry is the last motif position (shift 0); a
+    // stripped motif starts with a constrained position, so the chain ends aligned at position 0.
+    int n = 0, prev = -1;
+    for (int j = len - 1; j >= 0; --j) {
         int a = mt.allowed[rc ? (len - 1 - j) : j] & 0xF;
         if (rc) a = ((a & 5) << 1) | ((a & 10) >> 1);  // A<->T, G<->C (constants.py:14-20)
-        code[j] = (uint8_t)a;
-    }
-    // Gaps of 32 or more positions become "shift one word" pseudo entries so that every real entry
-    // (and the final alignment shifts sl / sr) carries a shift < 32.
-    int n = 0, prev = -1;
-    for (int j = 0; j <= mp; ++j) {  // left chain, ascending
-        if (code[j] == 0xF) continue;
-        int d = prev < 0 ? 0 : j - prev;
-        for (; d >= 32; d -= 32) pr.ent[n++] = kEntShift32;
-        pr.ent[n++] = (uint16_t)(code[j] | (d << 8));
-        prev = j;
-    }
-    {
-        int d = prev < 0 ? 0 : mp - prev;
-        for (; d >= 32; d -= 32) pr.ent[n++] = kEntShift32;
-        pr.sl = (uint8_t)d;
-    }
-    pr.n_left = (uint8_t)n;
-    prev = -1;
-    for (int j = len - 1; j > mp; --j) {  // right chain, descending
-        if (code[j] == 0xF) continue;
+        if (a == 0xF && j != 0) continue;
         int d = prev < 0 ? 0 : prev - j;
-        for (; d >= 32; d -= 32) pr.ent[n++] = kEntShift32;
-        pr.ent[n++] = (uint16_t)(code[j] | (d << 8));
+        for (; d >= 32 && n < kMaxLen - 1; d -= 32) pr.ent[n++] = kEntShift32;
+        if (n < kMaxLen) pr.ent[n++] = (uint16_t)(a | (d << 8));  // a == 0xF at j == 0: pure shift
         prev = j;
     }
-    {
-        int d = prev < 0 ? 0 : prev - mp;
-        for (; d >= 32; d -= 32) pr.ent[n++] = kEntShift32;
-        pr.sr = (uint8_t)d;
-    }
-    pr.n_right = (uint8_t)(n - pr.n_left);
+    pr.n = (uint8_t)n; pr.mod_pos = (uint8_t)mp; pr.len = (uint8_t)len;
     programs[t] = pr;
 }
 
@@ -314,19 +292,18 @@ int nmb_scan_count(const nmb_assembly *a, const uint32_t *class_records, const v
     if (grid <= 0) {
         int sms = nmb_device_sm_count();
         if (sms < 0) return sms;
-        grid = 2 * sms;
+        grid = 4 * sms;  // resident CTAs per SM (49.7 KB of shared memory, <= 128 registers each)
     }
     if (grid > n_items) grid = n_items;
-    const int smem = nmb::kStages * nmb::kStageBytes;
     cudaStream_t s = (cudaStream_t)stream;
     if (max_motif_len <= 33) {
-        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<1>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        nmb::scan_count_kernel<1><<<grid, nmb::kScanThreads, smem, s>>>(p);
+        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      nmb::kScanSmemBytes));
+        nmb::scan_count_kernel<1><<<grid, nmb::kScanThreads, nmb::kScanSmemBytes, s>>>(p);
     } else {
-        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<2>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        nmb::scan_count_kernel<2><<<grid, nmb::kScanThreads, smem, s>>>(p);
+        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      nmb::kScanSmemBytes));
+        nmb::scan_count_kernel<2><<<grid, nmb::kScanThreads, nmb::kScanSmemBytes, s>>>(p);
     }
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;

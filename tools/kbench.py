@@ -59,14 +59,19 @@ def main():
     ap.add_argument("--mpi", type=int, nargs="*", default=[1])
     ap.add_argument("--motifs", nargs="*", default=["GATC", "GRNGAAGY", "A", "L13"])
     ap.add_argument("--batch", type=int, default=1, help="replicate each motif this many times in the launch")
+    ap.add_argument("--random", type=int, default=0, help="also time a batch of N seeded random motifs (cfg2 work list)")
     args = ap.parse_args()
     device = torch.device("cuda", 0)
     asm, pile = build(device, args.bp, args.contigs)
     rec_bytes = asm.n_tiles * (_lib.SEQ_REC_WORDS + _lib.CLS_REC_WORDS) * 4
     print(json.dumps({"bp": asm.total_bp, "tiles": asm.n_tiles, "record_bytes": rec_bytes}))
-    for name in args.motifs:
-        s, p = MOTIFS[name]
-        progs = MotifPrograms([nmb.Motif(s, p)] * args.batch, device)
+    sets = [(name, [nmb.Motif(*MOTIFS[name])] * args.batch) for name in args.motifs]
+    if args.random:
+        from nanomotif_b200 import synth
+        sets.append((f"random{args.random}", [nmb.Motif(s, p) for s, p in synth.random_motifs(np.random.default_rng(1001), args.random, "A")]))
+    for name, motifs in sets:
+        args.batch = len(motifs)
+        progs = MotifPrograms(motifs, device)
         jobs = make_jobs(1)
         jobs["motif_count"], jobs["tile_count"] = args.batch, asm.n_tiles
         jobs["contig_end"], jobs["n_groups"] = asm.n_contigs, 1
