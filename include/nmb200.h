@@ -62,7 +62,7 @@ extern "C" {
 #define NMB_CLS_REC_WORDS (4 * NMB_TILE_WORDS)                              /* 8192 */
 #define NMB_MIN_GAP_BP 64
 #define NMB_MAX_MOTIF_LEN 62
-#define NMB_MAX_WINDOW 63
+#define NMB_MAX_WINDOW 61
 #define NMB_MAX_MOTIFS_PER_ITEM 32
 
 typedef enum nmb_status {
@@ -200,11 +200,14 @@ NMB_API int nmb_extract_windows(const nmb_assembly *assembly_h, const int64_t *g
 /* For each of n_motifs full-width masks (allowed[j] per window column, len = window width):
  * rows kept by filter_sequence_matches(keep_matches=True), i.e. one-hot(row) <= mask everywhere,
  * restricted to rows with alive[i] != 0 (alive may be NULL); hist[m][j][b] = column sums of the
- * kept one-hot rows (N adds 1 to all four), n_active[m] = kept rows. hist/n_active are
- * overwritten.  keep[m*n + i] (may be NULL) receives the per-row decision. */
+ * kept one-hot rows, n_active[m] = kept rows.  n_counts_all = 1: a non-ACGT letter adds 1 to all
+ * four bases (DNAarray.pssm, seq.py:41-48,537); 0: it adds nothing (EqualLengthDNASet.pssm exact-
+ * letter counts, seq.py:413-421).  hist/n_active are overwritten.  keep[m*n + i] (may be NULL)
+ * receives the per-row decision. */
 NMB_API int nmb_window_hist(const uint64_t *windows, const uint8_t *alive, int64_t n, int32_t width,
-                    const nmb_motif *masks, int32_t n_motifs, int32_t *hist /* [n_motifs][width][4] */,
-                    int64_t *n_active, uint8_t *keep, void *stream);
+                    const nmb_motif *masks, int32_t n_motifs, int32_t n_counts_all,
+                    int32_t *hist /* [n_motifs][width][4] */, int64_t *n_active, uint8_t *keep,
+                    void *stream);
 
 /* PSSM + KL(meth || background) per column in float64: pssm[m][b][j] = hist/n_active (4 x width,
  * rows A,T,G,C), kl[m][j] = sum_b p ln(p/q) after per-column renormalisation of both (scipy.stats.

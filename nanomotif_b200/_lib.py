@@ -26,7 +26,7 @@ SEQ_REC_WORDS = 2 * SEQ_PLANE_WORDS + TILE_CHUNKS
 CLS_REC_WORDS = 4 * TILE_WORDS
 MIN_GAP_BP = 64
 MAX_MOTIF_LEN = 62
-MAX_WINDOW = 63
+MAX_WINDOW = 61
 MAX_MOTIFS_PER_ITEM = 32
 
 
@@ -85,7 +85,7 @@ SIGNATURES = {
     "nmb_compact_positions": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P, _P]),
     "nmb_test_positions": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P]),
     "nmb_extract_windows": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _I64, _I32, _P, _P]),
-    "nmb_window_hist": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P, _P, _P, _P]),
+    "nmb_window_hist": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _P, _P, _P]),
     "nmb_pssm_kl": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P]),
 }
 

@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(256) extract_windows_kernel(
 // memory: allow[b] has bit j set when base b is accepted at column j.
 __global__ void __launch_bounds__(256) window_hist_kernel(
     const uint64_t *__restrict__ windows, const uint8_t *__restrict__ alive, int64_t n, int width,
-    const nmb_motif *__restrict__ masks, int *__restrict__ hist, unsigned long long *__restrict__ n_active,
-    uint8_t *__restrict__ keep) {
+    const nmb_motif *__restrict__ masks, int n_counts_all, int *__restrict__ hist,
+    unsigned long long *__restrict__ n_active, uint8_t *__restrict__ keep) {
     __shared__ uint64_t s_allow[4];
     __shared__ uint64_t s_wild;
     __shared__ int s_hist[NMB_MAX_WINDOW * 4];
@@ -101,10 +101,12 @@ __global__ void __launch_bounds__(256) window_hist_kernel(
         // one-hot(row) <= mask everywhere (seq.py:518); an N row is all ones and needs a wildcard
         const uint64_t bad = (isA & ~aA) | (isT & ~aT) | (isG & ~aG) | (isC & ~aC) | (nn & ~wild & full);
         kept = bad == 0;
-        isA |= nn & full;  // N adds one to all four bases (seq.py:41-48, 537)
-        isT |= nn & full;
-        isG |= nn & full;
-        isC |= nn & full;
+        if (n_counts_all) {  // N adds one to all four bases (seq.py:41-48, 537)
+            isA |= nn & full;
+            isT |= nn & full;
+            isG |= nn & full;
+            isC |= nn & full;
+        }
     }
     if (keep && i < n) keep[(int64_t)m * n + i] = kept ? 1 : 0;
     const uint32_t kb = __ballot_sync(0xFFFFFFFFu, kept);
@@ -180,8 +182,8 @@ int nmb_extract_windows(const nmb_assembly *a, const int64_t *gpos, const uint8_
 }
 
 int nmb_window_hist(const uint64_t *windows, const uint8_t *alive, int64_t n, int32_t width,
-                    const nmb_motif *masks, int32_t n_motifs, int32_t *hist, int64_t *n_active,
-                    uint8_t *keep, void *stream) {
+                    const nmb_motif *masks, int32_t n_motifs, int32_t n_counts_all, int32_t *hist,
+                    int64_t *n_active, uint8_t *keep, void *stream) {
     NMB_REQUIRE(width >= 1 && width <= NMB_MAX_WINDOW, "nmb_window_hist: width=%d", width);
     NMB_REQUIRE(n >= 0 && n_motifs >= 0, "nmb_window_hist: n=%lld n_motifs=%d", (long long)n, n_motifs);
     if (n_motifs == 0) return NMB_OK;
@@ -193,7 +195,7 @@ int nmb_window_hist(const uint64_t *windows, const uint8_t *alive, int64_t n, in
     if (n == 0) return NMB_OK;
     NMB_REQUIRE(windows, "nmb_window_hist: null windows");
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)n_motifs);
-    nmb::window_hist_kernel<<<grid, 256, 0, s>>>(windows, alive, n, width, masks, hist,
+    nmb::window_hist_kernel<<<grid, 256, 0, s>>>(windows, alive, n, width, masks, n_counts_all, hist,
                                                 (unsigned long long *)n_active, keep);
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;

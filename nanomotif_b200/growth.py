@@ -1,0 +1,243 @@
+"""Motif-growth step on the device: methylation windows, active-set filter, PSSM and KL children.
+
+Mirrors, for the part of ``find_best_candidates`` / ``MotifSearcher`` that touches sequence data:
+
+    DNAsequence.sample_at_indices              nanomotif/seq.py:170-189   (strict bounds)
+    EqualLengthDNASet.reverse_compliment       nanomotif/seq.py:387-389
+    EqualLengthDNASet.convert_to_DNAarray      nanomotif/seq.py:474-478
+    DNAarray.filter_sequence_matches / pssm    nanomotif/seq.py:499-537
+    EqualLengthDNASet.pssm (background)        nanomotif/seq.py:391-422
+    _motif_child_nodes_kl_dist_max             nanomotif/find_motifs_bin.py:957-1023
+
+A window is 3 x uint64 on the device instead of a (W, 4) int64 one-hot row; the search's control flow
+(heap, graph, thresholds) stays on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import random
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr
+from .device import DeviceAssembly, _stream, _to_device, sequence_of
+from .motif import BASES, Motif, as_motif, window_masks
+
+_WILD_ROW = np.ones(4, dtype=int)
+
+
+def _one_hot_to_masks(one_hot: np.ndarray) -> np.ndarray:
+    """(W, 4) 0/1 matrix in A,T,G,C order -> nmb_motif record (allowed-set per column)."""
+    oh = np.asarray(one_hot)
+    rec = np.zeros(1, dtype=_lib.MOTIF_DTYPE)
+    width = oh.shape[0]
+    if width > _lib.MAX_WINDOW:
+        raise ValueError(f"window width {width} exceeds {_lib.MAX_WINDOW}")
+    bits = ((oh[:, 0] >= 1) * 1 + (oh[:, 1] >= 1) * 2 + (oh[:, 2] >= 1) * 4 + (oh[:, 3] >= 1) * 8).astype(np.uint8)
+    rec["allowed"][0, :width] = bits
+    rec["len"][0] = width
+    return rec
+
+
+class DeviceDNAarray:
+    """Drop-in for the reference's ``DNAarray`` as the motif search uses it: ``shape``, ``copy()``,
+    ``filter_sequence_matches(one_hot, keep_matches)`` and ``pssm()``.  Rows live on the GPU as
+    bit-packed windows plus an `alive` mask; filtering never moves the windows."""
+
+    def __init__(self, windows: torch.Tensor, width: int, alive: torch.Tensor | None = None, n_alive: int | None = None,
+                 hist: np.ndarray | None = None):
+        self.windows = windows  # int64 tensor [N, 3] holding x / y / n bit words
+        self.width = int(width)
+        self.n_total = int(windows.shape[0])
+        self.alive = alive
+        self.n_alive = self.n_total if n_alive is None else int(n_alive)
+        self._hist = hist  # (W, 4) column sums of the alive rows when already known
+
+    # -- construction ---------------------------------------------------------------------------
+    @classmethod
+    def from_positions(cls, assembly: DeviceAssembly, contig_index, position, strand, padding: int):
+        """Windows of +-padding around forward-strand positions (strand 1 = reverse-complemented).
+        Positions violating the reference's strict bound padding < i < len - padding must already have
+        been dropped (see `methylation_windows`)."""
+        d = assembly.device
+        ci = np.asarray(contig_index, dtype=np.int64)
+        gpos = assembly.starts[ci] + np.asarray(position, dtype=np.int64)
+        n = len(gpos)
+        win = torch.empty((n, 3), dtype=torch.int64, device=d)
+        if n:
+            with torch.cuda.device(d):
+                g = _to_device(gpos, d)
+                st = _to_device(np.asarray(strand, dtype=np.uint8), d)
+                view = assembly.view()
+                check(lib.nmb_extract_windows(C.byref(view), ptr(g), ptr(st), n, int(padding), ptr(win), _stream()),
+                      "nmb_extract_windows")
+                torch.cuda.current_stream().synchronize()
+        return cls(win, 2 * padding + 1)
+
+    # -- DNAarray surface -----------------------------------------------------------------------
+    @property
+    def shape(self):
+        return (self.n_alive, self.width, 4)
+
+    def __len__(self):
+        return self.n_alive
+
+    def copy(self) -> "DeviceDNAarray":
+        return DeviceDNAarray(self.windows, self.width, self.alive, self.n_alive, self._hist)
+
+    def _hist_call(self, masks: np.ndarray, n_counts_all: int, want_keep: bool):
+        d = self.windows.device
+        m = len(masks)
+        with torch.cuda.device(d):
+            masks_d = _to_device(masks.view(np.uint8).reshape(-1), d)
+            hist = torch.empty((m, self.width, 4), dtype=torch.int32, device=d)
+            n_active = torch.empty(m, dtype=torch.int64, device=d)
+            keep = torch.empty((m, self.n_total), dtype=torch.uint8, device=d) if want_keep else None
+            check(lib.nmb_window_hist(ptr(self.windows), ptr(self.alive), self.n_total, self.width, ptr(masks_d), m,
+                                      n_counts_all, ptr(hist), ptr(n_active), ptr(keep), _stream()), "nmb_window_hist")
+        return hist, n_active, keep
+
+    def filter_sequence_matches(self, sequence: np.ndarray, keep_matches: bool = True):
+        """Rows whose one-hot encoding is <= `sequence` everywhere (keep_matches) or the others
+        (seq.py:499-524).  Returns a new array, or None with a warning when nothing is left."""
+        assert isinstance(sequence, np.ndarray), "Sequence must be a numpy array"
+        assert sequence.shape == (self.width, 4), "Sequence must have the same length as sequences in the array"
+        hist, n_active, keep = self._hist_call(_one_hot_to_masks(sequence), 1, True)
+        keep = keep[0]
+        if keep_matches:
+            n = int(n_active[0].item())
+            new_alive, new_hist = keep, hist[0].cpu().numpy().astype(np.int64)
+        else:
+            new_alive = (1 - keep) if self.alive is None else (self.alive & (1 - keep))
+            n = self.n_alive - int(n_active[0].item())
+            new_hist = None
+        if n == 0:
+            warnings.warn("No sequences left after filtering")
+            return None
+        return DeviceDNAarray(self.windows, self.width, new_alive, n, new_hist)
+
+    def column_counts(self, n_counts_all: int = 1) -> np.ndarray:
+        """(W, 4) integer column sums of the alive rows (A,T,G,C)."""
+        if self._hist is not None and n_counts_all == 1:
+            return self._hist
+        wild = np.zeros(1, dtype=_lib.MOTIF_DTYPE)
+        wild["allowed"][0, : self.width] = 0xF
+        wild["len"][0] = self.width
+        hist, _, _ = self._hist_call(wild, n_counts_all, False)
+        out = hist[0].cpu().numpy().astype(np.int64)
+        if n_counts_all == 1:
+            self._hist = out
+        return out
+
+    def pssm(self) -> np.ndarray:
+        """(4, W) float64 column frequencies, N counted for all four bases (seq.py:526-537)."""
+        return self.column_counts(1).transpose() / self.n_alive
+
+    def exact_pssm(self) -> np.ndarray:
+        """(4, W) exact-letter frequencies, N counted for none (EqualLengthDNASet.pssm, seq.py:391-422)."""
+        return self.column_counts(0).transpose() / self.n_alive
+
+    # -- batched expansion ----------------------------------------------------------------------
+    def expand(self, motifs, bin_pssm: np.ndarray):
+        """For every motif (full-width strings): active-set size, PSSM (4, W) and per-column
+        KL(meth || background) -- one hist launch + one PSSM/KL launch for the whole batch."""
+        motifs = list(motifs)
+        masks = window_masks(motifs, self.width)
+        d = self.windows.device
+        hist, n_active, _ = self._hist_call(masks, 1, False)
+        m = len(motifs)
+        with torch.cuda.device(d):
+            bg = _to_device(np.ascontiguousarray(bin_pssm, dtype=np.float64), d)
+            pssm = torch.empty((m, 4, self.width), dtype=torch.float64, device=d)
+            kl = torch.empty((m, self.width), dtype=torch.float64, device=d)
+            check(lib.nmb_pssm_kl(ptr(hist), ptr(n_active), m, self.width, ptr(bg), ptr(pssm), ptr(kl), _stream()),
+                  "nmb_pssm_kl")
+        return n_active.cpu().numpy(), pssm.cpu().numpy(), kl.cpu().numpy()
+
+
+def methylation_windows(assembly: DeviceAssembly, contig_id, position, strand, fraction_mod, high: float,
+                        padding: int) -> DeviceDNAarray | None:
+    """Windows around confidently methylated sites in the reference's row order: per contig, '+' sites
+    then reverse-complemented '-' sites (find_motifs_bin.py:625-672).  Columns as numpy arrays;
+    contig_id indexes the assembly, strand is 0/1."""
+    contig_id = np.asarray(contig_id)
+    position = np.asarray(position, dtype=np.int64)
+    strand = np.asarray(strand)
+    conf = np.asarray(fraction_mod, dtype=np.float64) >= high  # :625
+    lens = assembly.lengths
+    ci_out, pos_out, st_out = [], [], []
+    for c in range(assembly.n_contigs):
+        sel = conf & (contig_id == c)
+        for s in (0, 1):
+            p = position[sel & (strand == s)]
+            p = p[(p > padding) & (p < lens[c] - padding)]  # seq.py:186 (strict on both sides)
+            ci_out.append(np.full(len(p), c, dtype=np.int64))
+            pos_out.append(p)
+            st_out.append(np.full(len(p), s, dtype=np.uint8))
+    ci, pos, st = np.concatenate(ci_out), np.concatenate(pos_out), np.concatenate(st_out)
+    if len(pos) == 0:
+        return None
+    return DeviceDNAarray.from_positions(assembly, ci, pos, st, padding)
+
+
+def sample_background_starts(sequence: str, length: int, n: int, base: str) -> list[int]:
+    """Start positions chosen exactly like DNAsequence.sample_n_subsequences_unique (seq.py:202-225):
+    the same ``random.sample`` call on the same list, so a seeded run reproduces the reference's picks."""
+    sequence = sequence_of(sequence)
+    max_start = len(sequence) - length + 1
+    if n > max_start:
+        raise ValueError("Too many samples requested for unique subsequences")
+    mid = length // 2
+    arr = np.frombuffer(sequence.encode("ascii"), dtype=np.uint8)
+    valid = np.flatnonzero(arr[mid : mid + max_start] == ord(base)).tolist()
+    if len(valid) < n:
+        raise ValueError(f"Not enough subsequences with 'C' in the middle (found {len(valid)}, need {n})")
+    return random.sample(valid, n)
+
+
+def background_pssm(assembly: DeviceAssembly, contigs, mod_base: str, padding: int,
+                    sampling_frequency: float = 0.01) -> np.ndarray:
+    """bin_pssm of find_best_candidates (find_motifs_bin.py:629-650,685): per contig
+    max(ceil(0.01 L), 50) random windows centred on the canonical base, exact-letter frequencies."""
+    ci, pos = [], []
+    for name, seq in contigs.items():
+        s = sequence_of(seq)
+        n = int(max(math.ceil(len(s) * sampling_frequency), 50))  # :633
+        starts = sample_background_starts(s, 2 * padding + 1, n, mod_base)
+        ci.append(np.full(n, assembly.index[name], dtype=np.int64))
+        pos.append(np.asarray(starts, dtype=np.int64) + padding)
+    arr = DeviceDNAarray.from_positions(assembly, np.concatenate(ci), np.concatenate(pos),
+                                        np.zeros(sum(len(p) for p in pos), dtype=np.uint8), padding)
+    return arr.exact_pssm()
+
+
+def kl_children(motif, meth_pssm: np.ndarray, bin_pssm: np.ndarray, kl: np.ndarray | None = None, min_kl: float = 0.05,
+                freq_threshold: float = 0.15) -> list[Motif]:
+    """Children of `motif` at the wildcard position of maximum KL divergence
+    (_motif_child_nodes_kl_dist_max, find_motifs_bin.py:957-1023).  `kl` may come from
+    DeviceDNAarray.expand; otherwise it is computed here exactly like scipy.stats.entropy."""
+    m = as_motif(motif)
+    split = m.split()
+    if kl is None:
+        from scipy.stats import entropy
+
+        kl = entropy(meth_pssm, bin_pssm)
+    evaluated = np.array([i for i, b in enumerate(split) if b == "."])
+    if evaluated.size == 0:
+        return []
+    masked = np.array(kl, dtype=np.float64, copy=True)
+    masked[~np.isin(np.arange(len(split)), evaluated)] = 0
+    if np.max(masked) < min_kl:
+        return []
+    pos = int(np.argmax(masked))
+    ok = np.logical_and(meth_pssm[:, pos] > bin_pssm[:, pos] * 0.5, meth_pssm[:, pos] > freq_threshold)
+    out = []
+    for i in np.argwhere(ok).reshape(-1):
+        toks = list(split)
+        toks[pos] = BASES[int(i)]
+        out.append(Motif("".join(toks), m.mod_position))
+    return out
