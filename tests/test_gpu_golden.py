@@ -1,0 +1,77 @@
+"""The CUDA path against the committed golden vectors of the real reference (tests/golden)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def G():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    with open(os.path.join(HERE, "golden", "reference_vectors.json")) as f:
+        return json.load(f)
+
+
+def test_subseq_indices_golden(G):
+    import nanomotif_b200 as nmb
+
+    for c in G["subseq_indices"]:
+        if "N" in c["motif"]:  # a literal N in a motif is outside the motif alphabet of the device path
+            with pytest.raises(ValueError):
+                nmb.subseq_indices(c["motif"], c["seq"])
+            continue
+        assert nmb.subseq_indices(c["motif"], c["seq"]).tolist() == c["result"], c["motif"]
+
+
+def test_methylated_motif_occourances_golden(G):
+    import nanomotif_b200 as nmb
+
+    for c in G["methylated_motif_occourances"]:
+        seq = G["seq_a"] if c["seq"] == "seq_a" else c["seq"]
+        a, b = nmb.methylated_motif_occourances(nmb.Motif(c["motif"], c["mod_pos"]), seq,
+                                                np.array(c["meth"], dtype=np.int64), np.array(c["nonmeth"], dtype=np.int64))
+        assert [a.tolist(), b.tolist()] == c["result"]  # unsorted input order is preserved
+
+
+def test_growth_golden(G):
+    import nanomotif_b200 as nmb
+    from nanomotif_b200 import growth
+    from nanomotif_b200.device import DeviceAssembly
+
+    g = G["growth"]
+    pad = g["padding"]
+    asm = DeviceAssembly.from_sequences({"c": g["seq"]})
+    pos = np.array(g["plus"] + g["minus"], dtype=np.int64)
+    strand = np.array([0] * len(g["plus"]) + [1] * len(g["minus"]), dtype=np.uint8)
+    arr = growth.methylation_windows(asm, np.zeros(len(pos), np.int32), pos, strand, np.ones(len(pos)), 0.7, pad)
+    assert arr.shape == (len(g["windows"]), 2 * pad + 1, 4)
+    assert arr.column_counts().tolist() == g["one_hot_sum"]
+    np.testing.assert_array_equal(arr.pssm(), np.array(g["pssm_all"]))
+    np.testing.assert_array_equal(arr.exact_pssm(), np.array(g["exact_pssm_all"]))
+    random.seed(g["bg_seed"])
+    starts = growth.sample_background_starts(g["seq"], 2 * pad + 1, g["bg_n"], g["bg_base"])
+    assert [g["seq"][s:s + 2 * pad + 1] for s in starts] == g["bg_windows"]
+    bg = growth.DeviceDNAarray.from_positions(asm, np.zeros(len(starts), np.int64), np.array(starts) + pad,
+                                              np.zeros(len(starts), np.uint8), pad).exact_pssm()
+    np.testing.assert_array_equal(bg, np.array(g["bin_pssm"]))
+    for step in g["steps"]:
+        m = nmb.Motif(step["motif"], step["mod_pos"])
+        active = arr.copy().filter_sequence_matches(m.one_hot())
+        assert active.shape[0] == step["n_active"]
+        assert active.column_counts().tolist() == step["column_counts"]
+        np.testing.assert_array_equal(active.pssm(), np.array(step["pssm"]))
+        n_act, pssm, kl = arr.expand([m], bg)
+        assert n_act[0] == step["n_active"]
+        np.testing.assert_allclose(kl[0], np.array(step["kl"]), rtol=1e-6, atol=1e-12)
+        children = growth.kl_children(m, active.pssm(), bg, kl=kl[0])
+        assert [[c.string, c.mod_position] for c in children] == step["children"]
+        rest = arr.filter_sequence_matches(m.one_hot(), keep_matches=False)
+        assert (0 if rest is None else rest.shape[0]) == step["n_removed_rest"]

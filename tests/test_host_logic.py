@@ -1,0 +1,131 @@
+"""Host-side logic of nanomotif_b200 (no GPU): Motif type, motif compilation, posterior / scores, layout
+planning, pileup adapters, synthetic generators -- checked against the golden vectors of the reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import nanomotif_b200 as nmb
+from nanomotif_b200 import _lib, model, motif as M, synth
+from nanomotif_b200.device import choose_motifs_per_item, make_jobs, plan_layout
+from nanomotif_b200.pileup import PileupTable, strand_codes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def G():
+    with open(os.path.join(HERE, "golden", "reference_vectors.json")) as f:
+        return json.load(f)
+
+
+def test_motif_type_matches_reference(G):
+    for c in G["motif"]:
+        m = nmb.Motif(c["motif"], c["mod_pos"])
+        st = m.new_stripped_motif()
+        assert [st.string, st.mod_position] == c["stripped"]
+        rc = st.reverse_compliment()
+        assert [rc.string, rc.mod_position] == c["rc_of_stripped"]
+        assert m.one_hot().tolist() == c["one_hot"]
+        assert m.split() == c["split"] and m.length() == c["length"]
+        assert m.iupac() == c["iupac"]
+    for c in G["from_iupac"]:
+        assert nmb.Motif(c["iupac"], 0).from_iupac().string == c["regex"]
+    a, b = nmb.Motif("GATC", 1), nmb.Motif("GATC", 1)
+    assert a == b and hash(a) == hash(b) and a != nmb.Motif("GATC", 2) and repr(a) == "Motif('GATC', pos=1)"
+
+
+def test_pack_motifs():
+    rec = M.pack_motifs([nmb.Motif("....G[AG].GAAG[CT]....", 9), nmb.Motif("GATC", 1)])
+    assert rec.dtype.itemsize == 64
+    assert rec["len"].tolist() == [8, 4] and rec["mod_pos"].tolist() == [5, 1]
+    assert rec["allowed"][0, :8].tolist() == [4, 5, 15, 4, 1, 1, 4, 10]  # bit0=A bit1=T bit2=G bit3=C
+    assert rec["allowed"][1, :4].tolist() == [4, 1, 2, 8]
+    with pytest.raises(ValueError):
+        M.pack_motifs([nmb.Motif(".....", 2)])
+    with pytest.raises(ValueError):
+        M.pack_motifs([nmb.Motif("A" * 63, 0)])
+    with pytest.raises(ValueError):
+        M.pack_motifs([nmb.Motif("ANT", 0)])
+    with pytest.raises(TypeError):
+        M.pack_motifs(["GATC"])
+
+
+def test_scores_match_reference(G):
+    for c in G["scores"]:
+        nxt, cur = nmb.BetaBernoulliModel(), nmb.BetaBernoulliModel()
+        nxt.update(*c["next"])
+        cur.update(*c["cur"])
+        assert nmb.predictive_evaluation_score(nxt, cur) == pytest.approx(c["score"], rel=1e-12, abs=1e-15)
+        assert model.priority(nxt, cur) == pytest.approx(c["priority"], rel=1e-12, abs=1e-15)
+        assert nxt.mean() == pytest.approx(c["mean_next"], rel=1e-15)
+        assert nxt.variance() == pytest.approx(c["variance_next"], rel=1e-13)
+        assert nxt.get_raw_counts() == tuple(c["next"])
+    nx = np.array([c["next"] for c in G["scores"]]) + 5
+    cu = np.array([c["cur"] for c in G["scores"]]) + 5
+    got = model.predictive_evaluation_scores(nx[:, 0], nx[:, 1], cu[:, 0], cu[:, 1])
+    np.testing.assert_allclose(got, [c["score"] for c in G["scores"]], rtol=1e-12, atol=1e-15)
+
+
+def test_model_pickle_roundtrip():
+    import pickle
+
+    m = nmb.BetaBernoulliModel()
+    m.update(7, 9)
+    m2 = pickle.loads(pickle.dumps(m))
+    assert (m2._alpha, m2._beta, m2._alpha_prior, m2._beta_prior) == (12, 14, 5, 5)
+
+
+def test_plan_layout():
+    starts, n_tiles = plan_layout([300, 5000, 65536 * 2 + 17, 512, 1])
+    assert (starts % _lib.CHUNK_BP == 0).all()
+    lens = np.array([300, 5000, 65536 * 2 + 17, 512, 1])
+    assert ((starts[1:] - (starts[:-1] + lens[:-1])) >= _lib.MIN_GAP_BP).all()
+    assert n_tiles * _lib.TILE_BP >= starts[-1] + lens[-1] + _lib.MIN_GAP_BP
+    assert plan_layout([])[1] == 1
+
+
+def test_jobs_and_items():
+    jobs = make_jobs(2)
+    assert jobs.dtype.itemsize == 48
+    jobs["motif_count"] = [1000, 3]
+    jobs["tile_count"] = [71, 2]
+    assert choose_motifs_per_item(jobs, 148) == 29
+    jobs["motif_count"] = [1, 1]
+    assert choose_motifs_per_item(jobs, 148) == 1
+
+
+def test_pileup_adapters():
+    d = dict(contig=np.array(["a", "b"]), position=[3, 4], strand=np.array(["+", "-"]), fraction_mod=[0.1, 0.9],
+             mod_type=np.array(["a", "a"]), Nvalid_cov=[10, 20])
+    t = PileupTable.from_frame(d)
+    assert t.position.dtype == np.int64 and t.fraction_mod.dtype == np.float64 and len(t) == 2
+    assert strand_codes(t.strand).tolist() == [0, 1]
+    import pandas as pd
+
+    t2 = PileupTable.from_frame(pd.DataFrame(d))
+    assert t2.position.tolist() == [3, 4] and t2.contig.tolist() == ["a", "b"]
+    assert t.take(np.array([False, True])).position.tolist() == [4]
+    with pytest.raises(KeyError):
+        PileupTable.from_frame({"position": [1]})
+
+
+def test_synth_pileup_properties():
+    rng = np.random.default_rng(0)
+    seq = synth.random_sequence(rng, 20000, 0.5, 1e-4)
+    p = synth.synth_pileup(seq, rng, depth=30)
+    key = p["position"] * 8 + p["strand"] * 4 + p["mod_type"]
+    assert len(np.unique(key)) == len(key)  # rows unique per (position, strand, mod_type)
+    assert (np.diff(p["position"]) >= 0).all()
+    # 'a' rows sit on A ('+') or T ('-')
+    a = p["mod_type"] == 0
+    assert set(seq[p["position"][a & (p["strand"] == 0)]].tolist()) == {ord("A")}
+    assert set(seq[p["position"][a & (p["strand"] == 1)]].tolist()) == {ord("T")}
+    # two-decimal percentages: integer compare on round(100*percent) is exact
+    pct = np.round(p["fraction_mod"] * 100, 2)
+    assert np.array_equal(p["fraction_mod"] >= 0.7, np.round(pct * 100) >= 7000)
+    motifs = synth.random_motifs(np.random.default_rng(1), 50, "A")
+    for s, mp in motifs:
+        toks = M.tokenize(s)
+        assert toks[mp] == "A" and toks[0] != "." and toks[-1] != "." and 4 <= len(toks) <= 21
