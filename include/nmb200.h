@@ -142,6 +142,31 @@ NMB_API int nmb_build_class_planes(const int32_t *contig_id, const int64_t *pos,
                            double low, double high, const nmb_assembly *assembly_h,
                            int32_t n_modtypes, uint32_t *class_records, void *stream);
 
+/* ---- pileup filters (replace the polars expressions of nanomotif/dataload.py:191-247); every
+ *      function writes keep[r] in {0,1} in input row order ---- */
+
+/* filter_pileup (dataload.py:191-200): keep rows with Nvalid_cov > min_coverage (strict). */
+NMB_API int nmb_filter_coverage(const int64_t *n_valid_cov, int64_t n_rows, int64_t min_coverage, uint8_t *keep,
+                        void *stream);
+
+/* filter_pileup_minimummod_frequency (dataload.py:202-226): group_id[r] identifies the row's
+ * (contig, mod_type) pair (dense ids 0..n_groups-1); a group is kept when more than
+ * min_mods_pr_contig of its rows have fraction > methylation_threshold and that count divided by the
+ * group's row count exceeds min_mod_frequency.  group_counts: scratch of 2*n_groups int64 (returned
+ * holding [rows, rows above threshold] per group). */
+NMB_API int nmb_filter_min_mod_frequency(const int32_t *group_id, const double *fraction_mod, int64_t n_rows,
+                                 int32_t n_groups, double methylation_threshold, double min_mod_frequency,
+                                 int64_t min_mods_pr_contig, int64_t *group_counts, uint8_t *keep,
+                                 void *stream);
+
+/* filter_pileup_adjacency_filter (dataload.py:228-247): a row is kept when its fraction is below the
+ * threshold or equals the maximum fraction over the rows of the same (contig, strand) -- any mod
+ * type -- whose position lies within +-adjacency_distance.  Rows must be sorted by (contig_id, pos);
+ * *unsorted_flag (device int32) is set to 1 when they are not (the keep mask is then meaningless). */
+NMB_API int nmb_filter_adjacency(const int32_t *contig_id, const int64_t *pos, const uint8_t *strand,
+                         const double *fraction_mod, int64_t n_rows, double methylation_threshold,
+                         int32_t adjacency_distance, uint8_t *keep, int32_t *unsorted_flag, void *stream);
+
 /* ---- K2: scan + gather-join + segmented reduce (replaces utils.subseq_indices utils.py:44-67,
  *      methylated_motif_occourances find_motifs_bin.py:1234-1263, the count step of
  *      motif_model_contig :1285-1331 and the per-bin sum of motif_model_bin :1265-1283) ---- */
