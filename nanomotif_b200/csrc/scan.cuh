@@ -10,8 +10,9 @@
 // and the plane aligned at the modified base is M = C << mod_pos (one more funnel shift).  The chain
 // runs over words [-H, NW + H): the right halo feeds the >> shifts, the left halo the final <<.
 // Two register representations of the sequence:
-//   XY   the raw planes; a single-base indicator is folded into the lop3 immediate
-//        (C <- lop3<base>(x, y, shifted C)).  Used by warps whose chunks are pure ACGT.
+//   XY   the raw planes; the indicator of ANY allowed-set is a two-variable boolean function of (x, y),
+//        so it is folded into the lop3 immediate: C <- lop3<set>(x, y, shifted C).  Used by warps whose
+//        chunks are pure ACGT.
 //   XYN  additionally the non-ACGT plane n, ANDed out of every indicator so that such letters (and the
 //        inter-contig padding) fail every constrained position and only match '.', the regex
 //        semantics of the reference.  One extra logic op per word and
@@ -28,28 +29,19 @@ template <int H, bool HASN>
 struct LaneSeq;
 
 // lop3 immediates over inputs (a, b, c) = (0xF0, 0xCC, 0xAA)
-constexpr int kLutMux = 0xCA;       // a ? b : c
 constexpr int kLutAndNot = 0x30;    // a & ~b
-constexpr int kLutAnd = 0xC0;       // a & b
 
-// Every indicator below is written so that it depends on the running (shifted) plane s: otherwise the
-// compiler hoists the step-invariant part (e.g. ~y, or ind(x, y) & ~n) out of the motif loop and keeps
-// one extra register per word and plane alive.
+// ind_M(x, y) & s for an allowed-set M (bit0=A bit1=T bit2=G bit3=C) is ONE lop3 whose immediate is the
+// set's truth table.  Every indicator is written so that it depends on the running (shifted) plane s:
+// otherwise the compiler hoists the step-invariant part (e.g. ind(x, y) & ~n) out of the motif loop and
+// keeps one extra register per word and plane alive.
 template <int H>
 struct LaneSeq<H, false> {
     static constexpr int XW = NW + 2 * H;  // words held per plane: [-H, NW + H)
     uint32_t x[XW], y[XW];
-    template <int C>  // indicator of single base C (0=A 1=T 2=G 3=C) at plane word i, ANDed with s
-    __device__ __forceinline__ uint32_t and_base(int i, uint32_t s) const {
-        constexpr int T = (C == 0 ? 0x03 : C == 1 ? 0x0C : C == 2 ? 0x30 : 0xC0) & 0xAA;
-        return lop3<T>(x[i], y[i], s);
-    }
-    // indicator of an arbitrary set given as four uniform masks (0 / ~0), ANDed with s
-    __device__ __forceinline__ uint32_t and_set(int i, uint32_t mA, uint32_t mT, uint32_t mG,
-                                                uint32_t mC, uint32_t s) const {
-        const uint32_t g0 = lop3<kLutMux>(y[i], mT, mA);  // x = 0: T or A  (masks change every step,
-        const uint32_t g1 = lop3<kLutMux>(y[i], mC, mG);  // x = 1: C or G   so nothing is hoistable)
-        return lop3<kLutMux>(x[i], g1, g0) & s;
+    template <int M>
+    __device__ __forceinline__ uint32_t and_code(int i, uint32_t s) const {
+        return lop3<(set_truth(M) & 0xAA)>(x[i], y[i], s);
     }
 };
 
@@ -57,16 +49,9 @@ template <int H>
 struct LaneSeq<H, true> {
     static constexpr int XW = NW + 2 * H;
     uint32_t x[XW], y[XW], n[XW];  // n = non-ACGT plane (inter-contig padding included)
-    template <int C>
-    __device__ __forceinline__ uint32_t and_base(int i, uint32_t s) const {
-        constexpr int T = (C == 0 ? 0x03 : C == 1 ? 0x0C : C == 2 ? 0x30 : 0xC0) & 0xAA;
-        return lop3<T>(x[i], y[i], lop3<kLutAndNot>(s, n[i], 0u));
-    }
-    __device__ __forceinline__ uint32_t and_set(int i, uint32_t mA, uint32_t mT, uint32_t mG,
-                                                uint32_t mC, uint32_t s) const {
-        const uint32_t g0 = lop3<kLutMux>(y[i], mT, mA);
-        const uint32_t g1 = lop3<kLutMux>(y[i], mC, mG);
-        return lop3<kLutMux>(x[i], g1, g0) & lop3<kLutAndNot>(s, n[i], 0u);
+    template <int M>
+    __device__ __forceinline__ uint32_t and_code(int i, uint32_t s) const {
+        return lop3<(set_truth(M) & 0xAA)>(x[i], y[i], lop3<kLutAndNot>(s, n[i], 0u));
     }
 };
 
@@ -91,68 +76,48 @@ __device__ __forceinline__ uint32_t shifted(const uint32_t (&c)[NW + 2 * H], int
     return __funnelshift_r(c[i], (i + 1 < NW + 2 * H) ? c[i + 1] : 0u, s);
 }
 
-template <int C, int H, bool HASN>
-__device__ __forceinline__ void step_base(uint32_t (&c)[NW + 2 * H], const LaneSeq<H, HASN> &q, int s) {
+template <int M, int H, bool HASN>
+__device__ __forceinline__ void step_code(uint32_t (&c)[NW + 2 * H], const LaneSeq<H, HASN> &q, int s) {
 #pragma unroll
-    for (int i = 0; i < NW + 2 * H; ++i) c[i] = q.template and_base<C>(i, shifted<H>(c, i, s));
+    for (int i = 0; i < NW + 2 * H; ++i) c[i] = q.template and_code<M>(i, shifted<H>(c, i, s));
 }
 
-template <int H, bool HASN>
-__device__ __forceinline__ void step_set(uint32_t (&c)[NW + 2 * H], const LaneSeq<H, HASN> &q, int code,
-                                         int s) {
-    const uint32_t mA = (code & 1) ? 0xFFFFFFFFu : 0u, mT = (code & 2) ? 0xFFFFFFFFu : 0u;
-    const uint32_t mG = (code & 4) ? 0xFFFFFFFFu : 0u, mC = (code & 8) ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-    for (int i = 0; i < NW + 2 * H; ++i) c[i] = q.and_set(i, mA, mT, mG, mC, shifted<H>(c, i, s));
-}
-
-// First entry of the chain: the running plane is the indicator itself (no shift, no AND).
-template <int C, int H, bool HASN>
-__device__ __forceinline__ void init_base(uint32_t (&c)[NW + 2 * H], const LaneSeq<H, HASN> &q) {
-#pragma unroll
-    for (int i = 0; i < NW + 2 * H; ++i) c[i] = q.template and_base<C>(i, 0xFFFFFFFFu);
-}
-template <int H, bool HASN>
-__device__ __forceinline__ void init_set(uint32_t (&c)[NW + 2 * H], const LaneSeq<H, HASN> &q, int code) {
-    const uint32_t mA = (code & 1) ? 0xFFFFFFFFu : 0u, mT = (code & 2) ? 0xFFFFFFFFu : 0u;
-    const uint32_t mG = (code & 4) ? 0xFFFFFFFFu : 0u, mC = (code & 8) ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-    for (int i = 0; i < NW + 2 * H; ++i) c[i] = q.and_set(i, mA, mT, mG, mC, 0xFFFFFFFFu);
-}
-
-// Entry codes: 1/2/4/8 single base, kEntShift32 = "shift the chain by one word" (emitted by the motif
-// compiler for gaps >= 32), anything else a degenerate set (0 = empty set).  All shifts are < 32 and
-// the first entry's shift is 0.
+// Entry codes: 1..14 allowed-set (all fourteen have their own lop3 immediate, so degenerate positions
+// cost the same as single bases), kEntShift32 = "shift the chain by one word" (emitted by the motif
+// compiler for gaps >= 32), 0 = empty set (nothing matches), 15 = wildcard (pure shift; only produced
+// for a leading wildcard of an unstripped motif).  All shifts are < 32 and the first entry's shift is 0.
 constexpr int kEntShift32 = 0x10;
 
 // Start-aligned match words of the lane's words [-H, NW + H); valid for words [-H, NW).
 template <int H, bool HASN>
 __device__ __forceinline__ void run_chain(const ProgramView &pv, const LaneSeq<H, HASN> &q,
                                           uint32_t (&c)[NW + 2 * H]) {
+#pragma unroll
+    for (int i = 0; i < NW + 2 * H; ++i) c[i] = 0xFFFFFFFFu;
     uint32_t e = __ldg(pv.ent);
-    {
-        const int code = e & 0xFF;
-        if (pv.n > 1) e = __ldg(pv.ent + 1);
-        if (code == 1) init_base<0, H, HASN>(c, q);
-        else if (code == 2) init_base<1, H, HASN>(c, q);
-        else if (code == 4) init_base<2, H, HASN>(c, q);
-        else if (code == 8) init_base<3, H, HASN>(c, q);
-        else init_set<H, HASN>(c, q, code);
-    }
 #pragma unroll 1
-    for (int i = 1; i < pv.n; ++i) {
+    for (int i = 0; i < pv.n; ++i) {
         const uint32_t cur = e;
         if (i + 1 < pv.n) e = __ldg(pv.ent + i + 1);  // prefetch the next entry
         const int s = cur >> 8;
-        const int code = cur & 0xFF;
-        if (code == 1) step_base<0, H, HASN>(c, q, s);
-        else if (code == 2) step_base<1, H, HASN>(c, q, s);
-        else if (code == 4) step_base<2, H, HASN>(c, q, s);
-        else if (code == 8) step_base<3, H, HASN>(c, q, s);
-        else if (code == kEntShift32) {
+        switch (cur & 0xFF) {
+#define NMB_CASE(m) case m: step_code<m, H, HASN>(c, q, s); break;
+            NMB_CASE(1) NMB_CASE(2) NMB_CASE(3) NMB_CASE(4) NMB_CASE(5) NMB_CASE(6) NMB_CASE(7)
+            NMB_CASE(8) NMB_CASE(9) NMB_CASE(10) NMB_CASE(11) NMB_CASE(12) NMB_CASE(13) NMB_CASE(14)
+#undef NMB_CASE
+            case 15:
 #pragma unroll
-            for (int k = 0; k < NW + 2 * H; ++k) c[k] = (k + 1 < NW + 2 * H) ? c[k + 1] : 0u;
-        } else step_set<H, HASN>(c, q, code, s);
+                for (int k = 0; k < NW + 2 * H; ++k) c[k] = shifted<H>(c, k, s);
+                break;
+            case kEntShift32:
+#pragma unroll
+                for (int k = 0; k < NW + 2 * H; ++k) c[k] = (k + 1 < NW + 2 * H) ? c[k + 1] : 0u;
+                break;
+            default:
+#pragma unroll
+                for (int k = 0; k < NW + 2 * H; ++k) c[k] = 0u;
+                break;
+        }
     }
 }
 
