@@ -240,6 +240,29 @@ NMB_API int nmb_window_hist(const uint64_t *windows, const uint8_t *alive, int64
 NMB_API int nmb_pssm_kl(const int32_t *hist, const int64_t *n_active, int32_t n_motifs, int32_t width,
                 const double *bg_pssm, double *pssm, double *kl, void *stream);
 
+/* ---- K5: contig x motif methylation-pattern table (replaces the external Rust operator
+ *      epymetheus.methylation_pattern, call site nanomotif/main.py:167-178; spec in DESIGN.md) ----
+ * Rows = the pileup rows of ONE mod type that pass the read-coverage filters, sorted by contig:
+ * gpos (global position), strand (0 '+', 1 '-'), contig_id, n_mod, n_valid_cov.  plane_fwd /
+ * plane_rev = match planes (nmb_match_plane, aligned at mod_pos) of the motif and of its reverse
+ * complement.  A row is an observation when the bit of its strand's plane is set at gpos. */
+
+/* stats[c] = {n_motif_obs, sum n_mod, sum n_valid_cov}; offsets[0..n_contigs] = exclusive prefix sum
+ * of n_motif_obs (offsets[n_contigs] = total); cursor[c] = 0 (scratch for nmb_pattern_median). */
+NMB_API int nmb_pattern_stats(const int64_t *gpos, const uint8_t *strand, const int32_t *contig_id,
+                      const int32_t *n_mod, const int32_t *n_valid_cov, int64_t n_rows,
+                      const uint32_t *plane_fwd, const uint32_t *plane_rev, int32_t n_contigs,
+                      int64_t *stats, int64_t *offsets, int32_t *cursor, void *stream);
+
+/* median[c] = median of n_mod / n_valid_cov over the observations of contig c (mean of the two
+ * middle values for an even count, NaN without observations).  fractions: scratch of
+ * offsets[n_contigs] doubles.  Must follow nmb_pattern_stats on the same stream. */
+NMB_API int nmb_pattern_median(const int64_t *gpos, const uint8_t *strand, const int32_t *contig_id,
+                       const int32_t *n_mod, const int32_t *n_valid_cov, int64_t n_rows,
+                       const uint32_t *plane_fwd, const uint32_t *plane_rev, int32_t n_contigs,
+                       const int64_t *offsets, int32_t *cursor, double *fractions, double *median,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -322,3 +322,44 @@ def filter_pileup_adjacency_filter(contig, strand, position, fraction_mod, methy
             roll_max = f[left[k] : right[k]].max()
             keep[order[k]] = (f[k] == roll_max) or (f[k] < methylation_threshold)
     return keep
+
+
+# ---------------------------------------------------------------------------------------------
+# a14: contig x motif methylation-pattern table.  NOT a restatement of reference code: the operator is
+# the external Rust package epimetheus-py 0.7.5 (call site nanomotif/main.py:167-178) whose source is
+# not in the reference tree.  This is the written spec of SURVEY.md 8c / DESIGN.md K5 -- parity of the
+# CUDA path is "exact vs this spec, UNPINNED vs the reference".
+# ---------------------------------------------------------------------------------------------
+IUPAC_TO_REGEX = {"A": "A", "T": "T", "C": "C", "G": "G", "R": "[AG]", "Y": "[CT]", "S": "[CG]", "W": "[AT]",
+                  "K": "[GT]", "M": "[AC]", "B": "[CGT]", "D": "[AGT]", "H": "[ACT]", "V": "[ACG]", "N": "."}  # seq.py:571-601
+
+
+def methylation_pattern(contigs: dict, contig, position, strand, mod_type, n_mod, n_valid_cov, n_diff, motifs,
+                        min_valid_read_coverage=3, min_valid_cov_to_diff_fraction=0.8, weighted_mean=False):
+    """Returns rows (contig, motif, mod_type, mod_position, methylation_value, mean_read_cov, n_motif_obs)."""
+    contig = np.asarray(contig).astype(str)
+    position = np.asarray(position, dtype=np.int64)
+    strand = np.asarray(strand).astype(str)
+    mod_type = np.asarray(mod_type).astype(str)
+    n_mod = np.asarray(n_mod, dtype=np.int64)
+    cov = np.asarray(n_valid_cov, dtype=np.int64)
+    diff = np.asarray(n_diff, dtype=np.int64)
+    rows = []
+    for spec in motifs:
+        iupac, mt, mp = spec.rsplit("_", 2)
+        mp = int(mp)
+        rx = "".join(IUPAC_TO_REGEX[c] for c in iupac)
+        rc_rx, rc_mp = reverse_complement_motif(rx, mp)
+        for name, seq in contigs.items():
+            fwd = set((subseq_indices(rx, seq) + mp).tolist())
+            rev = set((subseq_indices(rc_rx, seq) + rc_mp).tolist())
+            sel = (contig == name) & (mod_type == mt) & (cov >= min_valid_read_coverage)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                sel &= (cov / (cov + diff)) >= min_valid_cov_to_diff_fraction
+            idx = [i for i in np.flatnonzero(sel) if (position[i] in fwd if strand[i] == "+" else position[i] in rev)]
+            if not idx:
+                continue
+            m, c = n_mod[idx], cov[idx]
+            value = m.sum() / c.sum() if weighted_mean else float(np.median(m / c))
+            rows.append((name, iupac, mt, mp, float(value), float(c.mean()), len(idx)))
+    return rows
