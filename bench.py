@@ -196,41 +196,10 @@ def stream_leg(device, total_bp: int = 1_500_000_000, n_contigs: int = 17000, re
     import torch
 
     import nanomotif_b200 as nmb
-    from nanomotif_b200 import _lib
-    from nanomotif_b200.device import DeviceAssembly, DevicePileup, MotifPrograms, make_jobs, scan_count
+    from nanomotif_b200 import _lib, synth
+    from nanomotif_b200.device import MotifPrograms, make_jobs, scan_count
 
-    g = torch.Generator(device=device)
-    g.manual_seed(3)
-    rng = np.random.default_rng(3)
-    lens = rng.lognormal(mean=0.0, sigma=1.0, size=n_contigs)
-    lens = np.maximum(2500, (lens / lens.sum() * total_bp).astype(np.int64))
-    off = np.zeros(n_contigs, dtype=np.int64)
-    off[1:] = np.cumsum(lens)[:-1]
-    codes = torch.randint(0, 4, (int(lens.sum()),), dtype=torch.uint8, device=device, generator=g)
-    # A=65 T=84 G=71 C=67 for codes 0..3 (order of nanomotif/constants.py:1)
-    ascii_d = 65 + (codes == 1).to(torch.uint8) * 19 + (codes == 2).to(torch.uint8) * 6 + (codes == 3).to(torch.uint8) * 2
-    del codes
-    asm = DeviceAssembly([f"c{i}" for i in range(n_contigs)], lens, ascii_d, off, device)
-    del ascii_d
-    # class planes straight from the packed planes: a random ~25 % / ~60 % of the A ('+') and T ('-') positions
-    pile = DevicePileup(asm, 1, 0.3, 0.7)
-    rec = asm.seq_records.view(asm.n_tiles, _lib.SEQ_REC_WORDS)
-    x = rec[:, _lib.HALO_WORDS:_lib.HALO_WORDS + _lib.TILE_WORDS]
-    y = rec[:, _lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS:_lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS + _lib.TILE_WORDS]
-    nn = asm.nonacgt[_lib.HALO_WORDS:_lib.HALO_WORDS + asm.n_words].view(asm.n_tiles, _lib.TILE_WORDS)
-    is_a, is_t = ~x & ~y & ~nn, ~x & y & ~nn
-    cls = pile.class_records.view(asm.n_tiles, 4, _lib.TILE_WORDS)
-
-    def rnd():
-        return torch.randint(-2**31, 2**31 - 1, x.shape, dtype=torch.int32, device=device, generator=g)
-
-    r1, r2 = rnd(), rnd()
-    cls[:, 0] = is_a & r1 & r2
-    cls[:, 1] = is_a & ~r1
-    r1, r2 = rnd(), rnd()
-    cls[:, 2] = is_t & r1 & r2
-    cls[:, 3] = is_t & ~r1
-    del r1, r2, is_a, is_t
+    asm, pile = synth.device_workload(device, total_bp, n_contigs)
     out = {}
     for name, motif in (("GATC", nmb.Motif("GATC", 1)), ("GRNGAAGY", nmb.Motif("G[AG].GAAG[CT]", 5))):
         progs = MotifPrograms([motif], device)

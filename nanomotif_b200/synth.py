@@ -125,3 +125,47 @@ def random_motifs(rng: np.random.Generator, n: int, canonical: str = "A") -> lis
             continue
         out.append(("".join(toks), mp))
     return out
+
+
+def device_workload(device, total_bp: int = 1_500_000_000, n_contigs: int = 17000, seed: int = 3, n_modtypes: int = 1):
+    """cfg3-shaped synthetic assembly built ON the device (text for 1.5 Gbp would not fit a host pipeline):
+    lognormal contig lengths (min 2.5 kbp), i.i.d. bases, and class planes drawn directly as random subsets
+    of the A ('+') / T ('-') positions (~25 % methylated, ~50 % unmethylated).  Returns
+    (DeviceAssembly, DevicePileup)."""
+    import torch
+
+    from . import _lib
+    from .device import DeviceAssembly, DevicePileup
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    lens = rng.lognormal(mean=0.0, sigma=1.0, size=n_contigs)
+    lens = np.maximum(2500, (lens / lens.sum() * total_bp).astype(np.int64))
+    off = np.zeros(n_contigs, dtype=np.int64)
+    off[1:] = np.cumsum(lens)[:-1]
+    codes = torch.randint(0, 4, (int(lens.sum()),), dtype=torch.uint8, device=device, generator=g)
+    # A=65 T=84 G=71 C=67 for codes 0..3 (order of nanomotif/constants.py:1)
+    ascii_d = 65 + (codes == 1).to(torch.uint8) * 19 + (codes == 2).to(torch.uint8) * 6 + (codes == 3).to(torch.uint8) * 2
+    del codes
+    asm = DeviceAssembly([f"c{i}" for i in range(n_contigs)], lens, ascii_d, off, device)
+    del ascii_d
+    pile = DevicePileup(asm, n_modtypes, 0.3, 0.7)
+    rec = asm.seq_records.view(asm.n_tiles, _lib.SEQ_REC_WORDS)
+    x = rec[:, _lib.HALO_WORDS:_lib.HALO_WORDS + _lib.TILE_WORDS]
+    y = rec[:, _lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS:_lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS + _lib.TILE_WORDS]
+    nn = asm.nonacgt[_lib.HALO_WORDS:_lib.HALO_WORDS + asm.n_words].view(asm.n_tiles, _lib.TILE_WORDS)
+    is_a, is_t = ~x & ~y & ~nn, ~x & y & ~nn
+    cls = pile.class_records.view(n_modtypes, asm.n_tiles, 4, _lib.TILE_WORDS)
+
+    def rnd():
+        return torch.randint(-2**31, 2**31 - 1, x.shape, dtype=torch.int32, device=device, generator=g)
+
+    for mt in range(n_modtypes):
+        r1, r2 = rnd(), rnd()
+        cls[mt, :, 0] = is_a & r1 & r2
+        cls[mt, :, 1] = is_a & ~r1
+        r1, r2 = rnd(), rnd()
+        cls[mt, :, 2] = is_t & r1 & r2
+        cls[mt, :, 3] = is_t & ~r1
+    return asm, pile

@@ -21,33 +21,9 @@ MOTIFS = {"A": ("A", 0), "GATC": ("GATC", 1), "CCWGG": ("CC[AT]GG", 1), "GRNGAAG
 
 
 def build(device, total_bp, n_contigs, seed=3):
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    rng = np.random.default_rng(seed)
-    lens = rng.lognormal(mean=0.0, sigma=1.0, size=n_contigs)
-    lens = np.maximum(2500, (lens / lens.sum() * total_bp).astype(np.int64))
-    off = np.zeros(n_contigs, dtype=np.int64)
-    off[1:] = np.cumsum(lens)[:-1]
-    codes = torch.randint(0, 4, (int(lens.sum()),), dtype=torch.uint8, device=device, generator=g)
-    ascii_d = 65 + (codes == 1).to(torch.uint8) * 19 + (codes == 2).to(torch.uint8) * 6 + (codes == 3).to(torch.uint8) * 2
-    del codes
-    asm = DeviceAssembly([f"c{i}" for i in range(n_contigs)], lens, ascii_d, off, device)
-    del ascii_d
-    pile = DevicePileup(asm, 1, 0.3, 0.7)
-    rec = asm.seq_records.view(asm.n_tiles, _lib.SEQ_REC_WORDS)
-    x = rec[:, _lib.HALO_WORDS:_lib.HALO_WORDS + _lib.TILE_WORDS]
-    y = rec[:, _lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS:_lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS + _lib.TILE_WORDS]
-    nn = asm.nonacgt[_lib.HALO_WORDS:_lib.HALO_WORDS + asm.n_words].view(asm.n_tiles, _lib.TILE_WORDS)
-    is_a, is_t = ~x & ~y & ~nn, ~x & y & ~nn
-    cls = pile.class_records.view(asm.n_tiles, 4, _lib.TILE_WORDS)
-    rnd = lambda: torch.randint(-2**31, 2**31 - 1, x.shape, dtype=torch.int32, device=device, generator=g)
-    r1, r2 = rnd(), rnd()
-    cls[:, 0] = is_a & r1 & r2
-    cls[:, 1] = is_a & ~r1
-    r1, r2 = rnd(), rnd()
-    cls[:, 2] = is_t & r1 & r2
-    cls[:, 3] = is_t & ~r1
-    return asm, pile
+    from nanomotif_b200 import synth
+
+    return synth.device_workload(device, total_bp, n_contigs, seed)
 
 
 def main():
