@@ -5,7 +5,9 @@ fails loudly when it is missing: there is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is absent)
 from .api import (  # noqa: F401
+    BinContext,
     BinScorer,
+    MultiBinScorer,
     clear_caches,
     get_parent_scores,
     methylated_motif_occourances,
@@ -15,7 +17,7 @@ from .api import (  # noqa: F401
     subseq_indices,
 )
 from .device import DeviceAssembly, DevicePileup, MotifPrograms, scan_count  # noqa: F401
-from . import dataload, growth, pattern, sharding  # noqa: F401
+from . import dataload, growth, pattern, search, sharding  # noqa: F401
 from .model import BetaBernoulliModel, predictive_evaluation_score  # noqa: F401
 from .motif import Motif  # noqa: F401
 from .pileup import PileupTable  # noqa: F401

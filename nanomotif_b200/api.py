@@ -234,6 +234,80 @@ class BinScorer:
         return np.stack([c[:, 0] + c[:, 2], c[:, 1] + c[:, 3]], axis=1)
 
 
+class BinContext:
+    """One (bin, mod_type) of a MultiBinScorer: a contig range, its tile span and a class-plane set."""
+
+    def __init__(self, owner: "MultiBinScorer", bin_name, mod_type, contig_begin, contig_end, modtype_index):
+        self.owner, self.bin_name, self.mod_type = owner, bin_name, mod_type
+        self.contig_begin, self.contig_end, self.modtype_index = contig_begin, contig_end, modtype_index
+        self.tile_begin, self.tile_count = owner.assembly.tile_span(contig_begin, contig_end)
+
+    def score(self, motifs) -> np.ndarray:
+        return self.owner.score_batch([(self, motifs)])[0]
+
+
+class MultiBinScorer:
+    """All bins and mod types of an assembly resident on one GPU; any number of (bin, mod_type, motifs)
+    requests are scored by ONE scan launch (one job per request).  This is the data-parallel replacement of
+    the reference's process pool over bins (nanomotif/find_motifs_bin.py:330-372)."""
+
+    def __init__(self, pileup, bins: dict, mod_types, low_meth_threshold: float, high_meth_threshold: float,
+                 device=None):
+        """bins: {bin name: {contig name: sequence}}; pileup needs contig and mod_type columns."""
+        table = PileupTable.from_frame(pileup)
+        contigs, self._ranges = {}, {}
+        for b, cs in bins.items():
+            begin = len(contigs)
+            for name, seq in cs.items():
+                if name in contigs:
+                    raise ValueError(f"contig {name} is assigned to more than one bin")
+                contigs[name] = seq
+            self._ranges[b] = (begin, len(contigs))
+        self.assembly = DeviceAssembly.from_sequences(contigs, device)
+        self.mod_types = list(mod_types)
+        names = np.asarray(table.contig).astype(str)
+        uniq, inv = np.unique(names, return_inverse=True)
+        lut = np.fromiter((self.assembly.index.get(u, -1) for u in uniq), dtype=np.int32, count=len(uniq))
+        self.contig_id = lut[inv] if len(uniq) else np.zeros(0, dtype=np.int32)
+        mt_names = np.asarray(table.mod_type).astype(str)
+        mt = np.full(len(table), 255, dtype=np.uint8)
+        for i, name in enumerate(self.mod_types):
+            mt[mt_names == str(name)] = i
+        self.mod_type_id = mt
+        self.table = table
+        self.pileup = DevicePileup.from_columns(self.assembly, self.contig_id, table.position,
+                                                strand_codes(table.strand), table.fraction_mod, low_meth_threshold,
+                                                high_meth_threshold, mt, n_modtypes=len(self.mod_types))
+
+    def context(self, bin_name, mod_type) -> BinContext:
+        begin, end = self._ranges[bin_name]
+        return BinContext(self, bin_name, mod_type, begin, end, self.mod_types.index(mod_type))
+
+    def score_batch(self, requests) -> list:
+        """requests: [(BinContext, motifs)] -> [int64 array [n_motifs, 2] = (n_mod, n_nomod)] per request."""
+        requests = [(ctx, list(motifs)) for ctx, motifs in requests]
+        all_motifs = [m for _, ms in requests for m in ms]
+        if not all_motifs:
+            return [np.zeros((0, 2), dtype=np.int64) for _ in requests]
+        progs = MotifPrograms(all_motifs, self.assembly.device, strip=True)
+        live = [(ctx, ms) for ctx, ms in requests if ms]
+        jobs = make_jobs(len(live))
+        base = 0
+        for j, (ctx, ms) in enumerate(live):
+            jobs[j]["motif_begin"], jobs[j]["motif_count"], jobs[j]["modtype"] = base, len(ms), ctx.modtype_index
+            jobs[j]["tile_begin"], jobs[j]["tile_count"] = ctx.tile_begin, ctx.tile_count
+            jobs[j]["contig_begin"], jobs[j]["contig_end"] = ctx.contig_begin, ctx.contig_end
+            jobs[j]["group_mode"], jobs[j]["n_groups"], jobs[j]["out_base"] = 0, 1, base
+            base += len(ms)
+        c = scan_count(self.assembly, self.pileup, progs, jobs, base).cpu().numpy()
+        counts = np.stack([c[:, 0] + c[:, 2], c[:, 1] + c[:, 3]], axis=1)
+        out, at = [], 0
+        for _, ms in requests:
+            out.append(counts[at:at + len(ms)])
+            at += len(ms)
+        return out
+
+
 def _scorer_for(pileup, contigs, low, high) -> BinScorer:
     key = ("bin", id(pileup), id(contigs), float(low), float(high))
     return _bin_cache.get(key, (pileup, contigs), lambda: BinScorer(pileup, contigs, low, high))

@@ -120,6 +120,46 @@ class Motif(str):
                 arr[i, b] = (m >> b) & 1
         return arr
 
+    def count_isolated_bases(self, isolation_size: int = 2) -> int:
+        """Constrained positions whose neighbourhood of +-isolation_size holds only wildcards.  Keeps the
+        reference's right-edge quirk: the window is clipped at len-1, not len (motif.py:178-194)."""
+        toks = self.split()
+        n = 0
+        for pos, tok in enumerate(toks):
+            if tok == ".":
+                continue
+            lo = max(pos - isolation_size, 0)
+            hi = min(pos + isolation_size + 1, len(toks) - 1)
+            around = set(toks[lo:pos] + toks[pos + 1 : hi])
+            n += (around == {"."}) + (around == {"N"})
+        return n
+
+    def sub_motif_of(self, other) -> bool:
+        """True when every occurrence of self is an occurrence of `other` aligned at the modified base
+        (motif.py:54-88, including its early exits)."""
+        other = as_motif(other)
+        if self.string == other.string:
+            return False
+        a, b = self.new_stripped_motif(), other.new_stripped_motif()
+        if a.length() < b.length():
+            return False
+        sa, sb = a.split(), b.split()
+        off = b.mod_position - a.mod_position
+        if off > 0:
+            return False
+        for i, base in enumerate(sa):
+            j = i + off
+            if j < 0:
+                continue
+            if j >= len(sb):
+                return True
+            if sb[j] != "." and not set(base) <= set(sb[j]):
+                return False
+        return True
+
+    def sub_motif_of_any(self, others) -> bool:
+        return any(self.sub_motif_of(o) for o in others)
+
     def iupac(self) -> str:
         out = []
         for tok in self.split():

@@ -81,7 +81,7 @@ def load_reference():
             sys.modules[name] = _make_stub(name)
     sys.dont_write_bytecode = True  # /root/reference is read-only
     if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.append(REFERENCE_ROOT)  # last: must never shadow this repo's own packages
     import nanomotif  # noqa: E402  (import-time side effects: np.random.seed(1), random.seed(2403))
 
     return nanomotif

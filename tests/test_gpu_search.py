@@ -1,0 +1,108 @@
+"""The motif search driven by the GPU operators reproduces the trace of the REAL reference search loop, and
+the lock-step multi-bin driver (one scan launch per step for all bins) gives the same result as bin-by-bin."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from search_common import build_inputs, check_against_trace, load_trace
+
+
+def _setup(nmb, contigs, pile, spec, scorer):
+    from nanomotif_b200 import growth, search
+
+    asm = scorer.owner.assembly if hasattr(scorer, "owner") else scorer.assembly
+    ids = np.array([asm.index[c] for c in contigs])
+    cid = np.full(len(pile["position"]), -1, dtype=np.int64)
+    for name, i in zip(contigs, ids):
+        cid[pile["contig"] == name] = i
+    strand = (pile["strand"] == "-").astype(np.uint8)
+    sel = cid >= 0
+    # windows in the reference's order: per contig '+' then '-' (growth.methylation_windows iterates assembly order)
+    sub = {k: v[sel] for k, v in pile.items()}
+    local = {c: i for i, c in enumerate(contigs)}
+    windows = _windows_for(growth, asm, contigs, sub, strand[sel], spec)
+    random.seed(spec["random_seed"])
+    bin_pssm = growth.background_pssm(asm, contigs, search.CANONICAL[spec["mod_type"]], spec["padding"])
+    return search.GpuBinBackend(scorer, windows), bin_pssm, windows.shape[0]
+
+
+def _windows_for(growth, asm, contigs, pile, strand, spec):
+    pad, high = spec["padding"], spec["high"]
+    ci, pos, st = [], [], []
+    conf = pile["fraction_mod"] >= high
+    for name, seq in contigs.items():
+        for s in (0, 1):
+            p = pile["position"][conf & (pile["contig"] == name) & (strand == s)]
+            p = p[(p > pad) & (p < len(seq) - pad)]
+            ci.append(np.full(len(p), asm.index[name]))
+            pos.append(p)
+            st.append(np.full(len(p), s, dtype=np.uint8))
+    return growth.DeviceDNAarray.from_positions(asm, np.concatenate(ci), np.concatenate(pos), np.concatenate(st), pad)
+
+
+@pytest.fixture(scope="module")
+def nmb():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import nanomotif_b200
+
+    return nanomotif_b200
+
+
+def test_gpu_search_reproduces_reference_trace(nmb):
+    from nanomotif_b200 import search
+
+    trace = load_trace()
+    spec = trace["spec"]
+    contigs, pile = build_inputs(spec)
+    scorer = nmb.BinScorer(pile, contigs, spec["low"], spec["high"])
+    backend, bin_pssm, total = _setup(nmb, contigs, pile, spec, scorer)
+    assert total == trace["total_windows"]
+    np.testing.assert_array_equal(bin_pssm, np.array(trace["bin_pssm"]))
+    rounds = []
+    co = search.find_candidates(spec["mod_type"], spec["padding"], bin_pssm, total, min_kl=spec["min_kl"],
+                                score_threshold=spec["score_threshold"], trace=rounds)
+    check_against_trace(trace, search.run(co, backend), rounds)
+
+
+def test_lockstep_multibin_search(nmb):
+    from nanomotif_b200 import search
+
+    trace = load_trace()
+    spec = trace["spec"]
+    bins, piles = {}, []
+    for b, seed in enumerate((spec["seed"], 77, 78)):
+        s = dict(spec, seed=seed, planted=spec["planted"] if b == 0 else [["CTGCAG", 4, "a"], ["GA[AG]TC", 1, "a"]])
+        contigs, pile = build_inputs(s)
+        contigs = {f"bin{b}_{k}": v for k, v in contigs.items()}
+        pile["contig"] = np.array([f"bin{b}_{c}" for c in pile["contig"]], dtype=object)
+        pile["mod_type"] = np.full(len(pile["position"]), "a", dtype=object)
+        bins[f"bin{b}"] = contigs
+        piles.append(pile)
+    pile = {k: np.concatenate([p[k] for p in piles]) for k in piles[0]}
+    multi = nmb.MultiBinScorer(pile, bins, ["a"], spec["low"], spec["high"])
+
+    def make(b):
+        ctx = multi.context(f"bin{b}", "a")
+        backend, bin_pssm, total = _setup(nmb, bins[f"bin{b}"], pile, spec, ctx)
+        t = []
+        co = search.find_candidates("a", spec["padding"], bin_pssm, total, min_kl=spec["min_kl"],
+                                    score_threshold=spec["score_threshold"], trace=t)
+        return co, backend, t
+
+    searches = [make(b) for b in range(3)]
+    results = search.run_lockstep([(co, be) for co, be, _ in searches], search.gpu_batch_score)
+    check_against_trace(trace, results[0], searches[0][2])  # bin 0 is the golden input
+    for b in (1, 2):  # the others equal their own sequential runs
+        co, be, t = make(b)
+        seq_graph, seq_best = search.run(co, be)
+        graph, best = results[b]
+        assert [m.string for m in best] == [m.string for m in seq_best] and len(best) >= 1
+        assert {m.string: (d["model"]._alpha, d["model"]._beta) for m, d in graph.nodes.items()} == \
+               {m.string: (d["model"]._alpha, d["model"]._beta) for m, d in seq_graph.nodes.items()}
+        assert searches[b][2] == t
