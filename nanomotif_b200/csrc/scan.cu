@@ -69,32 +69,35 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
     const int m_count = min(p.mpi, job.motif_count - meta.mblk * p.mpi);
 #pragma unroll 1
     for (int mi = 0; mi < m_count; ++mi) {
-        const Program *prog = p.programs + (size_t)(m_begin + mi) * 2;
-        uint32_t pk_f = 0, pk_r = 0;  // n_mod | n_nomod << 16 per strand (per-lane counts are <= 256)
-#pragma unroll 1
-        for (int st = 0; st < 2; ++st) {  // forward motif, then its reverse complement
-            const ProgramView pv = load_program(prog + st);
-            uint32_t c[NW + 2 * H];
-            run_chain<H, PLANES>(pv, q, c);
-            const bool far = pv.mod_pos >= 32;  // only possible when H == 2
-            const int sh = pv.mod_pos & 31;
-            const uint32_t *c0 = cl + 2 * st * kTileWords;
-            uint32_t n_mod = 0, n_non = 0;
+        // ONE program per motif serves both strands (scan.cuh: run_chain_pair)
+        const ProgramView pv = load_program(p.programs + (size_t)(m_begin + mi) * 2);
+        uint32_t c[NW + 2 * H], d[NW + 2 * H];
+        run_chain_pair<H, PLANES>(pv, q, c, d);
+        const bool far = pv.mod_pos >= 32;  // only possible when H == 2
+        const int sh = pv.mod_pos & 31;
+        uint32_t cnt[4] = {0, 0, 0, 0};  // n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'
 #pragma unroll
-            for (int h = 0; h < NW; h += 4) {
-                const uint4 a = *reinterpret_cast<const uint4 *>(c0 + h);
-                const uint4 b = *reinterpret_cast<const uint4 *>(c0 + kTileWords + h);
-                const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        for (int h = 0; h < NW; h += 4) {
+            uint4 pl[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t m = aligned_word<H>(c, h + k, sh, far);
-                    n_mod += __popc(m & av[k]);  // occurrences whose modified base is methylated
-                    n_non += __popc(m & bv[k]);  // ... unmethylated
-                }
+            for (int k = 0; k < 4; ++k) pl[k] = *reinterpret_cast<const uint4 *>(cl + k * kTileWords + h);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t mf = aligned_word<H>(c, h + k, sh, far);
+                const uint32_t mr = aligned_word_rc<H>(d, h + k, sh, far);
+                const uint32_t w0 = k == 0 ? pl[0].x : k == 1 ? pl[0].y : k == 2 ? pl[0].z : pl[0].w;
+                const uint32_t w1 = k == 0 ? pl[1].x : k == 1 ? pl[1].y : k == 2 ? pl[1].z : pl[1].w;
+                const uint32_t w2 = k == 0 ? pl[2].x : k == 1 ? pl[2].y : k == 2 ? pl[2].z : pl[2].w;
+                const uint32_t w3 = k == 0 ? pl[3].x : k == 1 ? pl[3].y : k == 2 ? pl[3].z : pl[3].w;
+                cnt[0] += __popc(mf & w0);  // occurrences whose modified base is methylated, '+'
+                cnt[1] += __popc(mf & w1);  // ... unmethylated, '+'
+                cnt[2] += __popc(mr & w2);  // reverse-complement occurrences, '-' strand rows
+                cnt[3] += __popc(mr & w3);
             }
-            const uint32_t pk = valid ? (n_mod | (n_non << 16)) : 0u;
-            if (st == 0) pk_f = pk; else pk_r = pk;
         }
+        // n_mod | n_nomod << 16 per strand (per-lane counts are <= 512)
+        uint32_t pk_f = valid ? (cnt[0] | (cnt[1] << 16)) : 0u;
+        uint32_t pk_r = valid ? (cnt[2] | (cnt[3] << 16)) : 0u;
         const long long row = job.out_base + (long long)(meta.mblk * p.mpi + mi) * job.n_groups;
         // two 16-bit fields per word survive a 32-lane sum (<= 8192)
         if (uniform) {  // all counted lanes of the warp feed the same output row (the common case)

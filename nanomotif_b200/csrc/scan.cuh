@@ -121,6 +121,80 @@ __device__ __forceinline__ void run_chain(const ProgramView &pv, const LaneSeq<H
     }
 }
 
+// Allowed-set of the complementary bases: A<->T (bits 0,1), G<->C (bits 2,3).
+__host__ __device__ constexpr int comp_set(int m) { return ((m & 5) << 1) | ((m & 10) >> 1); }
+
+template <int H>
+__device__ __forceinline__ uint32_t shifted_l(const uint32_t (&c)[NW + 2 * H], int i, int s) {
+    return __funnelshift_l((i > 0) ? c[i - 1] : 0u, c[i], s);
+}
+
+// Both strands in one pass.  The reverse-complement motif has the complementary set at the mirrored
+// position, so walking the SAME program (last constrained position first, same distances) with the
+// complementary lop3 immediate and the OPPOSITE shift direction yields its END-aligned match plane:
+//     C <- ind_S(x, y)       & (C >> d)     forward motif, start-aligned, valid on words [-H, NW)
+//     D <- ind_comp(S)(x, y) & (D << d)     reverse complement, end-aligned, valid on words [0, NW + H)
+// One dispatch per constrained position serves both chains (half the loop / branch overhead per chain
+// step) and the two dependency chains interleave (twice the ILP).
+template <int M, int H, bool HASN>
+__device__ __forceinline__ void step_pair(uint32_t (&c)[NW + 2 * H], uint32_t (&d)[NW + 2 * H],
+                                          const LaneSeq<H, HASN> &q, int s) {
+#pragma unroll
+    for (int i = 0; i < NW + 2 * H; ++i) c[i] = q.template and_code<M>(i, shifted<H>(c, i, s));
+#pragma unroll
+    for (int i = NW + 2 * H - 1; i >= 0; --i) d[i] = q.template and_code<comp_set(M)>(i, shifted_l<H>(d, i, s));
+}
+
+template <int H, bool HASN>
+__device__ __forceinline__ void run_chain_pair(const ProgramView &pv, const LaneSeq<H, HASN> &q,
+                                               uint32_t (&c)[NW + 2 * H], uint32_t (&d)[NW + 2 * H]) {
+#pragma unroll
+    for (int i = 0; i < NW + 2 * H; ++i) {
+        c[i] = 0xFFFFFFFFu;
+        d[i] = 0xFFFFFFFFu;
+    }
+    uint32_t e = __ldg(pv.ent);
+#pragma unroll 1
+    for (int i = 0; i < pv.n; ++i) {
+        const uint32_t cur = e;
+        if (i + 1 < pv.n) e = __ldg(pv.ent + i + 1);  // prefetch the next entry
+        const int s = cur >> 8;
+        switch (cur & 0xFF) {
+#define NMB_CASE(m) case m: step_pair<m, H, HASN>(c, d, q, s); break;
+            NMB_CASE(1) NMB_CASE(2) NMB_CASE(3) NMB_CASE(4) NMB_CASE(5) NMB_CASE(6) NMB_CASE(7)
+            NMB_CASE(8) NMB_CASE(9) NMB_CASE(10) NMB_CASE(11) NMB_CASE(12) NMB_CASE(13) NMB_CASE(14)
+#undef NMB_CASE
+            case 15:
+#pragma unroll
+                for (int k = 0; k < NW + 2 * H; ++k) c[k] = shifted<H>(c, k, s);
+#pragma unroll
+                for (int k = NW + 2 * H - 1; k >= 0; --k) d[k] = shifted_l<H>(d, k, s);
+                break;
+            case kEntShift32:
+#pragma unroll
+                for (int k = 0; k < NW + 2 * H; ++k) c[k] = (k + 1 < NW + 2 * H) ? c[k + 1] : 0u;
+#pragma unroll
+                for (int k = NW + 2 * H - 1; k >= 0; --k) d[k] = (k > 0) ? d[k - 1] : 0u;
+                break;
+            default:
+#pragma unroll
+                for (int k = 0; k < NW + 2 * H; ++k) {
+                    c[k] = 0u;
+                    d[k] = 0u;
+                }
+                break;
+        }
+    }
+}
+
+// Word k of the reverse-complement match plane aligned at ITS modified base: M_rc[p] = D[p + mod_pos]
+// (mod_pos = the forward motif's; the rc motif's is len - 1 - mod_pos, motif.py:264).
+template <int H>
+__device__ __forceinline__ uint32_t aligned_word_rc(const uint32_t (&d)[NW + 2 * H], int k, int sh, bool far) {
+    if (H == 1 || !far) return __funnelshift_r(d[k + H], d[k + H + 1], sh);
+    return __funnelshift_r(d[k + H + 1], (k + H + 2 < NW + 2 * H) ? d[k + H + 2] : 0u, sh);
+}
+
 // Word k (0 <= k < NW) of the match plane aligned at mod_pos: M[p] = S[p - mod_pos].
 template <int H>
 __device__ __forceinline__ uint32_t aligned_word(const uint32_t (&c)[NW + 2 * H], int k, int sh, bool far) {
