@@ -72,7 +72,7 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
         // ONE program per motif serves both strands (scan.cuh: run_chain_pair)
         const ProgramView pv = load_program(p.programs + (size_t)(m_begin + mi) * 2);
         uint32_t c[NW + 2 * H], d[NW + 2 * H];
-        run_chain_pair<H, PLANES>(pv, q, c, d);
+        if (!run_chain_pair<H, PLANES>(pv, q, c, d)) continue;  // no occurrence in this warp's chunk
         const bool far = pv.mod_pos >= 32;  // only possible when H == 2
         const int sh = pv.mod_pos & 31;
         uint32_t cnt[4] = {0, 0, 0, 0};  // n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'

@@ -145,8 +145,20 @@ __device__ __forceinline__ void step_pair(uint32_t (&c)[NW + 2 * H], uint32_t (&
     for (int i = NW + 2 * H - 1; i >= 0; --i) d[i] = q.template and_code<comp_set(M)>(i, shifted_l<H>(d, i, s));
 }
 
+// True when any lane of the warp still has a candidate occurrence on either strand.
+template <int H>
+__device__ __forceinline__ bool chains_alive(const uint32_t (&c)[NW + 2 * H], const uint32_t (&d)[NW + 2 * H]) {
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < NW + 2 * H; ++i) any |= c[i] | d[i];
+    return __any_sync(0xFFFFFFFFu, any != 0);
+}
+
+// Returns false when both chains died in every lane of the warp (no occurrence in the warp's 16 384
+// positions): after 8 constrained positions that is the common case, so the remaining steps and the
+// whole popcount stage are skipped.  The test is warp-uniform.
 template <int H, bool HASN>
-__device__ __forceinline__ void run_chain_pair(const ProgramView &pv, const LaneSeq<H, HASN> &q,
+__device__ __forceinline__ bool run_chain_pair(const ProgramView &pv, const LaneSeq<H, HASN> &q,
                                                uint32_t (&c)[NW + 2 * H], uint32_t (&d)[NW + 2 * H]) {
 #pragma unroll
     for (int i = 0; i < NW + 2 * H; ++i) {
@@ -159,6 +171,7 @@ __device__ __forceinline__ void run_chain_pair(const ProgramView &pv, const Lane
         const uint32_t cur = e;
         if (i + 1 < pv.n) e = __ldg(pv.ent + i + 1);  // prefetch the next entry
         const int s = cur >> 8;
+        if (i >= 8 && !(i & 1) && !chains_alive<H>(c, d)) return false;
         switch (cur & 0xFF) {
 #define NMB_CASE(m) case m: step_pair<m, H, HASN>(c, d, q, s); break;
             NMB_CASE(1) NMB_CASE(2) NMB_CASE(3) NMB_CASE(4) NMB_CASE(5) NMB_CASE(6) NMB_CASE(7)
@@ -185,6 +198,7 @@ __device__ __forceinline__ void run_chain_pair(const ProgramView &pv, const Lane
                 break;
         }
     }
+    return pv.n < 8 || chains_alive<H>(c, d);
 }
 
 // Word k of the reverse-complement match plane aligned at ITS modified base: M_rc[p] = D[p + mod_pos]
