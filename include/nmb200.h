@@ -142,6 +142,18 @@ NMB_API int nmb_build_class_planes(const int32_t *contig_id, const int64_t *pos,
                            double low, double high, const nmb_assembly *assembly_h,
                            int32_t n_modtypes, uint32_t *class_records, void *stream);
 
+/* Same class records from COMPACT rows (7 bytes per row instead of 22 over PCIe): pos int32, flags =
+ * strand | mod type index << 1, percent_x100 = modkit's two-decimal percentage as an exact integer key
+ * (0..10000).  Rows are grouped by contig: rows of contig c are [contig_row_off[c], contig_row_off[c+1]).
+ * A row is methylated iff key >= key_high and unmethylated iff key <= key_low, where the keys are the
+ * integer images of the reference's float64 tests fl(fl(key/100)/100) >= high / <= low computed by the
+ * caller over the 10001 grid values (nanomotif_b200.device.threshold_keys) -- bit-equivalent to
+ * nmb_build_class_planes on pileups whose column 11 has two decimals. */
+NMB_API int nmb_build_class_planes_compact(const int32_t *pos, const uint8_t *flags, const uint16_t *percent_x100,
+                                   const int64_t *contig_row_off, int64_t n_rows, int32_t key_low,
+                                   int32_t key_high, const nmb_assembly *assembly_h, int32_t n_modtypes,
+                                   uint32_t *class_records, void *stream);
+
 /* ---- pileup filters (replace the polars expressions of nanomotif/dataload.py:191-247); every
  *      function writes keep[r] in {0,1} in input row order ---- */
 

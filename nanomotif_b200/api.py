@@ -22,7 +22,8 @@ import torch
 
 from . import _lib
 from ._lib import check, lib, ptr
-from .device import DeviceAssembly, DevicePileup, MotifPrograms, _stream, make_jobs, scan_count, sequence_of
+from .device import (DeviceAssembly, DevicePileup, MotifPrograms, _stream, compact_rows, make_jobs, scan_count,
+                     sequence_of)
 from .model import BetaBernoulliModel, predictive_evaluation_score
 from .motif import Motif, as_motif, tokenize
 from .pileup import PileupTable, strand_codes
@@ -204,8 +205,13 @@ class BinScorer:
             cid = lut[inv] if len(uniq) else np.zeros(0, dtype=np.int32)
         self.table = table
         self.contig_id = cid
-        self.pileup = DevicePileup.from_columns(asm, cid, table.position, strand_codes(table.strand),
-                                                table.fraction_mod, low_meth_threshold, high_meth_threshold)
+        # modkit percentages have two decimals: ship 7-byte rows over PCIe when that holds, else float64 rows
+        compact = compact_rows(cid, table.position, strand_codes(table.strand), table.fraction_mod, None, asm.n_contigs)
+        if compact is not None:
+            self.pileup = DevicePileup.from_compact(asm, low=low_meth_threshold, high=high_meth_threshold, **compact)
+        else:
+            self.pileup = DevicePileup.from_columns(asm, cid, table.position, strand_codes(table.strand),
+                                                    table.fraction_mod, low_meth_threshold, high_meth_threshold)
 
     def _jobs(self, n_motifs: int, per_contig: bool) -> tuple[np.ndarray, int]:
         asm = self.assembly

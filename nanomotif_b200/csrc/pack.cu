@@ -143,6 +143,39 @@ __global__ void __launch_bounds__(256) class_planes_kernel(
     }
 }
 
+// Compact rows (7 bytes each): 32-bit position, flags = strand | mod type << 1, and the modkit percentage
+// as an exact fixed-point key (hundredths of a percent, 0..10000).  Rows are grouped by contig
+// (row_off[c] .. row_off[c+1]).  key >= key_high / key <= key_low are the host-derived integer images
+// of the reference's float64 tests (see nanomotif_b200/device.py::threshold_keys).
+__global__ void __launch_bounds__(256) class_planes_compact_kernel(
+    const int32_t *__restrict__ pos, const uint8_t *__restrict__ flags, const uint16_t *__restrict__ key,
+    const int64_t *__restrict__ row_off, int n_contigs, int64_t n_rows, int key_low, int key_high,
+    const int64_t *__restrict__ contig_start, const int64_t *__restrict__ contig_len, int n_tiles,
+    int n_modtypes, uint32_t *__restrict__ cls) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const int k = key[r];
+        const bool is_mod = k >= key_high, is_non = k <= key_low;
+        if (!is_mod && !is_non) continue;
+        int lo = 0, hi = n_contigs;  // largest c with row_off[c] <= r
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(row_off + mid) <= r) lo = mid; else hi = mid;
+        }
+        const int64_t p = pos[r];
+        if (p < 0 || p >= __ldg(contig_len + lo)) continue;
+        const int f = flags[r];
+        const int mt = f >> 1;
+        if (mt >= n_modtypes) continue;
+        const int64_t g = __ldg(contig_start + lo) + p;
+        uint32_t *rec = cls + ((int64_t)mt * n_tiles + (g >> 16)) * kClsRecWords + ((f & 1) ? 2 : 0) * kTileWords +
+                        (int)((g >> 5) & (kTileWords - 1));
+        const uint32_t bit = 1u << (g & 31);
+        if (is_mod) atomicOr(rec, bit);
+        if (is_non) atomicOr(rec + kTileWords, bit);
+    }
+}
+
 }  // namespace nmb
 
 extern "C" {
@@ -182,6 +215,26 @@ int nmb_build_class_planes(const int32_t *contig_id, const int64_t *pos, const u
     nmb::class_planes_kernel<<<(unsigned)blocks, 256, 0, s>>>(
         contig_id, pos, strand, modtype, fraction_mod, n_rows, low, high, a->contig_start,
         a->contig_len, a->n_contigs, a->n_tiles, n_modtypes, class_records);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_build_class_planes_compact(const int32_t *pos, const uint8_t *flags, const uint16_t *percent_x100,
+                                   const int64_t *contig_row_off, int64_t n_rows, int32_t key_low,
+                                   int32_t key_high, const nmb_assembly *a, int32_t n_modtypes,
+                                   uint32_t *class_records, void *stream) {
+    NMB_REQUIRE(a && class_records, "nmb_build_class_planes_compact: null argument");
+    NMB_REQUIRE(n_rows >= 0 && n_modtypes > 0 && n_modtypes <= 128 && a->n_tiles > 0 && a->n_contigs > 0,
+                "nmb_build_class_planes_compact: bad sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    NMB_CUDA(cudaMemsetAsync(class_records, 0, (size_t)n_modtypes * a->n_tiles * nmb::kClsRecBytes, s));
+    if (n_rows == 0) return NMB_OK;
+    NMB_REQUIRE(pos && flags && percent_x100 && contig_row_off, "nmb_build_class_planes_compact: null column");
+    int64_t blocks = (n_rows + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    nmb::class_planes_compact_kernel<<<(unsigned)blocks, 256, 0, s>>>(
+        pos, flags, percent_x100, contig_row_off, a->n_contigs, n_rows, key_low, key_high, a->contig_start,
+        a->contig_len, a->n_tiles, n_modtypes, class_records);
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;
 }

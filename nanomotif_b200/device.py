@@ -25,7 +25,8 @@ def _require_cuda(device=None) -> torch.device:
     return dev
 
 
-_NP_OF = {torch.int32: np.int32, torch.int64: np.int64, torch.uint8: np.uint8, torch.float64: np.float64}
+_NP_OF = {torch.int32: np.int32, torch.int64: np.int64, torch.uint8: np.uint8, torch.float64: np.float64,
+          torch.uint16: np.uint16}
 
 
 def _stream() -> int:
@@ -160,6 +161,88 @@ class DevicePileup:
             )
             torch.cuda.current_stream().synchronize()
         return self
+
+    @classmethod
+    def from_compact(cls, assembly: DeviceAssembly, position, flags, percent_x100, contig_row_off, low, high,
+                     n_modtypes: int = 1) -> "DevicePileup":
+        """Rows grouped by contig in 7 bytes each: position int32, flags uint8 (strand | mod type << 1),
+        percent_x100 uint16 (see threshold_keys); contig_row_off int64 [n_contigs + 1]."""
+        self = cls(assembly, n_modtypes, low, high)
+        d = assembly.device
+        key_low, key_high = threshold_keys(low, high)
+
+        def dev(a, dt):
+            if isinstance(a, torch.Tensor):
+                return a.to(device=d, dtype=dt, non_blocking=True).contiguous()
+            return _to_device(np.asarray(a).astype(_NP_OF[dt], copy=False), d)
+
+        with torch.cuda.device(d):
+            pos, fl = dev(position, torch.int32), dev(flags, torch.uint8)
+            key = dev(percent_x100, torch.uint16)
+            off = dev(contig_row_off, torch.int64)
+            n = int(pos.numel())
+            if int(fl.numel()) != n or int(key.numel()) != n or int(off.numel()) != assembly.n_contigs + 1:
+                raise ValueError("compact pileup columns differ in length")
+            view = assembly.view()
+            check(
+                lib.nmb_build_class_planes_compact(ptr(pos), ptr(fl), ptr(key), ptr(off), n, key_low, key_high,
+                                                   C.byref(view), self.n_modtypes, ptr(self.class_records), _stream()),
+                "nmb_build_class_planes_compact",
+            )
+            torch.cuda.current_stream().synchronize()
+        return self
+
+
+def threshold_keys(low: float, high: float) -> tuple[int, int]:
+    """Integer images of the reference's float64 classification on modkit's two-decimal grid.
+
+    A pileup percentage printed with two decimals is k/100 for an integer key k in 0..10000; the reference
+    turns it into fraction_mod = fl(fl(k/100)/100) (dataload.py:85) and tests >= high / <= low
+    (find_motifs_bin.py:1308-1309).  Both tests are monotone in k, so they equal k >= key_high / k <= key_low
+    with the keys found by evaluating the SAME float expression on all 10001 grid values."""
+    k = np.arange(10001, dtype=np.float64)
+    frac = (k / 100.0) / 100.0
+    is_high, is_low = frac >= high, frac <= low
+    key_high = int(np.argmax(is_high)) if is_high.any() else 10001
+    key_low = int(len(k) - 1 - np.argmax(is_low[::-1])) if is_low.any() else -1
+    if not (np.array_equal(is_high, np.arange(10001) >= key_high) and np.array_equal(is_low, np.arange(10001) <= key_low)):
+        raise AssertionError("threshold tests are not monotone on the percent grid")  # cannot happen
+    return key_low, key_high
+
+
+def percent_keys(fraction_mod: np.ndarray) -> np.ndarray | None:
+    """uint16 keys of fractions that sit exactly on modkit's two-decimal grid, else None."""
+    f = np.asarray(fraction_mod, dtype=np.float64)
+    k = np.rint(f * 10000.0)
+    if not np.all((k >= 0) & (k <= 10000)):
+        return None
+    if not np.array_equal((k / 100.0) / 100.0, f):  # the exact float the reference's loader produces
+        return None
+    return k.astype(np.uint16)
+
+
+def compact_rows(contig_id, position, strand, fraction_mod, mod_type=None, n_contigs: int = 1) -> dict | None:
+    """Columns of DevicePileup.from_compact for a pileup whose percentages sit on modkit's two-decimal grid,
+    or None when the pileup cannot be represented (off-grid fractions, positions >= 2^31, > 127 mod types).
+    Rows of unknown contigs (negative id) are dropped; rows are grouped by contig (stable)."""
+    key = percent_keys(fraction_mod)
+    position = np.asarray(position, dtype=np.int64)
+    if key is None or (len(position) and (position.max() >= 2**31 or position.min() < 0)):
+        return None
+    cid = np.asarray(contig_id, dtype=np.int64)
+    mt = np.zeros(len(position), dtype=np.uint8) if mod_type is None else np.asarray(mod_type, dtype=np.uint8)
+    if len(mt) and mt.max() > 127:
+        mt = np.where(mt > 127, 127, mt)  # out-of-range types are ignored by the kernel (>= n_modtypes)
+    flags = (np.asarray(strand, dtype=np.uint8) & 1) | (mt << 1)
+    keep = cid >= 0
+    if not keep.all():
+        cid, position, flags, key = cid[keep], position[keep], flags[keep], key[keep]
+    if len(cid) > 1 and np.any(cid[1:] < cid[:-1]):
+        order = np.argsort(cid, kind="stable")
+        cid, position, flags, key = cid[order], position[order], flags[order], key[order]
+    off = np.zeros(n_contigs + 1, dtype=np.int64)
+    np.cumsum(np.bincount(cid, minlength=n_contigs)[:n_contigs], out=off[1:])
+    return dict(position=position.astype(np.int32), flags=flags, percent_x100=key, contig_row_off=off)
 
 
 def make_jobs(n: int) -> np.ndarray:

@@ -115,3 +115,36 @@ def test_motif_model_contig_positions(nmb):
         assert (mdl._alpha - 5, mdl._beta - 5) == (a, b)
         for k in want:
             np.testing.assert_array_equal(data[k], want[k], err_msg=f"{s} {k}")
+
+
+@pytest.mark.parametrize("low,high", [(0.3, 0.7), (0.25, 0.75), (0.295, 0.705), (0.5, 0.5001), (0.0, 1.0)])
+def test_compact_rows_give_identical_class_planes(nmb, low, high):
+    """7-byte rows + integer threshold keys == float64 rows + the reference's float tests, bit for bit."""
+    import torch
+
+    from nanomotif_b200 import synth
+    from nanomotif_b200.device import DeviceAssembly, DevicePileup, compact_rows, threshold_keys
+
+    rng = np.random.default_rng(8)
+    seqs, cols = {}, {k: [] for k in ("cid", "position", "strand", "mod_type", "fraction_mod")}
+    for i, L in enumerate((70000, 900, 30000)):
+        seq = synth.random_sequence(rng, L, 0.5)
+        seqs[f"c{i}"] = seq.tobytes().decode()
+        p = synth.synth_pileup(seq, rng, depth=int(rng.integers(3, 200)))
+        cols["cid"].append(np.full(len(p["position"]), i if i != 1 else -1, dtype=np.int32))  # contig 1 unknown
+        for k in ("position", "strand", "mod_type", "fraction_mod"):
+            cols[k].append(p[k])
+    c = {k: np.concatenate(v) for k, v in cols.items()}
+    perm = rng.permutation(len(c["cid"]))  # not grouped by contig: compact_rows has to group
+    c = {k: v[perm] for k, v in c.items()}
+    asm = DeviceAssembly.from_sequences(seqs)
+    a = DevicePileup.from_columns(asm, c["cid"], c["position"], c["strand"], c["fraction_mod"], low, high, c["mod_type"], 3)
+    rows = compact_rows(c["cid"], c["position"], c["strand"], c["fraction_mod"], c["mod_type"], asm.n_contigs)
+    assert rows is not None and rows["percent_x100"].dtype == np.uint16
+    b = DevicePileup.from_compact(asm, low=low, high=high, n_modtypes=3, **rows)
+    assert torch.equal(a.class_records, b.class_records) and int(a.class_records.ne(0).sum()) > 1000
+    k_lo, k_hi = threshold_keys(low, high)
+    grid = (np.arange(10001) / 100.0) / 100.0
+    assert np.array_equal(grid >= high, np.arange(10001) >= k_hi) and np.array_equal(grid <= low, np.arange(10001) <= k_lo)
+    # fractions off the two-decimal grid cannot be compacted: the float64 path stays in charge
+    assert compact_rows(c["cid"], c["position"], c["strand"], c["fraction_mod"] + 1e-9, c["mod_type"], 3) is None
