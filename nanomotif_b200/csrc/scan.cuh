@@ -124,9 +124,12 @@ __device__ __forceinline__ void run_chain(const ProgramView &pv, const LaneSeq<H
 // Allowed-set of the complementary bases: A<->T (bits 0,1), G<->C (bits 2,3).
 __host__ __device__ constexpr int comp_set(int m) { return ((m & 5) << 1) | ((m & 10) >> 1); }
 
+// The reverse-complement chain D is kept in REVERSED word order (dr[j] = D[CW-1-j]) so that its in-place
+// update has the same shape as the forward chain's (new[j] from old[j] and old[j+1], ascending j); written
+// the natural way the compiler rotates the whole array through registers with 18 moves per step.
 template <int H>
-__device__ __forceinline__ uint32_t shifted_l(const uint32_t (&c)[NW + 2 * H], int i, int s) {
-    return __funnelshift_l((i > 0) ? c[i - 1] : 0u, c[i], s);
+__device__ __forceinline__ uint32_t shifted_l(const uint32_t (&dr)[NW + 2 * H], int j, int s) {
+    return __funnelshift_l((j + 1 < NW + 2 * H) ? dr[j + 1] : 0u, dr[j], s);
 }
 
 // Both strands in one pass.  The reverse-complement motif has the complementary set at the mirrored
@@ -137,12 +140,13 @@ __device__ __forceinline__ uint32_t shifted_l(const uint32_t (&c)[NW + 2 * H], i
 // One dispatch per constrained position serves both chains (half the loop / branch overhead per chain
 // step) and the two dependency chains interleave (twice the ILP).
 template <int M, int H, bool HASN>
-__device__ __forceinline__ void step_pair(uint32_t (&c)[NW + 2 * H], uint32_t (&d)[NW + 2 * H],
+__device__ __forceinline__ void step_pair(uint32_t (&c)[NW + 2 * H], uint32_t (&dr)[NW + 2 * H],
                                           const LaneSeq<H, HASN> &q, int s) {
+    constexpr int CW = NW + 2 * H;
 #pragma unroll
-    for (int i = 0; i < NW + 2 * H; ++i) c[i] = q.template and_code<M>(i, shifted<H>(c, i, s));
+    for (int i = 0; i < CW; ++i) c[i] = q.template and_code<M>(i, shifted<H>(c, i, s));
 #pragma unroll
-    for (int i = NW + 2 * H - 1; i >= 0; --i) d[i] = q.template and_code<comp_set(M)>(i, shifted_l<H>(d, i, s));
+    for (int j = 0; j < CW; ++j) dr[j] = q.template and_code<comp_set(M)>(CW - 1 - j, shifted_l<H>(dr, j, s));
 }
 
 // True when any lane of the warp still has a candidate occurrence on either strand.
@@ -181,13 +185,14 @@ __device__ __forceinline__ bool run_chain_pair(const ProgramView &pv, const Lane
 #pragma unroll
                 for (int k = 0; k < NW + 2 * H; ++k) c[k] = shifted<H>(c, k, s);
 #pragma unroll
-                for (int k = NW + 2 * H - 1; k >= 0; --k) d[k] = shifted_l<H>(d, k, s);
+                for (int k = 0; k < NW + 2 * H; ++k) d[k] = shifted_l<H>(d, k, s);
                 break;
             case kEntShift32:
 #pragma unroll
-                for (int k = 0; k < NW + 2 * H; ++k) c[k] = (k + 1 < NW + 2 * H) ? c[k + 1] : 0u;
-#pragma unroll
-                for (int k = NW + 2 * H - 1; k >= 0; --k) d[k] = (k > 0) ? d[k - 1] : 0u;
+                for (int k = 0; k < NW + 2 * H; ++k) {
+                    c[k] = (k + 1 < NW + 2 * H) ? c[k + 1] : 0u;
+                    d[k] = (k + 1 < NW + 2 * H) ? d[k + 1] : 0u;
+                }
                 break;
             default:
 #pragma unroll
@@ -202,11 +207,13 @@ __device__ __forceinline__ bool run_chain_pair(const ProgramView &pv, const Lane
 }
 
 // Word k of the reverse-complement match plane aligned at ITS modified base: M_rc[p] = D[p + mod_pos]
-// (mod_pos = the forward motif's; the rc motif's is len - 1 - mod_pos, motif.py:264).
+// (mod_pos = the forward motif's; the rc motif's is len - 1 - mod_pos, motif.py:264).  dr is the reversed
+// storage of D: D[i] = dr[CW - 1 - i].
 template <int H>
-__device__ __forceinline__ uint32_t aligned_word_rc(const uint32_t (&d)[NW + 2 * H], int k, int sh, bool far) {
-    if (H == 1 || !far) return __funnelshift_r(d[k + H], d[k + H + 1], sh);
-    return __funnelshift_r(d[k + H + 1], (k + H + 2 < NW + 2 * H) ? d[k + H + 2] : 0u, sh);
+__device__ __forceinline__ uint32_t aligned_word_rc(const uint32_t (&dr)[NW + 2 * H], int k, int sh, bool far) {
+    constexpr int CW = NW + 2 * H;
+    const int i = (H == 1 || !far) ? k + H : k + H + 1;  // D word holding the low part
+    return __funnelshift_r(dr[CW - 1 - i], (i + 1 < CW) ? dr[CW - 2 - i] : 0u, sh);
 }
 
 // Word k (0 <= k < NW) of the match plane aligned at mod_pos: M[p] = S[p - mod_pos].
