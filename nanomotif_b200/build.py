@@ -41,6 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd += os.environ.get("NMB_NVCC_EXTRA", "").split()  # extra nvcc flags for experiments
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]

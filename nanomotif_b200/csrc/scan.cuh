@@ -88,7 +88,8 @@ __device__ __forceinline__ void step_code(uint32_t (&c)[NW + 2 * H], const LaneS
 // for a leading wildcard of an unstripped motif).  All shifts are < 32 and the first entry's shift is 0.
 constexpr int kEntShift32 = 0x10;
 
-// Start-aligned match words of the lane's words [-H, NW + H); valid for words [-H, NW).
+// Single-strand chain (K3 match planes): start-aligned match words of the lane's words [-H, NW + H);
+// valid for words [-H, NW).
 template <int H, bool HASN>
 __device__ __forceinline__ void run_chain(const ProgramView &pv, const LaneSeq<H, HASN> &q,
                                           uint32_t (&c)[NW + 2 * H]) {
@@ -149,6 +150,17 @@ __device__ __forceinline__ void step_pair(uint32_t (&c)[NW + 2 * H], uint32_t (&
     for (int j = 0; j < CW; ++j) dr[j] = q.template and_code<comp_set(M)>(CW - 1 - j, shifted_l<H>(dr, j, s));
 }
 
+// First entry of a program: both chains start as the plain indicator planes (no shift, no AND).
+template <int M, int H, bool HASN>
+__device__ __forceinline__ void init_pair(uint32_t (&c)[NW + 2 * H], uint32_t (&dr)[NW + 2 * H],
+                                          const LaneSeq<H, HASN> &q) {
+    constexpr int CW = NW + 2 * H;
+#pragma unroll
+    for (int i = 0; i < CW; ++i) c[i] = q.template and_code<M>(i, 0xFFFFFFFFu);
+#pragma unroll
+    for (int j = 0; j < CW; ++j) dr[j] = q.template and_code<comp_set(M)>(CW - 1 - j, 0xFFFFFFFFu);
+}
+
 // True when any lane of the warp still has a candidate occurrence on either strand.
 template <int H>
 __device__ __forceinline__ bool chains_alive(const uint32_t (&c)[NW + 2 * H], const uint32_t (&d)[NW + 2 * H]) {
@@ -164,14 +176,27 @@ __device__ __forceinline__ bool chains_alive(const uint32_t (&c)[NW + 2 * H], co
 template <int H, bool HASN>
 __device__ __forceinline__ bool run_chain_pair(const ProgramView &pv, const LaneSeq<H, HASN> &q,
                                                uint32_t (&c)[NW + 2 * H], uint32_t (&d)[NW + 2 * H]) {
-#pragma unroll
-    for (int i = 0; i < NW + 2 * H; ++i) {
-        c[i] = 0xFFFFFFFFu;
-        d[i] = 0xFFFFFFFFu;
-    }
     uint32_t e = __ldg(pv.ent);
+    {   // first entry (shift 0 by construction): the chains ARE the indicator planes
+        const int code = e & 0xFF;
+        if (pv.n > 1) e = __ldg(pv.ent + 1);
+        switch (code) {
+#define NMB_CASE(m) case m: init_pair<m, H, HASN>(c, d, q); break;
+            NMB_CASE(1) NMB_CASE(2) NMB_CASE(3) NMB_CASE(4) NMB_CASE(5) NMB_CASE(6) NMB_CASE(7)
+            NMB_CASE(8) NMB_CASE(9) NMB_CASE(10) NMB_CASE(11) NMB_CASE(12) NMB_CASE(13) NMB_CASE(14)
+#undef NMB_CASE
+            case 15:
+#pragma unroll
+                for (int k = 0; k < NW + 2 * H; ++k) c[k] = d[k] = 0xFFFFFFFFu;
+                break;
+            default:
+#pragma unroll
+                for (int k = 0; k < NW + 2 * H; ++k) c[k] = d[k] = 0u;
+                break;
+        }
+    }
 #pragma unroll 1
-    for (int i = 0; i < pv.n; ++i) {
+    for (int i = 1; i < pv.n; ++i) {
         const uint32_t cur = e;
         if (i + 1 < pv.n) e = __ldg(pv.ent + i + 1);  // prefetch the next entry
         const int s = cur >> 8;
