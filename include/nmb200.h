@@ -246,6 +246,15 @@ NMB_API int nmb_window_hist(const uint64_t *windows, const uint8_t *alive, int64
                     int32_t *hist /* [n_motifs][width][4] */, int64_t *n_active, uint8_t *keep,
                     void *stream);
 
+/* Batched form for many searches at once: motif m examines rows [row_begin[m], row_end[m]) only
+ * (max_rows = the largest range, sizes the grid).  keep_rows (may be NULL) is ONE array of n flags:
+ * row i receives the decision of the motif whose range contains it, so the ranges of the motifs of
+ * one call must be disjoint when keep_rows is given. */
+NMB_API int nmb_window_hist_ranges(const uint64_t *windows, const uint8_t *alive, int64_t n, int32_t width,
+                           const nmb_motif *masks, int32_t n_motifs, const int64_t *row_begin,
+                           const int64_t *row_end, int64_t max_rows, int32_t n_counts_all, int32_t *hist,
+                           int64_t *n_active, uint8_t *keep_rows, void *stream);
+
 /* PSSM + KL(meth || background) per column in float64: pssm[m][b][j] = hist/n_active (4 x width,
  * rows A,T,G,C), kl[m][j] = sum_b p ln(p/q) after per-column renormalisation of both (scipy.stats.
  * entropy semantics: 0 ln 0 = 0, p>0 & q=0 -> inf).  bg_pssm is [4][width] float64. */

@@ -90,6 +90,7 @@ SIGNATURES = {
     "nmb_test_positions": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P]),
     "nmb_extract_windows": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _I64, _I32, _P, _P]),
     "nmb_window_hist": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _P, _P, _P]),
+    "nmb_window_hist_ranges": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P, _P, _I64, _I32, _P, _P, _P, _P]),
     "nmb_pattern_stats": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _I32, _P, _P, _P, _P]),
     "nmb_pattern_median": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _P]),
     "nmb_pssm_kl": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P]),

@@ -176,7 +176,7 @@ int nmb_match_plane(const nmb_assembly *a, const void *programs, int32_t motif_i
     if (tile_count == 0) return NMB_OK;
     const nmb::Program *prog = (const nmb::Program *)programs + (size_t)motif_index * 2 + strand;
     cudaStream_t s = (cudaStream_t)stream;
-    if (motif_len <= 33)
+    if (motif_len <= 32)  // one halo word covers a total shift (and a mod_pos) of at most 31
         nmb::match_plane_kernel<1><<<tile_count, nmb::kTileChunks, 0, s>>>(
             a->seq_records, a->nonacgt, prog, tile_begin, match_plane);
     else

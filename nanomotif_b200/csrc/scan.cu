@@ -299,7 +299,7 @@ int nmb_scan_count(const nmb_assembly *a, const uint32_t *class_records, const v
     }
     if (grid > n_items) grid = n_items;
     cudaStream_t s = (cudaStream_t)stream;
-    if (max_motif_len <= 33) {
+    if (max_motif_len <= 32) {  // one halo word covers a total shift (and a mod_pos) of at most 31
         NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       nmb::kScanSmemBytes));
         nmb::scan_count_kernel<1><<<grid, nmb::kScanThreads, nmb::kScanSmemBytes, s>>>(p);

@@ -60,10 +60,13 @@ __global__ void __launch_bounds__(256) extract_windows_kernel(
 
 // grid = (row blocks, n_motifs).  Column masks of the motif are built once per block in shared
 // memory: allow[b] has bit j set when base b is accepted at column j.
+// row_begin / row_end (may be NULL = all rows): rows examined by motif m.  keep_shared != 0: keep is one
+// array of n flags shared by all motifs (their ranges are disjoint), else keep is [n_motifs][n].
 __global__ void __launch_bounds__(256) window_hist_kernel(
     const uint64_t *__restrict__ windows, const uint8_t *__restrict__ alive, int64_t n, int width,
-    const nmb_motif *__restrict__ masks, int n_counts_all, int *__restrict__ hist,
-    unsigned long long *__restrict__ n_active, uint8_t *__restrict__ keep) {
+    const nmb_motif *__restrict__ masks, const int64_t *__restrict__ row_begin,
+    const int64_t *__restrict__ row_end, int n_counts_all, int *__restrict__ hist,
+    unsigned long long *__restrict__ n_active, uint8_t *__restrict__ keep, int keep_shared) {
     __shared__ uint64_t s_allow[4];
     __shared__ uint64_t s_wild;
     __shared__ int s_hist[NMB_MAX_WINDOW * 4];
@@ -87,11 +90,13 @@ __global__ void __launch_bounds__(256) window_hist_kernel(
     const uint64_t full = (width == 64) ? ~0ull : ((1ull << width) - 1ull);
     const uint64_t aA = s_allow[0], aT = s_allow[1], aG = s_allow[2], aC = s_allow[3], wild = s_wild;
 
-    const int64_t base_rows = (int64_t)blockIdx.x * 256;
+    const int64_t r0 = row_begin ? row_begin[m] : 0, r1 = row_end ? row_end[m] : n;
+    const int64_t base_rows = r0 + (int64_t)blockIdx.x * 256;
+    if (base_rows >= r1) return;  // uniform per block (after the barrier above)
     const int64_t i = base_rows + tid;
     bool kept = false;
     uint64_t isA = 0, isT = 0, isG = 0, isC = 0;
-    if (i < n && (!alive || alive[i])) {
+    if (i < r1 && (!alive || alive[i])) {
         const uint64_t x = windows[3 * i], y = windows[3 * i + 1], nn = windows[3 * i + 2];
         const uint64_t acgt = ~nn & full;
         isA = ~x & ~y & acgt;
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(256) window_hist_kernel(
             isC |= nn & full;
         }
     }
-    if (keep && i < n) keep[(int64_t)m * n + i] = kept ? 1 : 0;
+    if (keep && i < r1) keep[(keep_shared ? 0 : (int64_t)m * n) + i] = kept ? 1 : 0;
     const uint32_t kb = __ballot_sync(0xFFFFFFFFu, kept);
     if (kb) {
         if (lane == 0) atomicAdd(&s_active, __popc(kb));
@@ -195,8 +200,29 @@ int nmb_window_hist(const uint64_t *windows, const uint8_t *alive, int64_t n, in
     if (n == 0) return NMB_OK;
     NMB_REQUIRE(windows, "nmb_window_hist: null windows");
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)n_motifs);
-    nmb::window_hist_kernel<<<grid, 256, 0, s>>>(windows, alive, n, width, masks, n_counts_all, hist,
-                                                (unsigned long long *)n_active, keep);
+    nmb::window_hist_kernel<<<grid, 256, 0, s>>>(windows, alive, n, width, masks, nullptr, nullptr, n_counts_all,
+                                                hist, (unsigned long long *)n_active, keep, 0);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_window_hist_ranges(const uint64_t *windows, const uint8_t *alive, int64_t n, int32_t width,
+                           const nmb_motif *masks, int32_t n_motifs, const int64_t *row_begin,
+                           const int64_t *row_end, int64_t max_rows, int32_t n_counts_all, int32_t *hist,
+                           int64_t *n_active, uint8_t *keep_rows, void *stream) {
+    NMB_REQUIRE(width >= 1 && width <= NMB_MAX_WINDOW, "nmb_window_hist_ranges: width=%d", width);
+    NMB_REQUIRE(n >= 0 && n_motifs >= 0 && max_rows >= 0, "nmb_window_hist_ranges: bad sizes");
+    if (n_motifs == 0) return NMB_OK;
+    NMB_REQUIRE(masks && hist && n_active && row_begin && row_end, "nmb_window_hist_ranges: null argument");
+    NMB_REQUIRE(n_motifs <= 65535, "nmb_window_hist_ranges: at most 65535 motifs per call");
+    cudaStream_t s = (cudaStream_t)stream;
+    NMB_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_motifs * width * 4 * sizeof(int32_t), s));
+    NMB_CUDA(cudaMemsetAsync(n_active, 0, (size_t)n_motifs * sizeof(int64_t), s));
+    if (n == 0 || max_rows == 0) return NMB_OK;
+    NMB_REQUIRE(windows, "nmb_window_hist_ranges: null windows");
+    dim3 grid((unsigned)((max_rows + 255) / 256), (unsigned)n_motifs);
+    nmb::window_hist_kernel<<<grid, 256, 0, s>>>(windows, alive, n, width, masks, row_begin, row_end,
+                                                n_counts_all, hist, (unsigned long long *)n_active, keep_rows, 1);
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;
 }

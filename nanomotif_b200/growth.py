@@ -159,6 +159,68 @@ class DeviceDNAarray:
         return n_active.cpu().numpy(), pssm.cpu().numpy(), kl.cpu().numpy()
 
 
+class WindowPool:
+    """The methylation windows of MANY (bin, mod_type) searches in one device array, so that a lock-step
+    round of searches is served by ONE histogram launch (nmb_window_hist_ranges) instead of one per search.
+    Search `slot` owns rows [begin, end) and the matching slice of the shared `alive` mask."""
+
+    def __init__(self, arrays: list):
+        if not arrays:
+            raise ValueError("WindowPool needs at least one window array")
+        self.width = arrays[0].width
+        if any(a.width != self.width for a in arrays):
+            raise ValueError("all searches of a pool must use the same window width")
+        self.windows = torch.cat([a.windows for a in arrays], dim=0).contiguous()
+        d = self.windows.device
+        self.n_total = int(self.windows.shape[0])
+        self.alive = torch.ones(self.n_total, dtype=torch.uint8, device=d)
+        sizes = np.array([a.n_total for a in arrays], dtype=np.int64)
+        self.begin = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        self.end = (self.begin + sizes).astype(np.int64)
+        self.n_alive = sizes.copy()
+        for a, b, e in zip(arrays, self.begin, self.end):
+            if a.alive is not None:
+                self.alive[b:e] = a.alive
+
+    def _launch(self, slots, motifs, keep_rows):
+        d = self.windows.device
+        masks = window_masks(motifs, self.width)
+        m = len(motifs)
+        rb, re = self.begin[slots], self.end[slots]
+        with torch.cuda.device(d):
+            masks_d = _to_device(masks.view(np.uint8).reshape(-1), d)
+            rb_d, re_d = _to_device(rb, d), _to_device(re, d)
+            hist = torch.empty((m, self.width, 4), dtype=torch.int32, device=d)
+            n_active = torch.empty(m, dtype=torch.int64, device=d)
+            check(lib.nmb_window_hist_ranges(ptr(self.windows), ptr(self.alive), self.n_total, self.width, ptr(masks_d),
+                                             m, ptr(rb_d), ptr(re_d), int((re - rb).max()) if m else 0, 1, ptr(hist),
+                                             ptr(n_active), ptr(keep_rows), _stream()), "nmb_window_hist_ranges")
+        return hist, n_active
+
+    def expand_batch(self, requests: list) -> list:
+        """requests: [(slot, motif)] -> per request None | (n_active, pssm (4, W)); any number per slot."""
+        if not requests:
+            return []
+        slots = np.array([s for s, _ in requests], dtype=np.int64)
+        hist, n_active = self._launch(slots, [m for _, m in requests], None)
+        hist, n_active = hist.cpu().numpy().astype(np.int64), n_active.cpu().numpy()
+        return [None if n == 0 else (int(n), h.transpose() / n) for h, n in zip(hist, n_active)]
+
+    def remove_batch(self, requests: list) -> list:
+        """requests: [(slot, motif)], at most one per slot: drop the matching windows of each slot from its
+        alive set; returns the remaining count per request (None when nothing is left)."""
+        if not requests:
+            return []
+        slots = np.array([s for s, _ in requests], dtype=np.int64)
+        if len(set(slots.tolist())) != len(slots):
+            raise ValueError("remove_batch takes at most one request per search")
+        keep_rows = torch.zeros(self.n_total, dtype=torch.uint8, device=self.windows.device)
+        _, n_active = self._launch(slots, [m for _, m in requests], keep_rows)
+        self.alive &= 1 - keep_rows
+        self.n_alive[slots] -= n_active.cpu().numpy()
+        return [None if self.n_alive[s] == 0 else int(self.n_alive[s]) for s in slots]
+
+
 def methylation_windows(assembly: DeviceAssembly, contig_id, position, strand, fraction_mod, high: float,
                         padding: int) -> DeviceDNAarray | None:
     """Windows around confidently methylated sites in the reference's row order: per contig, '+' sites

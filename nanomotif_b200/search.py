@@ -277,6 +277,31 @@ class GpuBinBackend:
         return {"score": self.score, "expand": self.expand, "remove": self.remove}[kind](arg)
 
 
+class PoolBackend:
+    """Backend of one search whose windows live in a shared growth.WindowPool (slot = its row range) and whose
+    scorer is a BinContext of a shared MultiBinScorer: every request kind can be batched across searches."""
+
+    def __init__(self, scorer, pool, slot: int):
+        self.scorer, self.pool, self.slot = scorer, pool, slot
+
+    def handle(self, request):
+        kind, arg = request
+        if kind == "score":
+            return gpu_batch_score([(self, arg)])[0]
+        if kind == "expand":
+            return self.pool.expand_batch([(self.slot, arg)])[0]
+        return self.pool.remove_batch([(self.slot, arg)])[0]
+
+
+def gpu_batch_expand(requests):
+    """`batch_expand` for run_lockstep over PoolBackends of one WindowPool."""
+    return requests[0][0].pool.expand_batch([(b.slot, motif) for b, motif in requests])
+
+
+def gpu_batch_remove(requests):
+    return requests[0][0].pool.remove_batch([(b.slot, motif) for b, motif in requests])
+
+
 def gpu_batch_score(requests):
     """`batch_score` for run_lockstep when every backend's scorer is a BinContext of ONE MultiBinScorer:
     all pending motifs of all searches go into a single scan launch."""
@@ -303,10 +328,11 @@ def run(coroutine, backend):
         return stop.value
 
 
-def run_lockstep(searches: list, batch_score=None) -> list:
-    """Advance many searches together.  `searches` = [(coroutine, backend)].  Each round the pending "score"
-    requests of all searches are answered by ONE call `batch_score([(backend, motifs), ...])` (one K2 launch
-    with a job per search); window requests go to each search's own backend.  Returns the results in order."""
+def run_lockstep(searches: list, batch_score=None, batch_expand=None, batch_remove=None) -> list:
+    """Advance many searches together.  `searches` = [(coroutine, backend)].  Each round the pending requests
+    of one kind are answered by ONE call of the matching hook -- `batch_score([(backend, motifs)])` (one K2
+    launch with a job per search), `batch_expand` / `batch_remove` ([(backend, motif)], one K4 launch over a
+    shared WindowPool); kinds without a hook go to each search's own backend.  Returns the results in order."""
     n = len(searches)
     results: list = [None] * n
     pending: dict[int, tuple] = {}
@@ -317,10 +343,10 @@ def run_lockstep(searches: list, batch_score=None) -> list:
             results[i] = stop.value
     while pending:
         answers: dict[int, object] = {}
-        score_ids = [i for i, r in pending.items() if r[0] == "score"]
-        if batch_score is not None and len(score_ids) > 1:
-            replies = batch_score([(searches[i][1], pending[i][1]) for i in score_ids])
-            answers.update(zip(score_ids, replies))
+        for kind, hook in (("score", batch_score), ("expand", batch_expand), ("remove", batch_remove)):
+            ids = [i for i, r in pending.items() if r[0] == kind]
+            if hook is not None and len(ids) > 1:
+                answers.update(zip(ids, hook([(searches[i][1], pending[i][1]) for i in ids])))
         for i, r in pending.items():
             if i not in answers:
                 answers[i] = searches[i][1].handle(r)

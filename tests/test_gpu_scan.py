@@ -24,7 +24,9 @@ def _strand_str(codes):
 
 MOTIFS = [("GATC", 1), ("A", 0), ("CC[AT]GG", 1), ("G[AG].GAAG[CT]", 5), ("GCAC......GTT", 2), ("AAC......GTGC", 1),
           ("[ACG]A[CT]", 1), ("C", 0), ("TTAA", 3), ("A..............................T", 0),
-          ("A........................................................C", 0), ("ACGT", 0), ("ACG[AT]", 2)]
+          ("A........................................................C", 0), ("ACGT", 0), ("ACG[AT]", 2),
+          ("C" + "." * 31 + "A", 32), ("C" + "." * 30 + "A", 31), ("G" + "." * 40 + "A" + "." * 10 + "C", 41),
+          ("T" + "." * 60 + "A", 61), ("A" + "." * 60 + "G", 0), ("[CG]" + "." * 33 + "A..T", 34)]
 
 
 def test_subseq_indices_reference_kat(nmb):

@@ -95,8 +95,13 @@ def test_lockstep_multibin_search(nmb):
                                     score_threshold=spec["score_threshold"], trace=t)
         return co, backend, t
 
+    from nanomotif_b200 import growth
+
     searches = [make(b) for b in range(3)]
-    results = search.run_lockstep([(co, be) for co, be, _ in searches], search.gpu_batch_score)
+    # all windows in one pool: score, expand and remove requests of the three searches are each ONE launch
+    pool = growth.WindowPool([be.windows for _, be, _ in searches])
+    pooled = [(co, search.PoolBackend(be.scorer, pool, slot)) for slot, (co, be, _) in enumerate(searches)]
+    results = search.run_lockstep(pooled, search.gpu_batch_score, search.gpu_batch_expand, search.gpu_batch_remove)
     check_against_trace(trace, results[0], searches[0][2])  # bin 0 is the golden input
     for b in (1, 2):  # the others equal their own sequential runs
         co, be, t = make(b)
