@@ -78,7 +78,7 @@ def build_cfg2(seed: int, length: int = CFG2_LEN, n_motifs: int = MOTIFS_PER_MOD
     seq = synth.random_sequence(rng, length, CFG2_GC, 1e-6)
     pile = synth.synth_pileup(seq, rng, depth=CFG2_DEPTH, mod_types=MOD_TYPES)
     work = []  # (motif string, mod_pos, mod type index)
-    mrng = np.random.default_rng(1000 + seed)
+    mrng = np.random.default_rng(1001)  # the motif work list is replicated: every rank scores the SAME motifs
     for mt, name in enumerate(MOD_TYPES):
         for s, p in synth.random_motifs(mrng, n_motifs, synth.CANONICAL[name]):
             work.append((s, p, mt))
