@@ -151,16 +151,18 @@ def e2e_step(host, device, world=1):
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling during the timed region (rank 0 samples every GPU of the job)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, indices):
         self.proc = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
-                 str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 ",".join(str(i) for i in indices)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -174,22 +176,26 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons = {}, [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in out.strip().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                sm.setdefault(int(parts[0]), []).append(float(parts[1]))
+                mx.append(float(parts[2]))
             except ValueError:
                 continue
-            for name, v in zip(names, parts[3:7]):
+            for name, v in zip(names, parts[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        per_gpu = {g: float(np.median(v)) for g, v in sorted(sm.items())}
+        out = {"sm_mhz": min(per_gpu.values()) if per_gpu else None, "sm_max_mhz": float(max(mx)) if mx else None,
+               "samples": sum(len(v) for v in sm.values()), "reasons": sorted(reasons)}
+        if len(per_gpu) > 1:
+            out["per_gpu_sm_mhz"] = per_gpu  # the step time is the max over ranks: the slowest GPU sets it
+        return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -349,7 +355,7 @@ def main():
     for _ in range(args.warmup):
         full_step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(range(world)) if rank == 0 else None
     step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     scan_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
