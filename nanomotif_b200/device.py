@@ -278,35 +278,47 @@ class MotifPrograms:
         with torch.cuda.device(device):
             self.motifs_d = _to_device(packed.view(np.uint8).reshape(-1), device)
             self.programs = torch.empty(max(1, self.n) * lib.nmb_program_bytes(), dtype=torch.uint8, device=device)
-            check(lib.nmb_compile_motifs(ptr(self.motifs_d), self.n, ptr(self.programs), _stream()),
-                  "nmb_compile_motifs")
+            self.compile()
+
+    def compile(self) -> None:
+        """(Re)run the motif compiler on the device-resident motif records (one small launch, no copies)."""
+        check(lib.nmb_compile_motifs(ptr(self.motifs_d), self.n, ptr(self.programs), _stream()), "nmb_compile_motifs")
 
 
-def scan_count(assembly: DeviceAssembly, pileup: DevicePileup, programs: MotifPrograms, jobs: np.ndarray,
-               n_out_rows: int, motifs_per_item: int | None = None, contig_group: torch.Tensor | None = None,
-               grid_ctas: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
-    """Launch K2 for a batch of jobs.  Returns the int64 device tensor [n_out_rows, 4]
-    (n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'); nothing is synchronised."""
-    d = assembly.device
-    with torch.cuda.device(d):
-        mpi = motifs_per_item or choose_motifs_per_item(jobs, sm_count(d))
+class PreparedJobs:
+    """A job table resident on the device (item offsets filled in), reusable across launches."""
+
+    def __init__(self, jobs: np.ndarray, device: torch.device, motifs_per_item: int | None = None):
+        self.mpi = motifs_per_item or choose_motifs_per_item(jobs, sm_count(device))
         jobs = jobs.copy()
-        items = jobs["tile_count"].astype(np.int64) * (-(-jobs["motif_count"].astype(np.int64) // mpi))
+        items = jobs["tile_count"].astype(np.int64) * (-(-jobs["motif_count"].astype(np.int64) // self.mpi))
         offs = np.zeros(len(jobs), dtype=np.int64)
         offs[1:] = np.cumsum(items)[:-1]
-        n_items = int(items.sum())
-        if n_items >= 2**31:
+        self.n_items = int(items.sum())
+        if self.n_items >= 2**31:
             raise ValueError("too many work items for one launch")
         jobs["item_offset"] = offs.astype(np.int32)
-        jobs_d = _to_device(jobs.view(np.uint8).reshape(-1), d)
+        self.n_jobs = len(jobs)
+        with torch.cuda.device(device):
+            self.jobs_d = _to_device(jobs.view(np.uint8).reshape(-1), device)
+
+
+def scan_count(assembly: DeviceAssembly, pileup: DevicePileup, programs: MotifPrograms, jobs,
+               n_out_rows: int, motifs_per_item: int | None = None, contig_group: torch.Tensor | None = None,
+               grid_ctas: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Launch K2 for a batch of jobs (a numpy job table, or PreparedJobs already on the device).  Returns the
+    int64 device tensor [n_out_rows, 4] (n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'); nothing is synchronised."""
+    d = assembly.device
+    with torch.cuda.device(d):
+        prepared = jobs if isinstance(jobs, PreparedJobs) else PreparedJobs(jobs, d, motifs_per_item)
         if out is None:
             out = torch.zeros((n_out_rows, 4), dtype=torch.int64, device=d)
         view = assembly.view()
         check(
-            lib.nmb_scan_count(C.byref(view), ptr(pileup.class_records), ptr(programs.programs), ptr(jobs_d),
-                               len(jobs), n_items, mpi, programs.max_len, ptr(contig_group), ptr(out), grid_ctas,
-                               _stream()),
+            lib.nmb_scan_count(C.byref(view), ptr(pileup.class_records), ptr(programs.programs), ptr(prepared.jobs_d),
+                               prepared.n_jobs, prepared.n_items, prepared.mpi, programs.max_len, ptr(contig_group),
+                               ptr(out), grid_ctas, _stream()),
             "nmb_scan_count",
         )
-        # jobs_d goes back to torch's caching allocator; reuse is ordered on this same stream
+        # a temporary job table goes back to torch's caching allocator; reuse is ordered on this same stream
     return out
