@@ -25,11 +25,17 @@
  *   NMB_TILE_BP (65536) positions.  Per tile t:
  *     seq record  : uint32 x[NMB_TILE_WORDS+8], y[NMB_TILE_WORDS+8], int32 chunk_info[128]
  *                   x = high code bit, y = low code bit (A=0 T=1 G=2 C=3, nanomotif/constants.py:1);
- *                   4 halo words of the neighbouring tiles are duplicated on each side so that one
- *                   bulk copy (TMA) brings a self-contained tile into shared memory.
- *                   chunk_info[q] = contig id of 512-bp chunk q, bit 30 set when the chunk (or its
- *                   halo) touches a non-ACGT letter, -1 for an empty chunk.
- *     class record: uint32 plane[4][NMB_TILE_WORDS] per mod type:
+ *                   4 halo words of the neighbouring tiles are duplicated on each side (natural
+ *                   order) so that one bulk copy (TMA) brings a self-contained tile into shared memory.
+ *                   The 2048 body words of a plane are LANE-INTERLEAVED: word w of the tile (chunk
+ *                   t = w/16, word j = w%16 of the chunk) is stored at slot NMB_WORD_SLOT(w) =
+ *                   (j/4)*512 + t*4 + j%4, so that the 128 lanes of a CTA, each owning one chunk, read
+ *                   consecutive 16-byte vectors (bank-conflict-free LDS.128, coalesced LDG.128).
+ *                   chunk_info[q] = contig id (< 2^28) of 512-bp chunk q, -1 for an empty chunk; bit 30
+ *                   set when the chunk or a neighbouring chunk holds a non-ACGT letter of a contig,
+ *                   else bit 29 set when the chunk or its two halo words touch inter-contig padding
+ *                   (bit 28: the chunk itself holds a non-ACGT letter).
+ *     class record: uint32 plane[4][NMB_TILE_WORDS] per mod type, each plane lane-interleaved as above:
  *                   0 = methylated '+', 1 = unmethylated '+', 2 = methylated '-', 3 = unmethylated '-'
  *                   (fraction_mod >= high / <= low, nanomotif/find_motifs_bin.py:1308-1314).
  *   The non-ACGT plane is a flat uint32 array with 4 leading pad words.
@@ -60,6 +66,8 @@ extern "C" {
 #define NMB_SEQ_PLANE_WORDS (NMB_TILE_WORDS + 2 * NMB_HALO_WORDS)           /* 2056 */
 #define NMB_SEQ_REC_WORDS (2 * NMB_SEQ_PLANE_WORDS + NMB_TILE_CHUNKS)       /* 4240 */
 #define NMB_CLS_REC_WORDS (4 * NMB_TILE_WORDS)                              /* 8192 */
+/* slot of tile word w (0..2047) inside a lane-interleaved plane */
+#define NMB_WORD_SLOT(w) ((((w) & 12) << 7) | (((w) >> 4) << 2) | ((w) & 3))
 #define NMB_MIN_GAP_BP 64
 #define NMB_MAX_MOTIF_LEN 62
 #define NMB_MAX_WINDOW 61

@@ -24,6 +24,12 @@ HALO_WORDS = 4
 SEQ_PLANE_WORDS = TILE_WORDS + 2 * HALO_WORDS
 SEQ_REC_WORDS = 2 * SEQ_PLANE_WORDS + TILE_CHUNKS
 CLS_REC_WORDS = 4 * TILE_WORDS
+# lane-interleaved planes (nmb200.h NMB_WORD_SLOT): WORD_SLOT[w] = slot of tile word w, so
+# `plane_in_slot_order[..., WORD_SLOT]` is the plane in natural word order
+_w = np.arange(TILE_WORDS)
+WORD_SLOT = ((_w & 12) << 7) | ((_w >> 4) << 2) | (_w & 3)
+SLOT_WORD = np.argsort(WORD_SLOT)  # inverse: natural_plane[..., SLOT_WORD] is the plane in slot order
+del _w
 MIN_GAP_BP = 64
 MAX_MOTIF_LEN = 62
 MAX_WINDOW = 61

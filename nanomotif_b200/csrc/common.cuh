@@ -50,10 +50,16 @@ constexpr int kClsRecWords = NMB_CLS_REC_WORDS;
 constexpr int kSeqRecBytes = kSeqRecWords * 4;     // 16960
 constexpr int kClsRecBytes = kClsRecWords * 4;     // 32768
 constexpr int kMaxLen = NMB_MAX_MOTIF_LEN;
-constexpr int kChunkFlagN = 1 << 30;
-constexpr int kChunkIdMask = (1 << 30) - 1;
+// chunk_info flags (nmb200.h): the lane's words [-2, 18) ...
+constexpr int kChunkFlagN = 1 << 30;      // ... may hold a non-ACGT LETTER of a contig: every constrained position must test it
+constexpr int kChunkFlagEdge = 1 << 29;   // ... hold inter-contig padding only: first and last motif position must avoid it
+constexpr int kChunkFlagLetter = 1 << 28; // the chunk itself holds a non-ACGT letter (written by the packer, input of the two above)
+constexpr int kChunkIdMask = (1 << 28) - 1;
 
 static_assert(kTileWords == kTileChunks * kChunkWords, "tile = 128 lane chunks");
+static_assert(kChunkWords == 16 && kTileChunks == 128, "NMB_WORD_SLOT assumes 128 chunks of 16 words");
+constexpr int kSlotStride = kTileChunks * 4;       // words between the uint4 vectors of one lane (512)
+__host__ __device__ constexpr int word_slot(int w) { return NMB_WORD_SLOT(w); }
 static_assert(kChunkWords % 4 == 0 && kChunkWords <= 32, "lane chunk is a whole number of uint4");
 static_assert(kSeqRecBytes % 16 == 0 && kClsRecBytes % 16 == 0, "bulk copies need 16-byte sizes");
 

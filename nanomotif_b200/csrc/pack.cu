@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) pack_sequence_kernel(
             if (local0 >= len) c = -1;
         }
         uint32_t my_x = 0, my_y = 0, my_n = 0xFFFFFFFFu;
+        bool letter = false;  // a non-ACGT letter INSIDE the contig (padding does not count)
 #pragma unroll
         for (int w = 0; w < kChunkWords; ++w) {
             int code = 4;
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) pack_sequence_kernel(
                 if (local < len) {
                     int ch = ascii[aoff + local] & 0xDF;  // upper-case (seq.py:55)
                     code = ch == 'A' ? 0 : ch == 'T' ? 1 : ch == 'G' ? 2 : ch == 'C' ? 3 : 4;
+                    letter |= code == 4;
                 }
             }
             uint32_t xb = __ballot_sync(0xFFFFFFFFu, (code & 2) && code < 4);
@@ -53,8 +55,8 @@ __global__ void __launch_bounds__(256) pack_sequence_kernel(
             const int64_t tile = gw / kTileWords;
             const int wt = (int)(gw % kTileWords);
             uint32_t *rec = seq_records + tile * kSeqRecWords;
-            rec[kHalo + wt] = my_x;
-            rec[kSeqPlaneWords + kHalo + wt] = my_y;
+            rec[kHalo + word_slot(wt)] = my_x;
+            rec[kSeqPlaneWords + kHalo + word_slot(wt)] = my_y;
             if (wt < kHalo) {  // also the right halo of the previous tile / zero left edge
                 if (tile > 0) {
                     uint32_t *prev = rec - kSeqRecWords;
@@ -78,16 +80,24 @@ __global__ void __launch_bounds__(256) pack_sequence_kernel(
             }
             nonacgt[kHalo + gw] = my_n;
         }
+        letter = __any_sync(0xFFFFFFFFu, letter);
         if (lane == 0) {
             const int64_t tile = q / kTileChunks;
             seq_records[tile * kSeqRecWords + 2 * kSeqPlaneWords + (int)(q % kTileChunks)] =
-                (uint32_t)c;
+                (uint32_t)(c >= 0 && letter ? (c | kChunkFlagLetter) : c);
         }
     }
 }
 
-// Second pass: a chunk needs the non-ACGT path when any flagged letter lies within its words or
-// the two halo words on either side (motif length <= 62 < 64).
+// Second pass: which matcher a chunk needs.  A lane reads its 16 words plus two halo words on either side
+// (motif length <= 62 < 64).  Non-ACGT LETTERS of a contig within that reach (decided per neighbouring
+// chunk, conservatively) need the full path that tests every constrained position; inter-contig padding
+// alone needs only the cheap edge treatment (first and last motif position must lie in the contig: padding
+// runs are >= 64 > motif length, so a match cannot span one).
+__device__ __forceinline__ uint32_t *chunk_info_ptr(uint32_t *seq_records, int64_t q) {
+    return seq_records + (q / kTileChunks) * kSeqRecWords + 2 * kSeqPlaneWords + (int)(q % kTileChunks);
+}
+
 __global__ void __launch_bounds__(256) chunk_flags_kernel(int n_tiles,
                                                           uint32_t *__restrict__ seq_records,
                                                           uint32_t *__restrict__ nonacgt) {
@@ -108,10 +118,17 @@ __global__ void __launch_bounds__(256) chunk_flags_kernel(int n_tiles,
         int64_t gw = q * kChunkWords + i;
         any |= (gw < 0 || gw >= n_words) ? 0xFFFFFFFFu : p[i];
     }
-    uint32_t *info = seq_records + (q / kTileChunks) * kSeqRecWords + 2 * kSeqPlaneWords +
-                     (int)(q % kTileChunks);
-    int c = (int)*info;
-    if (c >= 0 && any) *info = (uint32_t)(c | kChunkFlagN);
+    uint32_t *info = chunk_info_ptr(seq_records, q);
+    // neighbours update their own words concurrently, but only bits 29/30: bit 28 is stable
+    const int c = (int)*(volatile uint32_t *)info;
+    if (c < 0 || !any) return;
+    bool letter = c & kChunkFlagLetter;
+    for (int dq = -1; dq <= 1; dq += 2) {
+        if (q + dq < 0 || q + dq >= n_chunks) continue;
+        const int cn = (int)*(volatile uint32_t *)chunk_info_ptr(seq_records, q + dq);
+        letter |= cn >= 0 && (cn & kChunkFlagLetter);
+    }
+    atomicOr(info, (uint32_t)(letter ? kChunkFlagN : kChunkFlagEdge));
 }
 
 __global__ void __launch_bounds__(256) class_planes_kernel(
@@ -134,7 +151,7 @@ __global__ void __launch_bounds__(256) class_planes_kernel(
         if (!is_mod && !is_non) continue;
         const int64_t g = __ldg(contig_start + c) + p;
         const int64_t tile = g >> 16;
-        const int w = (int)((g >> 5) & (kTileWords - 1));
+        const int w = word_slot((int)((g >> 5) & (kTileWords - 1)));
         const uint32_t bit = 1u << (g & 31);
         uint32_t *rec = cls + ((int64_t)mt * n_tiles + tile) * kClsRecWords +
                         (strand[r] ? 2 : 0) * kTileWords + w;
@@ -169,7 +186,7 @@ __global__ void __launch_bounds__(256) class_planes_compact_kernel(
         if (mt >= n_modtypes) continue;
         const int64_t g = __ldg(contig_start + lo) + p;
         uint32_t *rec = cls + ((int64_t)mt * n_tiles + (g >> 16)) * kClsRecWords + ((f & 1) ? 2 : 0) * kTileWords +
-                        (int)((g >> 5) & (kTileWords - 1));
+                        word_slot((int)((g >> 5) & (kTileWords - 1)));
         const uint32_t bit = 1u << (g & 31);
         if (is_mod) atomicOr(rec, bit);
         if (is_non) atomicOr(rec + kTileWords, bit);

@@ -11,6 +11,7 @@ namespace nmb {
 template <int H>
 __global__ void __launch_bounds__(kTileChunks) match_plane_kernel(
     const uint32_t *__restrict__ seq_records, const uint32_t *__restrict__ nonacgt,
+    const int64_t *__restrict__ contig_start, const int64_t *__restrict__ contig_len,
     const Program *__restrict__ program, int tile_begin, uint32_t *__restrict__ match_plane) {
     const int tid = threadIdx.x;
     const int tile = tile_begin + blockIdx.x;
@@ -22,16 +23,19 @@ __global__ void __launch_bounds__(kTileChunks) match_plane_kernel(
     const bool warp_any = __any_sync(0xFFFFFFFFu, info >= 0);
     if (warp_any) {
         const bool warp_n = __any_sync(0xFFFFFFFFu, info >= 0 && (info & kChunkFlagN));
+        const bool warp_edge = __any_sync(0xFFFFFFFFu, info >= 0 && (info & kChunkFlagEdge));
         const ProgramView pv = load_program(program);
-        const uint32_t *lx = rec + kHalo + tid * NW, *ly = rec + kSeqPlaneWords + kHalo + tid * NW;
+        const uint32_t *px = rec, *py = rec + kSeqPlaneWords;
         if (warp_n) {
             LaneSeq<H, true> q;
-            load_xyn<H>(lx, ly, nonacgt + kHalo + (size_t)tile * kTileWords + tid * NW - H, q);
-            match_words<H, true>(pv, q, m);
+            load_xyn<H>(px, py, tid, nonacgt + kHalo + (size_t)tile * kTileWords + tid * NW - H, q);
+            const LaneEdge edge = {0, false, false};
+            match_words<H, true>(pv, q, m, edge);
         } else {
             LaneSeq<H, false> q;
-            load_xy<H>(lx, ly, q);
-            match_words<H, false>(pv, q, m);
+            load_xy<H>(px, py, tid, q);
+            const LaneEdge edge = lane_edge(warp_edge, info, (int64_t)tile * kTileChunks + tid, contig_start, contig_len);
+            match_words<H, false>(pv, q, m, edge);
         }
         if (info < 0) {
 #pragma unroll
@@ -178,10 +182,10 @@ int nmb_match_plane(const nmb_assembly *a, const void *programs, int32_t motif_i
     cudaStream_t s = (cudaStream_t)stream;
     if (motif_len <= 32)  // one halo word covers a total shift (and a mod_pos) of at most 31
         nmb::match_plane_kernel<1><<<tile_count, nmb::kTileChunks, 0, s>>>(
-            a->seq_records, a->nonacgt, prog, tile_begin, match_plane);
+            a->seq_records, a->nonacgt, a->contig_start, a->contig_len, prog, tile_begin, match_plane);
     else
         nmb::match_plane_kernel<2><<<tile_count, nmb::kTileChunks, 0, s>>>(
-            a->seq_records, a->nonacgt, prog, tile_begin, match_plane);
+            a->seq_records, a->nonacgt, a->contig_start, a->contig_len, prog, tile_begin, match_plane);
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;
 }

@@ -28,6 +28,7 @@ struct ScanParams {
     const Program *programs;
     const nmb_job *jobs;
     const int32_t *contig_group;
+    const int64_t *contig_start, *contig_len;
     unsigned long long *out;
     int n_jobs, n_items, mpi, n_tiles;
 };
@@ -62,7 +63,8 @@ __device__ __forceinline__ int group_of(const nmb_job &job, int contig, const in
 // Evaluate the item's motifs on this lane's chunk and accumulate the four counters.
 template <int H, bool PLANES>
 __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job &job, const ItemMeta &meta,
-                                             const LaneSeq<H, PLANES> &q, const uint32_t *cl, bool valid,
+                                             const LaneSeq<H, PLANES> &q, const LaneEdge &edge, const uint32_t *cl,
+                                             bool valid,
                                              bool uniform, unsigned peers, bool leader, int g, int primary,
                                              uint32_t (*acc)[4]) {
     const int m_begin = job.motif_begin + meta.mblk * p.mpi;
@@ -72,7 +74,7 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
         // ONE program per motif serves both strands (scan.cuh: run_chain_pair)
         const ProgramView pv = load_program(p.programs + (size_t)(m_begin + mi) * 2);
         uint32_t c[NW + 2 * H], d[NW + 2 * H];
-        if (!run_chain_pair<H, PLANES>(pv, q, c, d)) continue;  // no occurrence in this warp's chunk
+        if (!run_chain_pair<H, PLANES>(pv, q, c, d, edge)) continue;  // no occurrence in this warp's chunk
         const bool far = pv.mod_pos >= 32;  // only possible when H == 2
         const int sh = pv.mod_pos & 31;
         uint32_t cnt[4] = {0, 0, 0, 0};  // n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'
@@ -80,7 +82,8 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
         for (int h = 0; h < NW; h += 4) {
             uint4 pl[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) pl[k] = *reinterpret_cast<const uint4 *>(cl + k * kTileWords + h);
+            for (int k = 0; k < 4; ++k)
+                pl[k] = *reinterpret_cast<const uint4 *>(cl + k * kTileWords + (h >> 2) * kSlotStride);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t mf = aligned_word<H>(c, h + k, sh, far);
@@ -188,18 +191,23 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_count_kernel(const ScanP
                 peers = __match_any_sync(0xFFFFFFFFu, g);
                 leader = valid && lane == __ffs(peers) - 1;
             }
+            // matcher variant (scan.cuh): non-ACGT letters of a contig in reach -> full test at every step
+            // (rare); inter-contig padding in reach -> plain steps, finished chains clipped to the contig
             const bool warp_n = __any_sync(0xFFFFFFFFu, valid && (info & kChunkFlagN));
+            const bool warp_edge = __any_sync(0xFFFFFFFFu, valid && (info & kChunkFlagEdge));
 
-            const uint32_t *lx = sx + kHalo + tid * NW, *ly = sy + kHalo + tid * NW;
-            const uint32_t *cl = scls + tid * NW;
-            if (warp_n) {  // chunk (or halo) touches non-ACGT letters / contig padding
+            const uint32_t *cl = scls + tid * 4;  // lane-interleaved planes: vector v at cl + v * kSlotStride
+            if (warp_n) {
                 LaneSeq<H, true> q;
-                load_xyn<H>(lx, ly, p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H, q);
-                score_motifs<H, true>(p, job, meta, q, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
+                load_xyn<H>(sx, sy, tid, p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H, q);
+                const LaneEdge edge = {0, false, false};
+                score_motifs<H, true>(p, job, meta, q, edge, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
             } else {
                 LaneSeq<H, false> q;
-                load_xy<H>(lx, ly, q);
-                score_motifs<H, false>(p, job, meta, q, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
+                load_xy<H>(sx, sy, tid, q);
+                const LaneEdge edge = lane_edge(warp_edge, info, (int64_t)meta.tile * kTileChunks + tid,
+                                                p.contig_start, p.contig_len);
+                score_motifs<H, false>(p, job, meta, q, edge, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
             }
         }
         __syncthreads();  // everyone is done with the tile and with s_acc[par]
@@ -285,6 +293,8 @@ int nmb_scan_count(const nmb_assembly *a, const uint32_t *class_records, const v
     p.programs = (const nmb::Program *)programs;
     p.jobs = jobs;
     p.contig_group = contig_group;
+    p.contig_start = a->contig_start;
+    p.contig_len = a->contig_len;
     p.out = (unsigned long long *)out;
     p.n_jobs = n_jobs;
     p.n_items = n_items;

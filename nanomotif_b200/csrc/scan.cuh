@@ -12,11 +12,15 @@
 // Two register representations of the sequence:
 //   XY   the raw planes; the indicator of ANY allowed-set is a two-variable boolean function of (x, y),
 //        so it is folded into the lop3 immediate: C <- lop3<set>(x, y, shifted C).  Used by warps whose
-//        chunks are pure ACGT.
-//   XYN  additionally the non-ACGT plane n, ANDed out of every indicator so that such letters (and the
-//        inter-contig padding) fail every constrained position and only match '.', the regex
-//        semantics of the reference.  One extra logic op per word and
-//        step; used only by warps that touch a flagged chunk.
+//        chunks hold no non-ACGT letter.  Inter-contig padding is stored as code 0 and kept out by
+//        CLIPPING the finished chains (LaneEdge below): padding runs are >= 64 > motif length, so an
+//        occurrence overlaps padding iff its first or last position does, i.e. iff its start lies outside
+//        [contig start, contig end - len].  That is ~3 integer ops per word and motif, only in warps that
+//        touch a contig edge, instead of a second code path.
+//   XYN  additionally the non-ACGT plane n, ANDed out of every indicator so that such letters fail every
+//        constrained position and only match '.', the regex semantics of the reference (SURVEY.md
+//        Appendix B item 5).  One extra logic op per word and step; used only by warps whose chunks (or
+//        neighbouring chunks) hold a non-ACGT letter of a contig -- rare.
 // The branch on the base is uniform across the CTA (it depends on the motif only).
 #pragma once
 #include "common.cuh"
@@ -55,11 +59,49 @@ struct LaneSeq<H, true> {
     }
 };
 
+// Where the lane's chunk sits in its contig (meaningful in warps that touch inter-contig padding).
+struct LaneEdge {
+    int hi;      // contig end relative to the chunk's first position (clamped; >= 32 * (NW + 2) when far away)
+    bool first;  // the chunk is the first of its contig: everything left of it is padding
+    bool edge;   // warp-uniform: some lane of the warp touches padding, clip the chains
+};
+
+// bits k of a word starting at bit offset b (relative to the chunk) with b + k < hi / b + k >= lo
+__device__ __forceinline__ uint32_t bits_below(int b, int hi) {
+    return __funnelshift_rc(0xFFFFFFFFu, 0u, max(b + 32 - hi, 0));  // shift clamps at 32 -> 0
+}
+__device__ __forceinline__ uint32_t bits_from(int b, int lo) {
+    return __funnelshift_lc(0u, 0xFFFFFFFFu, max(lo - b, 0));
+}
+
+// Start-aligned chain of a motif of `len` positions: keep starts p with contig_start <= p <= contig_end - len.
+template <int H>
+__device__ __forceinline__ void clip_start_aligned(uint32_t (&c)[NW + 2 * H], const LaneEdge &e, int len) {
+    const int hi = e.hi - (len - 1);
+#pragma unroll
+    for (int i = 0; i < NW + 2 * H; ++i) {
+        c[i] &= bits_below(32 * (i - H), hi);
+        if (i < H && e.first) c[i] = 0u;
+    }
+}
+// End-aligned chain (reverse-complement twin), stored reversed (dr[j] = D[CW-1-j]): keep ends q with
+// contig_start + len - 1 <= q < contig_end.  Words left of the chunk are never read (aligned_word_rc).
+template <int H>
+__device__ __forceinline__ void clip_end_aligned_rev(uint32_t (&dr)[NW + 2 * H], const LaneEdge &e, int len) {
+    constexpr int CW = NW + 2 * H;
+#pragma unroll
+    for (int i = H; i < CW; ++i) {
+        uint32_t m = bits_below(32 * (i - H), e.hi);
+        if (i < 2 * H && e.first) m &= bits_from(32 * (i - H), len - 1);  // len - 1 <= 32 * H - 1
+        dr[CW - 1 - i] &= m;
+    }
+}
+
 // Program (common.cuh): header n | mod_pos << 8 | len << 16, then n entries in processing order
 // (last constrained position first).  entry = set code | (distance to the previous entry) << 8.
 struct ProgramView {
     const uint16_t *ent;
-    int n, mod_pos;
+    int n, mod_pos, len;
 };
 
 __device__ __forceinline__ ProgramView load_program(const Program *p) {
@@ -67,6 +109,7 @@ __device__ __forceinline__ ProgramView load_program(const Program *p) {
     ProgramView v;
     v.n = hdr & 0xFF;
     v.mod_pos = (hdr >> 8) & 0xFF;
+    v.len = (hdr >> 16) & 0xFF;
     v.ent = p->ent;
     return v;
 }
@@ -92,7 +135,7 @@ constexpr int kEntShift32 = 0x10;
 // valid for words [-H, NW).
 template <int H, bool HASN>
 __device__ __forceinline__ void run_chain(const ProgramView &pv, const LaneSeq<H, HASN> &q,
-                                          uint32_t (&c)[NW + 2 * H]) {
+                                          uint32_t (&c)[NW + 2 * H], const LaneEdge &edge) {
 #pragma unroll
     for (int i = 0; i < NW + 2 * H; ++i) c[i] = 0xFFFFFFFFu;
     uint32_t e = __ldg(pv.ent);
@@ -120,6 +163,7 @@ __device__ __forceinline__ void run_chain(const ProgramView &pv, const LaneSeq<H
                 break;
         }
     }
+    if (!HASN && edge.edge) clip_start_aligned<H>(c, edge, pv.len);
 }
 
 // Allowed-set of the complementary bases: A<->T (bits 0,1), G<->C (bits 2,3).
@@ -175,7 +219,8 @@ __device__ __forceinline__ bool chains_alive(const uint32_t (&c)[NW + 2 * H], co
 // whole popcount stage are skipped.  The test is warp-uniform.
 template <int H, bool HASN>
 __device__ __forceinline__ bool run_chain_pair(const ProgramView &pv, const LaneSeq<H, HASN> &q,
-                                               uint32_t (&c)[NW + 2 * H], uint32_t (&d)[NW + 2 * H]) {
+                                               uint32_t (&c)[NW + 2 * H], uint32_t (&d)[NW + 2 * H],
+                                               const LaneEdge &edge) {
     uint32_t e = __ldg(pv.ent);
     {   // first entry (shift 0 by construction): the chains ARE the indicator planes
         const int code = e & 0xFF;
@@ -228,7 +273,12 @@ __device__ __forceinline__ bool run_chain_pair(const ProgramView &pv, const Lane
                 break;
         }
     }
-    return pv.n < 8 || chains_alive<H>(c, d);
+    if (pv.n >= 8 && !chains_alive<H>(c, d)) return false;
+    if (!HASN && edge.edge) {  // warp-uniform
+        clip_start_aligned<H>(c, edge, pv.len);
+        clip_end_aligned_rev<H>(d, edge, pv.len);
+    }
+    return true;
 }
 
 // Word k of the reverse-complement match plane aligned at ITS modified base: M_rc[p] = D[p + mod_pos]
@@ -250,45 +300,67 @@ __device__ __forceinline__ uint32_t aligned_word(const uint32_t (&c)[NW + 2 * H]
 
 template <int H, bool HASN>
 __device__ __forceinline__ void match_words(const ProgramView &pv, const LaneSeq<H, HASN> &q,
-                                            uint32_t (&m)[NW]) {
+                                            uint32_t (&m)[NW], const LaneEdge &edge) {
     uint32_t c[NW + 2 * H];
-    run_chain<H, HASN>(pv, q, c);
+    run_chain<H, HASN>(pv, q, c, edge);
     const bool far = pv.mod_pos >= 32;  // only possible when H == 2
     const int sh = pv.mod_pos & 31;
 #pragma unroll
     for (int k = 0; k < NW; ++k) m[k] = aligned_word<H>(c, k, sh, far);
 }
 
-// Load the lane's words [-H, NW+H) of one plane; `base` points at lane word 0 and is 16-byte
-// aligned (shared or global memory).
+// Load chunk t's words [-H, NW+H) of one record plane (shared or global memory).  `plane` points at the
+// plane's left halo (16-byte aligned): kHalo halo words in natural order, the 2048 body words
+// lane-interleaved (nmb200.h NMB_WORD_SLOT: the four uint4 vectors of chunk t sit at body + v*512 + t*4,
+// so the lanes of a warp read consecutive 16-byte vectors), then kHalo right halo words.
 template <int H>
-__device__ __forceinline__ void load_plane(const uint32_t *base, uint32_t (&w)[NW + 2 * H]) {
+__device__ __forceinline__ void load_plane(const uint32_t *plane, int t, uint32_t (&w)[NW + 2 * H]) {
+    const uint32_t *body = plane + kHalo;
 #pragma unroll
     for (int v = 0; v < NW / 4; ++v) {
-        const uint4 a = *reinterpret_cast<const uint4 *>(base + 4 * v);
+        const uint4 a = *reinterpret_cast<const uint4 *>(body + v * kSlotStride + t * 4);
         w[H + 4 * v + 0] = a.x; w[H + 4 * v + 1] = a.y; w[H + 4 * v + 2] = a.z; w[H + 4 * v + 3] = a.w;
     }
+    // halo: the last H words of chunk t-1 / the first H words of chunk t+1 (record halo at the tile edges)
+    const uint32_t *pl = t > 0 ? body + (NW / 4 - 1) * kSlotStride + (t - 1) * 4 + (4 - H) : plane + (kHalo - H);
+    const uint32_t *pr = t + 1 < kTileChunks ? body + (t + 1) * 4 : body + kTileWords;
 #pragma unroll
     for (int i = 0; i < H; ++i) {
-        w[i] = base[i - H];
-        w[NW + H + i] = base[NW + i];
+        w[i] = pl[i];
+        w[NW + H + i] = pr[i];
     }
 }
 
-// sx / sy point at lane word 0 of the x and y planes (shared or global); gn at word -H of the
-// non-ACGT plane (global).
+// px / py point at the x and y planes of a sequence record (shared or global); gn at word -H of the
+// chunk in the flat non-ACGT plane (global).
 template <int H>
-__device__ __forceinline__ void load_xy(const uint32_t *sx, const uint32_t *sy, LaneSeq<H, false> &q) {
-    load_plane<H>(sx, q.x);
-    load_plane<H>(sy, q.y);
+__device__ __forceinline__ void load_xy(const uint32_t *px, const uint32_t *py, int t, LaneSeq<H, false> &q) {
+    load_plane<H>(px, t, q.x);
+    load_plane<H>(py, t, q.y);
 }
 template <int H>
-__device__ __forceinline__ void load_xyn(const uint32_t *sx, const uint32_t *sy, const uint32_t *gn,
+__device__ __forceinline__ void load_xyn(const uint32_t *px, const uint32_t *py, int t, const uint32_t *gn,
                                          LaneSeq<H, true> &q) {
-    load_plane<H>(sx, q.x);
-    load_plane<H>(sy, q.y);
+    load_plane<H>(px, t, q.x);
+    load_plane<H>(py, t, q.y);
 #pragma unroll
     for (int i = 0; i < NW + 2 * H; ++i) q.n[i] = __ldg(gn + i);
+}
+
+// Position of global chunk `chunk` (info = its chunk_info word) inside its contig.
+__device__ __forceinline__ LaneEdge lane_edge(bool warp_edge, int info, int64_t chunk, const int64_t *contig_start,
+                                              const int64_t *contig_len) {
+    LaneEdge e;
+    e.edge = warp_edge;
+    e.hi = 1 << 20;
+    e.first = false;
+    if (warp_edge && info >= 0) {
+        const int c = info & kChunkIdMask;
+        const int64_t start = __ldg(contig_start + c), pos = chunk * NMB_CHUNK_BP;
+        e.hi = (int)min(start + __ldg(contig_len + c) - pos, (int64_t)(1 << 20));
+        e.first = pos == start;
+    }
+    return e;
 }
 
 }  // namespace nmb

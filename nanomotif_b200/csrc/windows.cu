@@ -17,7 +17,7 @@ __device__ __forceinline__ uint32_t seq_word(const uint32_t *seq_records, int pl
     if (gw < 0 || gw >= n_words) return 0u;
     const int64_t tile = gw / kTileWords;
     return __ldg(seq_records + tile * kSeqRecWords + plane * kSeqPlaneWords + kHalo +
-                 (int)(gw % kTileWords));
+                 word_slot((int)(gw % kTileWords)));
 }
 __device__ __forceinline__ uint32_t n_word(const uint32_t *nonacgt, int64_t gw, int64_t n_words) {
     if (gw < 0 || gw >= n_words) return 0xFFFFFFFFu;

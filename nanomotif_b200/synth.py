@@ -154,7 +154,9 @@ def device_workload(device, total_bp: int = 1_500_000_000, n_contigs: int = 1700
     rec = asm.seq_records.view(asm.n_tiles, _lib.SEQ_REC_WORDS)
     x = rec[:, _lib.HALO_WORDS:_lib.HALO_WORDS + _lib.TILE_WORDS]
     y = rec[:, _lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS:_lib.SEQ_PLANE_WORDS + _lib.HALO_WORDS + _lib.TILE_WORDS]
+    # x, y and the class planes are lane-interleaved (slot order); bring the flat non-ACGT plane to slot order
     nn = asm.nonacgt[_lib.HALO_WORDS:_lib.HALO_WORDS + asm.n_words].view(asm.n_tiles, _lib.TILE_WORDS)
+    nn = nn[:, torch.from_numpy(_lib.SLOT_WORD).to(device)]
     is_a, is_t = ~x & ~y & ~nn, ~x & y & ~nn
     cls = pile.class_records.view(n_modtypes, asm.n_tiles, 4, _lib.TILE_WORDS)
 

@@ -96,6 +96,7 @@ def test_counts_agree_with_match_planes(W):
             plane = torch.empty(asm.n_words, dtype=torch.int32, device=W["dev"])
             check(lib.nmb_match_plane(C.byref(view), ptr(progs.programs), 0, strand, progs.max_len, 0, asm.n_tiles,
                                       ptr(plane), _stream()))
-            m = plane.view(asm.n_tiles, _lib.TILE_WORDS)
+            # match planes are in natural word order, class planes lane-interleaved (NMB_WORD_SLOT)
+            m = plane.view(asm.n_tiles, _lib.TILE_WORDS)[:, torch.from_numpy(_lib.SLOT_WORD).to(W["dev"])]
             want += [_popcount(torch, m & cls[:, 2 * strand]), _popcount(torch, m & cls[:, 2 * strand + 1])]
         assert _scan(W, [(s, p)])[0, 0].tolist() == want

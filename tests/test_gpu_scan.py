@@ -150,3 +150,43 @@ def test_compact_rows_give_identical_class_planes(nmb, low, high):
     assert np.array_equal(grid >= high, np.arange(10001) >= k_hi) and np.array_equal(grid <= low, np.arange(10001) <= k_lo)
     # fractions off the two-decimal grid cannot be compacted: the float64 path stays in charge
     assert compact_rows(c["cid"], c["position"], c["strand"], c["fraction_mod"] + 1e-9, c["mod_type"], 3) is None
+
+
+def test_contig_edges_poly_a(nmb):
+    """Inter-contig padding is stored as code 0 (= 'A') and kept out by clipping the finished chains
+    (scan.cuh LaneEdge): poly-A / poly-T contigs whose ends sit on, before and after chunk and tile borders,
+    scored with motifs made of A / T only -- any occurrence leaking into the padding would be counted."""
+    rng = np.random.default_rng(21)
+    lengths = [1, 2, 31, 63, 64, 65, 450, 511, 512, 513, 540, 1023, 1024, 1025, 16384, 16383, 65536 - 513, 65536 - 1,
+               65536, 65537, 3 * 512 + 7, 70000, 33, 5]
+    contigs, cols = {}, {k: [] for k in ("contig", "position", "strand", "fraction_mod")}
+    for i, L in enumerate(lengths):
+        seq = np.full(L, ord("A") if i % 3 else ord("T"), dtype=np.uint8)
+        flip = rng.random(L) < 0.02  # a few other letters so that not everything matches
+        seq[flip] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(flip.sum()))]
+        name = f"edge_{i}"
+        contigs[name] = seq.tobytes().decode()
+        for strand in "+-":
+            cols["contig"].append(np.full(L, name, dtype=object))
+            cols["position"].append(np.arange(L, dtype=np.int64))
+            cols["strand"].append(np.full(L, strand, dtype=object))
+            cols["fraction_mod"].append(rng.choice([0.05, 0.5, 0.95], size=L))
+    pile = {k: np.concatenate(v) for k, v in cols.items()}
+    specs = [("A", 0), ("T", 0), ("AA", 1), ("AAAA", 0), ("AAAA", 3), ("TTTT", 1), ("A" * 31, 15), ("T" * 32, 31),
+             ("A......A", 0), ("A" + "." * 30 + "A", 31), ("T" + "." * 30 + "A", 0), ("A" + "." * 60 + "A", 0),
+             ("A" + "." * 60 + "A", 61), ("T" + "." * 45 + "TT", 46), ("A" * 40, 39), ("[AT]" * 33, 32)]
+    motifs = [nmb.Motif(s, p) for s, p in specs]
+    scorer = nmb.BinScorer(pile, contigs, 0.3, 0.7)
+    per = scorer.counts_by_strand(motifs, per_contig=True).cpu().numpy()
+    for mi, m in enumerate(motifs):
+        for ci, (name, seq) in enumerate(contigs.items()):
+            sel = pile["contig"] == name
+            a, b, d = O.motif_model_contig(pile["position"][sel], pile["strand"][sel], pile["fraction_mod"][sel], seq,
+                                           m.string, m.mod_position, 0.3, 0.7, fast=True)
+            want = [len(d["index_meth_fwd"]), len(d["index_nonmeth_fwd"]), len(d["index_meth_rev"]), len(d["index_nonmeth_rev"])]
+            assert per[mi, ci].tolist() == want, (m, name, len(seq))
+    assert per.sum() > 100000
+    # K3 shares the clip: positions on the same contigs
+    for s, _ in specs[:12]:
+        for name in ("edge_8", "edge_9", "edge_17", "edge_19"):
+            np.testing.assert_array_equal(nmb.subseq_indices(s, contigs[name]), O.subseq_indices(s, contigs[name]), err_msg=s)

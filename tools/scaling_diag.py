@@ -14,7 +14,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-seq, pile, work = bench.build_cfg2(1 + rank)
+seq, pile, work = bench.build_cfg2(1 + (rank + int(os.environ.get("SEED_SHIFT", "0"))) % world)
 state = bench.Cfg2Device(seq, pile, work, dev)
 
 
