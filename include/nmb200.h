@@ -162,6 +162,17 @@ NMB_API int nmb_build_class_planes_compact(const int32_t *pos, const uint8_t *fl
                                    int32_t key_high, const nmb_assembly *assembly_h, int32_t n_modtypes,
                                    uint32_t *class_records, void *stream);
 
+/* Block-wise variant for loaders that stream the pileup: nmb_clear_class_planes zeroes the records once,
+ * nmb_add_class_planes_compact ORs one block of compact rows into them (same arguments and semantics as
+ * nmb_build_class_planes_compact, which is clear + add).  Blocks may arrive in any order and on copies that
+ * overlap earlier blocks' scans; a mod type's planes are complete once every block holding its rows is in. */
+NMB_API int nmb_clear_class_planes(const nmb_assembly *assembly_h, int32_t n_modtypes, uint32_t *class_records,
+                                   void *stream);
+NMB_API int nmb_add_class_planes_compact(const int32_t *pos, const uint8_t *flags, const uint16_t *percent_x100,
+                                         const int64_t *contig_row_off, int64_t n_rows, int32_t key_low,
+                                         int32_t key_high, const nmb_assembly *assembly_h, int32_t n_modtypes,
+                                         uint32_t *class_records, void *stream);
+
 /* ---- pileup filters (replace the polars expressions of nanomotif/dataload.py:191-247); every
  *      function writes keep[r] in {0,1} in input row order ---- */
 

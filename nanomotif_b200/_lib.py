@@ -86,6 +86,8 @@ SIGNATURES = {
     "nmb_pack_sequence": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "nmb_build_class_planes": (C.c_int, [_P, _P, _P, _P, _P, _I64, _F64, _F64, C.POINTER(NmbAssembly), _I32, _P, _P]),
     "nmb_build_class_planes_compact": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, C.POINTER(NmbAssembly), _I32, _P, _P]),
+    "nmb_clear_class_planes": (C.c_int, [C.POINTER(NmbAssembly), _I32, _P, _P]),
+    "nmb_add_class_planes_compact": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, C.POINTER(NmbAssembly), _I32, _P, _P]),
     "nmb_filter_coverage": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "nmb_filter_min_mod_frequency": (C.c_int, [_P, _P, _I64, _I32, _F64, _F64, _I64, _P, _P, _P]),
     "nmb_filter_adjacency": (C.c_int, [_P, _P, _P, _P, _I64, _F64, _I32, _P, _P, _P]),
@@ -106,7 +108,7 @@ SIGNATURES = {
 def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m nanomotif_b200.build` "
+            f"{LIB_PATH} is missing: build it with `python nanomotif_b200/build.py` "
             "(nvcc, sm_100a). nanomotif_b200 has no CPU fallback."
         )
     lib = C.CDLL(LIB_PATH)
@@ -114,7 +116,7 @@ def _load() -> C.CDLL:
         try:
             fn = getattr(lib, name)
         except AttributeError as exc:  # pragma: no cover - ABI mismatch
-            raise ImportError(f"{LIB_PATH} does not export {name}; rebuild it") from exc
+            raise ImportError(f"{LIB_PATH} does not export {name}; rebuild it with `python nanomotif_b200/build.py`") from exc
         fn.restype = restype
         fn.argtypes = argtypes
     if lib.nmb_abi_version() != ABI_VERSION:

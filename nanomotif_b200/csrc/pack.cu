@@ -236,24 +236,39 @@ int nmb_build_class_planes(const int32_t *contig_id, const int64_t *pos, const u
     return NMB_OK;
 }
 
-int nmb_build_class_planes_compact(const int32_t *pos, const uint8_t *flags, const uint16_t *percent_x100,
-                                   const int64_t *contig_row_off, int64_t n_rows, int32_t key_low,
-                                   int32_t key_high, const nmb_assembly *a, int32_t n_modtypes,
-                                   uint32_t *class_records, void *stream) {
-    NMB_REQUIRE(a && class_records, "nmb_build_class_planes_compact: null argument");
+int nmb_clear_class_planes(const nmb_assembly *a, int32_t n_modtypes, uint32_t *class_records, void *stream) {
+    NMB_REQUIRE(a && class_records, "nmb_clear_class_planes: null argument");
+    NMB_REQUIRE(n_modtypes > 0 && a->n_tiles > 0, "nmb_clear_class_planes: bad sizes");
+    NMB_CUDA(cudaMemsetAsync(class_records, 0, (size_t)n_modtypes * a->n_tiles * nmb::kClsRecBytes,
+                             (cudaStream_t)stream));
+    return NMB_OK;
+}
+
+int nmb_add_class_planes_compact(const int32_t *pos, const uint8_t *flags, const uint16_t *percent_x100,
+                                 const int64_t *contig_row_off, int64_t n_rows, int32_t key_low, int32_t key_high,
+                                 const nmb_assembly *a, int32_t n_modtypes, uint32_t *class_records, void *stream) {
+    NMB_REQUIRE(a && class_records, "nmb_add_class_planes_compact: null argument");
     NMB_REQUIRE(n_rows >= 0 && n_modtypes > 0 && n_modtypes <= 128 && a->n_tiles > 0 && a->n_contigs > 0,
-                "nmb_build_class_planes_compact: bad sizes");
-    cudaStream_t s = (cudaStream_t)stream;
-    NMB_CUDA(cudaMemsetAsync(class_records, 0, (size_t)n_modtypes * a->n_tiles * nmb::kClsRecBytes, s));
+                "nmb_add_class_planes_compact: bad sizes");
     if (n_rows == 0) return NMB_OK;
-    NMB_REQUIRE(pos && flags && percent_x100 && contig_row_off, "nmb_build_class_planes_compact: null column");
+    NMB_REQUIRE(pos && flags && percent_x100 && contig_row_off, "nmb_add_class_planes_compact: null column");
     int64_t blocks = (n_rows + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    nmb::class_planes_compact_kernel<<<(unsigned)blocks, 256, 0, s>>>(
+    nmb::class_planes_compact_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         pos, flags, percent_x100, contig_row_off, a->n_contigs, n_rows, key_low, key_high, a->contig_start,
         a->contig_len, a->n_tiles, n_modtypes, class_records);
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;
+}
+
+int nmb_build_class_planes_compact(const int32_t *pos, const uint8_t *flags, const uint16_t *percent_x100,
+                                   const int64_t *contig_row_off, int64_t n_rows, int32_t key_low,
+                                   int32_t key_high, const nmb_assembly *a, int32_t n_modtypes,
+                                   uint32_t *class_records, void *stream) {
+    const int rc = nmb_clear_class_planes(a, n_modtypes, class_records, stream);
+    if (rc != NMB_OK) return rc;
+    return nmb_add_class_planes_compact(pos, flags, percent_x100, contig_row_off, n_rows, key_low, key_high, a,
+                                        n_modtypes, class_records, stream);
 }
 
 }  // extern "C"

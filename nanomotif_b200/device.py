@@ -61,7 +61,7 @@ class DeviceAssembly:
     """Contigs packed as 2-bit planes in tile records on one GPU (replaces the ``dict[str, DNAsequence]``
     of Python strings the reference scans, nanomotif/seq.py:11-19)."""
 
-    def __init__(self, names, lengths, ascii_u8, ascii_off, device=None):
+    def __init__(self, names, lengths, ascii_u8, ascii_off, device=None, sync: bool = True):
         self.device = _require_cuda(device)
         self.names = list(names)
         self.index = {n: i for i, n in enumerate(self.names)}
@@ -86,8 +86,10 @@ class DeviceAssembly:
                                       _stream()),
                 "nmb_pack_sequence",
             )
-            # ascii_d / off_d may be released once the kernels have run
-            torch.cuda.current_stream().synchronize()
+            # ascii_d / off_d go back to torch's caching allocator, whose reuse is ordered on this stream; the
+            # synchronisation only matters to callers that touch the records from ANOTHER stream right away
+            if sync:
+                torch.cuda.current_stream().synchronize()
         self._view = NmbAssembly(ptr(self.seq_records), ptr(self.nonacgt), ptr(self.contig_start),
                                  ptr(self.contig_len), self.n_contigs, self.n_tiles)
 

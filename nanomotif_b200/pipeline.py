@@ -1,0 +1,140 @@
+"""Streamed host -> device scoring: the pileup arrives in blocks and scans start while later blocks are
+still crossing PCIe.
+
+The reference loads the whole pileup, then scores (find_motifs_bin.py:382-427 then :1265-1331).  On a B200
+the scan of an E. coli-sized bin takes about as long as the host->device copy of its pileup rows, so the
+end-to-end path overlaps the two: block k's rows are copied on a side stream while the class planes of
+block k-1 are built and every job whose mod type is complete is scanned on the compute stream.  Results
+are identical to the one-shot path (DevicePileup.from_compact + scan_count): the class planes are a
+bitwise OR over rows, so the block order does not matter.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr
+from .device import (DeviceAssembly, DevicePileup, MotifPrograms, PreparedJobs, _require_cuda, _stream, scan_count,
+                     threshold_keys)
+
+
+class HostBlock(NamedTuple):
+    """Compact pileup rows (device.compact_rows) of some mod types; `modtypes` lists the mod-type indices
+    that may occur in the block's flags.  Arrays are numpy or (preferably pinned) host tensors."""
+
+    position: object        # int32 [n]
+    flags: object           # uint8 [n]  strand | mod type << 1
+    percent_x100: object    # uint16 [n]
+    contig_row_off: object  # int64 [n_contigs + 1]
+    modtypes: tuple
+
+
+def _host_tensor(a, dtype) -> torch.Tensor:
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t
+
+
+_SIDE_STREAMS: dict[int, torch.cuda.Stream] = {}
+
+
+def _side_stream(device: torch.device) -> torch.cuda.Stream:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[idx]
+
+
+def blocks_by_modtype(position, flags, percent_x100, contig_row_off, n_modtypes: int) -> list[HostBlock]:
+    """Split compact rows (grouped by contig) into one block per mod type, keeping the contig grouping."""
+    position, flags = np.asarray(position), np.asarray(flags)
+    percent_x100, off = np.asarray(percent_x100), np.asarray(contig_row_off, dtype=np.int64)
+    mt = flags >> 1
+    cid = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    out = []
+    for t in range(n_modtypes):
+        sel = np.flatnonzero(mt == t)
+        o = np.zeros(len(off), dtype=np.int64)
+        np.cumsum(np.bincount(cid[sel], minlength=len(off) - 1), out=o[1:])
+        out.append(HostBlock(position[sel], flags[sel], percent_x100[sel], o, (t,)))
+    return out
+
+
+def score_host_blocks(names: Sequence[str], lengths, ascii_u8, ascii_off, blocks: Sequence[HostBlock], packed_motifs,
+                      jobs: np.ndarray, n_out_rows: int, *, low: float = 0.3, high: float = 0.7, n_modtypes: int = 1,
+                      device=None, reduce_over_ranks: bool = False, out_host: torch.Tensor | None = None,
+                      motifs_per_item: int | None = None) -> torch.Tensor:
+    """Pack the contigs, stream the pileup blocks and run every job of `jobs` (numpy _lib.JOB_DTYPE table; a
+    job is launched as soon as every block that lists its mod type is on the device).  Returns the int64
+    counts [n_out_rows, 4] on the host (`out_host`, pinned, when given).  `reduce_over_ranks` all-reduces the
+    counts over the default process group before the copy back (contig-sharded multi-GPU runs)."""
+    d = _require_cuda(device)
+    key_low, key_high = threshold_keys(low, high)
+    with torch.cuda.device(d):
+        compute = torch.cuda.current_stream()
+        side = _side_stream(d)
+        side.wait_stream(compute)  # earlier work on the caller's stream stays ordered before ours
+        jobs = np.asarray(jobs).copy()
+        staged = []
+        with torch.cuda.stream(side):
+            # small things first so that the compute stream can start; then the blocks in order
+            asm = DeviceAssembly(names, lengths, ascii_u8, ascii_off, d, sync=False)
+            jobs["tile_count"] = np.where(jobs["tile_count"] > 0, jobs["tile_count"], asm.n_tiles)
+            progs = MotifPrograms(packed_motifs, d)
+            groups = {}
+            for j in range(len(jobs)):
+                groups.setdefault(int(jobs["modtype"][j]), []).append(j)
+            prepared = {mt: PreparedJobs(jobs[idx], d, motifs_per_item) for mt, idx in groups.items()}
+            ev_ready = torch.cuda.Event()
+            ev_ready.record(side)
+            for b in blocks:
+                cols = (_host_tensor(b.position, torch.int32), _host_tensor(b.flags, torch.uint8),
+                        _host_tensor(b.percent_x100, torch.uint16), _host_tensor(b.contig_row_off, torch.int64))
+                if int(cols[3].numel()) != asm.n_contigs + 1 or len({int(c.numel()) for c in cols[:3]}) != 1:
+                    raise ValueError("compact pileup columns differ in length")
+                dev_cols = tuple(c.to(d, non_blocking=True) for c in cols)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                staged.append((dev_cols, ev, tuple(b.modtypes)))
+
+        # compute stream: class planes block by block, scans as soon as their mod type is complete
+        pile = DevicePileup(asm, n_modtypes, low, high)
+        view = asm.view()
+        out = torch.zeros((n_out_rows, 4), dtype=torch.int64, device=d)
+        check(lib.nmb_clear_class_planes(C.byref(view), n_modtypes, ptr(pile.class_records), _stream()),
+              "nmb_clear_class_planes")
+        compute.wait_event(ev_ready)
+        pending = {mt: sum(mt in s[2] for s in staged) for mt in prepared}
+        launched = set()
+
+        def launch_ready():
+            for mt, left in pending.items():
+                if left == 0 and mt not in launched:
+                    launched.add(mt)
+                    scan_count(asm, pile, progs, prepared[mt], n_out_rows, out=out)
+
+        launch_ready()  # jobs whose mod type has no rows at all
+        for dev_cols, ev, mts in staged:
+            compute.wait_event(ev)
+            pos, fl, key, off = dev_cols
+            check(lib.nmb_add_class_planes_compact(ptr(pos), ptr(fl), ptr(key), ptr(off), int(pos.numel()), key_low,
+                                                   key_high, C.byref(view), n_modtypes, ptr(pile.class_records),
+                                                   _stream()), "nmb_add_class_planes_compact")
+            for mt in mts:
+                if mt in pending:
+                    pending[mt] -= 1
+            launch_ready()
+        if reduce_over_ranks:
+            import torch.distributed as dist
+
+            dist.all_reduce(out)
+        if out_host is None:
+            out_host = torch.empty((n_out_rows, 4), dtype=torch.int64, pin_memory=True)
+        out_host.copy_(out, non_blocking=True)
+        compute.synchronize()  # also the point after which the side stream's buffers may be reused
+        side.synchronize()
+    return out_host

@@ -190,3 +190,58 @@ def test_contig_edges_poly_a(nmb):
     for s, _ in specs[:12]:
         for name in ("edge_8", "edge_9", "edge_17", "edge_19"):
             np.testing.assert_array_equal(nmb.subseq_indices(s, contigs[name]), O.subseq_indices(s, contigs[name]), err_msg=s)
+
+
+def test_streamed_host_blocks_equal_one_shot(nmb):
+    """pipeline.score_host_blocks (copies overlapped with class-plane builds and scans) == DevicePileup.from_compact +
+    one scan launch, for blocks per mod type, blocks in scrambled order and a block mixing two mod types."""
+    import torch
+
+    from nanomotif_b200 import synth
+    from nanomotif_b200.device import DeviceAssembly, DevicePileup, MotifPrograms, compact_rows, make_jobs, scan_count
+    from nanomotif_b200.motif import pack_motifs
+    from nanomotif_b200.pipeline import HostBlock, blocks_by_modtype, score_host_blocks
+
+    rng = np.random.default_rng(31)
+    lens = [70000, 900, 140000, 5000]
+    seqs = [synth.random_sequence(rng, L, 0.5, 1e-4 if i == 2 else 0.0) for i, L in enumerate(lens)]
+    cols = {k: [] for k in ("cid", "position", "strand", "mod_type", "fraction_mod")}
+    for i, seq in enumerate(seqs):
+        p = synth.synth_pileup(seq, rng, depth=30)
+        cols["cid"].append(np.full(len(p["position"]), i, dtype=np.int32))
+        for k in ("position", "strand", "mod_type", "fraction_mod"):
+            cols[k].append(p[k])
+    c = {k: np.concatenate(v) for k, v in cols.items()}
+    rows = compact_rows(c["cid"], c["position"], c["strand"], c["fraction_mod"], c["mod_type"], len(lens))
+    ascii_u8 = np.concatenate(seqs)
+    off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    names = [f"c{i}" for i in range(len(lens))]
+    work = [(s, p, mt) for mt, base in enumerate("ACC") for s, p in synth.random_motifs(np.random.default_rng(5 + mt), 40, base)]
+    packed = pack_motifs([nmb.Motif(s, p) for s, p, _ in work])
+    jobs = make_jobs(4)  # mod types 0, 1, 2 over the whole bin + a per-contig job of mod type 1
+    for j, (mt, mode) in enumerate(((0, 0), (1, 0), (2, 0), (1, 1))):
+        jobs[j]["motif_begin"], jobs[j]["motif_count"], jobs[j]["modtype"] = 40 * mt, 40, mt
+        jobs[j]["contig_end"], jobs[j]["group_mode"] = len(lens), mode
+        jobs[j]["n_groups"] = len(lens) if mode else 1
+    jobs["out_base"] = np.concatenate([[0], np.cumsum(jobs["motif_count"] * jobs["n_groups"])[:-1]])
+    n_out = int((jobs["motif_count"] * jobs["n_groups"]).sum())
+
+    dev = torch.device("cuda", 0)
+    asm = DeviceAssembly(names, lens, ascii_u8, off, dev)
+    pile = DevicePileup.from_compact(asm, low=0.3, high=0.7, n_modtypes=3, **rows)
+    j1 = jobs.copy()
+    j1["tile_count"] = asm.n_tiles
+    want = scan_count(asm, pile, MotifPrograms(packed, dev), j1, n_out).cpu()
+    assert int(want.sum()) > 1000
+
+    per_mt = blocks_by_modtype(rows["position"], rows["flags"], rows["percent_x100"], rows["contig_row_off"], 3)
+    assert sum(len(b.position) for b in per_mt) == len(rows["position"])
+    mixed = blocks_by_modtype(rows["position"], rows["flags"] & 1 | (np.minimum(rows["flags"] >> 1, 1) << 1),
+                              rows["percent_x100"], rows["contig_row_off"], 2)
+    # block "1" of `mixed` holds the rows of mod types 1 and 2: restore their flags
+    sel = np.flatnonzero((rows["flags"] >> 1) >= 1)
+    mixed[1] = HostBlock(mixed[1].position, rows["flags"][sel], mixed[1].percent_x100, mixed[1].contig_row_off, (1, 2))
+    for blocks in (per_mt, per_mt[::-1], [per_mt[0], mixed[1]], [mixed[1], per_mt[0]]):
+        got = score_host_blocks(names, lens, ascii_u8, off, blocks, packed, jobs, n_out, low=0.3, high=0.7, n_modtypes=3,
+                                device=dev)
+        assert torch.equal(got, want)
