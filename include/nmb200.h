@@ -173,6 +173,37 @@ NMB_API int nmb_add_class_planes_compact(const int32_t *pos, const uint8_t *flag
                                          int32_t key_high, const nmb_assembly *assembly_h, int32_t n_modtypes,
                                          uint32_t *class_records, void *stream);
 
+/* ---- K6: modkit bedMethyl text -> pileup columns on the device (replaces the CSV scan of
+ *      nanomotif/dataload.py:72-100 and the row materialisation of epymetheus.query_pileup_records,
+ *      dataload.py:109-120) ---- */
+
+/* Ascending positions i with src[i] == value (e.g. '\n').  Two-call pattern like
+ * nmb_compact_positions: capacity 0 only counts (*n_out, device int64); scratch holds
+ * ceil(n_bytes/4096)+1 int64. */
+NMB_API int nmb_index_bytes(const uint8_t *src, int64_t n_bytes, int32_t value, int64_t *scratch,
+                            int64_t *out_index, int64_t capacity, int64_t *n_out, void *stream);
+
+/* One row per text line (line r starts at newline_pos[r-1]+1, line 0 at 0; a final line without '\n'
+ * counts; '\r' ends a line too).  Columns (1-based, tab separated, dataload.py:15-34): 1 contig name ->
+ * contig_id through the table (hash = FNV-1a 64 of the name, ascending; ids; name bytes by rank), -1 when
+ * unknown, -2 for an empty or malformed (< 18 fields) line; 2 -> position; 4 -> mod_type = index of the
+ * code in modtype_keys (the code's bytes, first byte most significant, <= 8 bytes) or 255; 6 -> strand 0
+ * '+', 1 '-', 2 other; 10 -> n_valid_cov; 11 -> fraction_mod = value/100 (dataload.py:85; value = the
+ * correctly rounded double of the decimal text) and percent_x100 = the exact two-decimal key 0..10000 or
+ * 0xFFFF when the text has more decimals or is out of range; 12 -> n_mod, 17 -> n_diff (outputs may be
+ * NULL).  Fields that are not plain decimal numbers (NA, null, exponents) give -1 / NaN.  status[4]
+ * (device int32) counts malformed lines, empty lines, non-numeric fields, rows of unknown contigs. */
+NMB_API int nmb_bed_parse(const uint8_t *text, int64_t n_bytes, const int64_t *newline_pos, int64_t n_lines,
+                          const uint64_t *contig_hash, const int32_t *contig_ids, const int64_t *contig_name_off,
+                          const uint8_t *contig_names, int32_t n_contigs, const uint64_t *modtype_keys,
+                          int32_t n_modtypes, int32_t *contig_id, int64_t *position, uint8_t *strand,
+                          uint8_t *mod_type, int64_t *n_valid_cov, double *fraction_mod, uint16_t *percent_x100,
+                          int64_t *n_mod, int64_t *n_diff, int32_t *status, void *stream);
+
+/* dst[i] = src[index[i]] for elements of 1, 2, 4 or 8 bytes (row compaction after the filters). */
+NMB_API int nmb_gather_rows(const void *src, int32_t elem_bytes, const int64_t *index, int64_t n, void *dst,
+                            void *stream);
+
 /* ---- pileup filters (replace the polars expressions of nanomotif/dataload.py:191-247); every
  *      function writes keep[r] in {0,1} in input row order ---- */
 

@@ -140,6 +140,38 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// ---- small building blocks shared by the compaction-style kernels (positions.cu, bedmethyl.cu) ----
+
+// Exclusive scan of n int64 in place by one block; total -> *n_out.
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) scan_counts_kernel(int64_t *__restrict__ v, int64_t n,
+                                                           int64_t *__restrict__ n_out) {
+    __shared__ int64_t s_part[kThreads];
+    const int t = threadIdx.x;
+    const int64_t per = (n + kThreads - 1) / kThreads;
+    const int64_t b = t * per, e = min(n, b + per);
+    int64_t sum = 0;
+    for (int64_t i = b; i < e; ++i) sum += v[i];
+    s_part[t] = sum;
+    __syncthreads();
+    if (t == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < kThreads; ++i) {
+            const int64_t x = s_part[i];
+            s_part[i] = run;
+            run += x;
+        }
+        *n_out = run;
+    }
+    __syncthreads();
+    int64_t run = s_part[t];
+    for (int64_t i = b; i < e; ++i) {
+        const int64_t x = v[i];
+        v[i] = run;
+        run += x;
+    }
+}
+
 #endif  // __CUDACC__
 
 }  // namespace nmb

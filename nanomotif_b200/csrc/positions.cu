@@ -80,35 +80,6 @@ __global__ void __launch_bounds__(256) count_bits_kernel(const uint32_t *__restr
     }
 }
 
-// Exclusive scan of n int64 in place by one block; total -> *n_out.
-__global__ void __launch_bounds__(1024) scan_counts_kernel(int64_t *__restrict__ v, int64_t n,
-                                                           int64_t *__restrict__ n_out) {
-    __shared__ int64_t s_part[1024];
-    const int t = threadIdx.x;
-    const int64_t per = (n + 1023) / 1024;
-    const int64_t b = t * per, e = min(n, b + per);
-    int64_t sum = 0;
-    for (int64_t i = b; i < e; ++i) sum += v[i];
-    s_part[t] = sum;
-    __syncthreads();
-    if (t == 0) {
-        int64_t run = 0;
-        for (int i = 0; i < 1024; ++i) {
-            const int64_t x = s_part[i];
-            s_part[i] = run;
-            run += x;
-        }
-        *n_out = run;
-    }
-    __syncthreads();
-    int64_t run = s_part[t];
-    for (int64_t i = b; i < e; ++i) {
-        const int64_t x = v[i];
-        v[i] = run;
-        run += x;
-    }
-}
-
 __global__ void __launch_bounds__(256) write_positions_kernel(
     const uint32_t *__restrict__ plane, const uint32_t *__restrict__ mask, int64_t word_begin,
     int64_t pos_begin, int64_t pos_end, const int64_t *__restrict__ block_offsets,
@@ -209,7 +180,7 @@ int nmb_compact_positions(const uint32_t *plane, const uint32_t *mask, int64_t p
     nmb::count_bits_kernel<<<(unsigned)n_blocks, 256, 0, s>>>(plane, mask, pos_begin / 32, pos_end,
                                                              tile_counts);
     NMB_CUDA(cudaGetLastError());
-    nmb::scan_counts_kernel<<<1, 1024, 0, s>>>(tile_counts, n_blocks, n_out);
+    nmb::scan_counts_kernel<1024><<<1, 1024, 0, s>>>(tile_counts, n_blocks, n_out);
     NMB_CUDA(cudaGetLastError());
     if (capacity > 0) {
         nmb::write_positions_kernel<<<(unsigned)n_blocks, 256, 0, s>>>(

@@ -151,3 +151,200 @@ def filter_pileup_adjacency_filter(pileup, methylation_threshold: float = 0.7, a
         inv[order] = k
         k = inv
     return t.take(k)
+
+
+# ---------------------------------------------------------------------------------------------
+# device ingest: bedMethyl text -> columns -> filters -> class planes without leaving the GPU (K6)
+# ---------------------------------------------------------------------------------------------
+
+_FNV_OFFSET, _FNV_PRIME, _U64 = 0xCBF29CE484222325, 0x100000001B3, (1 << 64) - 1
+
+
+def _fnv1a64(b: bytes) -> int:
+    h = _FNV_OFFSET
+    for c in b:
+        h = ((h ^ c) * _FNV_PRIME) & _U64
+    return h
+
+
+def _name_table(names, device):
+    """Device lookup table of nmb_bed_parse: hashes ascending, ids, name bytes by rank."""
+    enc = [str(n).encode() for n in names]
+    hashes = np.array([_fnv1a64(b) for b in enc], dtype=np.uint64)
+    order = np.argsort(hashes, kind="stable")
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    np.cumsum([len(enc[i]) for i in order], out=off[1:])
+    blob = np.frombuffer(b"".join(enc[i] for i in order) or b"\0", dtype=np.uint8)
+    return (_to_device(hashes[order].view(np.int64), device), _to_device(order.astype(np.int32), device),
+            _to_device(off, device), _to_device(blob, device))
+
+
+def _modtype_keys(mod_types) -> np.ndarray:
+    keys = []
+    for m in mod_types:
+        b = str(m).encode()
+        if not 1 <= len(b) <= 8:
+            raise ValueError(f"mod type code {m!r} must be 1..8 bytes")
+        keys.append(int.from_bytes(b, "big"))
+    return np.array(keys, dtype=np.uint64)
+
+
+class DeviceRows:
+    """Pileup rows as device columns (what nmb_bed_parse writes).  contig_id indexes `contig_names`,
+    mod_type indexes `mod_types`; strand 0 '+', 1 '-'."""
+
+    COLUMNS = ("contig_id", "position", "strand", "mod_type", "Nvalid_cov", "fraction_mod", "percent_x100", "n_mod", "n_diff")
+
+    def __init__(self, contig_names, mod_types, device, **cols):
+        self.contig_names, self.mod_types, self.device = list(contig_names), tuple(mod_types), device
+        for k in self.COLUMNS:
+            setattr(self, k, cols.get(k))
+
+    def __len__(self) -> int:
+        return int(self.position.numel())
+
+    def take_mask(self, keep: torch.Tensor) -> "DeviceRows":
+        """Rows with keep != 0, in order (nmb_index_bytes + nmb_gather_rows)."""
+        n = len(self)
+        with torch.cuda.device(self.device):
+            scratch = torch.empty((n + 4095) // 4096 + 2, dtype=torch.int64, device=self.device)
+            n_out = torch.zeros(1, dtype=torch.int64, device=self.device)
+            check(lib.nmb_index_bytes(ptr(keep), n, 1, ptr(scratch), None, 0, ptr(n_out), _stream()), "nmb_index_bytes")
+            m = int(n_out.item())
+            index = torch.empty(max(m, 1), dtype=torch.int64, device=self.device)
+            if m:
+                check(lib.nmb_index_bytes(ptr(keep), n, 1, ptr(scratch), ptr(index), m, ptr(n_out), _stream()),
+                      "nmb_index_bytes")
+            cols = {}
+            for k in self.COLUMNS:
+                src = getattr(self, k)
+                if src is None:
+                    continue
+                dst = torch.empty(m, dtype=src.dtype, device=self.device)
+                check(lib.nmb_gather_rows(ptr(src), src.element_size(), ptr(index), m, ptr(dst), _stream()),
+                      "nmb_gather_rows")
+                cols[k] = dst
+        return DeviceRows(self.contig_names, self.mod_types, self.device, **cols)
+
+    def to_table(self) -> PileupTable:
+        """Host copy with names restored (parity checks, hand-over to host code)."""
+        names = np.array(self.contig_names + ["?"], dtype=object)
+        mods = np.array(list(self.mod_types) + ["?"], dtype=object)
+        cid = self.contig_id.cpu().numpy()
+        mt = self.mod_type.cpu().numpy().astype(np.int64)
+        extra = {k: getattr(self, k).cpu().numpy() for k in ("n_mod", "n_diff", "percent_x100") if getattr(self, k) is not None}
+        return PileupTable(names[np.where(cid >= 0, cid, len(self.contig_names))], self.position.cpu().numpy(),
+                           np.array(["+", "-", "."], dtype=object)[self.strand.cpu().numpy()],
+                           self.fraction_mod.cpu().numpy(), mods[np.minimum(mt, len(self.mod_types))],
+                           self.Nvalid_cov.cpu().numpy(), extra)
+
+    # ---- the three loader filters, device to device (dataload.py:191-247) ----
+    def filter_coverage(self, min_coverage: int = 5) -> "DeviceRows":
+        n = len(self)
+        with torch.cuda.device(self.device):
+            keep = torch.empty(n, dtype=torch.uint8, device=self.device)
+            check(lib.nmb_filter_coverage(ptr(self.Nvalid_cov), n, int(min_coverage), ptr(keep), _stream()),
+                  "nmb_filter_coverage")
+        return self.take_mask(keep)
+
+    def filter_min_mod_frequency(self, methylation_threshold: float = 0.7, min_mod_frequency: float = 0.0001,
+                                 min_mods_pr_contig: int = 50) -> "DeviceRows":
+        n, M = len(self), max(1, len(self.mod_types))
+        n_groups = max(1, len(self.contig_names) * M)
+        with torch.cuda.device(self.device):
+            cid, mt = self.contig_id, self.mod_type.to(torch.int32)
+            group = torch.where((cid >= 0) & (mt < M), cid * M + mt, torch.full_like(cid, -1))  # index arithmetic only
+            counts = torch.empty(2 * n_groups, dtype=torch.int64, device=self.device)
+            keep = torch.empty(n, dtype=torch.uint8, device=self.device)
+            check(lib.nmb_filter_min_mod_frequency(ptr(group), ptr(self.fraction_mod), n, n_groups,
+                                                   float(methylation_threshold), float(min_mod_frequency),
+                                                   int(min_mods_pr_contig), ptr(counts), ptr(keep), _stream()),
+                  "nmb_filter_min_mod_frequency")
+        return self.take_mask(keep)
+
+    def filter_adjacency(self, methylation_threshold: float = 0.7, adjacency_distance: int = 8) -> "DeviceRows":
+        """Rows must be sorted by (contig, position), as modkit writes them."""
+        n = len(self)
+        with torch.cuda.device(self.device):
+            keep = torch.empty(n, dtype=torch.uint8, device=self.device)
+            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            check(lib.nmb_filter_adjacency(ptr(self.contig_id), ptr(self.position), ptr(self.strand), ptr(self.fraction_mod),
+                                           n, float(methylation_threshold), int(adjacency_distance), ptr(keep), ptr(flag),
+                                           _stream()), "nmb_filter_adjacency")
+            if int(flag.item()):
+                raise ValueError("filter_adjacency: rows are not sorted by (contig, position)")
+        return self.take_mask(keep)
+
+    def class_planes(self, assembly, low: float = 0.3, high: float = 0.7):
+        """DevicePileup of these rows; `assembly.names` must be the `contig_names` the rows were parsed with."""
+        from .device import DevicePileup
+
+        if list(assembly.names) != self.contig_names:
+            raise ValueError("rows were parsed against a different contig list than the assembly's")
+        rows = self
+        with torch.cuda.device(self.device):
+            if bool((self.strand > 1).any()):
+                rows = self.take_mask((self.strand < 2).to(torch.uint8))
+        return DevicePileup.from_columns(assembly, rows.contig_id, rows.position, rows.strand, rows.fraction_mod, low, high,
+                                         rows.mod_type, n_modtypes=max(1, len(self.mod_types)))
+
+
+def parse_bedmethyl(data, contig_names, mod_types=("a", "m", "21839"), with_counts: bool = False, device=None,
+                    keep_unknown_contigs: bool = False) -> DeviceRows:
+    """modkit bedMethyl TEXT (bytes, uint8 array / tensor on host or device) -> DeviceRows, parsed on the GPU.
+
+    Same columns and arithmetic as load_pileup (dataload.py:72-100): contig, position, mod_type, strand,
+    Nvalid_cov and fraction_mod = column 11 / 100.  Empty lines are skipped, lines with fewer than 18
+    tab-separated fields raise.  Rows of contigs outside `contig_names` are dropped unless asked for."""
+    d = _require_cuda(device)
+    if isinstance(data, (bytes, bytearray, memoryview)):
+        data = np.frombuffer(data, dtype=np.uint8)
+    with torch.cuda.device(d):
+        text = data.to(d, non_blocking=True) if isinstance(data, torch.Tensor) else _to_device(np.asarray(data, dtype=np.uint8), d)
+        n_bytes = int(text.numel())
+        scratch = torch.empty((n_bytes + 4095) // 4096 + 2, dtype=torch.int64, device=d)
+        n_nl = torch.zeros(1, dtype=torch.int64, device=d)
+        check(lib.nmb_index_bytes(ptr(text), n_bytes, 10, ptr(scratch), None, 0, ptr(n_nl), _stream()), "nmb_index_bytes")
+        n_newlines = int(n_nl.item())
+        newline_pos = torch.empty(max(n_newlines, 1), dtype=torch.int64, device=d)
+        if n_newlines:
+            check(lib.nmb_index_bytes(ptr(text), n_bytes, 10, ptr(scratch), ptr(newline_pos), n_newlines, ptr(n_nl),
+                                      _stream()), "nmb_index_bytes")
+        ends_with_newline = n_bytes > 0 and int(text[-1].item()) == 10
+        n_lines = n_newlines + (1 if n_bytes > 0 and not ends_with_newline else 0)
+        names = list(contig_names)
+        h, ids, off, blob = _name_table(names, d)
+        keys = _to_device(_modtype_keys(mod_types).view(np.int64), d) if len(mod_types) else None
+        new = lambda dt: torch.empty(n_lines, dtype=dt, device=d)
+        cols = dict(contig_id=new(torch.int32), position=new(torch.int64), strand=new(torch.uint8), mod_type=new(torch.uint8),
+                    Nvalid_cov=new(torch.int64), fraction_mod=new(torch.float64), percent_x100=new(torch.uint16))
+        if with_counts:
+            cols.update(n_mod=new(torch.int64), n_diff=new(torch.int64))
+        status = torch.zeros(4, dtype=torch.int32, device=d)
+        check(lib.nmb_bed_parse(ptr(text), n_bytes, ptr(newline_pos), n_lines, ptr(h), ptr(ids), ptr(off), ptr(blob),
+                                len(names), ptr(keys), len(mod_types), ptr(cols["contig_id"]), ptr(cols["position"]),
+                                ptr(cols["strand"]), ptr(cols["mod_type"]), ptr(cols["Nvalid_cov"]), ptr(cols["fraction_mod"]),
+                                ptr(cols["percent_x100"]), ptr(cols.get("n_mod")), ptr(cols.get("n_diff")), ptr(status),
+                                _stream()), "nmb_bed_parse")
+        malformed, empty, _notnum, unknown = (int(v) for v in status.cpu().tolist())
+        if malformed:
+            raise ValueError(f"bedMethyl: {malformed} line(s) with fewer than 18 tab-separated columns")
+        rows = DeviceRows(names, mod_types, d, **cols)
+        if empty or (unknown and not keep_unknown_contigs):
+            floor = -1 if keep_unknown_contigs else 0
+            rows = rows.take_mask((rows.contig_id >= floor).to(torch.uint8))
+    return rows
+
+
+def load_pileup_device(path: str, contig_names, mod_types=("a", "m", "21839"), with_counts: bool = False, device=None,
+                       keep_unknown_contigs: bool = False) -> DeviceRows:
+    """load_pileup with the parse on the GPU: the file's bytes (gzip / bgzf inflated on the host) go to the
+    device as they are."""
+    import gzip
+
+    opener = gzip.open if str(path).endswith((".gz", ".bgz")) else open
+    with opener(path, "rb") as f:
+        data = f.read()
+    if not data:
+        raise SystemExit("Pileup is empty after initial load")  # dataload.py:89-91
+    return parse_bedmethyl(data, contig_names, mod_types, with_counts, device, keep_unknown_contigs)

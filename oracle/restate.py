@@ -275,6 +275,36 @@ def kl_children(motif: str, mod_pos: int, meth_pssm: np.ndarray, bin_pssm: np.nd
 
 
 # ---------------------------------------------------------------------------------------------
+# a13: load_pileup (nanomotif/dataload.py:72-100), plain Python instead of polars' CSV reader
+# ---------------------------------------------------------------------------------------------
+def load_pileup_text(text: str) -> dict:
+    """dataload.py:72-100 on the text of a modkit bedMethyl file: tab-separated, no header, 18 columns
+    (schema :15-34); keeps columns 1, 2, 4, 6, 11, 10 and divides column 11 by 100 (:85).  polars parses
+    Float64 text to the correctly rounded double, which is what float() does.  "NA" / "null" are nulls
+    (:82) -> None here.  Extra columns 12 (n_mod) and 17 (n_diff) are returned for the pattern table."""
+    null = ("NA", "null", "")
+    num = lambda s, f: None if s in null else f(s)
+    cols = {k: [] for k in ("contig", "position", "mod_type", "strand", "fraction_mod", "Nvalid_cov", "n_mod", "n_diff")}
+    for line in text.split("\n"):
+        line = line.rstrip("\r")
+        if not line:
+            continue
+        f = line.split("\t")
+        if len(f) < 18:
+            raise ValueError("bedMethyl line with fewer than 18 columns")
+        pct = num(f[10], float)
+        cols["contig"].append(f[0])
+        cols["position"].append(num(f[1], int))
+        cols["mod_type"].append(f[3])
+        cols["strand"].append(f[5])
+        cols["fraction_mod"].append(None if pct is None else pct / 100)
+        cols["Nvalid_cov"].append(num(f[9], int))
+        cols["n_mod"].append(num(f[11], int))
+        cols["n_diff"].append(num(f[16], int))
+    return cols
+
+
+# ---------------------------------------------------------------------------------------------
 # a13: pileup filters (nanomotif/dataload.py:191-247), columns instead of a polars frame
 # ---------------------------------------------------------------------------------------------
 def filter_pileup(nvalid_cov, min_coverage: int = 5) -> np.ndarray:
