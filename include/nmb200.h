@@ -334,6 +334,40 @@ NMB_API int nmb_pattern_median(const int64_t *gpos, const uint8_t *strand, const
                        const int64_t *offsets, int32_t *cursor, double *fractions, double *median,
                        void *stream);
 
+/* ---- K5, tile-driven: many motifs per launch (pattern_scan.cu) ----
+ * Join index of ONE mod type.  Rows (any order; (contig, position, strand) unique) take part when their
+ * mod_type equals want_modtype (mod_type may be NULL), the contig / position is inside the assembly,
+ * n_valid_cov >= min_valid_read_coverage and n_valid_cov / (n_valid_cov + n_diff) >=
+ * min_valid_cov_to_diff_fraction (float64).  Outputs: valid_records [n_tiles][2][NMB_TILE_WORDS] (bit-planes
+ * valid '+', valid '-', lane-interleaved), rank_dir [2][n_tiles*NMB_TILE_WORDS] (rows before each word, in
+ * (strand, position) order), payload [n_rows][2] int32 = (n_mod, n_valid_cov) in that order, *n_valid_rows
+ * (device int64).  scratch: ceil(2*n_tiles*NMB_TILE_WORDS/2048)+2 int64. */
+NMB_API int nmb_pattern_index_build(const nmb_assembly *assembly_h, const int32_t *contig_id, const int64_t *pos,
+                                    const uint8_t *strand, const uint8_t *mod_type, int32_t want_modtype,
+                                    const int64_t *n_mod, const int64_t *n_valid_cov, const int64_t *n_diff,
+                                    int64_t n_rows, int64_t min_valid_read_coverage,
+                                    double min_valid_cov_to_diff_fraction, uint32_t *valid_records,
+                                    uint32_t *rank_dir, int64_t *scratch, int32_t *payload, int64_t *n_valid_rows,
+                                    void *stream);
+
+/* One pass of n_motifs compiled motifs (nmb_compile_motifs) over the whole assembly.  phase 0 ADDS into
+ * stats [n_motifs][n_contigs][3] = {n_motif_obs, sum n_mod, sum n_valid_cov}; phase 1 writes the
+ * per-occurrence fractions n_mod / n_valid_cov of segment (motif, contig) at fractions[offsets[seg] + k],
+ * k counted through cursor[seg] (nmb_segment_offsets sets both up from the phase-0 stats). */
+NMB_API int nmb_pattern_scan(const nmb_assembly *assembly_h, const uint32_t *valid_records, const uint32_t *rank_dir,
+                             const int32_t *payload, const void *programs, int32_t n_motifs, int32_t motifs_per_item,
+                             int32_t max_motif_len, int32_t phase, int64_t *stats, const int64_t *offsets,
+                             int32_t *cursor, double *fractions, int32_t grid_ctas, void *stream);
+
+/* offsets[0..n_segments] = exclusive prefix sum of stats[i][0]; cursor[i] = 0. */
+NMB_API int nmb_segment_offsets(const int64_t *stats, int64_t n_segments, int64_t *offsets, int32_t *cursor,
+                                void *stream);
+
+/* median[i] = exact median of fractions[offsets[i] .. offsets[i+1]) (mean of the two middle values for an
+ * even count, NaN for an empty segment). */
+NMB_API int nmb_segment_median(const double *fractions, const int64_t *offsets, int64_t n_segments, double *median,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -221,4 +221,14 @@ int nmb_pattern_median(const int64_t *gpos, const uint8_t *strand, const int32_t
     return NMB_OK;
 }
 
+int nmb_segment_median(const double *fractions, const int64_t *offsets, int64_t n_segments, double *median,
+                       void *stream) {
+    NMB_REQUIRE(offsets && median && n_segments >= 0 && n_segments < (1ll << 31), "nmb_segment_median: bad argument");
+    if (n_segments == 0) return NMB_OK;
+    nmb::pattern_median_kernel<<<(unsigned)n_segments, 128, 0, (cudaStream_t)stream>>>(
+        fractions, (const long long *)offsets, (int)n_segments, median);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
 }  // extern "C"

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib, ptr
-from .device import DeviceAssembly, MotifPrograms, _stream, _to_device
+from .device import DeviceAssembly, MotifPrograms, _stream, _to_device, sm_count
 from .motif import Motif
 from .pileup import PileupTable, strand_codes
 
@@ -54,6 +54,72 @@ def _planes(asm: DeviceAssembly, regex_motif: Motif):
     return out
 
 
+class PatternIndex:
+    """Join index of ONE mod type on the device (nmb_pattern_index_build): valid-row bit-planes per tile, rank
+    directory and (n_mod, n_valid_cov) payload.  `rows`: device tensors contig_id int32 (index into the
+    assembly), position int64, strand uint8, n_mod / Nvalid_cov / n_diff int64 and optionally mod_type uint8
+    (then only rows with mod_type == want_modtype take part)."""
+
+    def __init__(self, asm: DeviceAssembly, rows: dict, want_modtype: int = 0, min_valid_read_coverage: int = 3,
+                 min_valid_cov_to_diff_fraction: float = 0.8):
+        self.asm = asm
+        d = asm.device
+        n = int(rows["position"].numel())
+        with torch.cuda.device(d):
+            self.valid = torch.empty(asm.n_tiles * 2 * _lib.TILE_WORDS, dtype=torch.int32, device=d)
+            self.rank_dir = torch.empty(2 * asm.n_words, dtype=torch.int32, device=d)
+            self.payload = torch.empty((max(n, 1), 2), dtype=torch.int32, device=d)
+            scratch = torch.empty(2 * asm.n_words // 2048 + 3, dtype=torch.int64, device=d)
+            n_valid = torch.zeros(1, dtype=torch.int64, device=d)
+            view = asm.view()
+            check(lib.nmb_pattern_index_build(C.byref(view), ptr(rows["contig_id"]), ptr(rows["position"]), ptr(rows["strand"]),
+                                              ptr(rows.get("mod_type")), int(want_modtype), ptr(rows["n_mod"]),
+                                              ptr(rows["Nvalid_cov"]), ptr(rows["n_diff"]), n, int(min_valid_read_coverage),
+                                              float(min_valid_cov_to_diff_fraction), ptr(self.valid), ptr(self.rank_dir),
+                                              ptr(scratch), ptr(self.payload), ptr(n_valid), _stream()),
+                  "nmb_pattern_index_build")
+            self.n_valid_rows = int(n_valid.item())
+
+
+def pattern_table(index: PatternIndex, motifs, median: bool = True, batch: int = 64, motifs_per_item: int | None = None):
+    """(stats int64 [n_motifs, n_contigs, 3] = n_motif_obs / sum n_mod / sum n_valid_cov, value float64
+    [n_motifs, n_contigs] = median of the per-occurrence fractions, or None) on the host, for regex `Motif`s
+    scored against one mod type's index.  Two tile-driven passes per batch of motifs (count, then write +
+    exact medians)."""
+    asm = index.asm
+    d, nc = asm.device, asm.n_contigs
+    motifs = list(motifs)
+    stats_out = np.zeros((len(motifs), nc, 3), dtype=np.int64)
+    value_out = np.full((len(motifs), nc), np.nan) if median else None
+    view = asm.view()
+    with torch.cuda.device(d):
+        for b0 in range(0, len(motifs), batch):
+            chunk = motifs[b0:b0 + batch]
+            progs = MotifPrograms(chunk, d, strip=False)
+            nb = len(chunk)
+            mpi = motifs_per_item or int(min(_lib.MAX_MOTIFS_PER_ITEM, max(1, nb * asm.n_tiles // (16 * sm_count(d)))))
+            stats = torch.zeros((nb * nc, 3), dtype=torch.int64, device=d)
+
+            def scan(phase, offsets=None, cursor=None, fractions=None):
+                check(lib.nmb_pattern_scan(C.byref(view), ptr(index.valid), ptr(index.rank_dir), ptr(index.payload),
+                                           ptr(progs.programs), nb, mpi, progs.max_len, phase, ptr(stats), ptr(offsets),
+                                           ptr(cursor), ptr(fractions), 0, _stream()), "nmb_pattern_scan")
+
+            scan(0)
+            if median:
+                offsets = torch.empty(nb * nc + 1, dtype=torch.int64, device=d)
+                cursor = torch.empty(nb * nc, dtype=torch.int32, device=d)
+                check(lib.nmb_segment_offsets(ptr(stats), nb * nc, ptr(offsets), ptr(cursor), _stream()), "nmb_segment_offsets")
+                total = int(offsets[-1].item())
+                fractions = torch.empty(max(1, total), dtype=torch.float64, device=d)
+                med = torch.empty(nb * nc, dtype=torch.float64, device=d)
+                scan(1, offsets, cursor, fractions)
+                check(lib.nmb_segment_median(ptr(fractions), ptr(offsets), nb * nc, ptr(med), _stream()), "nmb_segment_median")
+                value_out[b0:b0 + nb] = med.cpu().numpy().reshape(nb, nc)
+            stats_out[b0:b0 + nb] = stats.cpu().numpy().reshape(nb, nc, 3)
+    return stats_out, value_out
+
+
 def methylation_pattern(pileup, assembly, motifs, threads: int = 1, min_valid_read_coverage: int = 3,
                         batch_size: int = 1000, min_valid_cov_to_diff_fraction: float = 0.8, output: str | None = None,
                         allow_assembly_pileup_mismatch: bool = True,
@@ -67,66 +133,106 @@ def methylation_pattern(pileup, assembly, motifs, threads: int = 1, min_valid_re
     from . import dataload
 
     contigs = dataload.load_fasta(assembly) if isinstance(assembly, str) else {k: (v if isinstance(v, str) else v.sequence) for k, v in assembly.items()}
-    table = dataload.load_pileup(pileup, with_counts=True) if isinstance(pileup, str) else PileupTable.from_frame(pileup)
-    if "n_mod" not in table.extra or "n_diff" not in table.extra:
-        raise KeyError("methylation_pattern needs the n_mod and n_diff pileup columns")
     asm = DeviceAssembly.from_sequences(contigs, device)
     d = asm.device
-    names = np.asarray(table.contig).astype(str)
-    uniq, inv = np.unique(names, return_inverse=True)
-    lut = np.fromiter((asm.index.get(u, -1) for u in uniq), dtype=np.int64, count=len(uniq))
-    cid_all = lut[inv] if len(uniq) else np.zeros(0, dtype=np.int64)
-    if not allow_assembly_pileup_mismatch and (cid_all < 0).any():
-        raise ValueError("pileup contains contigs that are absent from the assembly")
-    pos_all = np.asarray(table.position, dtype=np.int64)
-    cov_all = np.asarray(table.Nvalid_cov, dtype=np.int64)
-    nmod_all = np.asarray(table.extra["n_mod"], dtype=np.int64)
-    diff_all = np.asarray(table.extra["n_diff"], dtype=np.int64)
-    strand_all = strand_codes(table.strand)
-    mt_all = np.asarray(table.mod_type).astype(str)
-    in_range = (cid_all >= 0) & (pos_all >= 0) & (pos_all < asm.lengths[np.maximum(cid_all, 0)])
-    ok = in_range & (cov_all >= min_valid_read_coverage)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        ok &= (cov_all / (cov_all + diff_all)) >= min_valid_cov_to_diff_fraction
+    motifs = [str(m) for m in motifs]
+    specs = [parse_motif_spec(m) for m in motifs]
+    mod_types = sorted({mt for _, mt, _ in specs})
+    if isinstance(pileup, str):  # bedMethyl text parsed on the device (K6)
+        dr = dataload.load_pileup_device(pileup, asm.names, mod_types, with_counts=True, device=d,
+                                         keep_unknown_contigs=not allow_assembly_pileup_mismatch)
+        if not allow_assembly_pileup_mismatch and bool((dr.contig_id < 0).any()):
+            raise ValueError("pileup contains contigs that are absent from the assembly")
+        rows = dict(contig_id=dr.contig_id, position=dr.position, strand=dr.strand, mod_type=dr.mod_type, n_mod=dr.n_mod,
+                    Nvalid_cov=dr.Nvalid_cov, n_diff=dr.n_diff)
+    else:
+        table = PileupTable.from_frame(pileup)
+        if "n_mod" not in table.extra or "n_diff" not in table.extra:
+            raise KeyError("methylation_pattern needs the n_mod and n_diff pileup columns")
+        names = np.asarray(table.contig).astype(str)
+        uniq, inv = np.unique(names, return_inverse=True)
+        lut = np.fromiter((asm.index.get(u, -1) for u in uniq), dtype=np.int32, count=len(uniq))
+        cid = lut[inv] if len(uniq) else np.zeros(0, dtype=np.int32)
+        if not allow_assembly_pileup_mismatch and (cid < 0).any():
+            raise ValueError("pileup contains contigs that are absent from the assembly")
+        mt_names = np.asarray(table.mod_type).astype(str)
+        mt_code = np.full(len(mt_names), 255, dtype=np.uint8)
+        for i, m in enumerate(mod_types):
+            mt_code[mt_names == m] = i
+        with torch.cuda.device(d):
+            rows = dict(contig_id=_to_device(cid.astype(np.int32), d),
+                        position=_to_device(np.asarray(table.position, dtype=np.int64), d),
+                        strand=_to_device(strand_codes(table.strand), d), mod_type=_to_device(mt_code, d),
+                        n_mod=_to_device(np.asarray(table.extra["n_mod"], dtype=np.int64), d),
+                        Nvalid_cov=_to_device(np.asarray(table.Nvalid_cov, dtype=np.int64), d),
+                        n_diff=_to_device(np.asarray(table.extra["n_diff"], dtype=np.int64), d))
 
-    rows_by_mod: dict[str, tuple] = {}
-    out_rows = []
-    with torch.cuda.device(d):
-        for spec in motifs:
-            iupac, mod_type, mod_pos = parse_motif_spec(spec)
-            if mod_type not in rows_by_mod:
-                sel = np.flatnonzero(ok & (mt_all == mod_type))
-                sel = sel[np.lexsort((pos_all[sel], cid_all[sel]))]  # the kernels want contig-sorted rows
-                rows_by_mod[mod_type] = (
-                    _to_device(asm.starts[cid_all[sel]] + pos_all[sel], d), _to_device(strand_all[sel], d),
-                    _to_device(cid_all[sel].astype(np.int32), d), _to_device(nmod_all[sel].astype(np.int32), d),
-                    _to_device(cov_all[sel].astype(np.int32), d), len(sel))
-            gpos, st, cid, nmod, cov, n_rows = rows_by_mod[mod_type]
-            fwd, rev = _planes(asm, Motif(iupac, mod_pos).from_iupac())
-            nc = asm.n_contigs
-            stats = torch.empty((nc, 3), dtype=torch.int64, device=d)
-            offsets = torch.empty(nc + 1, dtype=torch.int64, device=d)
-            cursor = torch.empty(nc, dtype=torch.int32, device=d)
-            check(lib.nmb_pattern_stats(ptr(gpos), ptr(st), ptr(cid), ptr(nmod), ptr(cov), n_rows, ptr(fwd), ptr(rev), nc,
-                                        ptr(stats), ptr(offsets), ptr(cursor), _stream()), "nmb_pattern_stats")
-            s = stats.cpu().numpy()
-            n_obs = s[:, 0]
-            if output_type == MethylationOutput.Median:
-                total = int(n_obs.sum())
-                fractions = torch.empty(max(1, total), dtype=torch.float64, device=d)
-                median = torch.empty(nc, dtype=torch.float64, device=d)
-                check(lib.nmb_pattern_median(ptr(gpos), ptr(st), ptr(cid), ptr(nmod), ptr(cov), n_rows, ptr(fwd), ptr(rev),
-                                             nc, ptr(offsets), ptr(cursor), ptr(fractions), ptr(median), _stream()),
-                      "nmb_pattern_median")
-                value = median.cpu().numpy()
-            else:
-                with np.errstate(divide="ignore", invalid="ignore"):
-                    value = s[:, 1] / s[:, 2]
-            for c in np.flatnonzero(n_obs > 0):
-                out_rows.append((asm.names[c], iupac, mod_type, mod_pos, float(value[c]), float(s[c, 2] / s[c, 0]),
-                                 int(n_obs[c])))
-    df = pd.DataFrame(out_rows, columns=COLUMNS).astype({"mod_position": np.int8, "n_motif_obs": np.int32,
-                                                         "methylation_value": np.float64, "mean_read_cov": np.float64})
+    median = output_type == MethylationOutput.Median
+    nc = asm.n_contigs
+    stats = np.zeros((len(specs), nc, 3), dtype=np.int64)
+    value = np.full((len(specs), nc), np.nan)
+    for ti, mt in enumerate(mod_types):
+        sel = [i for i, s in enumerate(specs) if s[1] == mt]
+        index = PatternIndex(asm, rows, ti, min_valid_read_coverage, min_valid_cov_to_diff_fraction)
+        st, val = pattern_table(index, [Motif(specs[i][0], specs[i][2]).from_iupac() for i in sel], median)
+        stats[sel] = st
+        if median:
+            value[sel] = val
+        del index
+    if not median:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            value = stats[:, :, 1] / stats[:, :, 2]
+    mi, ci = np.nonzero(stats[:, :, 0] > 0)  # motif-major, contigs ascending; pairs without observations are omitted
+    obs = stats[mi, ci, 0]
+    df = pd.DataFrame({
+        "contig": np.array(asm.names, dtype=object)[ci],
+        "motif": np.array([s[0] for s in specs], dtype=object)[mi],
+        "mod_type": np.array([s[1] for s in specs], dtype=object)[mi],
+        "mod_position": np.array([s[2] for s in specs], dtype=np.int8)[mi],
+        "methylation_value": value[mi, ci].astype(np.float64),
+        "mean_read_cov": stats[mi, ci, 2] / obs,
+        "n_motif_obs": obs.astype(np.int32),
+    }, columns=COLUMNS)
     if output is not None:
         df.to_csv(output, sep="\t", index=False)
     return df
+
+
+def methylation_pattern_rows(table, contigs, spec: str, min_valid_read_coverage: int = 3,
+                             min_valid_cov_to_diff_fraction: float = 0.8, device=None):
+    """One motif through the ROW-driven kernels (nmb_pattern_stats / nmb_pattern_median: every filtered pileup row
+    tests its bit of the motif's match plane).  Kept as an independent implementation for cross-checks of the
+    tile-driven path; returns (stats [n_contigs, 3], median [n_contigs])."""
+    asm = DeviceAssembly.from_sequences(contigs, device)
+    d = asm.device
+    iupac, mod_type, mod_pos = parse_motif_spec(spec)
+    names = np.asarray(table.contig).astype(str)
+    cid = np.fromiter((asm.index.get(u, -1) for u in names), dtype=np.int64, count=len(names))
+    pos = np.asarray(table.position, dtype=np.int64)
+    cov = np.asarray(table.Nvalid_cov, dtype=np.int64)
+    diff = np.asarray(table.extra["n_diff"], dtype=np.int64)
+    ok = (cid >= 0) & (pos >= 0) & (pos < asm.lengths[np.maximum(cid, 0)]) & (cov >= min_valid_read_coverage)
+    ok &= np.asarray(table.mod_type).astype(str) == mod_type
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ok &= (cov / (cov + diff)) >= min_valid_cov_to_diff_fraction
+    sel = np.flatnonzero(ok)
+    sel = sel[np.lexsort((pos[sel], cid[sel]))]  # the row-driven kernels want contig-sorted rows
+    nc = asm.n_contigs
+    with torch.cuda.device(d):
+        gpos = _to_device(asm.starts[cid[sel]] + pos[sel], d)
+        st = _to_device(strand_codes(table.strand)[sel], d)
+        c32 = _to_device(cid[sel].astype(np.int32), d)
+        nmod = _to_device(np.asarray(table.extra["n_mod"], dtype=np.int64)[sel].astype(np.int32), d)
+        cv = _to_device(cov[sel].astype(np.int32), d)
+        fwd, rev = _planes(asm, Motif(iupac, mod_pos).from_iupac())
+        stats = torch.empty((nc, 3), dtype=torch.int64, device=d)
+        offsets = torch.empty(nc + 1, dtype=torch.int64, device=d)
+        cursor = torch.empty(nc, dtype=torch.int32, device=d)
+        check(lib.nmb_pattern_stats(ptr(gpos), ptr(st), ptr(c32), ptr(nmod), ptr(cv), len(sel), ptr(fwd), ptr(rev), nc,
+                                    ptr(stats), ptr(offsets), ptr(cursor), _stream()), "nmb_pattern_stats")
+        total = int(offsets[-1].item())
+        fractions = torch.empty(max(1, total), dtype=torch.float64, device=d)
+        median = torch.empty(nc, dtype=torch.float64, device=d)
+        check(lib.nmb_pattern_median(ptr(gpos), ptr(st), ptr(c32), ptr(nmod), ptr(cv), len(sel), ptr(fwd), ptr(rev), nc,
+                                     ptr(offsets), ptr(cursor), ptr(fractions), ptr(median), _stream()), "nmb_pattern_median")
+        return stats.cpu().numpy(), median.cpu().numpy()

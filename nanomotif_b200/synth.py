@@ -171,3 +171,42 @@ def device_workload(device, total_bp: int = 1_500_000_000, n_contigs: int = 1700
         cls[mt, :, 2] = is_t & r1 & r2
         cls[mt, :, 3] = is_t & ~r1
     return asm, pile
+
+
+def device_pattern_workload(device, total_bp: int = 1_500_000_000, n_contigs: int = 50_000, seed: int = 4, depth: int = 30):
+    """cfg4-shaped input of the contig x motif table built ON the device: `n_contigs` lognormal contigs and one
+    read-level pileup row (n_mod, Nvalid_cov, n_diff) for every A on '+' and every T on '-' (mod type 'a').
+    Returns (DeviceAssembly, rows) with rows = device tensors contig_id int32, position int64, strand uint8,
+    n_mod / Nvalid_cov / n_diff int64 in (strand, contig, position) order."""
+    import torch
+
+    from .device import DeviceAssembly
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    lens = rng.lognormal(mean=0.0, sigma=1.0, size=n_contigs)
+    lens = np.maximum(2500, (lens / lens.sum() * total_bp).astype(np.int64))
+    off = np.zeros(n_contigs, dtype=np.int64)
+    off[1:] = np.cumsum(lens)[:-1]
+    codes = torch.randint(0, 4, (int(lens.sum()),), dtype=torch.uint8, device=device, generator=g)
+    ascii_d = 65 + (codes == 1).to(torch.uint8) * 19 + (codes == 2).to(torch.uint8) * 6 + (codes == 3).to(torch.uint8) * 2
+    asm = DeviceAssembly([f"c{i}" for i in range(n_contigs)], lens, ascii_d, off, device)
+    del ascii_d
+    bounds = torch.from_numpy(off[1:].copy()).to(device)
+    off_d = torch.from_numpy(off).to(device)
+    cols = {k: [] for k in ("contig_id", "position", "strand", "n_mod", "Nvalid_cov", "n_diff")}
+    for strand, code in ((0, 0), (1, 1)):
+        idx = torch.nonzero(codes == code).view(-1)
+        cid = torch.bucketize(idx, bounds, right=True)
+        n = int(idx.numel())
+        cov = torch.randint(1, 2 * depth, (n,), dtype=torch.int64, device=device, generator=g)
+        cols["contig_id"].append(cid.to(torch.int32))
+        cols["position"].append(idx - off_d[cid])
+        cols["strand"].append(torch.full((n,), strand, dtype=torch.uint8, device=device))
+        cols["n_mod"].append((torch.rand(n, device=device, generator=g) * (cov + 1).to(torch.float32)).to(torch.int64).clamp_(max=cov))
+        cols["Nvalid_cov"].append(cov)
+        cols["n_diff"].append(torch.randint(0, depth // 3, (n,), dtype=torch.int64, device=device, generator=g))
+        del idx, cid
+    del codes
+    return asm, {k: torch.cat(v) for k, v in cols.items()}

@@ -100,3 +100,65 @@ def test_counts_agree_with_match_planes(W):
             m = plane.view(asm.n_tiles, _lib.TILE_WORDS)[:, torch.from_numpy(_lib.SLOT_WORD).to(W["dev"])]
             want += [_popcount(torch, m & cls[:, 2 * strand]), _popcount(torch, m & cls[:, 2 * strand + 1])]
         assert _scan(W, [(s, p)])[0, 0].tolist() == want
+
+
+def test_pattern_table_at_cfg4_size():
+    """BASELINE.json configs[3]: 50 000 contigs, 1.5 Gbp, read-level pileup (0.75e9 rows).  The CPU oracle cannot run
+    at this size; checked through properties: K5 n_motif_obs == K2 per-contig counts over planes built from the same
+    valid rows (two different kernels, two different joins), column sums against torch reductions of the rows, and
+    exact medians of a few contigs recomputed from their rows."""
+    import time
+
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import nanomotif_b200 as nmb
+    from nanomotif_b200 import synth
+    from nanomotif_b200.device import DevicePileup, MotifPrograms, make_jobs, scan_count
+    from nanomotif_b200.pattern import PatternIndex, pattern_table
+
+    dev = torch.device("cuda", 0)
+    asm, rows = synth.device_pattern_workload(dev, 1_500_000_000, 50_000, seed=4)
+    nc = asm.n_contigs
+    n_rows = int(rows["position"].numel())
+    assert n_rows > 7e8
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    index = PatternIndex(asm, rows, 0, 3, 0.8)
+    torch.cuda.synchronize()
+    t_index = time.perf_counter() - t0
+    cov, diff = rows["Nvalid_cov"], rows["n_diff"]
+    ok = (cov >= 3) & ((cov.double() / (cov + diff).double()) >= 0.8)
+    assert index.n_valid_rows == int(ok.sum()) and 0.5 * n_rows < index.n_valid_rows < n_rows
+
+    specs = [("GATC", 1), ("A", 0), ("CC[AT]GG", 2), ("G[AG].GAAG[CT]", 5), ("GCAC......GTT", 2), ("T", 0),
+             ("[AG]AA[CT]", 1), ("TTAA", 3)]
+    motifs = [nmb.Motif(s, p) for s, p in specs]
+    t0 = time.perf_counter()
+    stats, med = pattern_table(index, motifs, median=True)
+    t_table = time.perf_counter() - t0
+    print(f"cfg4: index {t_index * 1e3:.0f} ms, {len(motifs)} motifs x {nc} contigs (median) {t_table * 1e3:.0f} ms")
+
+    # (1) K2 on class planes made of the same valid rows: n_mod('+') + n_mod('-') per contig == n_motif_obs
+    frac = torch.where(ok, 1.0, 0.5).double()
+    pile = DevicePileup.from_columns(asm, rows["contig_id"], rows["position"], rows["strand"], frac, 0.3, 0.7, None, 1)
+    del frac
+    jobs = make_jobs(1)
+    jobs["motif_count"], jobs["tile_count"], jobs["contig_end"] = len(motifs), asm.n_tiles, nc
+    jobs["group_mode"], jobs["n_groups"] = 1, nc
+    k2 = scan_count(asm, pile, MotifPrograms(motifs, dev), jobs, len(motifs) * nc).view(len(motifs), nc, 4).cpu().numpy()
+    np.testing.assert_array_equal(stats[:, :, 0], k2[:, :, 0] + k2[:, :, 2])
+    assert stats[0, :, 0].sum() > 1e6
+    # (2) motif A: every valid '+' row is an occurrence, and T on '-' through the reverse complement
+    cid = rows["contig_id"].long()
+    for col, k in (("n_mod", 1), ("Nvalid_cov", 2)):
+        want = torch.zeros(nc, dtype=torch.int64, device=dev).index_add_(0, cid[ok], rows[col][ok]).cpu().numpy()
+        np.testing.assert_array_equal(stats[1, :, k], want)
+    # motif T: '+' occurrences at T have no '+' rows, its reverse complement A has no '-' rows
+    assert stats[5].sum() == 0 and np.isnan(med[5]).all()
+    # (3) exact medians of a few contigs from their rows
+    fr = rows["n_mod"].double() / cov.double()
+    for c in (0, 17, 4242, nc - 1):
+        sel = ok & (rows["contig_id"] == c)
+        assert med[1, c] == float(np.median(fr[sel].cpu().numpy()))

@@ -76,3 +76,40 @@ def test_large_segment_median_uses_radix_select():
     for name, motif, mt, mp, value, cov, n in want:
         r = got[(name, motif)]
         assert r.n_motif_obs == n and r.methylation_value == pytest.approx(value, rel=1e-12, abs=1e-15)
+
+
+def test_tile_driven_equals_row_driven_and_file_input(tmp_path):
+    """Two independent implementations of the join (tile-driven nmb_pattern_scan behind methylation_pattern, row-driven
+    nmb_pattern_stats / nmb_pattern_median) agree cell by cell; a bedMethyl FILE parsed on the device gives the same table."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from nanomotif_b200.pattern import methylation_pattern, methylation_pattern_rows
+
+    contigs, t = _data(seed=12)
+    specs = ["GATC_a_1", "CCWGG_m_1", "A_a_0", "GRNGAAGY_a_5", "C" + "N" * 33 + "AT_a_34", "T_m_0"]
+    df = methylation_pattern(t, contigs, specs)
+    names = list(contigs)
+    for spec in specs:
+        stats, med = methylation_pattern_rows(t, contigs, spec)
+        sub = df[(df["motif"] + "_" + df["mod_type"] + "_" + df["mod_position"].astype(str)) == spec]
+        assert len(sub) == int((stats[:, 0] > 0).sum())
+        for r in sub.itertuples():
+            c = names.index(r.contig)
+            assert r.n_motif_obs == stats[c, 0] and r.mean_read_cov == stats[c, 2] / stats[c, 0]
+            assert r.methylation_value == med[c]  # both take the exact median of the same multiset
+    # the same pileup as a bedMethyl file
+    keep = t.contig != "ghost"
+    path = tmp_path / "p.bed"
+    with open(path, "w") as f:
+        for i in np.flatnonzero(keep):
+            pos, cov = int(t.position[i]), int(t.Nvalid_cov[i])
+            row = [t.contig[i], pos, pos + 1, t.mod_type[i], cov, t.strand[i], pos, pos + 1, "255,0,0", cov,
+                   f"{t.fraction_mod[i] * 100:.2f}", int(t.extra["n_mod"][i]), 0, 0, 0, 0, int(t.extra["n_diff"][i]), 0]
+            f.write("\t".join(str(x) for x in row) + "\n")
+    fa = tmp_path / "a.fasta"
+    fa.write_text("".join(f">{n}\n{s}\n" for n, s in contigs.items()))
+    out = tmp_path / "table.tsv"
+    df2 = methylation_pattern(str(path), str(fa), specs, output=str(out))
+    assert df2.equals(df) and out.read_text().startswith("contig\tmotif\tmod_type")
