@@ -16,7 +16,7 @@ namespace nmb {
 
 constexpr int kValidRecWords = 2 * kTileWords;                  // valid '+', valid '-'
 constexpr int kValidRecBytes = kValidRecWords * 4;              // 16 KB
-constexpr int kPatSmemBytes = kSeqRecBytes + kValidRecBytes;    // 33.3 KB
+constexpr int kPatSmemBytes = kSeqRecBytes + kValidRecBytes + 2 * kChunkWords * kTileChunks * 2;  // 33.3 KB + 8 KB prefix counts
 constexpr int kPatThreads = kTileChunks;
 
 // ---- index build ------------------------------------------------------------------------------
@@ -144,31 +144,128 @@ struct PatParams {
     int n_motifs, mpi, n_mblk, n_tiles, n_contigs, n_items, write;
 };
 
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
-    return v;  // lane 0 holds the sum
+// ---- warp hit queue ---------------------------------------------------------------------------
+// Occurrences that have a pileup row ("hits") are found lane by lane, but fetching their payload lane by
+// lane would leave one dependent load in flight per warp.  Instead every lane pushes its hits (payload row,
+// contig, motif) into a per-warp queue in shared memory that lives across the motifs of a work item;
+// whenever 32 are waiting the warp drains them together: 32 independent payload loads, then one masked
+// warp reduction (REDUX) and one update per distinct (motif, contig) among them.
+constexpr int kQueueLen = 64;
+static_assert(NMB_MAX_MOTIFS_PER_ITEM == 32, "WarpQueue::acc is reset and flushed one motif per lane");
+
+struct WarpQueue {
+    uint32_t row[kQueueLen];
+    int32_t contig[kQueueLen];
+    uint8_t mi[kQueueLen];
+    int n;                                                // entries waiting (warp-uniform)
+    unsigned long long acc[NMB_MAX_MOTIFS_PER_ITEM][3];   // phase 0: counts of the warp's first contig, per motif
+};
+
+__device__ __forceinline__ unsigned long long redux_u64_of_u32(unsigned x) {  // sum over the warp, no overflow
+    return (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, x & 0xFFFFu) +
+           ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, x >> 16) << 16);
 }
 
+// Drain the first n (<= 32) queue entries.  Phase 0: {obs, sum n_mod, sum n_valid_cov} per (motif, contig)
+// -- into q.acc for the warp's first contig c0 (flushed once per work item), straight to global for the
+// other contigs of a warp that straddles contigs.  Phase 1: the fractions go to their (motif, contig)
+// segment; one cursor update per group, ranks inside the group give the slots.
+__device__ __noinline__ void drain_hits(const PatParams *p, WarpQueue *q, int n, int m_begin, int c0) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const bool on = lane < n;
+    const int c = on ? q->contig[lane] : -1;
+    const int mi = on ? q->mi[lane] : 0;
+    int2 pl = make_int2(0, 0);
+    if (on) pl = __ldg(p->payload + q->row[lane]);
+    unsigned remaining = __ballot_sync(0xFFFFFFFFu, on);
+    while (remaining) {  // one round per distinct (motif, contig); warp-uniform control flow
+        const int src = __ffs(remaining) - 1;
+        const int cl = __shfl_sync(0xFFFFFFFFu, c, src), ml = __shfl_sync(0xFFFFFFFFu, mi, src);
+        const bool in = on && c == cl && mi == ml;
+        const unsigned grp = __ballot_sync(0xFFFFFFFFu, in);
+        remaining &= ~grp;
+        const size_t seg = (size_t)(m_begin + ml) * p->n_contigs + cl;
+        if (p->write) {
+            int slot0 = 0;
+            if (lane == src) slot0 = atomicAdd(p->cursor + seg, __popc(grp));
+            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, src);
+            if (in) p->fractions[p->offsets[seg] + slot0 + __popc(grp & lt)] = (double)pl.x / (double)pl.y;
+        } else {
+            const unsigned long long sm = redux_u64_of_u32(in ? (unsigned)pl.x : 0u);
+            const unsigned long long sc = redux_u64_of_u32(in ? (unsigned)pl.y : 0u);
+            if (lane == src) {
+                const unsigned long long cnt = __popc(grp);
+                if (cl == c0) {  // only this warp touches q->acc, one lane per round
+                    q->acc[ml][0] += cnt;
+                    q->acc[ml][1] += sm;
+                    q->acc[ml][2] += sc;
+                } else {
+                    unsigned long long *st = p->stats + seg * 3;
+                    atomicAdd(st + 0, cnt);
+                    atomicAdd(st + 1, sm);
+                    atomicAdd(st + 2, sc);
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// Every lane pushes the set bits of `hits` (word-local occurrences with a valid row; v = the word of the
+// valid plane, base = rows before the word); drains whenever 32 entries wait.
+__device__ __noinline__ void push_hits(const PatParams *p, WarpQueue *q, uint32_t hits, uint32_t v, uint32_t base,
+                                       int contig, int mi, int m_begin, int c0) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int qn = q->n;
+    unsigned any = __ballot_sync(0xFFFFFFFFu, hits != 0);
+    while (any) {  // every lane with hits left pushes one
+        if (hits) {
+            const int b = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int slot = qn + __popc(any & lt);
+            q->row[slot] = base + __popc(v & ((1u << b) - 1u));
+            q->contig[slot] = contig;
+            q->mi[slot] = (uint8_t)mi;
+        }
+        qn += __popc(any);
+        __syncwarp();
+        if (qn >= 32) {
+            drain_hits(p, q, 32, m_begin, c0);
+            const int rest = qn - 32;  // <= 31: move the tail to the front
+            uint32_t r = 0;
+            int cc = 0, mm = 0;
+            if (lane < rest) { r = q->row[32 + lane]; cc = q->contig[32 + lane]; mm = q->mi[32 + lane]; }
+            __syncwarp();
+            if (lane < rest) { q->row[lane] = r; q->contig[lane] = cc; q->mi[lane] = (uint8_t)mm; }
+            __syncwarp();
+            qn = rest;
+        }
+        any = __ballot_sync(0xFFFFFFFFu, hits != 0);
+    }
+    if (lane == 0) q->n = qn;
+    __syncwarp();
+}
+
+// s_pref[(strand * NW + word) * 128 + chunk] = valid rows of the chunk's strand before that word (uint16)
 template <int H, bool HASN>
-__device__ __forceinline__ void pattern_motifs(const PatParams &p, int tile, int mblk, const LaneSeq<H, HASN> &q,
-                                               const LaneEdge &edge, const uint32_t *sv, int contig, bool uniform,
-                                               int first_lane) {
+__device__ __forceinline__ void pattern_motifs(const PatParams &p, int mblk, const LaneSeq<H, HASN> &q,
+                                               const LaneEdge &edge, const uint32_t *sv, const uint16_t *s_pref,
+                                               WarpQueue &wq, uint32_t rank_p, uint32_t rank_m, int contig, int c0) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int m_begin = mblk * p.mpi;
     const int m_count = min(p.mpi, p.n_motifs - m_begin);
-    const int64_t dir0 = (int64_t)tile * kTileWords + tid * NW;  // flat index of the lane's first word, '+' strand
+    wq.acc[lane][0] = wq.acc[lane][1] = wq.acc[lane][2] = 0;  // NMB_MAX_MOTIFS_PER_ITEM == 32 lanes
+    if (lane == 0) wq.n = 0;
+    __syncwarp();
 #pragma unroll 1
     for (int mi = 0; mi < m_count; ++mi) {
-        const int motif = m_begin + mi;
-        const ProgramView pv = load_program(p.programs + (size_t)motif * 2);
+        const ProgramView pv = load_program(p.programs + (size_t)(m_begin + mi) * 2);
         uint32_t c[NW + 2 * H], d[NW + 2 * H];
         if (!run_chain_pair<H, HASN>(pv, q, c, d, edge)) continue;
         const bool far = pv.mod_pos >= 32;
         const int sh = pv.mod_pos & 31;
-        const size_t seg = (size_t)motif * p.n_contigs + (contig < 0 ? 0 : contig);
-        unsigned obs = 0;
-        unsigned long long sm = 0, sc = 0;
 #pragma unroll
         for (int h = 0; h < NW; h += 4) {
             const uint4 vp = *reinterpret_cast<const uint4 *>(sv + (h >> 2) * kSlotStride);
@@ -179,55 +276,31 @@ __device__ __forceinline__ void pattern_motifs(const PatParams &p, int tile, int
                 const uint32_t v1 = k == 0 ? vm.x : k == 1 ? vm.y : k == 2 ? vm.z : vm.w;
                 uint32_t hit0 = aligned_word<H>(c, h + k, sh, far) & v0;
                 uint32_t hit1 = aligned_word_rc<H>(d, h + k, sh, far) & v1;
-                if (contig < 0 || !(hit0 | hit1)) continue;  // occurrences WITH a pileup row are sparse
-#pragma unroll 1
-                for (int s = 0; s < 2; ++s) {
-                    uint32_t hits = s ? hit1 : hit0;
-                    const uint32_t v = s ? v1 : v0;
-                    if (!hits) continue;
-                    const int64_t base = __ldg(p.rank_dir + (s ? p.n_words : 0) + dir0 + h + k);
-                    while (hits) {
-                        const int b = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        const int2 pl = __ldg(p.payload + base + __popc(v & ((1u << b) - 1u)));
-                        if (p.write) {
-                            const int slot = atomicAdd(p.cursor + seg, 1);
-                            p.fractions[p.offsets[seg] + slot] = (double)pl.x / (double)pl.y;
-                        } else {
-                            ++obs;
-                            sm += (unsigned)pl.x;
-                            sc += (unsigned)pl.y;
-                        }
-                    }
-                }
+                if (contig < 0) hit0 = hit1 = 0;
+                if (!__any_sync(0xFFFFFFFFu, (hit0 | hit1) != 0)) continue;  // occurrences WITH a pileup row are sparse
+                push_hits(&p, &wq, hit0, v0, rank_p + s_pref[(h + k) * kTileChunks + tid], contig, mi, m_begin, c0);
+                push_hits(&p, &wq, hit1, v1, rank_m + s_pref[(NW + h + k) * kTileChunks + tid], contig, mi, m_begin, c0);
             }
-        }
-        if (p.write) continue;
-        if (uniform) {  // every counted lane of the warp belongs to one contig
-            obs = __reduce_add_sync(0xFFFFFFFFu, obs);
-            if (obs == 0) continue;
-            sm = warp_sum_u64(sm);
-            sc = warp_sum_u64(sc);
-            const int c0 = __shfl_sync(0xFFFFFFFFu, contig, first_lane);
-            if (lane == 0) {
-                unsigned long long *st = p.stats + ((size_t)motif * p.n_contigs + c0) * 3;
-                atomicAdd(st + 0, (unsigned long long)obs);
-                atomicAdd(st + 1, sm);
-                atomicAdd(st + 2, sc);
-            }
-        } else if (obs) {
-            unsigned long long *st = p.stats + seg * 3;
-            atomicAdd(st + 0, (unsigned long long)obs);
-            atomicAdd(st + 1, sm);
-            atomicAdd(st + 2, sc);
         }
     }
+    if (wq.n) drain_hits(&p, &wq, wq.n, m_begin, c0);
+    __syncwarp();
+    if (!p.write && lane < m_count && wq.acc[lane][0]) {
+        unsigned long long *st = p.stats + ((size_t)(m_begin + lane) * p.n_contigs + c0) * 3;
+        atomicAdd(st + 0, wq.acc[lane][0]);
+        atomicAdd(st + 1, wq.acc[lane][1]);
+        atomicAdd(st + 2, wq.acc[lane][2]);
+    }
+    __syncwarp();
 }
+
+constexpr int kPrefBytes = 2 * NW * kTileChunks * 2;  // uint16 prefix counts: 8 KB
 
 template <int H>
 __global__ void __launch_bounds__(kPatThreads, 4) pattern_scan_kernel(const PatParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar;
+    __shared__ WarpQueue s_queue[kPatThreads / 32];
     const int tid = threadIdx.x;
     const int n_my = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (tid == 0) {
@@ -235,6 +308,7 @@ __global__ void __launch_bounds__(kPatThreads, 4) pattern_scan_kernel(const PatP
         fence_barrier_init();
     }
     __syncthreads();
+    uint16_t *s_pref = reinterpret_cast<uint16_t *>(smem + kSeqRecBytes + kValidRecBytes);
     for (int k = 0; k < n_my; ++k) {
         const int item = (int)blockIdx.x + k * (int)gridDim.x;
         const int tile = item / p.n_mblk, mblk = item % p.n_mblk;  // tile-major: concurrent CTAs share a tile in L2
@@ -244,31 +318,43 @@ __global__ void __launch_bounds__(kPatThreads, 4) pattern_scan_kernel(const PatP
             bulk_g2s(smem, p.seq_records + (size_t)tile * kSeqRecWords, kSeqRecBytes, &full_bar);
             bulk_g2s(smem + kSeqRecBytes, p.valid + (size_t)tile * kValidRecWords, kValidRecBytes, &full_bar);
         }
+        // rows before the lane's chunk on each strand: the only rank-directory reads of the tile
+        const int64_t dir0 = (int64_t)tile * kTileWords + tid * NW;
+        const uint32_t rank_p = __ldg(p.rank_dir + dir0), rank_m = __ldg(p.rank_dir + p.n_words + dir0);
         mbar_wait(&full_bar, (uint32_t)(k & 1));
         const uint32_t *sx = reinterpret_cast<const uint32_t *>(smem);
         const uint32_t *sy = sx + kSeqPlaneWords;
         const int32_t *sinfo = reinterpret_cast<const int32_t *>(sy + kSeqPlaneWords);
         const uint32_t *sv = sx + kSeqRecWords + tid * 4;
+        {   // per-word prefix counts of the lane's valid rows (only this lane reads them back)
+            int run_p = 0, run_m = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                s_pref[w * kTileChunks + tid] = (uint16_t)run_p;
+                s_pref[(NW + w) * kTileChunks + tid] = (uint16_t)run_m;
+                run_p += __popc(sv[(w >> 2) * kSlotStride + (w & 3)]);
+                run_m += __popc(sv[kTileWords + (w >> 2) * kSlotStride + (w & 3)]);
+            }
+        }
         const int info = sinfo[tid];
         const int contig = info < 0 ? -1 : (info & kChunkIdMask);
         const unsigned vmask = __ballot_sync(0xFFFFFFFFu, contig >= 0);
         if (vmask) {
-            const int first = __ffs(vmask) - 1;
-            const int c0 = __shfl_sync(0xFFFFFFFFu, contig, first);
-            const bool uniform = __all_sync(0xFFFFFFFFu, contig < 0 || contig == c0);
+            const int c0 = __shfl_sync(0xFFFFFFFFu, contig, __ffs(vmask) - 1);
             const bool warp_n = __any_sync(0xFFFFFFFFu, contig >= 0 && (info & kChunkFlagN));
             const bool warp_edge = __any_sync(0xFFFFFFFFu, contig >= 0 && (info & kChunkFlagEdge));
+            WarpQueue &wq = s_queue[tid >> 5];
             if (warp_n) {
                 LaneSeq<H, true> q;
                 load_xyn<H>(sx, sy, tid, p.nonacgt + kHalo + (size_t)tile * kTileWords + tid * NW - H, q);
                 const LaneEdge edge = {0, false, false};
-                pattern_motifs<H, true>(p, tile, mblk, q, edge, sv, contig, uniform, first);
+                pattern_motifs<H, true>(p, mblk, q, edge, sv, s_pref, wq, rank_p, rank_m, contig, c0);
             } else {
                 LaneSeq<H, false> q;
                 load_xy<H>(sx, sy, tid, q);
                 const LaneEdge edge = lane_edge(warp_edge, info, (int64_t)tile * kTileChunks + tid, p.contig_start,
                                                 p.contig_len);
-                pattern_motifs<H, false>(p, tile, mblk, q, edge, sv, contig, uniform, first);
+                pattern_motifs<H, false>(p, mblk, q, edge, sv, s_pref, wq, rank_p, rank_m, contig, c0);
             }
         }
         __syncthreads();  // everyone is done with the tile

@@ -85,15 +85,27 @@ def pattern_table(index: PatternIndex, motifs, median: bool = True, batch: int =
     """(stats int64 [n_motifs, n_contigs, 3] = n_motif_obs / sum n_mod / sum n_valid_cov, value float64
     [n_motifs, n_contigs] = median of the per-occurrence fractions, or None) on the host, for regex `Motif`s
     scored against one mod type's index.  Two tile-driven passes per batch of motifs (count, then write +
-    exact medians)."""
+    exact medians); a batch's results travel to pinned host memory while the next batch is scanned."""
     asm = index.asm
     d, nc = asm.device, asm.n_contigs
     motifs = list(motifs)
     stats_out = np.zeros((len(motifs), nc, 3), dtype=np.int64)
     value_out = np.full((len(motifs), nc), np.nan) if median else None
     view = asm.view()
+    batch = max(1, min(batch, len(motifs)))
     with torch.cuda.device(d):
-        for b0 in range(0, len(motifs), batch):
+        host = [(torch.empty((batch * nc, 3), dtype=torch.int64, pin_memory=True),
+                 torch.empty(batch * nc, dtype=torch.float64, pin_memory=True) if median else None) for _ in range(2)]
+        pending = None  # (b0, nb, slot, event, device tensors kept alive until the copy has finished)
+
+        def collect(job):
+            b0, nb, slot, ev, _keep = job
+            ev.synchronize()
+            stats_out[b0:b0 + nb] = host[slot][0][:nb * nc].numpy().reshape(nb, nc, 3)
+            if median:
+                value_out[b0:b0 + nb] = host[slot][1][:nb * nc].numpy().reshape(nb, nc)
+
+        for bi, b0 in enumerate(range(0, len(motifs), batch)):
             chunk = motifs[b0:b0 + batch]
             progs = MotifPrograms(chunk, d, strip=False)
             nb = len(chunk)
@@ -106,6 +118,7 @@ def pattern_table(index: PatternIndex, motifs, median: bool = True, batch: int =
                                            ptr(cursor), ptr(fractions), 0, _stream()), "nmb_pattern_scan")
 
             scan(0)
+            med = None
             if median:
                 offsets = torch.empty(nb * nc + 1, dtype=torch.int64, device=d)
                 cursor = torch.empty(nb * nc, dtype=torch.int32, device=d)
@@ -115,8 +128,17 @@ def pattern_table(index: PatternIndex, motifs, median: bool = True, batch: int =
                 med = torch.empty(nb * nc, dtype=torch.float64, device=d)
                 scan(1, offsets, cursor, fractions)
                 check(lib.nmb_segment_median(ptr(fractions), ptr(offsets), nb * nc, ptr(med), _stream()), "nmb_segment_median")
-                value_out[b0:b0 + nb] = med.cpu().numpy().reshape(nb, nc)
-            stats_out[b0:b0 + nb] = stats.cpu().numpy().reshape(nb, nc, 3)
+            slot = bi & 1
+            host[slot][0][:nb * nc].copy_(stats, non_blocking=True)
+            if median:
+                host[slot][1][:nb * nc].copy_(med, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if pending is not None:
+                collect(pending)  # the previous batch, while this one runs
+            pending = (b0, nb, slot, ev, (stats, med, progs))
+        if pending is not None:
+            collect(pending)
     return stats_out, value_out
 
 
