@@ -393,3 +393,51 @@ def methylation_pattern(contigs: dict, contig, position, strand, mod_type, n_mod
             value = m.sum() / c.sum() if weighted_mean else float(np.median(m / c))
             rows.append((name, iupac, mt, mp, float(value), float(c.mean()), len(idx)))
     return rows
+
+
+# ---------------------------------------------------------------------------------------------
+# 8f rank 3: table products (nanomotif/utils.py:15-34, binnary/data_processing.py:174-269), pandas instead of polars
+# ---------------------------------------------------------------------------------------------
+def motif_type(motif_str: str) -> str:
+    """utils.py:26-34 with seq.reverse_compliment (seq.py:645-647, constants.py:14-20)."""
+    import re
+
+    comp = {"A": "T", "T": "A", "G": "C", "C": "G", "N": "N", "R": "Y", "Y": "R", "S": "S", "W": "W", "K": "M", "M": "K",
+            "B": "V", "D": "H", "H": "D", "V": "B"}
+    if len(re.findall(r"(N){2,}", motif_str)) >= 2:
+        return "ambiguous"
+    if re.search(r"(N){3,}", motif_str):
+        return "bipartite"
+    if "".join(comp[b] for b in reversed(motif_str)) == motif_str:
+        return "palindrome"
+    return "non-palindrome"
+
+
+def binnary_matrix(contig_methylation, contig_bins: dict, methylation_threshold: float = 24.0):
+    """main.py:192-193 filter, then add_bin (:174-187), impute_contig_methylation_within_bin (:189-213) and
+    create_matrix (:255-269) on a pandas frame with the columns of main.py:157-161.  Returns (contig names,
+    matrix, feature names)."""
+    import pandas as pd
+
+    df = contig_methylation
+    df = df[df["n_motif_obs"].astype(np.float64) * df["mean_read_cov"] >= methylation_threshold].copy()
+    df["motif_mod"] = df["motif"] + "_" + df["mod_type"] + "_" + df["mod_position"].astype(str)
+    df["bin"] = [contig_bins.get(c, "unbinned") for c in df["contig"]]
+    df = df.drop(columns=["mod_position", "mod_type", "motif"])
+    df = df[df["bin"] != "unbinned"]
+    g = df.assign(w=df["methylation_value"] * df["n_motif_obs"]).groupby(["bin", "motif_mod"], as_index=False).agg(
+        num=("w", "sum"), den=("n_motif_obs", "sum"))
+    g["mean_bin_methylation"] = g["num"] / g["den"]
+    cross = df.drop_duplicates(subset=["contig", "bin"])[["contig", "bin"]]
+    imp = cross.merge(g[["bin", "motif_mod", "mean_bin_methylation"]], on="bin", how="left")
+    imp = imp.merge(df[["bin", "contig", "motif_mod", "methylation_value"]], on=["bin", "contig", "motif_mod"], how="left")
+    imp = imp.sort_values(["bin", "contig", "motif_mod"], kind="stable")
+    imp["methylation_value"] = imp["methylation_value"].where(imp["methylation_value"].notna(), imp["mean_bin_methylation"])
+    contigs = list(dict.fromkeys(imp["contig"]))  # pivot keeps the order of first appearance
+    feats = sorted(imp["motif_mod"].unique())
+    mat = np.zeros((len(contigs), len(feats)))
+    ci = {c: i for i, c in enumerate(contigs)}
+    fi = {f: i for i, f in enumerate(feats)}
+    for c, f, v in zip(imp["contig"], imp["motif_mod"], imp["methylation_value"]):
+        mat[ci[c], fi[f]] = v
+    return np.array(contigs, dtype=object), mat, np.array(feats, dtype=object)

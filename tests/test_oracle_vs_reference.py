@@ -71,3 +71,16 @@ def test_growth_functions(nm):
     random.seed(4)
     want_bg = [s.sequence for s in D.sample_n_subsequences_unique(41, 60, "C").sequences]
     assert O.sample_background(seq, 41, 60, "C", random.Random(4)) == want_bg
+
+
+def test_motif_type_and_reverse_compliment(nm):
+    """utils.motif_type / seq.reverse_compliment of the real reference on random IUPAC motifs."""
+    from nanomotif_b200 import tables
+
+    rng = np.random.default_rng(5)
+    letters = list("ACGTRYSWKMBDHVN")
+    for _ in range(300):
+        L = int(rng.integers(1, 16))
+        m = "".join(rng.choice(letters, size=L, p=[0.15] * 4 + [0.02] * 10 + [0.2]))
+        assert O.motif_type(m) == nm.utils.motif_type(m) == tables.motif_type(m), m
+        assert tables.reverse_compliment(m) == nm.seq.reverse_compliment(m)
