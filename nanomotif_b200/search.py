@@ -236,6 +236,82 @@ def find_candidates(mod_type: str, padding: int, bin_pssm: np.ndarray, total_win
 
 
 # ---------------------------------------------------------------------------------------------
+# merge re-scoring
+# ---------------------------------------------------------------------------------------------
+
+
+def merge_group(rows: list, clusters, merge_threshold: float = 0.5, trace: list | None = None):
+    """Coroutine form of the per-(bin, mod_type) body of merge_motifs_in_df (find_motifs_bin.py:1438-1533).
+
+    `rows`: this group's motif rows (dicts with motif, mod_position, score, reference, mod_type, model);
+    `clusters`: the values of nanomotif.motif.merge_motifs(motifs) (motif.py:519-560): (merged motif, pre-merge
+    motifs, pre-merge variants, new variants).  The reference scores the merged motif and every exploded variant
+    with one motif_model_bin call each, cluster after cluster, then every accepted motif and its parents; here
+    the group issues TWO score requests (all clusters at once, then all accepted motifs with their parents), and
+    run_lockstep folds the requests of all groups into one launch each.  Returns the new rows."""
+    clusters = [tuple(c) for c in clusters]
+    request, layout = [], []
+    for merged, _premerge, pre_variants, new_variants in clusters:
+        if len(new_variants) == 0:  # :1456-1460
+            layout.append(None)
+            continue
+        variants = list(pre_variants)
+        layout.append((len(request), len(variants)))
+        request += [merged] + variants
+    models = (yield ("score", request)) if request else []
+    merged_motifs, premerge_motifs = [], []
+    for (merged, premerge, _pre, _new), where in zip(clusters, layout):
+        rec = dict(merged=merged, scored=where is not None)
+        if where is not None:
+            at, n = where
+            merge_model = models[at]
+            variants_model = BetaBernoulliModel()  # :1470-1479: one model threaded through all variants
+            for m in models[at + 1:at + 1 + n]:
+                variants_model.update(m._alpha - m._alpha_prior, m._beta - m._beta_prior)
+            rec["merge_score"] = predictive_evaluation_score(variants_model, merge_model)  # :1480
+            rec["merge_model"], rec["variants_model"] = merge_model, variants_model
+            rec["accepted"] = rec["merge_score"] < merge_threshold
+        else:
+            rec["accepted"] = True
+        if trace is not None:
+            trace.append(rec)
+        if rec["accepted"]:
+            merged_motifs.append(merged)
+            premerge_motifs.extend(premerge)
+    if not premerge_motifs:  # :1492-1496
+        return list(rows)
+    gone = {str.__str__(m) for m in premerge_motifs}
+    out = [r for r in rows if str(r["motif"]) not in gone]  # :1498
+    request, layout = [], []
+    for motif in merged_motifs:  # :1501-1517, one request for every motif and all its parents
+        split = motif.split()
+        parents = []
+        for i, base in enumerate(split):
+            if i == motif.mod_position or base in (".", "N"):
+                continue
+            toks = list(split)
+            toks[i] = "."
+            parents.append(Motif("".join(toks), motif.mod_position))
+        layout.append((len(request), len(parents)))
+        request += [motif] + parents
+    models = yield ("score", request)
+    for motif, (at, n) in zip(merged_motifs, layout):
+        model = models[at]
+        scores = [predictive_evaluation_score(model, pm) for pm in models[at + 1:at + 1 + n]]
+        out.append(dict(motif=motif.string, score=float(np.mean(scores)) if scores else -1, mod_position=motif.mod_position,
+                        reference=rows[0]["reference"] if rows else None, mod_type=rows[0]["mod_type"] if rows else None,
+                        model=model))  # :1518-1527
+    return out
+
+
+def merge_motifs_in_groups(groups: list, batch_score=None) -> list:
+    """merge_motifs_in_df over many (bin, mod_type) groups in lock-step.  groups = [(rows, clusters, backend)] or
+    [(rows, clusters, backend, merge_threshold)]; returns the new rows of every group, in order."""
+    searches = [(merge_group(g[0], g[1], *(g[3:4])), g[2]) for g in groups]
+    return run_lockstep(searches, batch_score)
+
+
+# ---------------------------------------------------------------------------------------------
 # drivers
 # ---------------------------------------------------------------------------------------------
 

@@ -99,3 +99,33 @@ def check_against_trace(trace, result, rounds):
         assert abs(d["priority"] - n["priority"]) <= 1e-9 * max(1.0, abs(n["priority"]))
         assert d["depth"] == n["depth"] and bool(d["visited"]) == n["visited"]
     assert sorted([u.string, v.string] for u, v in graph.edges()) == sorted(trace["edges"])
+
+
+def load_merge_trace():
+    with open(os.path.join(HERE, "golden", "merge_trace.json")) as f:
+        return json.load(f)
+
+
+def merge_inputs(golden, run, Motif, Model):
+    """(rows, clusters) of one golden merge run as nanomotif_b200 objects."""
+    rows = [dict(motif=s, mod_position=p, score=1.0, reference="bin1", mod_type="a", model=Model()) for s, p in golden["motifs"]]
+    mk = lambda sp: Motif(sp[0], sp[1])
+    clusters = [(mk(c["merged"]), [mk(m) for m in c["premerge"]], {mk(m) for m in c["pre_variants"]},
+                 {mk(m) for m in c["new_variants"]}) for c in run["clusters"]]
+    return rows, clusters
+
+
+def check_merge_against_trace(run, rows_out, decisions):
+    assert len(decisions) == len(run["decisions"])
+    for got, want in zip(decisions, run["decisions"]):
+        assert got["scored"] == want["scored"] and got["accepted"] == want["accepted"]
+        if want["scored"]:
+            assert [got["merge_model"]._alpha, got["merge_model"]._beta] == want["merge_model"]
+            assert [got["variants_model"]._alpha, got["variants_model"]._beta] == want["variants_model"]
+            assert abs(got["merge_score"] - want["merge_score"]) <= 1e-9 * max(1.0, abs(want["merge_score"]))
+    assert [(r["motif"], r["mod_position"]) for r in rows_out] == [(r["motif"], r["mod_position"]) for r in run["rows"]]
+    for got, want in zip(rows_out, run["rows"]):
+        if want["merged"]:
+            assert [got["model"]._alpha, got["model"]._beta] == want["model"]
+            assert abs(got["score"] - want["score"]) <= 1e-9 * max(1.0, abs(want["score"]))
+            assert got["reference"] == "bin1" and got["mod_type"] == "a"

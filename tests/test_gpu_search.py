@@ -111,3 +111,41 @@ def test_lockstep_multibin_search(nmb):
         assert {m.string: (d["model"]._alpha, d["model"]._beta) for m, d in graph.nodes.items()} == \
                {m.string: (d["model"]._alpha, d["model"]._beta) for m, d in seq_graph.nodes.items()}
         assert searches[b][2] == t
+
+
+def test_merge_groups_on_gpu_reproduce_reference_decisions(nmb):
+    """The merge re-scoring step (find_motifs_bin.py:1438-1533) of three (bin, mod_type) groups in lock-step: the two
+    score requests of every group share one K2 launch each; bin 0 is the golden input recorded from the reference."""
+    from nanomotif_b200 import search
+    from nanomotif_b200.model import BetaBernoulliModel
+    from search_common import check_merge_against_trace, load_merge_trace, merge_inputs
+
+    golden = load_merge_trace()
+    spec = load_trace()["spec"]
+    bins, piles = {}, []
+    for b, seed in enumerate((spec["seed"], 77)):
+        contigs, pile = build_inputs(dict(spec, seed=seed))
+        contigs = {f"bin{b}_{k}": v for k, v in contigs.items()}
+        pile["contig"] = np.array([f"bin{b}_{c}" for c in pile["contig"]], dtype=object)
+        pile["mod_type"] = np.full(len(pile["position"]), "a", dtype=object)
+        bins[f"bin{b}"] = contigs
+        piles.append(pile)
+    pile = {k: np.concatenate([p[k] for p in piles]) for k in piles[0]}
+    multi = nmb.MultiBinScorer(pile, bins, ["a"], spec["low"], spec["high"])
+    launches = []
+    real = multi.score_batch
+    multi.score_batch = lambda reqs: (launches.append(len(reqs)), real(reqs))[1]
+    for run in golden["runs"]:
+        groups, traces = [], []
+        for b in (0, 1, 0):
+            rows, clusters = merge_inputs(golden, run, search.Motif, BetaBernoulliModel)
+            t = []
+            traces.append(t)
+            backend = search.PoolBackend(multi.context(f"bin{b}", "a"), None, 0)
+            groups.append((search.merge_group(rows, clusters, run["merge_threshold"], trace=t), backend))
+        launches.clear()
+        results = search.run_lockstep(groups, search.gpu_batch_score)
+        assert launches == [3, 3]  # two launches for all groups together
+        for g in (0, 2):
+            check_merge_against_trace(run, results[g], traces[g])
+        assert len(results[1]) >= 1

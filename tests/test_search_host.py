@@ -56,3 +56,49 @@ def test_motif_graph_queries():
     assert g.ancestors(c) == {a, b} and g.descendants(a) == {b, c, d}
     assert g.get_missed_candidates([c], 3) == {d}          # b has a kept descendant, c is kept
     assert g.get_missed_candidates([], 3) == {b, d}        # c has a high-scoring ancestor
+
+
+def test_merge_group_reproduces_reference_decisions():
+    """search.merge_group (two batched score requests per group) against the golden trace of the reference's
+    merge_motifs_in_df body (real merge_motifs / predictive_evaluation_score / get_parent_scores)."""
+    from nanomotif_b200.model import BetaBernoulliModel
+    from search_common import check_merge_against_trace, load_merge_trace, merge_inputs
+
+    golden = load_merge_trace()
+    spec = load_trace()["spec"]
+    contigs, pile = build_inputs(spec)
+    for run in golden["runs"]:
+        backend = OracleBackend(contigs, pile, spec)
+        rows, clusters = merge_inputs(golden, run, search.Motif, BetaBernoulliModel)
+        requests = []
+
+        class Counting:
+            def handle(self, request):
+                requests.append(len(request[1]))
+                return backend.handle(request)
+
+        decisions = []
+        out = search.run(search.merge_group(rows, clusters, run["merge_threshold"], trace=decisions), Counting())
+        check_merge_against_trace(run, out, decisions)
+        n_accepted = sum(d["accepted"] for d in run["decisions"])
+        # the reference scores an accepted motif twice (:1502 and inside get_parent_scores :1400); one request holds it once
+        assert len(requests) == 2 and sum(requests) == run["scoring_calls"] - n_accepted
+    # several groups in lock-step: the score requests of all groups arrive together
+    run = golden["runs"][0]
+    groups, batches = [], []
+    for _ in range(3):
+        rows, clusters = merge_inputs(golden, run, search.Motif, BetaBernoulliModel)
+        groups.append((rows, clusters, OracleBackend(contigs, pile, spec), run["merge_threshold"]))
+
+    def batch_score(reqs):
+        batches.append(len(reqs))
+        return [b.handle(("score", motifs)) for b, motifs in reqs]
+
+    for out in search.merge_motifs_in_groups(groups, batch_score):
+        check_merge_against_trace(run, out, run["decisions"] and [dict(d, merge_model=_M(d.get("merge_model")), variants_model=_M(d.get("variants_model"))) for d in run["decisions"]])
+    assert batches == [3, 3]
+
+
+class _M:
+    def __init__(self, ab):
+        self._alpha, self._beta = ab if ab else (None, None)
