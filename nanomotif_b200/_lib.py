@@ -90,6 +90,7 @@ SIGNATURES = {
     "nmb_index_bytes": (C.c_int, [_P, _I64, _I32, _P, _P, _I64, _P, _P]),
     "nmb_bed_parse": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nmb_gather_rows": (C.c_int, [_P, _I32, _P, _I64, _P, _P]),
+    "nmb_bgzf_inflate": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _P, _P]),
     "nmb_add_class_planes_compact": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, C.POINTER(NmbAssembly), _I32, _P, _P]),
     "nmb_filter_coverage": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "nmb_filter_min_mod_frequency": (C.c_int, [_P, _P, _I64, _I32, _F64, _F64, _I64, _P, _P, _P]),

@@ -1,0 +1,275 @@
+// K7 -- BGZF (blocked gzip) inflate on the device.
+//
+// modkit pileups are usually shipped bgzip-compressed with a tabix index (docs/source/required_files.md:21;
+// the reference reads them through epymetheus.query_pileup_records / bgzf_pileup, dataload.py:109-120).  A
+// BGZF file is a series of independent gzip members of at most 64 KB of text each, so the blocks inflate in
+// parallel: ONE THREAD PER BLOCK runs a complete DEFLATE decoder (RFC 1951: stored, fixed and dynamic
+// Huffman blocks; canonical-code decoding with count/symbol tables in local memory) and writes its text at
+// the block's offset in the output, where K6 parses it.  The host only walks the 18-byte block headers
+// (BSIZE, ISIZE, CRC32) to lay the blocks out.  Every block is verified: ISIZE and CRC-32 must match.
+#include "common.cuh"
+
+namespace nmb {
+
+__device__ const uint32_t kCrcTable[256] = {
+    0x00000000u, 0x77073096u, 0xee0e612cu, 0x990951bau, 0x076dc419u, 0x706af48fu, 0xe963a535u, 0x9e6495a3u,
+    0x0edb8832u, 0x79dcb8a4u, 0xe0d5e91eu, 0x97d2d988u, 0x09b64c2bu, 0x7eb17cbdu, 0xe7b82d07u, 0x90bf1d91u,
+    0x1db71064u, 0x6ab020f2u, 0xf3b97148u, 0x84be41deu, 0x1adad47du, 0x6ddde4ebu, 0xf4d4b551u, 0x83d385c7u,
+    0x136c9856u, 0x646ba8c0u, 0xfd62f97au, 0x8a65c9ecu, 0x14015c4fu, 0x63066cd9u, 0xfa0f3d63u, 0x8d080df5u,
+    0x3b6e20c8u, 0x4c69105eu, 0xd56041e4u, 0xa2677172u, 0x3c03e4d1u, 0x4b04d447u, 0xd20d85fdu, 0xa50ab56bu,
+    0x35b5a8fau, 0x42b2986cu, 0xdbbbc9d6u, 0xacbcf940u, 0x32d86ce3u, 0x45df5c75u, 0xdcd60dcfu, 0xabd13d59u,
+    0x26d930acu, 0x51de003au, 0xc8d75180u, 0xbfd06116u, 0x21b4f4b5u, 0x56b3c423u, 0xcfba9599u, 0xb8bda50fu,
+    0x2802b89eu, 0x5f058808u, 0xc60cd9b2u, 0xb10be924u, 0x2f6f7c87u, 0x58684c11u, 0xc1611dabu, 0xb6662d3du,
+    0x76dc4190u, 0x01db7106u, 0x98d220bcu, 0xefd5102au, 0x71b18589u, 0x06b6b51fu, 0x9fbfe4a5u, 0xe8b8d433u,
+    0x7807c9a2u, 0x0f00f934u, 0x9609a88eu, 0xe10e9818u, 0x7f6a0dbbu, 0x086d3d2du, 0x91646c97u, 0xe6635c01u,
+    0x6b6b51f4u, 0x1c6c6162u, 0x856530d8u, 0xf262004eu, 0x6c0695edu, 0x1b01a57bu, 0x8208f4c1u, 0xf50fc457u,
+    0x65b0d9c6u, 0x12b7e950u, 0x8bbeb8eau, 0xfcb9887cu, 0x62dd1ddfu, 0x15da2d49u, 0x8cd37cf3u, 0xfbd44c65u,
+    0x4db26158u, 0x3ab551ceu, 0xa3bc0074u, 0xd4bb30e2u, 0x4adfa541u, 0x3dd895d7u, 0xa4d1c46du, 0xd3d6f4fbu,
+    0x4369e96au, 0x346ed9fcu, 0xad678846u, 0xda60b8d0u, 0x44042d73u, 0x33031de5u, 0xaa0a4c5fu, 0xdd0d7cc9u,
+    0x5005713cu, 0x270241aau, 0xbe0b1010u, 0xc90c2086u, 0x5768b525u, 0x206f85b3u, 0xb966d409u, 0xce61e49fu,
+    0x5edef90eu, 0x29d9c998u, 0xb0d09822u, 0xc7d7a8b4u, 0x59b33d17u, 0x2eb40d81u, 0xb7bd5c3bu, 0xc0ba6cadu,
+    0xedb88320u, 0x9abfb3b6u, 0x03b6e20cu, 0x74b1d29au, 0xead54739u, 0x9dd277afu, 0x04db2615u, 0x73dc1683u,
+    0xe3630b12u, 0x94643b84u, 0x0d6d6a3eu, 0x7a6a5aa8u, 0xe40ecf0bu, 0x9309ff9du, 0x0a00ae27u, 0x7d079eb1u,
+    0xf00f9344u, 0x8708a3d2u, 0x1e01f268u, 0x6906c2feu, 0xf762575du, 0x806567cbu, 0x196c3671u, 0x6e6b06e7u,
+    0xfed41b76u, 0x89d32be0u, 0x10da7a5au, 0x67dd4accu, 0xf9b9df6fu, 0x8ebeeff9u, 0x17b7be43u, 0x60b08ed5u,
+    0xd6d6a3e8u, 0xa1d1937eu, 0x38d8c2c4u, 0x4fdff252u, 0xd1bb67f1u, 0xa6bc5767u, 0x3fb506ddu, 0x48b2364bu,
+    0xd80d2bdau, 0xaf0a1b4cu, 0x36034af6u, 0x41047a60u, 0xdf60efc3u, 0xa867df55u, 0x316e8eefu, 0x4669be79u,
+    0xcb61b38cu, 0xbc66831au, 0x256fd2a0u, 0x5268e236u, 0xcc0c7795u, 0xbb0b4703u, 0x220216b9u, 0x5505262fu,
+    0xc5ba3bbeu, 0xb2bd0b28u, 0x2bb45a92u, 0x5cb36a04u, 0xc2d7ffa7u, 0xb5d0cf31u, 0x2cd99e8bu, 0x5bdeae1du,
+    0x9b64c2b0u, 0xec63f226u, 0x756aa39cu, 0x026d930au, 0x9c0906a9u, 0xeb0e363fu, 0x72076785u, 0x05005713u,
+    0x95bf4a82u, 0xe2b87a14u, 0x7bb12baeu, 0x0cb61b38u, 0x92d28e9bu, 0xe5d5be0du, 0x7cdcefb7u, 0x0bdbdf21u,
+    0x86d3d2d4u, 0xf1d4e242u, 0x68ddb3f8u, 0x1fda836eu, 0x81be16cdu, 0xf6b9265bu, 0x6fb077e1u, 0x18b74777u,
+    0x88085ae6u, 0xff0f6a70u, 0x66063bcau, 0x11010b5cu, 0x8f659effu, 0xf862ae69u, 0x616bffd3u, 0x166ccf45u,
+    0xa00ae278u, 0xd70dd2eeu, 0x4e048354u, 0x3903b3c2u, 0xa7672661u, 0xd06016f7u, 0x4969474du, 0x3e6e77dbu,
+    0xaed16a4au, 0xd9d65adcu, 0x40df0b66u, 0x37d83bf0u, 0xa9bcae53u, 0xdebb9ec5u, 0x47b2cf7fu, 0x30b5ffe9u,
+    0xbdbdf21cu, 0xcabac28au, 0x53b39330u, 0x24b4a3a6u, 0xbad03605u, 0xcdd70693u, 0x54de5729u, 0x23d967bfu,
+    0xb3667a2eu, 0xc4614ab8u, 0x5d681b02u, 0x2a6f2b94u, 0xb40bbe37u, 0xc30c8ea1u, 0x5a05df1bu, 0x2d02ef8du,
+};
+
+// RFC 1951 3.2.5 / 3.2.7
+__device__ const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31,
+                                          35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__device__ const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__device__ const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
+                                           1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__device__ const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8,
+                                           9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__device__ const uint8_t kClenOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+enum InflateStatus {
+    kInfOk = 0,
+    kInfBadBlockType = 1,
+    kInfBadStored = 2,
+    kInfBadCodeLengths = 3,
+    kInfBadSymbol = 4,
+    kInfBadDistance = 5,
+    kInfOutputOverflow = 6,
+    kInfInputOverrun = 7,
+    kInfSizeMismatch = 8,
+    kInfCrcMismatch = 9,
+};
+
+struct BitReader {
+    const uint8_t *p, *end;
+    uint64_t buf;
+    int cnt;       // valid bits in buf
+    int overrun;   // bytes requested past the end (zeros are shifted in)
+};
+
+__device__ __forceinline__ void refill(BitReader &b) {
+    while (b.cnt <= 56) {
+        uint64_t byte = 0;
+        if (b.p < b.end) byte = *b.p; else ++b.overrun;
+        ++b.p;
+        b.buf |= byte << b.cnt;
+        b.cnt += 8;
+    }
+}
+__device__ __forceinline__ uint32_t take(BitReader &b, int n) {  // n <= 16
+    if (b.cnt < n) refill(b);
+    const uint32_t v = (uint32_t)(b.buf & ((1ull << n) - 1ull));
+    b.buf >>= n;
+    b.cnt -= n;
+    return v;
+}
+
+constexpr int kMaxBits = 15, kMaxLit = 288, kMaxDist = 30;
+
+struct Huffman {
+    int16_t count[kMaxBits + 1];
+    int16_t *symbol;
+};
+
+// Canonical code from code lengths; returns 0 for a complete code, > 0 incomplete, < 0 over-subscribed.
+__device__ int build_code(Huffman &h, const int16_t *length, int n) {
+    for (int l = 0; l <= kMaxBits; ++l) h.count[l] = 0;
+    for (int s = 0; s < n; ++s) ++h.count[length[s]];
+    if (h.count[0] == n) return 0;  // no codes: complete, but decoding will fail
+    int left = 1;
+    for (int l = 1; l <= kMaxBits; ++l) {
+        left <<= 1;
+        left -= h.count[l];
+        if (left < 0) return left;
+    }
+    int16_t offs[kMaxBits + 1];
+    offs[1] = 0;
+    for (int l = 1; l < kMaxBits; ++l) offs[l + 1] = offs[l] + h.count[l];
+    for (int s = 0; s < n; ++s)
+        if (length[s] != 0) h.symbol[offs[length[s]]++] = (int16_t)s;
+    return left;
+}
+
+// One symbol: the code's bits arrive most significant first.
+__device__ __forceinline__ int decode_symbol(BitReader &b, const Huffman &h) {
+    if (b.cnt < kMaxBits) refill(b);
+    uint32_t bits = (uint32_t)b.buf;
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= kMaxBits; ++len) {
+        code |= bits & 1;
+        bits >>= 1;
+        const int count = h.count[len];
+        if (code - count < first) {
+            b.buf >>= len;
+            b.cnt -= len;
+            return h.symbol[index + (code - first)];
+        }
+        index += count;
+        first += count;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+// Inflate one raw DEFLATE stream; returns a status and the number of bytes produced.
+__device__ int inflate_stream(const uint8_t *in, int in_len, uint8_t *out, int out_cap, int *produced) {
+    BitReader b{in, in + in_len, 0, 0, 0};
+    int16_t len_sym[kMaxLit], dist_sym[kMaxDist], lengths[kMaxLit + kMaxDist + 2];
+    Huffman lencode, distcode;
+    lencode.symbol = len_sym;
+    distcode.symbol = dist_sym;
+    int n_out = 0, last;
+    do {
+        last = (int)take(b, 1);
+        const int type = (int)take(b, 2);
+        if (type == 0) {  // stored
+            b.buf >>= (b.cnt & 7);  // to the byte boundary
+            b.cnt -= (b.cnt & 7);
+            const uint32_t len = take(b, 16), nlen = take(b, 16);
+            if ((len ^ 0xFFFFu) != nlen) return kInfBadStored;
+            if (n_out + (int)len > out_cap) return kInfOutputOverflow;
+            for (uint32_t i = 0; i < len; ++i) out[n_out++] = (uint8_t)take(b, 8);
+        } else if (type == 1 || type == 2) {
+            if (type == 1) {  // fixed codes (RFC 1951 3.2.6)
+                int s = 0;
+                for (; s < 144; ++s) lengths[s] = 8;
+                for (; s < 256; ++s) lengths[s] = 9;
+                for (; s < 280; ++s) lengths[s] = 7;
+                for (; s < 288; ++s) lengths[s] = 8;
+                build_code(lencode, lengths, 288);
+                for (s = 0; s < 30; ++s) lengths[s] = 5;
+                build_code(distcode, lengths, 30);
+            } else {  // dynamic codes (3.2.7)
+                const int nlen = (int)take(b, 5) + 257, ndist = (int)take(b, 5) + 1, ncode = (int)take(b, 4) + 4;
+                if (nlen > 286 || ndist > kMaxDist) return kInfBadCodeLengths;
+                int i = 0;
+                for (; i < ncode; ++i) lengths[kClenOrder[i]] = (int16_t)take(b, 3);
+                for (; i < 19; ++i) lengths[kClenOrder[i]] = 0;
+                if (build_code(lencode, lengths, 19) != 0) return kInfBadCodeLengths;  // must be complete
+                i = 0;
+                while (i < nlen + ndist) {
+                    int sym = decode_symbol(b, lencode);
+                    if (sym < 0) return kInfBadSymbol;
+                    if (sym < 16) {
+                        lengths[i++] = (int16_t)sym;
+                    } else {
+                        int prev = 0, rep;
+                        if (sym == 16) {
+                            if (i == 0) return kInfBadCodeLengths;
+                            prev = lengths[i - 1];
+                            rep = 3 + (int)take(b, 2);
+                        } else if (sym == 17) {
+                            rep = 3 + (int)take(b, 3);
+                        } else {
+                            rep = 11 + (int)take(b, 7);
+                        }
+                        if (i + rep > nlen + ndist) return kInfBadCodeLengths;
+                        while (rep--) lengths[i++] = (int16_t)prev;
+                    }
+                }
+                if (lengths[256] == 0) return kInfBadCodeLengths;  // no end-of-block code
+                int err = build_code(lencode, lengths, nlen);
+                if (err < 0 || (err > 0 && nlen - lencode.count[0] != 1)) return kInfBadCodeLengths;
+                err = build_code(distcode, lengths + nlen, ndist);
+                if (err < 0 || (err > 0 && ndist - distcode.count[0] != 1)) return kInfBadCodeLengths;
+            }
+            for (;;) {  // literals and length/distance pairs
+                int sym = decode_symbol(b, lencode);
+                if (sym < 0) return kInfBadSymbol;
+                if (sym < 256) {
+                    if (n_out >= out_cap) return kInfOutputOverflow;
+                    out[n_out++] = (uint8_t)sym;
+                } else if (sym == 256) {
+                    break;
+                } else {
+                    sym -= 257;
+                    if (sym >= 29) return kInfBadSymbol;
+                    const int len = kLenBase[sym] + (int)take(b, kLenExtra[sym]);
+                    const int ds = decode_symbol(b, distcode);
+                    if (ds < 0 || ds >= 30) return kInfBadSymbol;
+                    const int dist = kDistBase[ds] + (int)take(b, kDistExtra[ds]);
+                    if (dist > n_out) return kInfBadDistance;
+                    if (n_out + len > out_cap) return kInfOutputOverflow;
+                    for (int k = 0; k < len; ++k, ++n_out) out[n_out] = out[n_out - dist];  // may overlap itself
+                }
+            }
+        } else {
+            return kInfBadBlockType;
+        }
+        if (b.overrun > 8) return kInfInputOverrun;
+    } while (!last);
+    // bytes that were pulled into the bit buffer but never used do not count as consumed
+    if (b.overrun * 8 > b.cnt) return kInfInputOverrun;
+    *produced = n_out;
+    return kInfOk;
+}
+
+__global__ void __launch_bounds__(32) bgzf_inflate_kernel(const uint8_t *__restrict__ comp,
+                                                          const int64_t *__restrict__ in_off,
+                                                          const int32_t *__restrict__ in_len,
+                                                          const int64_t *__restrict__ out_off,
+                                                          const int32_t *__restrict__ out_len,
+                                                          const uint32_t *__restrict__ crc, int n_blocks,
+                                                          uint8_t *out, int32_t *__restrict__ status) {
+    const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= n_blocks) return;
+    uint8_t *dst = out + out_off[blk];
+    int produced = 0;
+    int st = inflate_stream(comp + in_off[blk], in_len[blk], dst, out_len[blk], &produced);
+    if (st == kInfOk && produced != out_len[blk]) st = kInfSizeMismatch;
+    if (st == kInfOk && crc) {
+        uint32_t c = 0xFFFFFFFFu;
+        for (int i = 0; i < produced; ++i) c = kCrcTable[(c ^ dst[i]) & 0xFF] ^ (c >> 8);
+        if ((c ^ 0xFFFFFFFFu) != crc[blk]) st = kInfCrcMismatch;
+    }
+    status[blk] = st;
+}
+
+}  // namespace nmb
+
+extern "C" {
+
+int nmb_bgzf_inflate(const uint8_t *comp, const int64_t *block_in_off, const int32_t *block_in_len,
+                     const int64_t *block_out_off, const int32_t *block_out_len, const uint32_t *block_crc32,
+                     int32_t n_blocks, uint8_t *out, int32_t *status, void *stream) {
+    NMB_REQUIRE(n_blocks >= 0, "nmb_bgzf_inflate: n_blocks=%d", n_blocks);
+    if (n_blocks == 0) return NMB_OK;
+    NMB_REQUIRE(comp && block_in_off && block_in_len && block_out_off && block_out_len && out && status,
+                "nmb_bgzf_inflate: null argument");
+    nmb::bgzf_inflate_kernel<<<(n_blocks + 31) / 32, 32, 0, (cudaStream_t)stream>>>(
+        comp, block_in_off, block_in_len, block_out_off, block_out_len, block_crc32, n_blocks, out, status);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+}  // extern "C"

@@ -336,15 +336,76 @@ def parse_bedmethyl(data, contig_names, mod_types=("a", "m", "21839"), with_coun
     return rows
 
 
+def bgzf_blocks(data) -> dict | None:
+    """Block table of a BGZF file (SAM spec 4.1: gzip members whose extra field carries 'BC' + BSIZE), or None
+    when `data` is not BGZF (plain gzip, text).  Only the 18-byte headers and 8-byte trailers are read."""
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    n = len(buf)
+    in_off, in_len, out_len, crc = [], [], [], []
+    at = 0
+    while at < n:
+        if at + 18 > n or buf[at] != 31 or buf[at + 1] != 139 or buf[at + 2] != 8 or not (buf[at + 3] & 4):
+            return None
+        xlen = int(buf[at + 10]) | (int(buf[at + 11]) << 8)
+        bsize, x = None, at + 12
+        while x + 4 <= at + 12 + xlen:  # extra subfields: SI1 SI2 SLEN(2) data
+            slen = int(buf[x + 2]) | (int(buf[x + 3]) << 8)
+            if buf[x] == 66 and buf[x + 1] == 67 and slen == 2:
+                bsize = (int(buf[x + 4]) | (int(buf[x + 5]) << 8)) + 1
+            x += 4 + slen
+        if bsize is None or at + bsize > n or bsize < 12 + xlen + 8:
+            return None
+        tail = at + bsize - 8
+        in_off.append(at + 12 + xlen)
+        in_len.append(tail - (at + 12 + xlen))
+        crc.append(int.from_bytes(buf[tail:tail + 4].tobytes(), "little"))
+        out_len.append(int.from_bytes(buf[tail + 4:tail + 8].tobytes(), "little"))
+        at += bsize
+    out_off = np.zeros(len(out_len) + 1, dtype=np.int64)
+    np.cumsum(out_len, out=out_off[1:])
+    return dict(in_off=np.array(in_off, dtype=np.int64), in_len=np.array(in_len, dtype=np.int32),
+                out_off=out_off[:-1].copy(), out_len=np.array(out_len, dtype=np.int32),
+                crc=np.array(crc, dtype=np.uint32), total=int(out_off[-1]))
+
+
+def inflate_bgzf_device(data, device=None, verify_crc: bool = True) -> torch.Tensor:
+    """The inflated bytes of a BGZF file as a device uint8 tensor (K7: one thread per 64 KB block)."""
+    d = _require_cuda(device)
+    blocks = bgzf_blocks(data)
+    if blocks is None:
+        raise ValueError("not a BGZF file (no 'BC' extra subfield); use gzip on the host")
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    nb = len(blocks["in_len"])
+    with torch.cuda.device(d):
+        comp = _to_device(buf, d)
+        out = torch.empty(max(1, blocks["total"]), dtype=torch.uint8, device=d)
+        status = torch.zeros(max(1, nb), dtype=torch.int32, device=d)
+        crc = _to_device(blocks["crc"].view(np.int32), d) if verify_crc else None
+        # named, so that the block table stays allocated until the launch has been enqueued
+        in_off, in_len = _to_device(blocks["in_off"], d), _to_device(blocks["in_len"], d)
+        out_off, out_len = _to_device(blocks["out_off"], d), _to_device(blocks["out_len"], d)
+        check(lib.nmb_bgzf_inflate(ptr(comp), ptr(in_off), ptr(in_len), ptr(out_off), ptr(out_len), ptr(crc),
+                                   nb, ptr(out), ptr(status), _stream()), "nmb_bgzf_inflate")
+        bad = torch.nonzero(status[:nb]).view(-1)
+        if int(bad.numel()):
+            b = int(bad[0].item())
+            raise ValueError(f"BGZF block {b} of {nb} failed to inflate (status {int(status[b].item())})")
+    return out[:blocks["total"]]
+
+
 def load_pileup_device(path: str, contig_names, mod_types=("a", "m", "21839"), with_counts: bool = False, device=None,
                        keep_unknown_contigs: bool = False) -> DeviceRows:
-    """load_pileup with the parse on the GPU: the file's bytes (gzip / bgzf inflated on the host) go to the
-    device as they are."""
-    import gzip
-
-    opener = gzip.open if str(path).endswith((".gz", ".bgz")) else open
-    with opener(path, "rb") as f:
+    """load_pileup with inflate and parse on the GPU: a bgzip-compressed pileup goes to the device compressed
+    (K7), plain text as it is; only a non-BGZF gzip file is inflated on the host."""
+    with open(path, "rb") as f:
         data = f.read()
-    if not data:
+    if data[:2] == b"\x1f\x8b":
+        if bgzf_blocks(data) is not None:
+            data = inflate_bgzf_device(data, device)
+        else:
+            import gzip
+
+            data = gzip.decompress(data)
+    if len(data) == 0:
         raise SystemExit("Pileup is empty after initial load")  # dataload.py:89-91
     return parse_bedmethyl(data, contig_names, mod_types, with_counts, device, keep_unknown_contigs)

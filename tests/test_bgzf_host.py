@@ -1,0 +1,72 @@
+"""The DEFLATE decoder of nanomotif_b200/csrc/bgzf.cu (K7), compiled AS HOST CODE by g++ (the device qualifiers are
+stripped) and fuzzed against zlib -- the reference implementation of RFC 1951 -- on streams of every block type.
+CPU only: checks the algorithm the GPU threads run, not the launch."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+MAIN = r'''
+#include "core.h"
+#include <vector>
+#include <zlib.h>
+#include <string.h>
+#include <stdlib.h>
+int main() {
+    srand(1);
+    for (int t = 0; t < 600; ++t) {
+        int n = (t % 7 == 0) ? 0 : rand() % 66000;
+        std::vector<uint8_t> data(n + 1);
+        int mode = t % 4;
+        for (int i = 0; i < n; ++i)
+            data[i] = mode == 0 ? rand() & 0xFF : mode == 1 ? "ACGT\t\n0123456789."[rand() % 17] : mode == 2 ? 'A'
+                      : (uint8_t)("contig_1\t12\t13\ta\t"[i % 18]);
+        int level = (t / 4) % 10, strat = (t / 40) % 5;  // default, filtered, huffman only, rle, fixed
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        deflateInit2(&zs, level, Z_DEFLATED, -15, 9, strat);
+        std::vector<uint8_t> comp(deflateBound(&zs, n) + 64);
+        zs.next_in = data.data(); zs.avail_in = n; zs.next_out = comp.data(); zs.avail_out = comp.size();
+        deflate(&zs, Z_FINISH);
+        int clen = zs.total_out;
+        deflateEnd(&zs);
+        std::vector<uint8_t> c2(comp.begin(), comp.begin() + clen), out(n + 1);
+        int produced = -1;
+        int st = nmb::inflate_stream(c2.data(), clen, out.data(), n, &produced);
+        if (st != 0 || produced != n || memcmp(out.data(), data.data(), n)) {
+            printf("FAIL t=%d n=%d level=%d strategy=%d status=%d produced=%d\n", t, n, level, strat, st, produced);
+            return 1;
+        }
+        if (clen > 8) {  // truncated and corrupted streams end with an error or different bytes, never out of bounds
+            nmb::inflate_stream(c2.data(), clen / 2, out.data(), n, &produced);
+            c2[clen / 3] ^= 0x5A;
+            nmb::inflate_stream(c2.data(), clen, out.data(), n, &produced);
+        }
+    }
+    printf("all ok\n");
+    return 0;
+}
+'''
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+def test_device_inflate_algorithm_against_zlib(tmp_path):
+    src = open(os.path.join(ROOT, "nanomotif_b200", "csrc", "bgzf.cu")).read()
+    core = src[src.index("namespace nmb {"):src.index("__global__ void __launch_bounds__(32) bgzf_inflate_kernel")]
+    core = core.replace("__device__ __forceinline__", "static inline").replace("__device__ const", "static const")
+    core = core.replace("__device__ ", "static ")
+    (tmp_path / "core.h").write_text("#include <stdint.h>\n#include <stdio.h>\n" + core + "}\n")
+    (tmp_path / "main.cpp").write_text(MAIN)
+    exe = tmp_path / "fuzz"
+    build = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address", "-o", str(exe), str(tmp_path / "main.cpp"), "-lz"],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "zlib.h" in build.stderr:
+        pytest.skip("zlib development header not available")
+    if build.returncode != 0:  # no sanitizer runtime: plain build
+        build = subprocess.run(["g++", "-O1", "-o", str(exe), str(tmp_path / "main.cpp"), "-lz"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "all ok" in run.stdout, run.stdout + run.stderr

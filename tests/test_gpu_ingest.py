@@ -149,3 +149,54 @@ def test_filters_and_class_planes_on_device(dl):
     mt = np.array([("a", "m", "21839").index(m) for m in t3.mod_type], dtype=np.uint8)
     b = DevicePileup.from_columns(asm, cid, t3.position, strand_codes(t3.strand), t3.fraction_mod, 0.3, 0.7, mt, 3)
     assert torch.equal(a.class_records, b.class_records) and int(a.class_records.ne(0).sum()) > 1000
+
+
+def write_bgzf(data: bytes, level=6, strategy=0, block=0xff00) -> bytes:
+    """BGZF writer (SAM spec 4.1) for the tests: independent gzip members with the BC extra subfield + EOF marker."""
+    import struct
+    import zlib
+
+    out = bytearray()
+    chunks = [data[i:i + block] for i in range(0, len(data), block)] + [b""]
+    for c in chunks:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+        raw = co.compress(c) + co.flush()
+        bsize = 12 + 6 + len(raw) + 8
+        out += struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+        out += raw + struct.pack("<II", zlib.crc32(c), len(c))
+    return bytes(out)
+
+
+def test_bgzf_inflate_on_device(dl, tmp_path):
+    import gzip
+    import zlib
+
+    rng = np.random.default_rng(29)
+    lines, contigs = bed_text(rng, n_contigs=3, length=9000)
+    text = ("\n".join(lines) + "\n").encode()
+    cases = {
+        "text": text,
+        "runs": b"A" * 70000 + b"ACGT" * 30000 + bytes(200000),          # long matches, distance 1 and 4 overlaps
+        "random": rng.integers(0, 256, 200001, dtype=np.uint8).tobytes(),  # incompressible: stored blocks
+        "tiny": b"x",
+        "empty": b"",
+    }
+    for name, data in cases.items():
+        for level, strategy in ((6, 0), (9, 0), (1, 0), (0, 0), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)):
+            z = write_bgzf(data, level, strategy)
+            assert gzip.decompress(z) == data  # the writer produces valid gzip members
+            got = dl.inflate_bgzf_device(z)
+            assert got.cpu().numpy().tobytes() == data, (name, level, strategy)
+    # corruption is reported: a flipped payload byte breaks the CRC (or the code tables)
+    z = bytearray(write_bgzf(text))
+    z[len(z) // 2] ^= 0x55
+    with pytest.raises(ValueError):
+        dl.inflate_bgzf_device(bytes(z))
+    assert dl.bgzf_blocks(gzip.compress(text)) is None  # plain gzip is not BGZF
+    # the loader: bgzip-compressed, gzip-compressed and plain files give the same rows
+    names = list(contigs)
+    want = O.load_pileup_text(text.decode())
+    for fname, payload in (("p.bed.gz", write_bgzf(text)), ("q.bed.gz", gzip.compress(text)), ("r.bed", text)):
+        path = tmp_path / fname
+        path.write_bytes(payload)
+        check_rows(dl.load_pileup_device(str(path), names).to_table(), want)
