@@ -204,7 +204,7 @@ NMB_API int nmb_bed_parse(const uint8_t *text, int64_t n_bytes, const int64_t *n
  *      through epymetheus.query_pileup_records / bgzf_pileup, dataload.py:109-120) ----
  * Block b holds block_in_len[b] bytes of raw DEFLATE data at comp + block_in_off[b] (after its gzip header) and
  * inflates to exactly block_out_len[b] bytes (its ISIZE) at out + block_out_off[b]; block_crc32 (may be NULL)
- * is the CRC-32 of the inflated bytes.  One thread per block, blocks are independent.  status[b] = 0 or the
+ * is the CRC-32 of the inflated bytes.  One warp per block, blocks are independent.  status[b] = 0 or the
  * first error (1 block type, 2 stored header, 3 code lengths, 4 symbol, 5 distance, 6 output overflow,
  * 7 input overrun, 8 size mismatch, 9 CRC mismatch). */
 NMB_API int nmb_bgzf_inflate(const uint8_t *comp, const int64_t *block_in_off, const int32_t *block_in_len,

@@ -15,6 +15,7 @@ MAIN = r'''
 #include <zlib.h>
 #include <string.h>
 #include <stdlib.h>
+#include <algorithm>
 int main() {
     srand(1);
     for (int t = 0; t < 600; ++t) {
@@ -35,15 +36,26 @@ int main() {
         deflateEnd(&zs);
         std::vector<uint8_t> c2(comp.begin(), comp.begin() + clen), out(n + 1);
         int produced = -1;
-        int st = nmb::inflate_stream(c2.data(), clen, out.data(), n, &produced);
+        int st = nmb::inflate_stream(c2.data(), clen, out.data(), n, &produced, 0, 1);
         if (st != 0 || produced != n || memcmp(out.data(), data.data(), n)) {
             printf("FAIL t=%d n=%d level=%d strategy=%d status=%d produced=%d\n", t, n, level, strat, st, produced);
             return 1;
         }
+        {   // the chunked CRC-32 of the kernel: chunks combined like zlib's crc32_combine
+            int chunk = (n + 31) / 32;
+            uint32_t total = 0, shift = nmb::crc_x8n((uint32_t)chunk);
+            for (int l = 0; l < 32; ++l) {
+                int b0 = std::min(l * chunk, n), b1 = std::min(b0 + chunk, n);
+                if (b1 == b0) continue;
+                uint32_t c = nmb::crc32_bytes(out.data() + b0, b1 - b0);
+                total = l == 0 ? c : nmb::crc_multmodp(b1 - b0 == chunk ? shift : nmb::crc_x8n(b1 - b0), total) ^ c;
+            }
+            if (total != (uint32_t)crc32(0, data.data(), n)) { printf("CRC FAIL t=%d n=%d\n", t, n); return 1; }
+        }
         if (clen > 8) {  // truncated and corrupted streams end with an error or different bytes, never out of bounds
-            nmb::inflate_stream(c2.data(), clen / 2, out.data(), n, &produced);
+            nmb::inflate_stream(c2.data(), clen / 2, out.data(), n, &produced, 0, 1);
             c2[clen / 3] ^= 0x5A;
-            nmb::inflate_stream(c2.data(), clen, out.data(), n, &produced);
+            nmb::inflate_stream(c2.data(), clen, out.data(), n, &produced, 0, 1);
         }
     }
     printf("all ok\n");
@@ -55,9 +67,10 @@ int main() {
 @pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
 def test_device_inflate_algorithm_against_zlib(tmp_path):
     src = open(os.path.join(ROOT, "nanomotif_b200", "csrc", "bgzf.cu")).read()
-    core = src[src.index("namespace nmb {"):src.index("__global__ void __launch_bounds__(32) bgzf_inflate_kernel")]
+    core = src[src.index("namespace nmb {"):src.index("__global__ void __launch_bounds__(128) bgzf_inflate_kernel")]
     core = core.replace("__device__ __forceinline__", "static inline").replace("__device__ const", "static const")
     core = core.replace("__device__ ", "static ")
+    core = core.replace("static const volatile", "const volatile")
     (tmp_path / "core.h").write_text("#include <stdint.h>\n#include <stdio.h>\n" + core + "}\n")
     (tmp_path / "main.cpp").write_text(MAIN)
     exe = tmp_path / "fuzz"
