@@ -252,8 +252,13 @@ def make_jobs(n: int) -> np.ndarray:
 
 
 def choose_motifs_per_item(jobs: np.ndarray, sm_count: int) -> int:
+    """Motifs per work item (tile x motif block): as many as the kernel takes (the tile copy, the barrier and the
+    flush are paid per item), unless that leaves fewer than ~16 items per SM.  Measured on B200: tuning the block
+    size to fill the last round of the persistent grid (28 instead of 32 for bench.py's cfg2) is 5 % SLOWER --
+    the four resident CTAs of an SM share its ALUs, so a CTA that runs out of items early just speeds up its
+    neighbours, while every extra item costs a tile copy and a flush."""
     motif_tiles = int((jobs["motif_count"].astype(np.int64) * jobs["tile_count"]).sum())
-    target_items = 16 * sm_count  # ~8 items per resident CTA keeps the tail short
+    target_items = 16 * sm_count  # ~4 items per resident CTA keeps the tail short
     mpi = motif_tiles // max(1, target_items)
     return int(min(_lib.MAX_MOTIFS_PER_ITEM, max(1, mpi)))
 

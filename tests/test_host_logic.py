@@ -129,3 +129,19 @@ def test_synth_pileup_properties():
     for s, mp in motifs:
         toks = M.tokenize(s)
         assert toks[mp] == "A" and toks[0] != "." and toks[-1] != "." and 4 <= len(toks) <= 21
+
+
+def test_motifs_per_item():
+    from nanomotif_b200.device import choose_motifs_per_item, make_jobs
+
+    sms = 148
+    j = make_jobs(3)  # bench.py cfg2: 3 mod types x 1000 motifs x 71 tiles
+    j["motif_count"], j["tile_count"] = 1000, 71
+    assert choose_motifs_per_item(j, sms) == 32
+    j = make_jobs(1)  # a search step: few motifs, many items wanted
+    j["motif_count"], j["tile_count"] = 4, 71
+    assert choose_motifs_per_item(j, sms) == 1
+    j["motif_count"], j["tile_count"] = 640, 71
+    assert choose_motifs_per_item(j, sms) == 19
+    j["motif_count"], j["tile_count"] = 0, 0
+    assert choose_motifs_per_item(j, sms) == 1
