@@ -253,10 +253,10 @@ def make_jobs(n: int) -> np.ndarray:
 
 def choose_motifs_per_item(jobs: np.ndarray, sm_count: int) -> int:
     """Motifs per work item (tile x motif block): as many as the kernel takes (the tile copy, the barrier and the
-    flush are paid per item), unless that leaves fewer than ~16 items per SM.  Measured on B200: tuning the block
-    size to fill the last round of the persistent grid (28 instead of 32 for bench.py's cfg2) is 5 % SLOWER --
-    the four resident CTAs of an SM share its ALUs, so a CTA that runs out of items early just speeds up its
-    neighbours, while every extra item costs a tile copy and a flush."""
+    flush are paid per item), unless that leaves fewer than ~16 items per SM.  Measured on one B200 (3000 motifs x
+    71 tiles, tools/kbench.py --mpi 32 28 30 24 16): 1.354 / 1.380 / 1.357 / 1.356 / 1.358 ms -- flat: the four
+    resident CTAs of an SM share its ALUs, so neither the fill of the last round of the persistent grid nor the
+    per-item overhead matters at this size."""
     motif_tiles = int((jobs["motif_count"].astype(np.int64) * jobs["tile_count"]).sum())
     target_items = 16 * sm_count  # ~4 items per resident CTA keeps the tail short
     mpi = motif_tiles // max(1, target_items)
