@@ -245,3 +245,56 @@ def test_streamed_host_blocks_equal_one_shot(nmb):
         got = score_host_blocks(names, lens, ascii_u8, off, blocks, packed, jobs, n_out, low=0.3, high=0.7, n_modtypes=3,
                                 device=dev)
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_layouts_against_oracle(nmb, seed):
+    """Differential fuzz of K2 (per-contig counts) and K5-style joins' matcher: hundreds of short contigs per tile (every
+    warp straddles contigs), non-ACGT letters in the interior and right at contig ends, motifs of every length class
+    (one- and two-word halos, gaps, bracket classes) -- the three matcher paths (plain, edge clip, non-ACGT) and their
+    combinations inside one warp."""
+    rng = np.random.default_rng(1000 + seed)
+    n_contigs = 120
+    lengths = np.concatenate([rng.integers(1, 80, 30), rng.integers(400, 700, 40), rng.integers(1000, 4000, 40),
+                              rng.integers(20000, 70000, 10)])
+    rng.shuffle(lengths)
+    contigs, cols = {}, {k: [] for k in ("contig", "position", "strand", "fraction_mod")}
+    for i, L in enumerate(lengths[:n_contigs]):
+        L = int(L)
+        seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L, p=[0.4, 0.1, 0.1, 0.4]).copy()
+        kind = i % 4
+        if kind == 1 and L > 3:      # N at the very ends
+            seq[0] = seq[-1] = ord("N")
+        elif kind == 2 and L > 50:   # IUPAC letters in the interior
+            for s in rng.integers(0, L - 5, 3):
+                seq[s:s + int(rng.integers(1, 5))] = ord(rng.choice(list("NRYK")))
+        name = f"f{i}"
+        contigs[name] = seq.tobytes().decode()
+        for strand in "+-":
+            keep = rng.random(L) < 0.7
+            pos = np.flatnonzero(keep).astype(np.int64)
+            cols["contig"].append(np.full(len(pos), name, dtype=object))
+            cols["position"].append(pos)
+            cols["strand"].append(np.full(len(pos), strand, dtype=object))
+            cols["fraction_mod"].append(rng.choice([0.0, 0.3, 0.31, 0.69, 0.7, 1.0], size=len(pos)))
+    pile = {k: np.concatenate(v) for k, v in cols.items()}
+    specs = [("A", 0), ("TA", 1), ("CA[AT]", 1), ("A.A", 2), ("T" + "." * 29 + "A", 30), ("A" + "." * 30 + "T", 0),
+             ("AC" + "." * 40 + "[AG]T", 1), ("T" + "." * 60 + "A", 61), ("A" + "." * 55 + "CA", 0), ("[ACT]A[AGT]", 1),
+             ("AAAAAAAAT", 3), ("TTTTTTTTTTTA", 11), ("ATATATATATATAT", 6), ("GA.C", 1), ("A....T....A", 5)]
+    motifs = [nmb.Motif(s, p) for s, p in specs]
+    scorer = nmb.BinScorer(pile, contigs, 0.3, 0.7)
+    per = scorer.counts_by_strand(motifs, per_contig=True).cpu().numpy()
+    total = 0
+    for mi, m in enumerate(motifs):
+        for ci, (name, seq) in enumerate(contigs.items()):
+            sel = pile["contig"] == name
+            a, b, d = O.motif_model_contig(pile["position"][sel], pile["strand"][sel], pile["fraction_mod"][sel], seq,
+                                           m.string, m.mod_position, 0.3, 0.7, fast=True)
+            want = [len(d["index_meth_fwd"]), len(d["index_nonmeth_fwd"]), len(d["index_meth_rev"]), len(d["index_nonmeth_rev"])]
+            assert per[mi, ci].tolist() == want, (m, name, len(seq))
+            total += sum(want)
+    assert total > 50000
+    # whole-bin sums through the other group mode
+    models = nmb.motif_model_bin_many(pile, contigs, motifs, 0.3, 0.7)
+    for mi, mdl in enumerate(models):
+        assert (mdl._alpha - 5, mdl._beta - 5) == (int(per[mi, :, [0, 2]].sum()), int(per[mi, :, [1, 3]].sum()))
