@@ -185,10 +185,45 @@ __device__ __forceinline__ int decode_symbol(BitReader &b, const Huffman &h) {
     return -1;
 }
 
+// Primary lookup tables (shared memory, one pair per warp): entry = symbol << 4 | code length for codes of at
+// most `bits` bits, indexed by the next `bits` stream bits (codes arrive most significant bit first, the stream
+// is read least significant bit first, hence the bit reversal); 0 = longer code, decoded by decode_symbol.
+constexpr int kLitBits = 10, kDistBits = 8;
+
+__device__ void fill_table(uint16_t *tab, int bits, const Huffman &h, int lane, int lanes) {
+    for (int i = lane; i < (1 << bits); i += lanes) tab[i] = 0;
+    NMB_SYNC_LANES();
+    int first = 0, index = 0;
+    for (int len = 1; len <= bits; ++len) {
+        const int count = h.count[len];
+        for (int j = lane; j < count; j += lanes) {  // the lanes share the symbols of this length
+            const int sym = h.symbol[index + j];
+            int code = first + j, rev = 0;
+            for (int k = 0; k < len; ++k, code >>= 1) rev = (rev << 1) | (code & 1);
+            for (int k = rev; k < (1 << bits); k += 1 << len) tab[k] = (uint16_t)((sym << 4) | len);
+        }
+        index += count;
+        first = (first + count) << 1;
+    }
+    NMB_SYNC_LANES();
+}
+
+__device__ __forceinline__ int decode_fast(BitReader &b, const uint16_t *tab, int bits, const Huffman &h) {
+    if (b.cnt < kMaxBits) refill(b);
+    const uint32_t e = tab[(uint32_t)b.buf & ((1u << bits) - 1u)];
+    if (e) {
+        b.buf >>= (e & 15);
+        b.cnt -= (int)(e & 15);
+        return (int)(e >> 4);
+    }
+    return decode_symbol(b, h);
+}
+
 // Inflate one raw DEFLATE stream; returns a status and the number of bytes produced.  Called by `lanes`
 // converged threads (a warp, or 1 on the host) that all decode the same stream and share the writes.
+// lit_tab / dist_tab: (1 << kLitBits) / (1 << kDistBits) uint16 entries shared by the lanes.
 __device__ int inflate_stream(const uint8_t *in, int in_len, uint8_t *out, int out_cap, int *produced, int lane,
-                              int lanes) {
+                              int lanes, uint16_t *lit_tab, uint16_t *dist_tab) {
     BitReader b{in, in + in_len, 0, 0, 0};
     int16_t len_sym[kMaxLit], dist_sym[kMaxDist], lengths[kMaxLit + kMaxDist + 2];
     Huffman lencode, distcode;
@@ -252,8 +287,10 @@ __device__ int inflate_stream(const uint8_t *in, int in_len, uint8_t *out, int o
                 err = build_code(distcode, lengths + nlen, ndist);
                 if (err < 0 || (err > 0 && ndist - distcode.count[0] != 1)) return kInfBadCodeLengths;
             }
+            fill_table(lit_tab, kLitBits, lencode, lane, lanes);
+            fill_table(dist_tab, kDistBits, distcode, lane, lanes);
             for (;;) {  // literals and length/distance pairs
-                int sym = decode_symbol(b, lencode);
+                int sym = decode_fast(b, lit_tab, kLitBits, lencode);
                 if (sym < 0) return kInfBadSymbol;
                 if (sym < 256) {
                     if (n_out >= out_cap) return kInfOutputOverflow;
@@ -265,15 +302,15 @@ __device__ int inflate_stream(const uint8_t *in, int in_len, uint8_t *out, int o
                     sym -= 257;
                     if (sym >= 29) return kInfBadSymbol;
                     const int len = kLenBase[sym] + (int)take(b, kLenExtra[sym]);
-                    const int ds = decode_symbol(b, distcode);
+                    const int ds = decode_fast(b, dist_tab, kDistBits, distcode);
                     if (ds < 0 || ds >= 30) return kInfBadSymbol;
                     const int dist = kDistBase[ds] + (int)take(b, kDistExtra[ds]);
                     if (dist > n_out) return kInfBadDistance;
                     if (n_out + len > out_cap) return kInfOutputOverflow;
                     // byte k of the match = window byte k mod dist (an overlapping copy repeats the last dist
                     // bytes): every source byte precedes the match, so the lanes copy independently
-                    NMB_SYNC_LANES();  // bytes written by other lanes so far
-                    const volatile uint8_t *src = out + n_out - dist;
+                    NMB_SYNC_LANES();  // orders the other lanes' earlier writes before these reads (same SM, same L1)
+                    const uint8_t *src = out + n_out - dist;
                     if (dist >= len) {
                         for (int k = lane; k < len; k += lanes) out[n_out + k] = src[k];
                     } else {
@@ -301,12 +338,13 @@ __global__ void __launch_bounds__(128) bgzf_inflate_kernel(const uint8_t *__rest
                                                            const int32_t *__restrict__ out_len,
                                                            const uint32_t *__restrict__ crc, int n_blocks,
                                                            uint8_t *out, int32_t *__restrict__ status) {
+    __shared__ uint16_t s_lit[4][1 << kLitBits], s_dist[4][1 << kDistBits];
     const int blk = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // one warp per BGZF block
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (blk >= n_blocks) return;
     uint8_t *dst = out + out_off[blk];
     int produced = 0;
-    int st = inflate_stream(comp + in_off[blk], in_len[blk], dst, out_len[blk], &produced, lane, 32);
+    int st = inflate_stream(comp + in_off[blk], in_len[blk], dst, out_len[blk], &produced, lane, 32, s_lit[warp], s_dist[warp]);
     if (st == kInfOk && produced != out_len[blk]) st = kInfSizeMismatch;
     if (st == kInfOk && crc) {  // one chunk per lane, combined in order: crc(A || B) = crc(A) * x^(8 |B|) + crc(B)
         const int chunk = (produced + 31) / 32;
