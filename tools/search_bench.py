@@ -1,0 +1,138 @@
+#!/usr/bin/env python
+"""Lock-step motif search over many bins (scaled-down BASELINE cfg 3): every (bin, mod type) search advances together,
+one K2 launch per score round and one K4 launch per expand / remove round (development tool).
+
+    python tools/search_bench.py [--bins 16] [--bin-bp 1000000] [--cpu-bins 1]
+"""
+import argparse
+import os
+import random
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import nanomotif_b200 as nmb  # noqa: E402
+from nanomotif_b200 import growth, search, synth  # noqa: E402
+
+PLANTED = [("GATC", 1), ("CTGCAG", 4), ("GA[AG]TC", 1), ("GCAC......GTT", 2), ("CAA..[AT]TG", 2), ("TTAA", 3), ("ACC.GT", 0),
+           ("GAAG[CT]", 2)]
+
+
+def build_bin(b, rng, bin_bp, depth):
+    contigs, cols = {}, {k: [] for k in ("contig", "position", "strand", "fraction_mod")}
+    n = int(rng.integers(2, 6))
+    lens = np.maximum(20000, (rng.dirichlet(np.ones(n)) * bin_bp).astype(int))
+    planted = [(PLANTED[i][0], PLANTED[i][1], "a") for i in rng.choice(len(PLANTED), size=int(rng.integers(1, 4)), replace=False)]
+    for i, L in enumerate(lens):
+        seq = synth.random_sequence(rng, int(L), float(rng.uniform(0.35, 0.65)), 2e-5)
+        name = f"bin{b}_contig_{i}"
+        contigs[name] = seq.tobytes().decode()
+        p = synth.synth_pileup(seq, rng, depth=depth, mod_types=("a",), planted=planted)
+        cols["contig"].append(np.full(len(p["position"]), name, dtype=object))
+        cols["position"].append(p["position"])
+        cols["strand"].append(np.where(p["strand"] == 0, "+", "-").astype(object))
+        cols["fraction_mod"].append(p["fraction_mod"])
+    return contigs, {k: np.concatenate(v) for k, v in cols.items()}, planted
+
+
+def windows_for(asm, contigs, pile, pad, high):
+    strand = (pile["strand"] == "-").astype(np.uint8)
+    conf = pile["fraction_mod"] >= high
+    ci, pos, st = [], [], []
+    for name, seq in contigs.items():
+        in_contig = conf & (pile["contig"] == name)
+        for s in (0, 1):
+            p = pile["position"][in_contig & (strand == s)]
+            p = p[(p > pad) & (p < len(seq) - pad)]
+            ci.append(np.full(len(p), asm.index[name]))
+            pos.append(p)
+            st.append(np.full(len(p), s, dtype=np.uint8))
+    return growth.DeviceDNAarray.from_positions(asm, np.concatenate(ci), np.concatenate(pos), np.concatenate(st), pad)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bins", type=int, default=16)
+    ap.add_argument("--bin-bp", type=int, default=1_000_000)
+    ap.add_argument("--depth", type=int, default=20)
+    ap.add_argument("--cpu-bins", type=int, default=1, help="bins also searched with the CPU oracle backend (slow)")
+    args = ap.parse_args()
+    pad, low, high, min_kl, thr = 20, 0.3, 0.7, 0.05, 1.5
+    rng = np.random.default_rng(5)
+    t0 = time.perf_counter()
+    bins, piles, truth = {}, [], {}
+    for b in range(args.bins):
+        contigs, pile, planted = build_bin(b, rng, args.bin_bp, args.depth)
+        pile["mod_type"] = np.full(len(pile["position"]), "a", dtype=object)
+        bins[f"bin{b}"], truth[f"bin{b}"] = contigs, planted
+        piles.append(pile)
+    pile = {k: np.concatenate([p[k] for p in piles]) for k in piles[0]}
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    multi = nmb.MultiBinScorer(pile, bins, ["a"], low, high)
+    asm = multi.assembly
+    setups = []
+    for b in range(args.bins):
+        random.seed(1 + b)
+        w = windows_for(asm, bins[f"bin{b}"], piles[b], pad, high)
+        bg = growth.background_pssm(asm, bins[f"bin{b}"], "A", pad)
+        setups.append((w, bg))
+    pool = growth.WindowPool([w for w, _ in setups])
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    counts = {"score": 0, "expand": 0, "remove": 0, "motifs": 0}
+
+    def counting(kind, fn):
+        def hook(reqs):
+            counts[kind] += 1
+            if kind == "score":
+                counts["motifs"] += sum(len(m) for _, m in reqs)
+            return fn(reqs)
+        return hook
+
+    searches = []
+    for b, (w, bg) in enumerate(setups):
+        co = search.find_candidates("a", pad, bg, w.shape[0], min_kl=min_kl, score_threshold=thr)
+        searches.append((co, search.PoolBackend(multi.context(f"bin{b}", "a"), pool, b)))
+    t0 = time.perf_counter()
+    results = search.run_lockstep(searches, counting("score", search.gpu_batch_score), counting("expand", search.gpu_batch_expand),
+                                  counting("remove", search.gpu_batch_remove))
+    torch.cuda.synchronize()
+    t_search = time.perf_counter() - t0
+    def expansions(m):  # concrete strings of a planted motif: the search reports bracket classes as separate motifs
+        out = [""]
+        for t in nmb.motif.tokenize(m):
+            out = [o + c for o in out for c in (t[1:-1] if t.startswith("[") else t)]
+        return out
+
+    found = 0
+    for b, res in enumerate(results):
+        best = set() if res is None else {m.string.strip(".") for m in res[1]}
+        found += all(p[0] in best or all(e in best for e in expansions(p[0])) for p in truth[f"bin{b}"])
+    total_bp = sum(len(s) for cs in bins.values() for s in cs.values())
+    print(f"{args.bins} bins, {total_bp / 1e6:.1f} Mbp, {len(pile['position']) / 1e6:.1f} M pileup rows (host generation {t_gen:.1f} s)")
+    print(f"device setup (pack, class planes, windows, background)  {t_setup:7.2f} s")
+    print(f"lock-step search of {args.bins} (bin, mod type) pairs          {t_search:7.2f} s   rounds: score {counts['score']} "
+          f"({counts['motifs']} motifs), expand {counts['expand']}, remove {counts['remove']}")
+    print(f"bins whose planted motifs were all recovered: {found} / {args.bins}")
+    if args.cpu_bins:
+        from search_common import OracleBackend
+
+        t0 = time.perf_counter()
+        for b in range(args.cpu_bins):
+            spec = dict(padding=pad, high=high, low=low, mod_type="a", random_seed=1 + b)
+            be = OracleBackend(bins[f"bin{b}"], piles[b], spec)
+            co = search.find_candidates("a", pad, be.bin_pssm, be.arr.shape[0], min_kl=min_kl, score_threshold=thr)
+            search.run(co, be)
+        t_cpu = (time.perf_counter() - t0) / args.cpu_bins
+        print(f"same search with the CPU oracle backend (regex + np.isin, one core): {t_cpu:7.2f} s per bin "
+              f"-> {t_cpu * args.bins:.0f} s for {args.bins} bins sequentially; lock-step GPU speed-up {t_cpu * args.bins / t_search:.0f}x")
+
+
+if __name__ == "__main__":
+    main()
