@@ -380,6 +380,34 @@ NMB_API int nmb_segment_offsets(const int64_t *stats, int64_t n_segments, int64_
 NMB_API int nmb_segment_median(const double *fractions, const int64_t *offsets, int64_t n_segments, double *median,
                                void *stream);
 
+/* ---- K8: exhaustive candidate sweep (BASELINE.json configs[4]): counts of EVERY IUPAC motif of length 4..8
+ *      at every modified position from one pass over the assembly (csrc/sweep.cu) ----
+ * hist: nmb_sweep_hist_size() uint32 counters, zeroed by the caller; counters ADD, so several calls (contig
+ * ranges, GPUs after an all-reduce) accumulate.  For k = 4..8 the block at sum_{j<k} j*2*5^j holds
+ * [o = 0..k-1][class: 0 methylated, 1 unmethylated][5^k windows]; a window's index is its letters as base-5
+ * digits, first letter most significant, letter states A=0 T=1 G=2 C=3 other=4.  Counted: every pileup row of
+ * the class planes (one mod type) under every window that lies inside one contig of [contig_begin, contig_end);
+ * '-' rows count under the reverse complement of the window at the mirrored offset. */
+NMB_API int64_t nmb_sweep_hist_size(void);
+NMB_API int nmb_sweep_hist(const nmb_assembly *assembly_h, const uint32_t *class_records_of_modtype, int32_t tile_begin,
+                           int32_t tile_count, int32_t contig_begin, int32_t contig_end, uint32_t *hist, void *stream);
+
+/* dst[hi][lo] = src[hi][digit][lo] with lo < axis_stride: fixes one base-5 axis (the modified position's own
+ * letter) and drops it.  n_out = elements of dst. */
+NMB_API int nmb_sweep_slice(const uint32_t *src, uint32_t *dst, int64_t n_out, int64_t axis_stride, int32_t digit,
+                            void *stream);
+
+/* dst[outer][15][inner] = sums of src[outer][5][inner] over the letters of each IUPAC code, in the order of
+ * nanomotif/constants.py:2 (A T G C R Y S W K M B D H V N; N also takes the "other" state, like the regex
+ * wildcard).  Applied to every axis in turn it turns window counts into the counts of every IUPAC motif. */
+NMB_API int nmb_sweep_expand(const uint32_t *src, uint32_t *dst, int64_t outer, int64_t inner, void *stream);
+
+/* Indices i of a finished table with n_mod[i] >= min_mod and posterior mean (5 + n_mod) / (10 + n_mod +
+ * n_nomod) >= min_mean (Beta(5,5) prior, nanomotif/model.py:8-9), in no particular order; *n_out (device int64)
+ * = number of hits, of which at most `capacity` are written. */
+NMB_API int nmb_sweep_filter(const uint32_t *n_mod, const uint32_t *n_nomod, int64_t n, double min_mean,
+                             int64_t min_mod, int64_t *out_index, int64_t capacity, int64_t *n_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

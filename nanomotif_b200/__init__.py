@@ -17,7 +17,7 @@ from .api import (  # noqa: F401
     subseq_indices,
 )
 from .device import DeviceAssembly, DevicePileup, MotifPrograms, scan_count  # noqa: F401
-from . import dataload, growth, pattern, pipeline, search, sharding  # noqa: F401
+from . import dataload, growth, pattern, pipeline, search, sharding, sweep, tables  # noqa: F401
 from .model import BetaBernoulliModel, predictive_evaluation_score  # noqa: F401
 from .motif import Motif  # noqa: F401
 from .pileup import PileupTable  # noqa: F401

@@ -1,0 +1,263 @@
+// K8 -- exhaustive candidate sweep (BASELINE.json configs[4]): the counts of EVERY IUPAC motif of length 4..8
+// at every modified position, without scanning per motif.
+//
+// Brute force is motif x bp work: 15^4 + ... + 15^8 = 2.7e9 motifs over a 2 Gbp assembly is ~5e18 motif*bp.  The
+// counts that motif_model_bin returns (find_motifs_bin.py:1265-1331: pileup rows classified methylated /
+// unmethylated whose position is the modified base of an occurrence, both strands) are additive over the
+// CONCRETE sequence contexts of the rows, so one pass over the assembly suffices:
+//   sweep_hist_kernel    for every window of k = 4..8 letters inside a contig and every classified row under
+//                        it: hist[k][o][class][window] += 1, o = offset of the row in the window ('+' rows use
+//                        the window, '-' rows its reverse complement with the offset mirrored -- the reference
+//                        scans the reverse-complement motif on the forward text, find_motifs_bin.py:1317).
+//                        Letters have FIVE states: A, T, G, C and "other" (non-ACGT), because the regex
+//                        wildcard matches any character while sets do not.
+//   sweep_expand_kernel  subset-sum (zeta) transform, one axis at a time: 5 letter states -> 15 IUPAC letters
+//                        (N includes "other").  After all axes, table[L_0 .. L_{k-1}] is the count of motif L.
+//   sweep_filter_kernel  posterior-mean / support filter over a finished table -> candidate list.
+// The modified position's own letter is fixed to one concrete base by the caller (a row under any other base
+// cannot exist), which keeps the largest table at 15^7 entries.
+#include "scan.cuh"
+
+namespace nmb {
+
+constexpr int kSweepMinK = 4, kSweepMaxK = 8;
+__host__ __device__ constexpr int pow5(int k) { return k == 0 ? 1 : 5 * pow5(k - 1); }
+// first counter of length k in the histogram array: sum_{j<k} j * 2 * 5^j
+__host__ __device__ constexpr int64_t sweep_hist_offset(int k) {
+    return k <= kSweepMinK ? 0 : sweep_hist_offset(k - 1) + (int64_t)(k - 1) * 2 * pow5(k - 1);
+}
+constexpr int64_t kSweepHistSize = sweep_hist_offset(kSweepMaxK + 1);  // 7 567 500 counters
+
+struct SweepParams {
+    const uint32_t *seq_records, *nonacgt, *cls;  // cls: the class records of ONE mod type
+    const int64_t *contig_start, *contig_len;
+    uint32_t *hist;
+    int tile_begin, n_tiles_total, contig_begin, contig_end;
+};
+
+constexpr int kSweepSmemBytes = kSeqRecBytes + kClsRecBytes;
+
+// word w (0..16) of chunk t in a lane-interleaved shared-memory plane; word 16 = first word of chunk t + 1
+// (`next` supplies it for the last chunk of the tile)
+__device__ __forceinline__ uint32_t chunk_word(const uint32_t *body, int t, int w, uint32_t next) {
+    if (w < NW) return body[(w >> 2) * kSlotStride + t * 4 + (w & 3)];
+    return t + 1 < kTileChunks ? body[(t + 1) * 4] : next;
+}
+
+template <int K>
+__device__ __forceinline__ void sweep_add(uint32_t *hist, int code8, int rc8, unsigned plus, unsigned minus, int cls,
+                                          int rem) {
+    if (rem < K) return;  // the window of K letters must lie inside the contig
+    uint32_t *h = hist + sweep_hist_offset(K);
+    const int code = code8 / pow5(kSweepMaxK - K);  // first K letters
+    const int rc = rc8 % pow5(K);                   // reverse complement of the first K letters
+    for (unsigned b = plus & ((1u << K) - 1u); b; b &= b - 1) {
+        const int o = __ffs(b) - 1;
+        atomicAdd(h + (size_t)(o * 2 + cls) * pow5(K) + code, 1u);
+    }
+    for (unsigned b = minus & ((1u << K) - 1u); b; b &= b - 1) {
+        const int o = K - 1 - (__ffs(b) - 1);  // offset of the row in the reverse-complement window
+        atomicAdd(h + (size_t)(o * 2 + cls) * pow5(K) + rc, 1u);
+    }
+}
+
+// One CTA per tile, one lane per 512-bp chunk, positions in order: the 8-letter window code slides by one letter
+// per position (base-5 digits, most significant first; the reverse-complement code slides the other way).
+__global__ void __launch_bounds__(kTileChunks) sweep_hist_kernel(const SweepParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar;
+    const int tid = threadIdx.x;
+    const int tile = p.tile_begin + blockIdx.x;
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+        mbar_expect_tx(&full_bar, kSeqRecBytes + kClsRecBytes);
+        bulk_g2s(smem, p.seq_records + (size_t)tile * kSeqRecWords, kSeqRecBytes, &full_bar);
+        bulk_g2s(smem + kSeqRecBytes, p.cls + (size_t)tile * kClsRecWords, kClsRecBytes, &full_bar);
+    }
+    __syncthreads();
+    mbar_wait(&full_bar, 0);
+    const uint32_t *sx = reinterpret_cast<const uint32_t *>(smem);
+    const uint32_t *sy = sx + kSeqPlaneWords;
+    const int info = reinterpret_cast<const int32_t *>(sy + kSeqPlaneWords)[tid];
+    if (info < 0) return;
+    const int contig = info & kChunkIdMask;
+    if (contig < p.contig_begin || contig >= p.contig_end) return;
+    const uint32_t *scls = sx + kSeqRecWords;
+    const int64_t chunk_pos = ((int64_t)tile * kTileChunks + tid) * NMB_CHUNK_BP;
+    const int64_t contig_end_pos = __ldg(p.contig_start + contig) + __ldg(p.contig_len + contig);
+    const int n_here = (int)min((int64_t)NMB_CHUNK_BP, contig_end_pos - chunk_pos);  // window starts in this chunk
+    // word 16 of every plane: the record halo / the next tile's class record for the last chunk
+    const bool last_chunk = tid + 1 == kTileChunks;
+    const bool has_next = tile + 1 < p.n_tiles_total;
+    uint32_t next_cls[4] = {0, 0, 0, 0};
+    if (last_chunk && has_next)
+        for (int k = 0; k < 4; ++k) next_cls[k] = __ldg(p.cls + (size_t)(tile + 1) * kClsRecWords + k * kTileWords);
+    const uint32_t next_x = sx[kHalo + kTileWords], next_y = sy[kHalo + kTileWords];
+    const uint32_t *gn = p.nonacgt + kHalo + (size_t)tile * kTileWords + tid * NW;
+
+    uint64_t X = 0, Y = 0, N = 0, C0 = 0, C1 = 0, C2 = 0, C3 = 0;  // bit i = position (32 * word + i) of the current pair
+    auto load_pair = [&](int w) {  // words w and w + 1 of the seven planes
+        const uint64_t x0 = chunk_word(sx + kHalo, tid, w, next_x), x1 = w + 1 <= NW ? chunk_word(sx + kHalo, tid, w + 1, next_x) : 0;
+        const uint64_t y0 = chunk_word(sy + kHalo, tid, w, next_y), y1 = w + 1 <= NW ? chunk_word(sy + kHalo, tid, w + 1, next_y) : 0;
+        X = x0 | (x1 << 32);
+        Y = y0 | (y1 << 32);
+        N = (uint64_t)__ldg(gn + w) | ((uint64_t)(w + 1 <= NW ? __ldg(gn + w + 1) : 0xFFFFFFFFu) << 32);
+        const uint64_t a0 = chunk_word(scls, tid, w, next_cls[0]), a1 = w + 1 <= NW ? chunk_word(scls, tid, w + 1, next_cls[0]) : 0;
+        const uint64_t b0 = chunk_word(scls + kTileWords, tid, w, next_cls[1]), b1 = w + 1 <= NW ? chunk_word(scls + kTileWords, tid, w + 1, next_cls[1]) : 0;
+        const uint64_t c0 = chunk_word(scls + 2 * kTileWords, tid, w, next_cls[2]), c1 = w + 1 <= NW ? chunk_word(scls + 2 * kTileWords, tid, w + 1, next_cls[2]) : 0;
+        const uint64_t d0 = chunk_word(scls + 3 * kTileWords, tid, w, next_cls[3]), d1 = w + 1 <= NW ? chunk_word(scls + 3 * kTileWords, tid, w + 1, next_cls[3]) : 0;
+        C0 = a0 | (a1 << 32);
+        C1 = b0 | (b1 << 32);
+        C2 = c0 | (c1 << 32);
+        C3 = d0 | (d1 << 32);
+    };
+    auto letter = [&](int i) -> int {  // state of position i (0..63) of the current pair: A T G C other
+        return ((N >> i) & 1) ? 4 : (int)((((X >> i) & 1) << 1) | ((Y >> i) & 1));
+    };
+    auto comp = [](int d) -> int { return d < 4 ? (d ^ 1) : 4; };  // A<->T, G<->C
+
+    load_pair(0);
+    int code8 = 0, rc8 = 0, first = 0;  // first = the window's leading letter (leaves on the next slide)
+    for (int i = 0; i < kSweepMaxK; ++i) {
+        const int d = letter(i);
+        code8 = code8 * 5 + d;
+        rc8 += comp(d) * pow5(i);
+        if (i == 0) first = d;
+    }
+    for (int s = 0; s < n_here; ++s) {
+        const int b = s & 31;
+        if (b == 0 && s) load_pair(s >> 5);
+        const int rem = (int)min((int64_t)kSweepMaxK, contig_end_pos - (chunk_pos + s));
+        const unsigned mp = (unsigned)(C0 >> b) & 0xFF, np = (unsigned)(C1 >> b) & 0xFF;  // rows under the window, '+'
+        const unsigned mm = (unsigned)(C2 >> b) & 0xFF, nm = (unsigned)(C3 >> b) & 0xFF;  // '-'
+        if (mp | mm) {
+            sweep_add<4>(p.hist, code8, rc8, mp, mm, 0, rem);
+            sweep_add<5>(p.hist, code8, rc8, mp, mm, 0, rem);
+            sweep_add<6>(p.hist, code8, rc8, mp, mm, 0, rem);
+            sweep_add<7>(p.hist, code8, rc8, mp, mm, 0, rem);
+            sweep_add<8>(p.hist, code8, rc8, mp, mm, 0, rem);
+        }
+        if (np | nm) {
+            sweep_add<4>(p.hist, code8, rc8, np, nm, 1, rem);
+            sweep_add<5>(p.hist, code8, rc8, np, nm, 1, rem);
+            sweep_add<6>(p.hist, code8, rc8, np, nm, 1, rem);
+            sweep_add<7>(p.hist, code8, rc8, np, nm, 1, rem);
+            sweep_add<8>(p.hist, code8, rc8, np, nm, 1, rem);
+        }
+        // slide: drop the leading letter, append the letter at s + 8
+        const int d_new = letter(b + kSweepMaxK);
+        code8 = (code8 - first * pow5(kSweepMaxK - 1)) * 5 + d_new;
+        rc8 = (rc8 - comp(first)) / 5 + comp(d_new) * pow5(kSweepMaxK - 1);
+        first = letter(b + 1);
+    }
+}
+
+// dst[outer][15][inner] = subset sums of src[outer][5][inner] over the letters of each IUPAC code.
+// Letter states: A T G C other; IUPAC order = nanomotif/constants.py:2 (A T G C R Y S W K M B D H V N).
+__global__ void __launch_bounds__(256) sweep_expand_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
+                                                           int64_t outer, int64_t inner) {
+    const int64_t n = outer * inner;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t o = i / inner, r = i - o * inner;
+        const uint32_t *s = src + o * 5 * inner + r;
+        const uint32_t a = s[0], t = s[inner], g = s[2 * inner], c = s[3 * inner], x = s[4 * inner];
+        uint32_t *d = dst + o * 15 * inner + r;
+        d[0] = a; d[inner] = t; d[2 * inner] = g; d[3 * inner] = c;
+        d[4 * inner] = a + g;           // R
+        d[5 * inner] = c + t;           // Y
+        d[6 * inner] = g + c;           // S
+        d[7 * inner] = a + t;           // W
+        d[8 * inner] = g + t;           // K
+        d[9 * inner] = a + c;           // M
+        d[10 * inner] = c + g + t;      // B
+        d[11 * inner] = a + g + t;      // D
+        d[12 * inner] = a + c + t;      // H
+        d[13 * inner] = a + c + g;      // V
+        d[14 * inner] = a + c + g + t + x;  // N: the regex wildcard also matches non-ACGT letters
+    }
+}
+
+// dst[...] = src[... with the digit of axis `axis_stride` fixed to `digit` ...]: drops one base-5 axis.
+__global__ void __launch_bounds__(256) sweep_slice_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
+                                                          int64_t n_out, int64_t axis_stride, int digit) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const int64_t hi = i / axis_stride, lo = i - hi * axis_stride;
+    dst[i] = src[(hi * 5 + digit) * axis_stride + lo];
+}
+
+// Candidates of one finished table pair: posterior mean (5 + n_mod) / (10 + n_mod + n_nomod) >= min_mean and
+// n_mod >= min_mod (Beta(5, 5) prior, nanomotif/model.py:8-9).  Appends the table index; *n_out counts all hits.
+__global__ void __launch_bounds__(256) sweep_filter_kernel(const uint32_t *__restrict__ n_mod,
+                                                           const uint32_t *__restrict__ n_nomod, int64_t n,
+                                                           double min_mean, uint32_t min_mod, int64_t *__restrict__ out,
+                                                           int64_t capacity, unsigned long long *__restrict__ n_out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t m = n_mod[i];
+        if (m < min_mod) continue;
+        const double mean = (5.0 + m) / (10.0 + m + n_nomod[i]);
+        if (mean < min_mean) continue;
+        const unsigned long long slot = atomicAdd(n_out, 1ull);
+        if ((int64_t)slot < capacity) out[slot] = i;
+    }
+}
+
+}  // namespace nmb
+
+extern "C" {
+
+int64_t nmb_sweep_hist_size(void) { return nmb::kSweepHistSize; }
+
+int nmb_sweep_hist(const nmb_assembly *a, const uint32_t *class_records_of_modtype, int32_t tile_begin,
+                   int32_t tile_count, int32_t contig_begin, int32_t contig_end, uint32_t *hist, void *stream) {
+    NMB_REQUIRE(a && class_records_of_modtype && hist, "nmb_sweep_hist: null argument");
+    NMB_REQUIRE(tile_begin >= 0 && tile_count >= 0 && tile_begin + tile_count <= a->n_tiles,
+                "nmb_sweep_hist: tiles [%d, %d) outside the assembly", tile_begin, tile_begin + tile_count);
+    if (tile_count == 0) return NMB_OK;
+    nmb::SweepParams p{a->seq_records, a->nonacgt, class_records_of_modtype, a->contig_start, a->contig_len, hist,
+                       tile_begin, a->n_tiles, contig_begin, contig_end};
+    NMB_CUDA(cudaFuncSetAttribute(nmb::sweep_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  nmb::kSweepSmemBytes));
+    nmb::sweep_hist_kernel<<<tile_count, nmb::kTileChunks, nmb::kSweepSmemBytes, (cudaStream_t)stream>>>(p);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_sweep_slice(const uint32_t *src, uint32_t *dst, int64_t n_out, int64_t axis_stride, int32_t digit,
+                    void *stream) {
+    NMB_REQUIRE(src && dst && n_out > 0 && axis_stride > 0 && digit >= 0 && digit < 5, "nmb_sweep_slice: bad argument");
+    nmb::sweep_slice_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n_out,
+                                                                                             axis_stride, digit);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_sweep_expand(const uint32_t *src, uint32_t *dst, int64_t outer, int64_t inner, void *stream) {
+    NMB_REQUIRE(src && dst && outer > 0 && inner > 0, "nmb_sweep_expand: bad argument");
+    int64_t blocks = (outer * inner + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    nmb::sweep_expand_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, outer, inner);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_sweep_filter(const uint32_t *n_mod, const uint32_t *n_nomod, int64_t n, double min_mean, int64_t min_mod,
+                     int64_t *out_index, int64_t capacity, int64_t *n_out, void *stream) {
+    NMB_REQUIRE(n_mod && n_nomod && n_out && n >= 0 && capacity >= 0 && min_mod >= 0, "nmb_sweep_filter: bad argument");
+    NMB_REQUIRE(capacity == 0 || out_index, "nmb_sweep_filter: null output");
+    NMB_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int64_t), (cudaStream_t)stream));
+    if (n == 0) return NMB_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    nmb::sweep_filter_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        n_mod, n_nomod, n, min_mean, (uint32_t)(min_mod > 0xFFFFFFFFll ? 0xFFFFFFFFll : min_mod), out_index, capacity,
+        (unsigned long long *)n_out);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+}  // extern "C"

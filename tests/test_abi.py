@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     text = open(os.path.join(ROOT, "include", "nmb200.h")).read()
-    return re.findall(r"NMB_API\s+(?:const\s+char\s*\*|int)\s*(nmb_[a-z0-9_]+)\s*\(", text)
+    return re.findall(r"NMB_API\s+(?:const\s+char\s*\*|int64_t|int)\s*(nmb_[a-z0-9_]+)\s*\(", text)
 
 
 def test_every_declared_symbol_is_exported_and_bound():

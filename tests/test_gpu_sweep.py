@@ -59,3 +59,73 @@ def test_iupac_sweep_sample_matches_oracle():
         assert tuple(g) == want, (s, p)
         nonzero += sum(want) > 0
     assert nonzero > 100
+
+
+def test_exhaustive_tables_equal_per_motif_counts():
+    """K8: the histogram + subset-sum tables hold, for EVERY IUPAC motif of length 4..8, exactly the counts that a scan of
+    that motif gives -- checked on a seeded sample against the CPU oracle (small assembly with non-ACGT letters, contigs
+    shorter than a window, contig ends) and against K2 for whole tables' worth of motifs."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import nanomotif_b200 as nmb
+    from nanomotif_b200 import synth
+    from nanomotif_b200.sweep import SweepIndex
+
+    rng = np.random.default_rng(16)
+    contigs, cols = {}, {k: [] for k in ("contig", "position", "strand", "fraction_mod")}
+    for i, L in enumerate((90000, 40000, 2600, 7, 5, 70000, 3)):
+        seq = synth.random_sequence(rng, L, 0.4 + 0.03 * i, 2e-4 if L > 100 else 0.0)
+        if L > 1000:
+            seq[rng.integers(0, L, 20)] = ord("N")  # isolated non-ACGT letters: the wildcard matches them, sets do not
+            seq[-1] = ord("R")
+        contigs[f"c{i}"] = seq.tobytes().decode()
+        p = synth.synth_pileup(seq, rng, depth=12, mod_types=("a",))
+        cols["contig"].append(np.full(len(p["position"]), f"c{i}", dtype=object))
+        cols["position"].append(p["position"])
+        cols["strand"].append(np.where(p["strand"] == 0, "+", "-"))
+        cols["fraction_mod"].append(p["fraction_mod"])
+    pile = {k: np.concatenate(v) for k, v in cols.items()}
+    scorer = nmb.BinScorer(pile, contigs, 0.3, 0.7)
+    index = SweepIndex(scorer.assembly, scorer.pileup, 0).add()
+    sample = [(s, p) for s, p in _sample_motifs(rng, 400) if 4 <= len(s) <= 8]
+    sample += [("ANNNA", 0), ("NANN", 1), ("NNNNNNNA", 7), ("ANNNNNNN", 0), ("GATC", 1), ("TTAA", 3), ("NNANN", 2)]
+    assert len(sample) > 180
+    nonzero = 0
+    for s, p in sample:
+        got = index.counts(s, p)
+        ref = _oracle_counts(pile, contigs, s, p)
+        assert got == ref, (s, p, got, ref)
+        nonzero += sum(ref) > 0
+    assert nonzero > 100
+    # one whole table against K2: all 15^3 motifs of length 4 with the modified A at position 1
+    n_mod, n_nomod = index.table(4, 1, "A")
+    all4 = [SweepIndex.index_motif(i, 4, 1, "A") for i in range(15 ** 3)]
+    inner = [(i, s) for i, s in enumerate(all4) if s[0] != "N" and s[-1] != "N"]  # K2 strips flanking wildcards
+    got = scorer.score([nmb.Motif(s, 1).from_iupac() for _, s in inner])
+    sel = torch.tensor([i for i, _ in inner], device=n_mod.device)
+    np.testing.assert_array_equal(got[:, 0], n_mod[sel].cpu().numpy())
+    np.testing.assert_array_equal(got[:, 1], n_nomod[sel].cpu().numpy())
+    # candidates: the planted GATC stands out among all 4-mers
+    cand = index.candidates(4, 1, "A", min_mean=0.8, min_mod=100)
+    assert ("GATC", int(n_mod[SweepIndex.motif_index("GATC", 1)]), int(n_nomod[SweepIndex.motif_index("GATC", 1)])) in cand
+    assert all(s[1] == "A" and s[0] != "N" and s[-1] != "N" for s, _, _ in cand)
+
+
+def _oracle_counts(pile, contigs, iupac, mod_pos, low=0.3, high=0.7):
+    """Counts of an IUPAC motif AS WRITTEN (a flanking N is a regex '.', which needs a character of the contig) with the
+    reference's scan + join restated in oracle/restate.py; for motifs without flanking N this is motif_model_bin."""
+    rx = "".join(O.IUPAC_TO_REGEX[c] for c in iupac)
+    rc_rx, rc_pos = O.reverse_complement_motif(rx, mod_pos)
+    n_mod = n_nomod = 0
+    for name, seq in contigs.items():
+        sel = pile["contig"] == name
+        pos, strand, frac = pile["position"][sel], pile["strand"][sel], pile["fraction_mod"][sel]
+        arr = np.frombuffer(seq.encode(), dtype=np.uint8)
+        for st, motif, mp in (("+", rx, mod_pos), ("-", rc_rx, rc_pos)):
+            on = strand == st
+            a, b = O.methylated_motif_occourances(motif, mp, arr, pos[on & (frac >= high)], pos[on & (frac <= low)], True)
+            n_mod += len(a)
+            n_nomod += len(b)
+    return n_mod, n_nomod
