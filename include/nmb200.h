@@ -392,6 +392,16 @@ NMB_API int64_t nmb_sweep_hist_size(void);
 NMB_API int nmb_sweep_hist(const nmb_assembly *assembly_h, const uint32_t *class_records_of_modtype, int32_t tile_begin,
                            int32_t tile_count, int32_t contig_begin, int32_t contig_end, uint32_t *hist, void *stream);
 
+/* The bipartite half of the sweep: shapes X{a} N{g} Y{b}, a, b in {3, 4}, g in 4..8, concrete letters only.
+ * hist: nmb_sweep_bipartite_size() uint32 counters (zeroed by the caller, counters add); shapes are stored g major,
+ * then (3,3) (3,4) (4,3) (4,4); a shape's block is [o = 0..a+b-1 over the concrete letters][class][4^(a+b)] with
+ * window index xL | yL << a | xR << 2a | yR << (2a + b), x / y = high / low code bit of each letter (A=0 T=1 G=2
+ * C=3), letter i of a part at bit i. */
+NMB_API int64_t nmb_sweep_bipartite_size(void);
+NMB_API int nmb_sweep_bipartite(const nmb_assembly *assembly_h, const uint32_t *class_records_of_modtype,
+                                int32_t tile_begin, int32_t tile_count, int32_t contig_begin, int32_t contig_end,
+                                uint32_t *hist, void *stream);
+
 /* dst[hi][lo] = src[hi][digit][lo] with lo < axis_stride: fixes one base-5 axis (the modified position's own
  * letter) and drops it.  n_out = elements of dst. */
 NMB_API int nmb_sweep_slice(const uint32_t *src, uint32_t *dst, int64_t n_out, int64_t axis_stride, int32_t digit,

@@ -61,8 +61,72 @@ __device__ __forceinline__ void sweep_add(uint32_t *hist, int code8, int rc8, un
     }
 }
 
+// ---- bipartite shapes X{3,4} N{4..8} Y{3,4} over ACGT (the second half of BASELINE config 5) ----
+// Shape (a, g, b): a concrete letters, g wildcards, b concrete letters.  Block of shape (a, g, b):
+// [o = 0..a+b-1][class][4^(a+b)], o counted over the concrete letters only; window index =
+// xL | yL << a | xR << 2a | yR << (2a + b) with x / y the high / low code bits of the letters, letter i at bit i.
+constexpr int kBipMinGap = 4, kBipMaxGap = 8;
+__host__ __device__ constexpr int64_t bip_block(int a, int b) { return (int64_t)(a + b) * 2 * (1 << (2 * (a + b))); }
+__host__ __device__ constexpr int64_t bip_offset(int a, int g, int b) {
+    // order: g major, then (3,3) (3,4) (4,3) (4,4)
+    return (int64_t)(g - kBipMinGap) * (bip_block(3, 3) + bip_block(3, 4) + bip_block(4, 3) + bip_block(4, 4)) +
+           (a == 3 ? (b == 3 ? 0 : bip_block(3, 3)) : bip_block(3, 3) + bip_block(3, 4) + (b == 3 ? 0 : bip_block(4, 3)));
+}
+constexpr int64_t kBipHistSize = bip_offset(3, kBipMaxGap + 1, 3);
+
+__device__ __forceinline__ unsigned rev_bits(unsigned v, int n) { return __brev(v) >> (32 - n); }
+
+// Window of shape (A, G, B) starting at bit `s` of the 64-bit planes: '+' rows count under the window, '-' rows
+// under its reverse complement, whose shape is (B, G, A).
+template <int A, int G, int B>
+__device__ __forceinline__ void bip_add(uint32_t *hist, uint64_t X, uint64_t Y, uint64_t N, uint64_t plus, uint64_t minus,
+                                        int s, int cls, int rem) {
+    constexpr int span = A + G + B;
+    if (rem < span) return;
+    constexpr unsigned ma = (1u << A) - 1u, mb = (1u << B) - 1u;
+    const unsigned nl = (unsigned)(N >> s) & ma, nr = (unsigned)(N >> (s + A + G)) & mb;
+    if (nl | nr) return;  // a concrete letter cannot match a non-ACGT letter
+    const unsigned pl = (unsigned)(plus >> s) & ma, pr = (unsigned)(plus >> (s + A + G)) & mb;
+    const unsigned ql = (unsigned)(minus >> s) & ma, qr = (unsigned)(minus >> (s + A + G)) & mb;
+    if (!(pl | pr | ql | qr)) return;
+    const unsigned xl = (unsigned)(X >> s) & ma, yl = (unsigned)(Y >> s) & ma;
+    const unsigned xr = (unsigned)(X >> (s + A + G)) & mb, yr = (unsigned)(Y >> (s + A + G)) & mb;
+    if (pl | pr) {
+        uint32_t *h = hist + bip_offset(A, G, B);
+        const unsigned code = xl | (yl << A) | (xr << (2 * A)) | (yr << (2 * A + B));
+        for (unsigned b = pl | (pr << A); b; b &= b - 1) {
+            const int o = __ffs(b) - 1;
+            atomicAdd(h + (size_t)(o * 2 + cls) * (1u << (2 * (A + B))) + code, 1u);
+        }
+    }
+    if (ql | qr) {  // the motif is the reverse complement of the window: shape (B, G, A), letters reversed, A<->T G<->C
+        uint32_t *h = hist + bip_offset(B, G, A);
+        const unsigned code = rev_bits(xr, B) | (rev_bits(~yr & mb, B) << B) | (rev_bits(xl, A) << (2 * B)) |
+                              (rev_bits(~yl & ma, A) << (2 * B + A));
+        // forward offset j (left part) -> motif offset B + (A - 1 - j); right part j -> B - 1 - j
+        for (unsigned b = ql; b; b &= b - 1) {
+            const int o = B + (A - 1 - (__ffs(b) - 1));
+            atomicAdd(h + (size_t)(o * 2 + cls) * (1u << (2 * (A + B))) + code, 1u);
+        }
+        for (unsigned b = qr; b; b &= b - 1) {
+            const int o = B - 1 - (__ffs(b) - 1);
+            atomicAdd(h + (size_t)(o * 2 + cls) * (1u << (2 * (A + B))) + code, 1u);
+        }
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void bip_add_gap(uint32_t *hist, uint64_t X, uint64_t Y, uint64_t N, uint64_t plus,
+                                            uint64_t minus, int s, int cls, int rem) {
+    bip_add<3, G, 3>(hist, X, Y, N, plus, minus, s, cls, rem);
+    bip_add<3, G, 4>(hist, X, Y, N, plus, minus, s, cls, rem);
+    bip_add<4, G, 3>(hist, X, Y, N, plus, minus, s, cls, rem);
+    bip_add<4, G, 4>(hist, X, Y, N, plus, minus, s, cls, rem);
+}
+
 // One CTA per tile, one lane per 512-bp chunk, positions in order: the 8-letter window code slides by one letter
 // per position (base-5 digits, most significant first; the reverse-complement code slides the other way).
+template <bool BIPARTITE>
 __global__ void __launch_bounds__(kTileChunks) sweep_hist_kernel(const SweepParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar;
@@ -129,6 +193,24 @@ __global__ void __launch_bounds__(kTileChunks) sweep_hist_kernel(const SweepPara
     for (int s = 0; s < n_here; ++s) {
         const int b = s & 31;
         if (b == 0 && s) load_pair(s >> 5);
+        if (BIPARTITE) {  // spans of 10..16 letters: bits b .. b + 15 of the pairs
+            const int rem16 = (int)min((int64_t)16, contig_end_pos - (chunk_pos + s));
+            if ((C0 | C2) >> b & 0xFFFF) {
+                bip_add_gap<4>(p.hist, X, Y, N, C0, C2, b, 0, rem16);
+                bip_add_gap<5>(p.hist, X, Y, N, C0, C2, b, 0, rem16);
+                bip_add_gap<6>(p.hist, X, Y, N, C0, C2, b, 0, rem16);
+                bip_add_gap<7>(p.hist, X, Y, N, C0, C2, b, 0, rem16);
+                bip_add_gap<8>(p.hist, X, Y, N, C0, C2, b, 0, rem16);
+            }
+            if ((C1 | C3) >> b & 0xFFFF) {
+                bip_add_gap<4>(p.hist, X, Y, N, C1, C3, b, 1, rem16);
+                bip_add_gap<5>(p.hist, X, Y, N, C1, C3, b, 1, rem16);
+                bip_add_gap<6>(p.hist, X, Y, N, C1, C3, b, 1, rem16);
+                bip_add_gap<7>(p.hist, X, Y, N, C1, C3, b, 1, rem16);
+                bip_add_gap<8>(p.hist, X, Y, N, C1, C3, b, 1, rem16);
+            }
+            continue;
+        }
         const int rem = (int)min((int64_t)kSweepMaxK, contig_end_pos - (chunk_pos + s));
         const unsigned mp = (unsigned)(C0 >> b) & 0xFF, np = (unsigned)(C1 >> b) & 0xFF;  // rows under the window, '+'
         const unsigned mm = (unsigned)(C2 >> b) & 0xFF, nm = (unsigned)(C3 >> b) & 0xFF;  // '-'
@@ -212,17 +294,40 @@ extern "C" {
 
 int64_t nmb_sweep_hist_size(void) { return nmb::kSweepHistSize; }
 
+int64_t nmb_sweep_bipartite_size(void) { return nmb::kBipHistSize; }
+
+static int sweep_launch(bool bipartite, const nmb_assembly *a, const uint32_t *class_records_of_modtype,
+                        int32_t tile_begin, int32_t tile_count, int32_t contig_begin, int32_t contig_end, uint32_t *hist,
+                        void *stream);
+
 int nmb_sweep_hist(const nmb_assembly *a, const uint32_t *class_records_of_modtype, int32_t tile_begin,
                    int32_t tile_count, int32_t contig_begin, int32_t contig_end, uint32_t *hist, void *stream) {
+    return sweep_launch(false, a, class_records_of_modtype, tile_begin, tile_count, contig_begin, contig_end, hist, stream);
+}
+
+int nmb_sweep_bipartite(const nmb_assembly *a, const uint32_t *class_records_of_modtype, int32_t tile_begin,
+                        int32_t tile_count, int32_t contig_begin, int32_t contig_end, uint32_t *hist, void *stream) {
+    return sweep_launch(true, a, class_records_of_modtype, tile_begin, tile_count, contig_begin, contig_end, hist, stream);
+}
+
+static int sweep_launch(bool bipartite, const nmb_assembly *a, const uint32_t *class_records_of_modtype,
+                        int32_t tile_begin, int32_t tile_count, int32_t contig_begin, int32_t contig_end, uint32_t *hist,
+                        void *stream) {
     NMB_REQUIRE(a && class_records_of_modtype && hist, "nmb_sweep_hist: null argument");
     NMB_REQUIRE(tile_begin >= 0 && tile_count >= 0 && tile_begin + tile_count <= a->n_tiles,
                 "nmb_sweep_hist: tiles [%d, %d) outside the assembly", tile_begin, tile_begin + tile_count);
     if (tile_count == 0) return NMB_OK;
     nmb::SweepParams p{a->seq_records, a->nonacgt, class_records_of_modtype, a->contig_start, a->contig_len, hist,
                        tile_begin, a->n_tiles, contig_begin, contig_end};
-    NMB_CUDA(cudaFuncSetAttribute(nmb::sweep_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  nmb::kSweepSmemBytes));
-    nmb::sweep_hist_kernel<<<tile_count, nmb::kTileChunks, nmb::kSweepSmemBytes, (cudaStream_t)stream>>>(p);
+    if (bipartite) {
+        NMB_CUDA(cudaFuncSetAttribute(nmb::sweep_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      nmb::kSweepSmemBytes));
+        nmb::sweep_hist_kernel<true><<<tile_count, nmb::kTileChunks, nmb::kSweepSmemBytes, (cudaStream_t)stream>>>(p);
+    } else {
+        NMB_CUDA(cudaFuncSetAttribute(nmb::sweep_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      nmb::kSweepSmemBytes));
+        nmb::sweep_hist_kernel<false><<<tile_count, nmb::kTileChunks, nmb::kSweepSmemBytes, (cudaStream_t)stream>>>(p);
+    }
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;
 }

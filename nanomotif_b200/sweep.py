@@ -41,6 +41,7 @@ class SweepIndex:
             raise ValueError("mod type index outside the pileup's class records")
         with torch.cuda.device(assembly.device):
             self.hist = torch.zeros(int(lib.nmb_sweep_hist_size()), dtype=torch.int32, device=assembly.device)
+        self.bip = None
         self._tables: dict = {}
 
     def add(self, contig_begin: int = 0, contig_end: int | None = None) -> "SweepIndex":
@@ -56,11 +57,61 @@ class SweepIndex:
         self._tables.clear()
         return self
 
+    # ---- bipartite shapes X{3,4} N{4..8} Y{3,4} over ACGT ----
+    def add_bipartite(self, contig_begin: int = 0, contig_end: int | None = None) -> "SweepIndex":
+        asm = self.asm
+        contig_end = asm.n_contigs if contig_end is None else contig_end
+        tile_begin, tile_count = asm.tile_span(contig_begin, contig_end)
+        view = asm.view()
+        with torch.cuda.device(asm.device):
+            if getattr(self, "bip", None) is None:
+                self.bip = torch.zeros(int(lib.nmb_sweep_bipartite_size()), dtype=torch.int32, device=asm.device)
+            base = ptr(self.pileup.class_records) + self.modtype * asm.n_tiles * _lib.CLS_REC_WORDS * 4
+            check(lib.nmb_sweep_bipartite(C.byref(view), base, tile_begin, tile_count, contig_begin, contig_end,
+                                          ptr(self.bip), _stream()), "nmb_sweep_bipartite")
+        return self
+
+    @staticmethod
+    def bipartite_block(a: int, g: int, b: int) -> tuple[int, int]:
+        """(first counter, counters per (offset, class)) of shape X{a} N{g} Y{b} in the bipartite histogram."""
+        if a not in (3, 4) or b not in (3, 4) or not 4 <= g <= 8:
+            raise ValueError("bipartite shapes are X{3,4} N{4..8} Y{3,4}")
+        block = lambda x, y: (x + y) * 2 * 4 ** (x + y)
+        per_gap = block(3, 3) + block(3, 4) + block(4, 3) + block(4, 4)
+        within = {(3, 3): 0, (3, 4): block(3, 3), (4, 3): block(3, 3) + block(3, 4),
+                  (4, 4): block(3, 3) + block(3, 4) + block(4, 3)}[(a, b)]
+        return (g - 4) * per_gap + within, 4 ** (a + b)
+
+    def bipartite_table(self, a: int, g: int, b: int, mod_pos: int):
+        """(n_mod, n_nomod) device views over all 4^(a+b) motifs of shape X{a} N{g} Y{b} with the modified base at
+        motif position mod_pos (inside X or Y).  Entry index: bipartite_index(left, right)."""
+        if a <= mod_pos < a + g or not 0 <= mod_pos < a + g + b:
+            raise ValueError("the modified position must lie in one of the two concrete parts")
+        o = mod_pos if mod_pos < a else mod_pos - g
+        first, n = self.bipartite_block(a, g, b)
+        base = first + o * 2 * n
+        return self.bip[base:base + n], self.bip[base + n:base + 2 * n]
+
+    @staticmethod
+    def bipartite_index(left: str, right: str) -> int:
+        a, b = len(left), len(right)
+        x = lambda part: sum((_BASE_DIGIT[c] >> 1) << i for i, c in enumerate(part))
+        y = lambda part: sum((_BASE_DIGIT[c] & 1) << i for i, c in enumerate(part))
+        return x(left) | (y(left) << a) | (x(right) << (2 * a)) | (y(right) << (2 * a + b))
+
+    def bipartite_counts(self, left: str, gap: int, right: str, mod_pos: int) -> tuple[int, int]:
+        """(n_mod, n_nomod) of the motif left + N*gap + right with the modified base at mod_pos."""
+        n_mod, n_nomod = self.bipartite_table(len(left), gap, len(right), mod_pos)
+        i = self.bipartite_index(left, right)
+        return int(n_mod[i].item()) & 0xFFFFFFFF, int(n_nomod[i].item()) & 0xFFFFFFFF
+
     def all_reduce(self) -> "SweepIndex":
         """Sum the histograms over the ranks of the default process group (contig-sharded assemblies)."""
         import torch.distributed as dist
 
         dist.all_reduce(self.hist)
+        if getattr(self, "bip", None) is not None:
+            dist.all_reduce(self.bip)
         self._tables.clear()
         return self
 

@@ -107,6 +107,34 @@ def test_exhaustive_tables_equal_per_motif_counts():
     sel = torch.tensor([i for i, _ in inner], device=n_mod.device)
     np.testing.assert_array_equal(got[:, 0], n_mod[sel].cpu().numpy())
     np.testing.assert_array_equal(got[:, 1], n_nomod[sel].cpu().numpy())
+    # bipartite shapes X{3,4} N{4..8} Y{3,4}: a sample against the oracle, one whole (3, 6, 3) table against K2
+    index.add_bipartite()
+    hits = 0
+    for _ in range(120):
+        a, g, b = int(rng.integers(3, 5)), int(rng.integers(4, 9)), int(rng.integers(3, 5))
+        left, right = "".join(rng.choice(list("ACGT"), a)), "".join(rng.choice(list("ACGT"), b))
+        s = left + "N" * g + right
+        pos = [i for i, ch in enumerate(s) if ch == "A"]
+        if not pos:
+            continue
+        p = int(rng.choice(pos))
+        got, ref = index.bipartite_counts(left, g, right, p), _oracle_counts(pile, contigs, s, p)
+        assert got == ref, (s, p, got, ref)
+        hits += sum(ref) > 0
+    assert hits > 30
+    bip_mod, bip_nomod = index.bipartite_table(3, 6, 3, 1)
+    motifs, idx = [], []
+    for l0 in "ACGT":
+        for l2 in "ACGT":
+            for r in ("".join(x) for x in __import__("itertools").product("ACGT", repeat=3)):
+                left = l0 + "A" + l2
+                motifs.append(nmb.Motif(left + "N" * 6 + r, 1).from_iupac())
+                idx.append(SweepIndex.bipartite_index(left, r))
+    got = scorer.score(motifs)
+    sel = torch.tensor(idx, device=bip_mod.device)
+    np.testing.assert_array_equal(got[:, 0], bip_mod[sel].cpu().numpy())
+    np.testing.assert_array_equal(got[:, 1], bip_nomod[sel].cpu().numpy())
+    assert int(got.sum()) > 1000
     # candidates: the planted GATC stands out among all 4-mers
     cand = index.candidates(4, 1, "A", min_mean=0.8, min_mod=100)
     assert ("GATC", int(n_mod[SweepIndex.motif_index("GATC", 1)]), int(n_nomod[SweepIndex.motif_index("GATC", 1)])) in cand

@@ -54,6 +54,14 @@ def main():
           f"(+ filters for k <= 6: {t_filt * 1e3:.0f} ms, {n_cand} candidates)")
     print(f"equivalent brute-force work {units:.2e} motif*bp -> {units / (t_hist + t_tab):.1e} motif*bp/s equivalent; "
           f"at K2's 1e13 motif*bp/s the same table would take {units / 1e13 / 3600:.1f} GPU-hours")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    index.add_bipartite()
+    torch.cuda.synchronize()
+    t_bip = time.perf_counter() - t0
+    n_bip = sum(4 ** (a + b) * (a + b) for a in (3, 4) for b in (3, 4)) * 5
+    print(f"bipartite X{{3,4}} N{{4..8}} Y{{3,4}}: {n_bip / 1e6:.2f} M (motif, position) pairs in {t_bip * 1e3:.0f} ms, "
+          f"{int(index.bip.long().sum().item()) / 1e9:.1f} G increments (K2 brute force: {n_bip * asm.total_bp / 1e13:.0f} s)")
     # cross-check against K2
     rng = np.random.default_rng(3)
     motifs, want = [], []
