@@ -131,11 +131,14 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
 // resident CTAs, and a split ring with three, were both slower -- profiles/r01_notes.md.)
 constexpr int kScanSmemBytes = kSeqRecBytes + kClsRecBytes;
 
-template <int H>
-__global__ void __launch_bounds__(kScanThreads, 4) scan_count_kernel(const ScanParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar;
-    __shared__ ItemMeta s_meta;
+// STAGES = 1 (the product configuration): one tile buffer per CTA, four CTAs per SM; sixteen resident warps hide
+// each other's latencies and the copy latency.  STAGES = 2 (experiment, NMB_SCAN_STAGES=2): two buffers per CTA, two
+// CTAs per SM, the next tile in flight while this one is evaluated -- measured slower, see nmb_scan_count.
+template <int H, int STAGES>
+__global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem_all[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ ItemMeta s_meta_st[STAGES];
     __shared__ uint32_t s_acc[2][kMaxMpi][4];
 
     const int tid = threadIdx.x;
@@ -143,24 +146,36 @@ __global__ void __launch_bounds__(kScanThreads, 4) scan_count_kernel(const ScanP
     const int n_my = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
-        mbar_init(&full_bar, 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
         fence_barrier_init();
     }
     for (int i = tid; i < 2 * kMaxMpi * 4; i += kScanThreads) (&s_acc[0][0][0])[i] = 0;
     __syncthreads();
 
+    // two bulk copies (TMA) bring the self-contained tile of item k into buffer k % STAGES; completion on its mbarrier
+    auto issue = [&](int k) {
+        const int st = k % STAGES;
+        const ItemMeta m = decode_item(p, (int)blockIdx.x + k * (int)gridDim.x);
+        s_meta_st[st] = m;
+        const int modtype = __ldg(&p.jobs[m.job].modtype);
+        uint8_t *buf = smem_all + (size_t)st * kScanSmemBytes;
+        fence_proxy_async();  // order the earlier generic reads of this buffer before the async writes
+        mbar_expect_tx(&full_bar[st], kSeqRecBytes + kClsRecBytes);
+        bulk_g2s(buf, p.seq_records + (size_t)m.tile * kSeqRecWords, kSeqRecBytes, &full_bar[st]);
+        bulk_g2s(buf + kSeqRecBytes, p.cls + ((size_t)modtype * p.n_tiles + m.tile) * kClsRecWords, kClsRecBytes,
+                 &full_bar[st]);
+    };
+    if (STAGES > 1 && tid == 0 && n_my > 0) issue(0);
+
     for (int k = 0; k < n_my; ++k) {
-        if (tid == 0) {  // two bulk copies (TMA) bring the self-contained tile; completion on the mbarrier
-            const ItemMeta m = decode_item(p, (int)blockIdx.x + k * (int)gridDim.x);
-            s_meta = m;
-            const int modtype = __ldg(&p.jobs[m.job].modtype);
-            fence_proxy_async();  // order the previous item's generic reads before the async writes
-            mbar_expect_tx(&full_bar, kSeqRecBytes + kClsRecBytes);
-            bulk_g2s(smem, p.seq_records + (size_t)m.tile * kSeqRecWords, kSeqRecBytes, &full_bar);
-            bulk_g2s(smem + kSeqRecBytes, p.cls + ((size_t)modtype * p.n_tiles + m.tile) * kClsRecWords,
-                     kClsRecBytes, &full_bar);
+        if (tid == 0) {
+            if (STAGES == 1) issue(k);
+            else if (k + 1 < n_my) issue(k + 1);  // its buffer was released by the barrier that ended item k - 1
         }
-        mbar_wait(&full_bar, (uint32_t)(k & 1));
+        const int st = k % STAGES;
+        mbar_wait(&full_bar[st], (uint32_t)((k / STAGES) & 1));
+        const uint8_t *smem = smem_all + (size_t)st * kScanSmemBytes;
+        const ItemMeta &s_meta = s_meta_st[st];
 
         const ItemMeta meta = s_meta;
         const nmb_job job = p.jobs[meta.job];
@@ -301,23 +316,34 @@ int nmb_scan_count(const nmb_assembly *a, const uint32_t *class_records, const v
     p.mpi = motifs_per_item;
     p.n_tiles = a->n_tiles;
 
+    // One buffer x four CTAs per SM everywhere.  The double-buffered variant (two buffers x two CTAs) is kept for
+    // experiments only: with conflict-free shared memory it is still SLOWER in the streaming regime it was meant for
+    // (same box, 1.5 Gbp, M = 1: GATC 0.206 vs 0.195 ms, GRNGAAGY 0.263 vs 0.234, 13-mer 0.258 vs 0.228; A 0.166 vs
+    // 0.168) -- eight resident warps hide the ALU latencies worse than sixteen, which costs more than the guaranteed
+    // copy/compute overlap gains.
+    int stages = 1;
+    if (const char *e = getenv("NMB_SCAN_STAGES")) stages = atoi(e) == 2 ? 2 : 1;
     int grid = grid_ctas;
     if (grid <= 0) {
         int sms = nmb_device_sm_count();
         if (sms < 0) return sms;
-        grid = 4 * sms;  // resident CTAs per SM (49.7 KB of shared memory, <= 128 registers each)
+        grid = (4 / stages) * sms;  // resident CTAs per SM (49.7 KB of shared memory per stage, <= 128 registers)
     }
     if (grid > n_items) grid = n_items;
     cudaStream_t s = (cudaStream_t)stream;
+    const int smem_bytes = stages * nmb::kScanSmemBytes;
+#define NMB_LAUNCH_SCAN(H, S)                                                                                         \
+    do {                                                                                                              \
+        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<H, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                      smem_bytes));                                                                   \
+        nmb::scan_count_kernel<H, S><<<grid, nmb::kScanThreads, smem_bytes, s>>>(p);                                   \
+    } while (0)
     if (max_motif_len <= 32) {  // one halo word covers a total shift (and a mod_pos) of at most 31
-        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      nmb::kScanSmemBytes));
-        nmb::scan_count_kernel<1><<<grid, nmb::kScanThreads, nmb::kScanSmemBytes, s>>>(p);
+        if (stages == 2) NMB_LAUNCH_SCAN(1, 2); else NMB_LAUNCH_SCAN(1, 1);
     } else {
-        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      nmb::kScanSmemBytes));
-        nmb::scan_count_kernel<2><<<grid, nmb::kScanThreads, nmb::kScanSmemBytes, s>>>(p);
+        if (stages == 2) NMB_LAUNCH_SCAN(2, 2); else NMB_LAUNCH_SCAN(2, 1);
     }
+#undef NMB_LAUNCH_SCAN
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;
 }
