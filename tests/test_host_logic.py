@@ -145,3 +145,46 @@ def test_motifs_per_item():
     assert choose_motifs_per_item(j, sms) == 19
     j["motif_count"], j["tile_count"] = 0, 0
     assert choose_motifs_per_item(j, sms) == 1
+
+
+def test_bgzf_block_table_and_pileup_blocks():
+    """Host-side pieces of the ingest path: the BGZF header walk and the per-mod-type split of compact rows."""
+    import gzip
+    import struct
+    import zlib
+
+    from nanomotif_b200 import dataload
+    from nanomotif_b200.pipeline import blocks_by_modtype
+
+    payload = [b"contig_1\t0\t1\ta\n" * 3000, b"", b"x" * 70000]
+    z = bytearray()
+    for chunk in payload + [b""]:
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        raw = co.compress(chunk[:0xff00]) + co.flush()
+        z += struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(raw) + 8 - 1)
+        z += raw + struct.pack("<II", zlib.crc32(chunk[:0xff00]), len(chunk[:0xff00]))
+    blocks = dataload.bgzf_blocks(bytes(z))
+    assert blocks is not None and len(blocks["in_len"]) == 4
+    assert blocks["out_len"].tolist() == [len(payload[0]), 0, 0xff00, 0] and blocks["total"] == len(payload[0]) + 0xff00
+    assert blocks["out_off"].tolist() == [0, len(payload[0]), len(payload[0]), len(payload[0]) + 0xff00]
+    for off, n, want, crc in zip(blocks["in_off"], blocks["in_len"], [payload[0], b"", payload[2][:0xff00], b""], blocks["crc"]):
+        data = zlib.decompress(bytes(z[off:off + n]), -15)
+        assert data == want and zlib.crc32(data) == crc
+    assert dataload.bgzf_blocks(gzip.compress(b"plain gzip member")) is None
+    assert dataload.bgzf_blocks(b"contig_1\t0\t1\n") is None
+    assert dataload.bgzf_blocks(bytes(z[:-5])) is None  # truncated file
+
+    rng = np.random.default_rng(0)
+    n_contigs, n = 3, 1000
+    cid = np.sort(rng.integers(0, n_contigs, n))
+    flags = (rng.integers(0, 2, n) | (rng.integers(0, 3, n) << 1)).astype(np.uint8)
+    pos = rng.integers(0, 10**6, n).astype(np.int32)
+    key = rng.integers(0, 10001, n).astype(np.uint16)
+    off = np.concatenate([[0], np.cumsum(np.bincount(cid, minlength=n_contigs))]).astype(np.int64)
+    blocks = blocks_by_modtype(pos, flags, key, off, 3)
+    assert [b.modtypes for b in blocks] == [(0,), (1,), (2,)] and sum(len(b.position) for b in blocks) == n
+    for t, b in enumerate(blocks):
+        sel = (flags >> 1) == t
+        np.testing.assert_array_equal(b.position, pos[sel])
+        np.testing.assert_array_equal(b.percent_x100, key[sel])
+        np.testing.assert_array_equal(np.diff(b.contig_row_off), np.bincount(cid[sel], minlength=n_contigs))
