@@ -67,47 +67,57 @@ def blocks_by_modtype(position, flags, percent_x100, contig_row_off, n_modtypes:
 def score_host_blocks(names: Sequence[str], lengths, ascii_u8, ascii_off, blocks: Sequence[HostBlock], packed_motifs,
                       jobs: np.ndarray, n_out_rows: int, *, low: float = 0.3, high: float = 0.7, n_modtypes: int = 1,
                       device=None, reduce_over_ranks: bool = False, out_host: torch.Tensor | None = None,
-                      motifs_per_item: int | None = None) -> torch.Tensor:
+                      motifs_per_item: int | None = None, timeline: dict | None = None) -> torch.Tensor:
     """Pack the contigs, stream the pileup blocks and run every job of `jobs` (numpy _lib.JOB_DTYPE table; a
     job is launched as soon as every block that lists its mod type is on the device).  Returns the int64
     counts [n_out_rows, 4] on the host (`out_host`, pinned, when given).  `reduce_over_ranks` all-reduces the
     counts over the default process group before the copy back (contig-sharded multi-GPU runs)."""
+    import time
+
     d = _require_cuda(device)
     key_low, key_high = threshold_keys(low, high)
+    t_start = time.perf_counter()
+    mark = (lambda name: timeline.__setitem__(name, (time.perf_counter() - t_start) * 1e3)) if timeline is not None else (lambda name: None)
     with torch.cuda.device(d):
         compute = torch.cuda.current_stream()
         side = _side_stream(d)
         side.wait_stream(compute)  # earlier work on the caller's stream stays ordered before ours
         jobs = np.asarray(jobs).copy()
         staged = []
+        n_contigs = len(names)
         with torch.cuda.stream(side):
-            # small things first so that the compute stream can start; then the blocks in order
-            asm = DeviceAssembly(names, lengths, ascii_u8, ascii_off, d, sync=False)
-            jobs["tile_count"] = np.where(jobs["tile_count"] > 0, jobs["tile_count"], asm.n_tiles)
-            progs = MotifPrograms(packed_motifs, d)
-            groups = {}
-            for j in range(len(jobs)):
-                groups.setdefault(int(jobs["modtype"][j]), []).append(j)
-            prepared = {mt: PreparedJobs(jobs[idx], d, motifs_per_item) for mt, idx in groups.items()}
-            ev_ready = torch.cuda.Event()
-            ev_ready.record(side)
+            # the big copies first, in the order they are needed: nothing else stands between the call and PCIe
+            ascii_t = ascii_u8 if isinstance(ascii_u8, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(ascii_u8))
+            ascii_d = ascii_t.to(d, non_blocking=True)
+            ev_ascii = torch.cuda.Event()
+            ev_ascii.record(side)
             for b in blocks:
                 cols = (_host_tensor(b.position, torch.int32), _host_tensor(b.flags, torch.uint8),
                         _host_tensor(b.percent_x100, torch.uint16), _host_tensor(b.contig_row_off, torch.int64))
-                if int(cols[3].numel()) != asm.n_contigs + 1 or len({int(c.numel()) for c in cols[:3]}) != 1:
+                if int(cols[3].numel()) != n_contigs + 1 or len({int(c.numel()) for c in cols[:3]}) != 1:
                     raise ValueError("compact pileup columns differ in length")
                 dev_cols = tuple(c.to(d, non_blocking=True) for c in cols)
                 ev = torch.cuda.Event()
                 ev.record(side)
                 staged.append((dev_cols, ev, tuple(b.modtypes)))
+        mark("host: big copies issued")
 
-        # compute stream: class planes block by block, scans as soon as their mod type is complete
+        # compute stream, while the copies run: layout, pack, motif programs, job tables (small H2D copies of their own)
+        compute.wait_event(ev_ascii)
+        asm = DeviceAssembly(names, lengths, ascii_d, ascii_off, d, sync=False)
+        jobs["tile_count"] = np.where(jobs["tile_count"] > 0, jobs["tile_count"], asm.n_tiles)
+        progs = MotifPrograms(packed_motifs, d)
+        groups = {}
+        for j in range(len(jobs)):
+            groups.setdefault(int(jobs["modtype"][j]), []).append(j)
+        prepared = {mt: PreparedJobs(jobs[idx], d, motifs_per_item) for mt, idx in groups.items()}
+        mark("host: assembly, motifs, jobs issued")
+        # class planes block by block, scans as soon as their mod type is complete
         pile = DevicePileup(asm, n_modtypes, low, high)
         view = asm.view()
         out = torch.zeros((n_out_rows, 4), dtype=torch.int64, device=d)
         check(lib.nmb_clear_class_planes(C.byref(view), n_modtypes, ptr(pile.class_records), _stream()),
               "nmb_clear_class_planes")
-        compute.wait_event(ev_ready)
         pending = {mt: sum(mt in s[2] for s in staged) for mt in prepared}
         launched = set()
 
@@ -132,9 +142,11 @@ def score_host_blocks(names: Sequence[str], lengths, ascii_u8, ascii_off, blocks
             import torch.distributed as dist
 
             dist.all_reduce(out)
+        mark("host: all launches issued")
         if out_host is None:
             out_host = torch.empty((n_out_rows, 4), dtype=torch.int64, pin_memory=True)
         out_host.copy_(out, non_blocking=True)
         compute.synchronize()  # also the point after which the side stream's buffers may be reused
         side.synchronize()
+        mark("done")
     return out_host

@@ -48,3 +48,20 @@ print(f"D2H counts                                       {ms:7.3f} ms")
 hostd = dict(host, length=len(seq), packed=state.packed, jobs=state.jobs)
 ms, _ = t(lambda: bench.e2e_step(hostd, dev))
 print(f"e2e_step total                                   {ms:7.3f} ms")
+
+# ---- streamed path (pipeline.score_host_blocks): host-side timeline of one step, ms since the call ----
+from nanomotif_b200.device import compact_rows  # noqa: E402
+from nanomotif_b200.pipeline import HostBlock, blocks_by_modtype, score_host_blocks  # noqa: E402
+
+rows = compact_rows(np.zeros(n, np.int32), pile["position"], pile["strand"], pile["fraction_mod"], pile["mod_type"], 1)
+blocks = [HostBlock(*(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in b[:4]), b.modtypes)
+          for b in blocks_by_modtype(rows["position"], rows["flags"], rows["percent_x100"], rows["contig_row_off"], 3)]
+jobs0 = state.jobs.copy()
+jobs0["tile_count"] = 0
+out_host = torch.empty((len(state.packed), 4), dtype=torch.int64).pin_memory()
+for rep in range(4):
+    tl = {}
+    torch.cuda.synchronize()
+    score_host_blocks(["c"], [len(seq)], host["ascii"], [0], blocks, state.packed, jobs0, len(state.packed), n_modtypes=3,
+                      device=dev, out_host=out_host, timeline=tl)
+print("streamed step, host timeline (ms):", {k: round(v, 3) for k, v in tl.items()})
