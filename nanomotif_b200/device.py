@@ -297,17 +297,44 @@ class PreparedJobs:
 
     def __init__(self, jobs: np.ndarray, device: torch.device, motifs_per_item: int | None = None):
         self.mpi = motifs_per_item or choose_motifs_per_item(jobs, sm_count(device))
-        jobs = jobs.copy()
-        items = jobs["tile_count"].astype(np.int64) * (-(-jobs["motif_count"].astype(np.int64) // self.mpi))
-        offs = np.zeros(len(jobs), dtype=np.int64)
-        offs[1:] = np.cumsum(items)[:-1]
-        self.n_items = int(items.sum())
-        if self.n_items >= 2**31:
-            raise ValueError("too many work items for one launch")
-        jobs["item_offset"] = offs.astype(np.int32)
+        jobs, self.n_items = self.finalize(jobs, self.mpi)
         self.n_jobs = len(jobs)
         with torch.cuda.device(device):
             self.jobs_d = _to_device(jobs.view(np.uint8).reshape(-1), device)
+
+    @staticmethod
+    def finalize(jobs: np.ndarray, mpi: int) -> tuple[np.ndarray, int]:
+        """Copy of the table with item_offset filled in for `mpi` motifs per item, and the number of items."""
+        jobs = jobs.copy()
+        items = jobs["tile_count"].astype(np.int64) * (-(-jobs["motif_count"].astype(np.int64) // mpi))
+        offs = np.zeros(len(jobs), dtype=np.int64)
+        offs[1:] = np.cumsum(items)[:-1]
+        n_items = int(items.sum())
+        if n_items >= 2**31:
+            raise ValueError("too many work items for one launch")
+        jobs["item_offset"] = offs.astype(np.int32)
+        return jobs, n_items
+
+    @classmethod
+    def many(cls, tables: Sequence[np.ndarray], device: torch.device, motifs_per_item: int | None = None) -> list:
+        """Several job tables through ONE host-to-device copy (the tables of a streamed run's launches)."""
+        out, parts = [], []
+        for t in tables:
+            p = cls.__new__(cls)
+            p.mpi = motifs_per_item or choose_motifs_per_item(t, sm_count(device))
+            fin, p.n_items = cls.finalize(t, p.mpi)
+            p.n_jobs = len(fin)
+            parts.append(fin)
+            out.append(p)
+        if not out:
+            return out
+        with torch.cuda.device(device):
+            blob = _to_device(np.concatenate(parts).view(np.uint8).reshape(-1), device)
+        at = 0
+        for p, fin in zip(out, parts):
+            p.jobs_d = blob[at:at + fin.nbytes]
+            at += fin.nbytes
+        return out
 
 
 def scan_count(assembly: DeviceAssembly, pileup: DevicePileup, programs: MotifPrograms, jobs,

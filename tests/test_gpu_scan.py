@@ -241,7 +241,13 @@ def test_streamed_host_blocks_equal_one_shot(nmb):
     # block "1" of `mixed` holds the rows of mod types 1 and 2: restore their flags
     sel = np.flatnonzero((rows["flags"] >> 1) >= 1)
     mixed[1] = HostBlock(mixed[1].position, rows["flags"][sel], mixed[1].percent_x100, mixed[1].contig_row_off, (1, 2))
-    for blocks in (per_mt, per_mt[::-1], [per_mt[0], mixed[1]], [mixed[1], per_mt[0]]):
+    from nanomotif_b200.pipeline import blocks_by_position
+
+    by_pos = blocks_by_position(rows["position"], rows["flags"], rows["percent_x100"], rows["contig_row_off"], lens, 3)
+    assert len(by_pos) >= 3 and all(b.tiles is not None for b in by_pos)
+    assert sum(len(b.position) for b in by_pos) == len(rows["position"])
+    halves = blocks_by_position(rows["position"], rows["flags"], rows["percent_x100"], rows["contig_row_off"], lens, 3, (0.5, 0.5))
+    for blocks in (per_mt, per_mt[::-1], [per_mt[0], mixed[1]], [mixed[1], per_mt[0]], by_pos, by_pos[::-1], halves):
         got = score_host_blocks(names, lens, ascii_u8, off, blocks, packed, jobs, n_out, low=0.3, high=0.7, n_modtypes=3,
                                 device=dev)
         assert torch.equal(got, want)

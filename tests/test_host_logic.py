@@ -188,3 +188,35 @@ def test_bgzf_block_table_and_pileup_blocks():
         np.testing.assert_array_equal(b.position, pos[sel])
         np.testing.assert_array_equal(b.percent_x100, key[sel])
         np.testing.assert_array_equal(np.diff(b.contig_row_off), np.bincount(cid[sel], minlength=n_contigs))
+
+
+def test_blocks_by_position_cut_on_tile_borders():
+    from nanomotif_b200 import _lib
+    from nanomotif_b200.device import plan_layout
+    from nanomotif_b200.pipeline import blocks_by_position
+
+    rng = np.random.default_rng(1)
+    lengths = [200000, 50000, 300000]
+    pos, cid = [], []
+    for c, L in enumerate(lengths):
+        p = np.sort(rng.choice(L, size=L // 3, replace=False))
+        pos.append(p)
+        cid.append(np.full(len(p), c))
+    pos, cid = np.concatenate(pos).astype(np.int32), np.concatenate(cid)
+    flags = (rng.integers(0, 2, len(pos)) | (rng.integers(0, 3, len(pos)) << 1)).astype(np.uint8)
+    key = rng.integers(0, 10001, len(pos)).astype(np.uint16)
+    off = np.concatenate([[0], np.cumsum(np.bincount(cid, minlength=3))]).astype(np.int64)
+    starts, n_tiles = plan_layout(np.array(lengths))
+    blocks = blocks_by_position(pos, flags, key, off, lengths, 3)
+    assert 2 <= len(blocks) <= 4 and sum(len(b.position) for b in blocks) == len(pos)
+    covered = []
+    at = 0
+    for b in blocks:
+        n = len(b.position)
+        tiles = (starts[cid[at:at + n]] + pos[at:at + n]) // _lib.TILE_BP
+        t0, tn = b.tiles
+        assert tiles.min() == t0 and tiles.max() == t0 + tn - 1 and b.modtypes == (0, 1, 2)
+        np.testing.assert_array_equal(np.diff(b.contig_row_off), np.bincount(cid[at:at + n], minlength=3))
+        covered.append((t0, t0 + tn))
+        at += n
+    assert all(a[1] <= b[0] for a, b in zip(covered[:-1], covered[1:]))  # disjoint tile ranges, ascending

@@ -51,17 +51,24 @@ print(f"e2e_step total                                   {ms:7.3f} ms")
 
 # ---- streamed path (pipeline.score_host_blocks): host-side timeline of one step, ms since the call ----
 from nanomotif_b200.device import compact_rows  # noqa: E402
-from nanomotif_b200.pipeline import HostBlock, blocks_by_modtype, score_host_blocks  # noqa: E402
+from nanomotif_b200.pipeline import HostBlock, blocks_by_modtype, blocks_by_position, score_host_blocks  # noqa: E402
 
 rows = compact_rows(np.zeros(n, np.int32), pile["position"], pile["strand"], pile["fraction_mod"], pile["mod_type"], 1)
-blocks = [HostBlock(*(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in b[:4]), b.modtypes)
-          for b in blocks_by_modtype(rows["position"], rows["flags"], rows["percent_x100"], rows["contig_row_off"], 3)]
+pin = lambda bs: [HostBlock(*(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in b[:4]), b.modtypes, b.tiles) for b in bs]
+args4 = (rows["position"], rows["flags"], rows["percent_x100"], rows["contig_row_off"])
+styles = {"one block per mod type": pin(blocks_by_modtype(*args4, 3)),
+          "tile ranges 1/8 + 3 x 7/24": pin(blocks_by_position(*args4, [len(seq)], 3)),
+          "tile ranges 1/4 x 4": pin(blocks_by_position(*args4, [len(seq)], 3, (0.25, 0.25, 0.25, 0.25))),
+          "tile ranges 1/6 + 5/12 x 2": pin(blocks_by_position(*args4, [len(seq)], 3, (1 / 6, 5 / 12, 5 / 12)))}
 jobs0 = state.jobs.copy()
 jobs0["tile_count"] = 0
 out_host = torch.empty((len(state.packed), 4), dtype=torch.int64).pin_memory()
-for rep in range(4):
-    tl = {}
-    torch.cuda.synchronize()
-    score_host_blocks(["c"], [len(seq)], host["ascii"], [0], blocks, state.packed, jobs0, len(state.packed), n_modtypes=3,
-                      device=dev, out_host=out_host, timeline=tl)
-print("streamed step, host timeline (ms):", {k: round(v, 3) for k, v in tl.items()})
+for name, blocks in styles.items():
+    done = []
+    for rep in range(8):
+        tl = {}
+        torch.cuda.synchronize()
+        score_host_blocks(["c"], [len(seq)], host["ascii"], [0], blocks, state.packed, jobs0, len(state.packed), n_modtypes=3,
+                          device=dev, out_host=out_host, timeline=tl)
+        done.append(tl["done"])
+    print(f"streamed step, {name}: median {np.median(done[2:]):.3f} ms; last timeline", {k: round(v, 3) for k, v in tl.items()})
