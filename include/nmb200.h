@@ -212,6 +212,20 @@ NMB_API int nmb_bgzf_inflate(const uint8_t *comp, const int64_t *block_in_off, c
                              const uint32_t *block_crc32, int32_t n_blocks, uint8_t *out, int32_t *status,
                              void *stream);
 
+/* FASTA text on the device (replaces the host parse of nanomotif/fasta.py:35-49 load_fasta_fastx): lines as in
+ * nmb_bed_parse (newline index from nmb_index_bytes; n_lines = n_newlines + 1 when the text does not end with a
+ * newline); blanks and '\r' at both ends of a line are stripped.  nmb_fasta_lines: kind[r] = 1 for a header line
+ * ('>'), payload[r] = bytes nmb_fasta_copy will write for line r -- the sequence bytes of sequence lines
+ * (want_headers = 0) or the header text after '>' (want_headers = 1).  nmb_fasta_copy writes each line's payload at
+ * out + out_off[r] (out_off = exclusive scan of payload, nmb_exclusive_scan_i64).  Contig k = the sequence lines
+ * between header k and header k + 1; case is kept (nmb_pack_sequence upper-cases). */
+NMB_API int nmb_fasta_lines(const uint8_t *text, int64_t n_bytes, const int64_t *newline_pos, int64_t n_newlines,
+                            int64_t n_lines, int32_t want_headers, uint8_t *kind, int64_t *payload, void *stream);
+NMB_API int nmb_fasta_copy(const uint8_t *text, int64_t n_bytes, const int64_t *newline_pos, int64_t n_newlines,
+                           int64_t n_lines, int32_t want_headers, const int64_t *out_off, uint8_t *out, void *stream);
+/* In-place exclusive prefix sum of n int64 (one block); *total (device) = the sum. */
+NMB_API int nmb_exclusive_scan_i64(int64_t *values, int64_t n, int64_t *total, void *stream);
+
 /* dst[i] = src[index[i]] for elements of 1, 2, 4 or 8 bytes (row compaction after the filters). */
 NMB_API int nmb_gather_rows(const void *src, int32_t elem_bytes, const int64_t *index, int64_t n, void *dst,
                             void *stream);

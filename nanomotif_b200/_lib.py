@@ -89,6 +89,9 @@ SIGNATURES = {
     "nmb_clear_class_planes": (C.c_int, [C.POINTER(NmbAssembly), _I32, _P, _P]),
     "nmb_index_bytes": (C.c_int, [_P, _I64, _I32, _P, _P, _I64, _P, _P]),
     "nmb_bed_parse": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nmb_fasta_lines": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _P, _P, _P]),
+    "nmb_fasta_copy": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _P, _P, _P]),
+    "nmb_exclusive_scan_i64": (C.c_int, [_P, _I64, _P, _P]),
     "nmb_gather_rows": (C.c_int, [_P, _I32, _P, _I64, _P, _P]),
     "nmb_bgzf_inflate": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _P, _P]),
     "nmb_sweep_hist_size": (C.c_int64, []),

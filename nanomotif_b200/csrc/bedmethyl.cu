@@ -210,6 +210,51 @@ __global__ void __launch_bounds__(128) bed_parse_kernel(
     if (out.n_diff) out.n_diff[r] = n_diff;
 }
 
+// ---- FASTA text -> concatenated sequence bytes (nanomotif/fasta.py:35-49 load_fasta_fastx) ----
+// Line r spans [begin, end) of the text (newline index as in bed_parse_kernel); leading / trailing blanks and '\r'
+// are stripped like the host loader's line.strip().  kind[r] = 1 header ('>' first), 0 sequence; payload[r] = bytes
+// this pass copies for the line: sequence bytes of sequence lines (want_headers = 0) or the header text after '>'
+// of header lines (want_headers = 1).
+__device__ __forceinline__ void fasta_line_span(const uint8_t *__restrict__ text, int64_t n_bytes,
+                                                const int64_t *__restrict__ newline_pos, int64_t n_newlines, int64_t r,
+                                                int64_t &b, int64_t &e) {
+    b = r == 0 ? 0 : newline_pos[r - 1] + 1;
+    e = r < n_newlines ? newline_pos[r] : n_bytes;
+    while (e > b && (text[e - 1] == '\r' || text[e - 1] == ' ' || text[e - 1] == '\t')) --e;
+    while (b < e && (text[b] == ' ' || text[b] == '\t')) ++b;
+}
+
+__global__ void __launch_bounds__(256) fasta_lines_kernel(const uint8_t *__restrict__ text, int64_t n_bytes,
+                                                          const int64_t *__restrict__ newline_pos, int64_t n_newlines,
+                                                          int64_t n_lines, int want_headers, uint8_t *__restrict__ kind,
+                                                          int64_t *__restrict__ payload) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_lines) return;
+    int64_t b, e;
+    fasta_line_span(text, n_bytes, newline_pos, n_newlines, r, b, e);
+    const bool header = e > b && text[b] == '>';
+    kind[r] = header;
+    payload[r] = want_headers ? (header ? e - b - 1 : 0) : (header ? 0 : e - b);
+}
+
+// One warp per line: copy its payload to out + out_off[r] (coalesced).
+__global__ void __launch_bounds__(256) fasta_copy_kernel(const uint8_t *__restrict__ text, int64_t n_bytes,
+                                                         const int64_t *__restrict__ newline_pos, int64_t n_newlines,
+                                                         int64_t n_lines, int want_headers, const int64_t *__restrict__ out_off,
+                                                         uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_lines; r += warps) {
+        int64_t b, e;
+        fasta_line_span(text, n_bytes, newline_pos, n_newlines, r, b, e);
+        const bool header = e > b && text[b] == '>';
+        if (header != (want_headers != 0)) continue;
+        if (header) ++b;
+        uint8_t *dst = out + out_off[r];
+        for (int64_t i = lane; i < e - b; i += 32) dst[i] = text[b + i];
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const T *__restrict__ src, const int64_t *__restrict__ index,
                                                           int64_t n, T *__restrict__ dst) {
@@ -268,6 +313,37 @@ int nmb_bed_parse(const uint8_t *text, int64_t n_bytes, const int64_t *newline_p
     nmb::BedColumns o{contig_id, position, strand, mod_type, n_valid_cov, fraction_mod, percent_x100, n_mod, n_diff};
     nmb::bed_parse_kernel<<<(unsigned)((n_lines + 127) / 128), 128, 0, s>>>(text, n_bytes, newline_pos, n_lines, t,
                                                                            modtype_keys, n_modtypes, o, status);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_fasta_lines(const uint8_t *text, int64_t n_bytes, const int64_t *newline_pos, int64_t n_newlines,
+                    int64_t n_lines, int32_t want_headers, uint8_t *kind, int64_t *payload, void *stream) {
+    NMB_REQUIRE(n_bytes >= 0 && n_lines >= 0 && n_newlines >= 0, "nmb_fasta_lines: bad sizes");
+    if (n_lines == 0) return NMB_OK;
+    NMB_REQUIRE(text && kind && payload && (n_newlines == 0 || newline_pos), "nmb_fasta_lines: null argument");
+    nmb::fasta_lines_kernel<<<(unsigned)((n_lines + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        text, n_bytes, newline_pos, n_newlines, n_lines, want_headers, kind, payload);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_fasta_copy(const uint8_t *text, int64_t n_bytes, const int64_t *newline_pos, int64_t n_newlines,
+                   int64_t n_lines, int32_t want_headers, const int64_t *out_off, uint8_t *out, void *stream) {
+    NMB_REQUIRE(n_bytes >= 0 && n_lines >= 0 && n_newlines >= 0, "nmb_fasta_copy: bad sizes");
+    if (n_lines == 0) return NMB_OK;
+    NMB_REQUIRE(text && out_off && out && (n_newlines == 0 || newline_pos), "nmb_fasta_copy: null argument");
+    int64_t blocks = (n_lines + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    nmb::fasta_copy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(text, n_bytes, newline_pos, n_newlines,
+                                                                              n_lines, want_headers, out_off, out);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_exclusive_scan_i64(int64_t *values, int64_t n, int64_t *total, void *stream) {
+    NMB_REQUIRE(values && total && n >= 0, "nmb_exclusive_scan_i64: bad argument");
+    nmb::scan_counts_kernel<1024><<<1, 1024, 0, (cudaStream_t)stream>>>(values, n, total);
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;
 }

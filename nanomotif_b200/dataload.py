@@ -409,3 +409,82 @@ def load_pileup_device(path: str, contig_names, mod_types=("a", "m", "21839"), w
     if len(data) == 0:
         raise SystemExit("Pileup is empty after initial load")  # dataload.py:89-91
     return parse_bedmethyl(data, contig_names, mod_types, with_counts, device, keep_unknown_contigs)
+
+
+def parse_fasta_device(data, trim_names: bool = False, trim_character: str = " ", device=None):
+    """FASTA TEXT (bytes / uint8 array / tensor, host or device) -> DeviceAssembly, parsed on the GPU: the sequence lines
+    of every record are concatenated on the device and packed (nmb_fasta_lines / nmb_fasta_copy / nmb_pack_sequence);
+    only the header lines come back to the host, for the names.  Same names and sequences as load_fasta
+    (fasta.py:35-49 + the upper-casing of seq.py:55, done by the packer)."""
+    from .device import DeviceAssembly
+
+    d = _require_cuda(device)
+    if isinstance(data, (bytes, bytearray, memoryview)):
+        data = np.frombuffer(data, dtype=np.uint8)
+    with torch.cuda.device(d):
+        text = data.to(d, non_blocking=True) if isinstance(data, torch.Tensor) else _to_device(np.asarray(data, dtype=np.uint8), d)
+        n_bytes = int(text.numel())
+        scratch = torch.empty((n_bytes + 4095) // 4096 + 2, dtype=torch.int64, device=d)
+        n_nl = torch.zeros(1, dtype=torch.int64, device=d)
+        check(lib.nmb_index_bytes(ptr(text), n_bytes, 10, ptr(scratch), None, 0, ptr(n_nl), _stream()), "nmb_index_bytes")
+        n_newlines = int(n_nl.item())
+        newline_pos = torch.empty(max(n_newlines, 1), dtype=torch.int64, device=d)
+        if n_newlines:
+            check(lib.nmb_index_bytes(ptr(text), n_bytes, 10, ptr(scratch), ptr(newline_pos), n_newlines, ptr(n_nl),
+                                      _stream()), "nmb_index_bytes")
+        n_lines = n_newlines + (1 if n_bytes > 0 and int(text[-1].item()) != 10 else 0)
+        if n_lines == 0:
+            raise ValueError("empty FASTA")
+        kind = torch.empty(n_lines, dtype=torch.uint8, device=d)
+        total = torch.zeros(1, dtype=torch.int64, device=d)
+
+        def copy_pass(want_headers: int):
+            payload = torch.empty(n_lines + 1, dtype=torch.int64, device=d)
+            payload[n_lines] = 0
+            check(lib.nmb_fasta_lines(ptr(text), n_bytes, ptr(newline_pos), n_newlines, n_lines, want_headers, ptr(kind),
+                                      ptr(payload), _stream()), "nmb_fasta_lines")
+            check(lib.nmb_exclusive_scan_i64(ptr(payload), n_lines + 1, ptr(total), _stream()), "nmb_exclusive_scan_i64")
+            n_out = int(total.item())
+            out = torch.empty(max(n_out, 1), dtype=torch.uint8, device=d)
+            check(lib.nmb_fasta_copy(ptr(text), n_bytes, ptr(newline_pos), n_newlines, n_lines, want_headers, ptr(payload),
+                                     ptr(out), _stream()), "nmb_fasta_copy")
+            return payload, out[:n_out]
+
+        seq_off, seq = copy_pass(0)  # seq_off[r] = sequence bytes before line r
+        # header lines: their line numbers (ascending) through the generic byte index
+        n_hdr = torch.zeros(1, dtype=torch.int64, device=d)
+        scratch2 = torch.empty((n_lines + 4095) // 4096 + 2, dtype=torch.int64, device=d)
+        check(lib.nmb_index_bytes(ptr(kind), n_lines, 1, ptr(scratch2), None, 0, ptr(n_hdr), _stream()), "nmb_index_bytes")
+        n_contigs = int(n_hdr.item())
+        if n_contigs == 0:
+            raise ValueError("FASTA without a header line")
+        hdr_lines = torch.empty(n_contigs, dtype=torch.int64, device=d)
+        check(lib.nmb_index_bytes(ptr(kind), n_lines, 1, ptr(scratch2), ptr(hdr_lines), n_contigs, ptr(n_hdr), _stream()),
+              "nmb_index_bytes")
+        starts = seq_off[hdr_lines].cpu().numpy()  # a header line carries no sequence bytes: the offset of its record
+        hdr_off, hdr = copy_pass(1)
+        hdr_starts = hdr_off[hdr_lines].cpu().numpy()
+        hdr_bytes = hdr.cpu().numpy().tobytes()
+    ends = np.append(starts[1:], int(seq.numel()))
+    hdr_ends = np.append(hdr_starts[1:], len(hdr_bytes))
+    names = []
+    for b, e in zip(hdr_starts, hdr_ends):
+        name = hdr_bytes[b:e].decode().strip()
+        names.append(name.split(trim_character)[0] if trim_names else (name.split()[0] if name.split() else ""))
+    lengths = (ends - starts).astype(np.int64)
+    return DeviceAssembly(names, lengths, seq if int(seq.numel()) else torch.zeros(1, dtype=torch.uint8, device=d),
+                          starts.astype(np.int64), d)
+
+
+def load_fasta_device(path: str, trim_names: bool = False, trim_character: str = " ", device=None):
+    """load_fasta with the parse and the 2-bit packing on the GPU (bgzip files are inflated there as well)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:2] == b"\x1f\x8b":
+        if bgzf_blocks(data) is not None:
+            data = inflate_bgzf_device(data, device)
+        else:
+            import gzip
+
+            data = gzip.decompress(data)
+    return parse_fasta_device(data, trim_names, trim_character, device)

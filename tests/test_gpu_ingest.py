@@ -200,3 +200,45 @@ def test_bgzf_inflate_on_device(dl, tmp_path):
         path = tmp_path / fname
         path.write_bytes(payload)
         check_rows(dl.load_pileup_device(str(path), names).to_table(), want)
+
+
+def test_fasta_parsed_on_device(dl, tmp_path):
+    """parse_fasta_device == load_fasta (names, lengths) and the packed records equal those of the host-loaded strings."""
+    import gzip
+
+    import torch
+
+    from nanomotif_b200.device import DeviceAssembly
+
+    rng = np.random.default_rng(41)
+    recs = []
+    for i, L in enumerate((70001, 1, 5, 131072, 900, 61)):
+        seq = "".join(rng.choice(list("ACGTacgtNnRY"), size=L, p=[0.2] * 4 + [0.04] * 4 + [0.01] * 4))
+        recs.append((f"contig_{i} some description {i}", seq))
+    variants = []
+    for width, eol, tail in ((60, "\n", "\n"), (80, "\r\n", "\r\n"), (10 ** 9, "\n", ""), (70, "\n", "\n\n")):
+        parts = []
+        for name, seq in recs:
+            parts.append(">" + name + eol)
+            for j in range(0, len(seq), width):
+                parts.append(seq[j:j + width] + eol)
+            if rng.random() < 0.5:
+                parts.append(eol)  # blank line inside / after a record
+        text = "".join(parts)
+        variants.append(text[:len(text) - len(eol)] + tail if tail != eol else text)
+    want = {name.split()[0]: seq.upper() for name, seq in recs}
+    ref = DeviceAssembly.from_sequences(want)
+    for text in variants:
+        asm = dl.parse_fasta_device(text.encode())
+        assert asm.names == list(want) and asm.lengths.tolist() == [len(s) for s in want.values()]
+        assert torch.equal(asm.seq_records, ref.seq_records) and torch.equal(asm.nonacgt, ref.nonacgt)
+    asm = dl.parse_fasta_device(variants[0].encode(), trim_names=True, trim_character="_")
+    assert asm.names == ["contig"] * len(recs)
+    # files: plain, gzip, bgzip
+    for fname, payload in (("a.fa", variants[0].encode()), ("b.fa.gz", gzip.compress(variants[0].encode())),
+                           ("c.fa.gz", write_bgzf(variants[0].encode()))):
+        path = tmp_path / fname
+        path.write_bytes(payload)
+        asm = dl.load_fasta_device(str(path))
+        assert asm.names == list(want) and torch.equal(asm.seq_records, ref.seq_records)
+        assert dl.load_fasta(str(path)) == want
