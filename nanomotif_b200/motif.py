@@ -27,6 +27,8 @@ _SET_TO_IUPAC = {frozenset(v): k for k, v in _IUPAC_SETS.items()}
 
 def tokenize(motif_string: str) -> list[str]:
     """Split into per-position tokens, keeping bracket classes together (motif.py:226-245)."""
+    if "[" not in motif_string:  # the common case in the search: one token per character
+        return list(motif_string)
     out, i, n = [], 0, len(motif_string)
     while i < n:
         ch = motif_string[i]

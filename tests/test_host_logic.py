@@ -220,3 +220,23 @@ def test_blocks_by_position_cut_on_tile_borders():
         covered.append((t0, t0 + tn))
         at += n
     assert all(a[1] <= b[0] for a, b in zip(covered[:-1], covered[1:]))  # disjoint tile ranges, ascending
+
+
+def test_column_kl_is_scipy_entropy_bit_for_bit():
+    from scipy.stats import entropy
+
+    from nanomotif_b200.growth import column_kl
+
+    rng = np.random.default_rng(9)
+    for _ in range(200):
+        w = int(rng.integers(1, 62))
+        p = rng.integers(0, 50, size=(4, w)).astype(np.float64)
+        q = rng.integers(0, 50, size=(4, w)).astype(np.float64)
+        p[:, rng.integers(0, w)] = [7, 0, 0, 0]      # a column with zeros in p
+        q[rng.integers(0, 4), rng.integers(0, w)] = 0  # q = 0 where p may be > 0 -> inf
+        if rng.random() < 0.3:
+            p, q = p / max(p.sum(), 1), q / max(q.sum(), 1)
+        with np.errstate(all="ignore"):
+            want = entropy(p, q)
+        got = column_kl(p, q)
+        assert got.tobytes() == np.asarray(want, dtype=np.float64).tobytes()
