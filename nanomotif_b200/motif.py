@@ -188,9 +188,19 @@ def as_motif(motif) -> Motif:
     return Motif(str.__str__(motif), int(motif.mod_position))
 
 
+_PLAIN_TABLE = bytes(_BIT.get(chr(c), _WILD if chr(c) == "." else 0) for c in range(256))  # 0 = not a plain token
+
+
 def motif_masks(motif) -> tuple[np.ndarray, int]:
     """(allowed-set per position as uint8 array, mod_position) of the motif as given (not stripped)."""
     m = as_motif(motif)
+    s = m.string
+    if "[" not in s:  # one token per character (what the search generates): one table lookup for the whole motif
+        masks = np.frombuffer(s.encode("latin-1", "replace").translate(_PLAIN_TABLE), dtype=np.uint8)
+        if masks.size and masks.min() == 0:
+            bad = s[int(np.argmin(masks))]
+            raise ValueError(f"motif token {bad!r}: only A, C, G, T, '.' and [..] classes are supported")
+        return masks, int(m.mod_position)
     toks = m.split()
     return np.fromiter((token_mask(t) for t in toks), dtype=np.uint8, count=len(toks)), int(m.mod_position)
 
@@ -202,6 +212,7 @@ def pack_motifs(motifs, strip: bool = True, mod_pos_override: int | None = None)
     (find_motifs_bin.py:1307).  Raises ValueError for motifs the device path cannot represent.
     """
     out = np.zeros(len(motifs), dtype=_lib.MOTIF_DTYPE)
+    allowed, lens, mod_pos = out["allowed"], out["len"], out["mod_pos"]  # field views, taken once
     for i, mo in enumerate(motifs):
         m = as_motif(mo)
         if strip:
@@ -212,15 +223,15 @@ def pack_motifs(motifs, strip: bool = True, mod_pos_override: int | None = None)
             raise ValueError("Motif is empty")
         if n > _lib.MAX_MOTIF_LEN:
             raise ValueError(f"motif {m!r}: stripped length {n} exceeds {_lib.MAX_MOTIF_LEN}")
-        if np.all(masks == _WILD):
+        if int(masks.min()) == _WILD:
             raise ValueError(f"motif {m!r} has no constrained position")
         if mod_pos_override is not None:
             mp = mod_pos_override
         if not (0 <= mp < n):
             raise ValueError(f"motif {m!r}: mod_position {mp} outside the stripped motif")
-        out["allowed"][i, :n] = masks
-        out["len"][i] = n
-        out["mod_pos"][i] = mp
+        allowed[i, :n] = masks
+        lens[i] = n
+        mod_pos[i] = mp
     return out
 
 
