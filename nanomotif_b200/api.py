@@ -259,8 +259,12 @@ class MultiBinScorer:
 
     def __init__(self, pileup, bins: dict, mod_types, low_meth_threshold: float, high_meth_threshold: float,
                  device=None):
-        """bins: {bin name: {contig name: sequence}}; pileup needs contig and mod_type columns."""
-        table = PileupTable.from_frame(pileup)
+        """bins: {bin name: {contig name: sequence}}; pileup needs contig and mod_type columns -- a frame / table with
+        contig names, or dataload.DeviceRows (rows parsed on the device: no strings, no host copy of the pileup)."""
+        from .dataload import DeviceRows
+
+        rows = pileup if isinstance(pileup, DeviceRows) else None
+        table = None if rows is not None else PileupTable.from_frame(pileup)
         contigs, self._ranges = {}, {}
         for b, cs in bins.items():
             begin = len(contigs)
@@ -271,6 +275,25 @@ class MultiBinScorer:
             self._ranges[b] = (begin, len(contigs))
         self.assembly = DeviceAssembly.from_sequences(contigs, device)
         self.mod_types = list(mod_types)
+        if rows is not None:
+            d = self.assembly.device
+            with torch.cuda.device(d):
+                # ids of the rows' contig / mod-type tables -> ids of this assembly / this mod-type list
+                c_lut = np.fromiter((self.assembly.index.get(n, -1) for n in rows.contig_names), dtype=np.int32,
+                                    count=len(rows.contig_names))
+                m_lut = np.full(256, 255, dtype=np.uint8)
+                for i, name in enumerate(rows.mod_types):
+                    if str(name) in [str(m) for m in self.mod_types]:
+                        m_lut[i] = [str(m) for m in self.mod_types].index(str(name))
+                c_lut_d = torch.from_numpy(np.append(c_lut, np.int32(-1))).to(d)  # index -1 (unknown) -> -1
+                cid = c_lut_d[rows.contig_id.long()]
+                mt = torch.from_numpy(m_lut).to(d)[rows.mod_type.long()]
+                cid = torch.where(rows.strand <= 1, cid, torch.full_like(cid, -1))  # strand '.' rows take no part
+            self.contig_id, self.mod_type_id, self.table = cid, mt, None
+            self.pileup = DevicePileup.from_columns(self.assembly, cid, rows.position, rows.strand, rows.fraction_mod,
+                                                    low_meth_threshold, high_meth_threshold, mt,
+                                                    n_modtypes=len(self.mod_types))
+            return
         names = np.asarray(table.contig).astype(str)
         uniq, inv = np.unique(names, return_inverse=True)
         lut = np.fromiter((self.assembly.index.get(u, -1) for u in uniq), dtype=np.int32, count=len(uniq))

@@ -221,26 +221,27 @@ class WindowPool:
         return [None if self.n_alive[s] == 0 else int(self.n_alive[s]) for s in slots]
 
 
+def window_rows(lengths, contig_id, position, strand, fraction_mod, high: float, padding: int):
+    """(contig index, position, strand) of the confidently methylated rows that get a window, in the reference's
+    order: per contig, '+' sites then '-' sites, each in row order (find_motifs_bin.py:625-672); a site needs
+    padding < position < len - padding (seq.py:186, strict on both sides).  One stable sort, no per-contig pass."""
+    contig_id = np.asarray(contig_id, dtype=np.int64)
+    position = np.asarray(position, dtype=np.int64)
+    strand = np.asarray(strand).astype(np.uint8)
+    lens = np.asarray(lengths, dtype=np.int64)
+    keep = (np.asarray(fraction_mod, dtype=np.float64) >= high) & (contig_id >= 0) & (contig_id < len(lens)) & (strand <= 1)
+    keep &= (position > padding) & (position < lens[np.clip(contig_id, 0, max(len(lens) - 1, 0))] - padding)
+    rows = np.flatnonzero(keep)
+    rows = rows[np.lexsort((strand[rows], contig_id[rows]))]  # stable: row order survives inside (contig, strand)
+    return contig_id[rows], position[rows], strand[rows]
+
+
 def methylation_windows(assembly: DeviceAssembly, contig_id, position, strand, fraction_mod, high: float,
                         padding: int) -> DeviceDNAarray | None:
     """Windows around confidently methylated sites in the reference's row order: per contig, '+' sites
     then reverse-complemented '-' sites (find_motifs_bin.py:625-672).  Columns as numpy arrays;
     contig_id indexes the assembly, strand is 0/1."""
-    contig_id = np.asarray(contig_id)
-    position = np.asarray(position, dtype=np.int64)
-    strand = np.asarray(strand)
-    conf = np.asarray(fraction_mod, dtype=np.float64) >= high  # :625
-    lens = assembly.lengths
-    ci_out, pos_out, st_out = [], [], []
-    for c in range(assembly.n_contigs):
-        sel = conf & (contig_id == c)
-        for s in (0, 1):
-            p = position[sel & (strand == s)]
-            p = p[(p > padding) & (p < lens[c] - padding)]  # seq.py:186 (strict on both sides)
-            ci_out.append(np.full(len(p), c, dtype=np.int64))
-            pos_out.append(p)
-            st_out.append(np.full(len(p), s, dtype=np.uint8))
-    ci, pos, st = np.concatenate(ci_out), np.concatenate(pos_out), np.concatenate(st_out)
+    ci, pos, st = window_rows(assembly.lengths, contig_id, position, strand, fraction_mod, high, padding)
     if len(pos) == 0:
         return None
     return DeviceDNAarray.from_positions(assembly, ci, pos, st, padding)

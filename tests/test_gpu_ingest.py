@@ -242,3 +242,27 @@ def test_fasta_parsed_on_device(dl, tmp_path):
         asm = dl.load_fasta_device(str(path))
         assert asm.names == list(want) and torch.equal(asm.seq_records, ref.seq_records)
         assert dl.load_fasta(str(path)) == want
+
+
+def test_scoring_straight_from_device_rows(dl):
+    """bedMethyl text -> K6 rows -> MultiBinScorer without a host copy of the pileup == the string-table path."""
+    import nanomotif_b200 as nmb
+
+    rng = np.random.default_rng(51)
+    lines, contigs = bed_text(rng, n_contigs=4, length=15000)
+    text = "\n".join(lines) + "\n"
+    names = list(contigs)
+    bins = {"b0": {n: contigs[n] for n in names[:2]}, "b1": {n: contigs[n] for n in names[2:]}}
+    want = O.load_pileup_text(text)
+    table = dict(contig=np.array(want["contig"], dtype=object), position=np.array(want["position"]),
+                 strand=np.array(want["strand"], dtype=object), fraction_mod=np.array(want["fraction_mod"]),
+                 mod_type=np.array(want["mod_type"], dtype=object))
+    # rows parsed against a DIFFERENT contig order and mod-type list than the scorer's
+    rows = dl.parse_bedmethyl(text.encode(), names[::-1] + ["absent"], mod_types=("21839", "a", "m"))
+    motifs = [nmb.Motif("GATC", 1), nmb.Motif("CC[AT]GG", 1), nmb.Motif("A", 0), nmb.Motif("CCGG", 0)]
+    a = nmb.MultiBinScorer(table, bins, ["a", "m", "21839"], 0.3, 0.7)
+    b = nmb.MultiBinScorer(rows, bins, ["a", "m", "21839"], 0.3, 0.7)
+    reqs = lambda s: [(s.context(bn, mt), motifs) for bn in bins for mt in ("a", "m", "21839")]
+    for x, y in zip(a.score_batch(reqs(a)), b.score_batch(reqs(b))):
+        np.testing.assert_array_equal(x, y)
+    assert sum(int(x.sum()) for x in a.score_batch(reqs(a))) > 1000

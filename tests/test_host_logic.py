@@ -240,3 +240,27 @@ def test_column_kl_is_scipy_entropy_bit_for_bit():
             want = entropy(p, q)
         got = column_kl(p, q)
         assert got.tobytes() == np.asarray(want, dtype=np.float64).tobytes()
+
+
+def test_window_rows_keep_the_reference_order():
+    from nanomotif_b200.growth import window_rows
+
+    rng = np.random.default_rng(12)
+    lens = np.array([500, 90, 41, 42, 3000])
+    n = 4000
+    cid = rng.integers(-1, 5, n)
+    pos = rng.integers(0, 3000, n)
+    strand = rng.integers(0, 2, n)
+    frac = rng.choice([0.2, 0.69, 0.7, 0.9], n)
+    pad, high = 20, 0.7
+    want_c, want_p, want_s = [], [], []
+    for c in range(len(lens)):  # the per-contig, per-strand passes of find_motifs_bin.py:625-672
+        sel = (frac >= high) & (cid == c)
+        for s in (0, 1):
+            p = pos[sel & (strand == s)]
+            p = p[(p > pad) & (p < lens[c] - pad)]
+            want_c += [c] * len(p)
+            want_p += p.tolist()
+            want_s += [s] * len(p)
+    got_c, got_p, got_s = window_rows(lens, cid, pos, strand, frac, high, pad)
+    assert got_c.tolist() == want_c and got_p.tolist() == want_p and got_s.tolist() == want_s and len(want_p) > 300
