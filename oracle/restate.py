@@ -441,3 +441,57 @@ def binnary_matrix(contig_methylation, contig_bins: dict, methylation_threshold:
     for c, f, v in zip(imp["contig"], imp["motif_mod"], imp["methylation_value"]):
         mat[ci[c], fi[f]] = v
     return np.array(contigs, dtype=object), mat, np.array(feats, dtype=object)
+
+
+# ---------------------------------------------------------------------------------------------
+# K8: the exhaustive sweep as a table computation (no reference callable: the counts are those of motif_model_bin,
+# find_motifs_bin.py:1265-1331, for every IUPAC motif of one length at once).  Used to check the identity the CUDA
+# kernels rely on -- counts are additive over the concrete context of each classified row -- against brute force.
+# ---------------------------------------------------------------------------------------------
+IUPAC_ORDER = "ATGCRYSWKMBDHVN"  # nanomotif/constants.py:2
+_IUPAC_MEMBERS = {"A": "A", "T": "T", "G": "G", "C": "C", "R": "AG", "Y": "CT", "S": "GC", "W": "AT", "K": "GT", "M": "AC",
+                  "B": "CGT", "D": "AGT", "H": "ACT", "V": "ACG", "N": "ACGT"}
+
+
+def sweep_table(contigs: dict, contig, position, strand, fraction_mod, k: int, mod_pos: int, canonical: str = "A",
+                low=0.3, high=0.7):
+    """(n_mod, n_nomod) int64 arrays of 15^(k-1) entries: entry = the motif's letters except the modified position as
+    base-15 digits in IUPAC_ORDER, first letter most significant.  Step 1: every classified pileup row adds one to
+    hist[class][window], window = the k letters around it with the row at offset mod_pos ('-' rows: the reverse
+    complement of the forward window, offset mirrored -- find_motifs_bin.py:1317), five letter states A T G C other.
+    Step 2: per axis, sum the states that each IUPAC letter stands for (N, the regex wildcard, includes other)."""
+    state = {"A": 0, "T": 1, "G": 2, "C": 3}
+    comp = {0: 1, 1: 0, 2: 3, 3: 2, 4: 4}
+    contig = np.asarray(contig).astype(str)
+    position = np.asarray(position, dtype=np.int64)
+    strand = np.asarray(strand).astype(str)
+    fraction_mod = np.asarray(fraction_mod, dtype=np.float64)
+    hist = np.zeros((2,) + (5,) * k, dtype=np.int64)
+    for name, seq in contigs.items():
+        d = [state.get(ch, 4) for ch in seq.upper()]
+        sel = np.flatnonzero(contig == name)
+        for p, st, f in zip(position[sel], strand[sel], fraction_mod[sel]):
+            cls = 0 if f >= high else 1 if f <= low else -1
+            if cls < 0 or not 0 <= p < len(d):
+                continue
+            if st == "+":
+                s = p - mod_pos                      # window start on the forward strand
+                letters = d[s:s + k] if s >= 0 and s + k <= len(d) else None
+            else:
+                s = p - (k - 1 - mod_pos)            # the motif is the reverse complement of the forward window
+                letters = [comp[x] for x in reversed(d[s:s + k])] if s >= 0 and s + k <= len(d) else None
+            if letters is not None:
+                hist[(cls,) + tuple(letters)] += 1
+    # fix the modified position's own letter, then expand every remaining axis 5 -> 15
+    expand = np.zeros((15, 5), dtype=np.int64)
+    for i, letter in enumerate(IUPAC_ORDER):
+        for b in _IUPAC_MEMBERS[letter]:
+            expand[i, state[b]] = 1
+    expand[14, 4] = 1
+    out = []
+    for cls in (0, 1):
+        t = np.take(hist[cls], state[canonical], axis=mod_pos)
+        for axis in range(k - 1):
+            t = np.moveaxis(np.tensordot(expand, t, axes=([1], [axis])), 0, axis)
+        out.append(t.reshape(-1))
+    return out[0], out[1]

@@ -107,6 +107,18 @@ def test_exhaustive_tables_equal_per_motif_counts():
     sel = torch.tensor([i for i, _ in inner], device=n_mod.device)
     np.testing.assert_array_equal(got[:, 0], n_mod[sel].cpu().numpy())
     np.testing.assert_array_equal(got[:, 1], n_nomod[sel].cpu().numpy())
+    # whole tables against the oracle's table computation (histogram + subset sums in numpy): small contigs only
+    small = {n: s for n, s in contigs.items() if len(s) < 3000}
+    sel_rows = np.isin(pile["contig"], list(small))
+    sub = {k: v[sel_rows] for k, v in pile.items()}
+    small_scorer = nmb.BinScorer(sub, small, 0.3, 0.7)
+    small_index = SweepIndex(small_scorer.assembly, small_scorer.pileup, 0).add()
+    for k, mp in ((4, 0), (5, 2), (6, 5)):
+        want_mod, want_nomod = O.sweep_table(small, sub["contig"], sub["position"], sub["strand"], sub["fraction_mod"], k, mp)
+        got_mod, got_nomod = small_index.table(k, mp, "A")
+        np.testing.assert_array_equal(got_mod.cpu().numpy(), want_mod)
+        np.testing.assert_array_equal(got_nomod.cpu().numpy(), want_nomod)
+        assert want_mod.sum() + want_nomod.sum() > 0
     # bipartite shapes X{3,4} N{4..8} Y{3,4}: a sample against the oracle, one whole (3, 6, 3) table against K2
     index.add_bipartite()
     hits = 0
