@@ -264,3 +264,18 @@ def test_window_rows_keep_the_reference_order():
             want_s += [s] * len(p)
     got_c, got_p, got_s = window_rows(lens, cid, pos, strand, frac, high, pad)
     assert got_c.tolist() == want_c and got_p.tolist() == want_p and got_s.tolist() == want_s and len(want_p) > 300
+
+
+def test_load_fasta_host(tmp_path):
+    """fasta.py:35-49 + the upper-casing of seq.py:55: names cut at the first blank, multi-line records, gzip."""
+    import gzip
+
+    from nanomotif_b200 import dataload
+
+    text = ">c1 first contig\nacgtNN\nACGT\n\n>c2\tx\nTTTT\r\n>c3\n"
+    (tmp_path / "a.fa").write_text(text)
+    (tmp_path / "a.fa.gz").write_bytes(gzip.compress(text.encode()))
+    want = {"c1": "ACGTNNACGT", "c2": "TTTT", "c3": ""}
+    assert dataload.load_fasta(str(tmp_path / "a.fa")) == want
+    assert dataload.load_fasta(str(tmp_path / "a.fa.gz")) == want
+    assert list(dataload.load_fasta(str(tmp_path / "a.fa"), trim_names=True, trim_character="1")) == ["c", "c2\tx", "c3"]
