@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define NMB_ABI_VERSION 1
+#define NMB_ABI_VERSION 2 /* 2: lane-interleaved tile records (NMB_WORD_SLOT), chunk_info flag bits 28-30 */
 
 #if defined(__GNUC__)
 #define NMB_API __attribute__((visibility("default")))

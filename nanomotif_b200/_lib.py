@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnmb200.so")
 
 # ---- constants mirrored from include/nmb200.h -------------------------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 CHUNK_WORDS = 16
 CHUNK_BP = 512
 TILE_WORDS = 2048
