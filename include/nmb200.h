@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define NMB_ABI_VERSION 2 /* 2: lane-interleaved tile records (NMB_WORD_SLOT), chunk_info flag bits 28-30 */
+#define NMB_ABI_VERSION 3 /* 2: lane-interleaved tile records (NMB_WORD_SLOT), chunk_info flag bits 28-30; 3: table ingest */
 
 #if defined(__GNUC__)
 #define NMB_API __attribute__((visibility("default")))
@@ -150,6 +150,15 @@ NMB_API int nmb_build_class_planes(const int32_t *contig_id, const int64_t *pos,
                            double low, double high, const nmb_assembly *assembly_h,
                            int32_t n_modtypes, uint32_t *class_records, void *stream);
 
+/* nmb_build_class_planes without the clear: ORs the rows into existing records (several tables, e.g. one per
+ * (bin, mod_type) as nanomotif partitions its pileup, find_motifs_bin.py:416).  *dup_count (device int64, may be
+ * NULL; ADDED to) counts rows whose class bit was already set, i.e. rows that repeat a (contig, pos, strand,
+ * modtype): the reference counts such rows twice (np.isin keeps duplicates), bit-planes cannot. */
+NMB_API int nmb_add_class_planes(const int32_t *contig_id, const int64_t *pos, const uint8_t *strand,
+                                 const uint8_t *modtype, const double *fraction_mod, int64_t n_rows, double low,
+                                 double high, const nmb_assembly *assembly_h, int32_t n_modtypes,
+                                 uint32_t *class_records, int64_t *dup_count, void *stream);
+
 /* Same class records from COMPACT rows (7 bytes per row instead of 22 over PCIe): pos int32, flags =
  * strand | mod type index << 1, percent_x100 = modkit's two-decimal percentage as an exact integer key
  * (0..10000).  Rows are grouped by contig: rows of contig c are [contig_row_off[c], contig_row_off[c+1]).
@@ -199,6 +208,16 @@ NMB_API int nmb_bed_parse(const uint8_t *text, int64_t n_bytes, const int64_t *n
                           int32_t n_modtypes, int32_t *contig_id, int64_t *position, uint8_t *strand,
                           uint8_t *mod_type, int64_t *n_valid_cov, double *fraction_mod, uint16_t *percent_x100,
                           int64_t *n_mod, int64_t *n_diff, int32_t *status, void *stream);
+
+/* String column of a host TABLE (the frames nanomotif hands to its workers, find_motifs_bin.py:399-427: contig,
+ * strand and mod_type are polars Utf8 columns, i.e. Arrow utf8 / large_utf8 buffers) -> ids on the device.
+ * Row r's string is data[offsets[r] .. offsets[r+1]) with 4- or 8-byte offsets (offset_bytes); it is looked up
+ * in a name table laid out as for nmb_bed_parse (FNV-1a 64 hashes ascending, ids, name bytes by rank) and
+ * out[r] = its id, or `missing`.  out is int32 (out_bytes 4) or uint8 (out_bytes 1). */
+NMB_API int nmb_lookup_strings(const uint8_t *data, const void *offsets, int32_t offset_bytes, int64_t n_rows,
+                               const uint64_t *name_hash, const int32_t *name_ids, const int64_t *name_off,
+                               const uint8_t *names, int32_t n_names, int32_t missing, void *out, int32_t out_bytes,
+                               void *stream);
 
 /* ---- K7: BGZF inflate (bgzip-compressed pileups, docs/source/required_files.md:21; the reference reads them
  *      through epymetheus.query_pileup_records / bgzf_pileup, dataload.py:109-120) ----

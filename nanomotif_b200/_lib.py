@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnmb200.so")
 
 # ---- constants mirrored from include/nmb200.h -------------------------------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 CHUNK_WORDS = 16
 CHUNK_BP = 512
 TILE_WORDS = 2048
@@ -85,6 +85,8 @@ SIGNATURES = {
     "nmb_program_bytes": (C.c_int, []),
     "nmb_pack_sequence": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "nmb_build_class_planes": (C.c_int, [_P, _P, _P, _P, _P, _I64, _F64, _F64, C.POINTER(NmbAssembly), _I32, _P, _P]),
+    "nmb_add_class_planes": (C.c_int, [_P, _P, _P, _P, _P, _I64, _F64, _F64, C.POINTER(NmbAssembly), _I32, _P, _P, _P]),
+    "nmb_lookup_strings": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P, _P, _I32, _I32, _P, _I32, _P]),
     "nmb_build_class_planes_compact": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, C.POINTER(NmbAssembly), _I32, _P, _P]),
     "nmb_clear_class_planes": (C.c_int, [C.POINTER(NmbAssembly), _I32, _P, _P]),
     "nmb_index_bytes": (C.c_int, [_P, _I64, _I32, _P, _P, _I64, _P, _P]),

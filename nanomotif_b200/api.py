@@ -258,13 +258,15 @@ class MultiBinScorer:
     the reference's process pool over bins (nanomotif/find_motifs_bin.py:330-372)."""
 
     def __init__(self, pileup, bins: dict, mod_types, low_meth_threshold: float, high_meth_threshold: float,
-                 device=None):
-        """bins: {bin name: {contig name: sequence}}; pileup needs contig and mod_type columns -- a frame / table with
-        contig names, or dataload.DeviceRows (rows parsed on the device: no strings, no host copy of the pileup)."""
-        from .dataload import DeviceRows
+                 device=None, keep_rows: bool = True):
+        """bins: {bin name: {contig name: sequence}}.  pileup: what the reference hands to its workers
+        (find_motifs_bin.py:399-427) -- ONE table with contig / position / strand / mod_type / fraction_mod columns
+        (pyarrow Table, polars or pandas frame, PileupTable, dict of arrays), or the partitioned form
+        {(bin, mod_type): table} / a list of tables -- or dataload.DeviceRows (rows already parsed on the device).
+        String columns cross PCIe as their Arrow buffers and are resolved to ids on the device
+        (dataload.rows_from_table): no per-row host work."""
+        from .dataload import DeviceRows, rows_from_table
 
-        rows = pileup if isinstance(pileup, DeviceRows) else None
-        table = None if rows is not None else PileupTable.from_frame(pileup)
         contigs, self._ranges = {}, {}
         for b, cs in bins.items():
             begin = len(contigs)
@@ -275,66 +277,100 @@ class MultiBinScorer:
             self._ranges[b] = (begin, len(contigs))
         self.assembly = DeviceAssembly.from_sequences(contigs, device)
         self.mod_types = list(mod_types)
-        if rows is not None:
-            d = self.assembly.device
-            with torch.cuda.device(d):
-                # ids of the rows' contig / mod-type tables -> ids of this assembly / this mod-type list
-                c_lut = np.fromiter((self.assembly.index.get(n, -1) for n in rows.contig_names), dtype=np.int32,
-                                    count=len(rows.contig_names))
-                m_lut = np.full(256, 255, dtype=np.uint8)
-                for i, name in enumerate(rows.mod_types):
-                    if str(name) in [str(m) for m in self.mod_types]:
-                        m_lut[i] = [str(m) for m in self.mod_types].index(str(name))
-                c_lut_d = torch.from_numpy(np.append(c_lut, np.int32(-1))).to(d)  # index -1 (unknown) -> -1
-                cid = c_lut_d[rows.contig_id.long()]
-                mt = torch.from_numpy(m_lut).to(d)[rows.mod_type.long()]
-                cid = torch.where(rows.strand <= 1, cid, torch.full_like(cid, -1))  # strand '.' rows take no part
-            self.contig_id, self.mod_type_id, self.table = cid, mt, None
-            self.pileup = DevicePileup.from_columns(self.assembly, cid, rows.position, rows.strand, rows.fraction_mod,
-                                                    low_meth_threshold, high_meth_threshold, mt,
-                                                    n_modtypes=len(self.mod_types))
-            return
-        names = np.asarray(table.contig).astype(str)
-        uniq, inv = np.unique(names, return_inverse=True)
-        lut = np.fromiter((self.assembly.index.get(u, -1) for u in uniq), dtype=np.int32, count=len(uniq))
-        self.contig_id = lut[inv] if len(uniq) else np.zeros(0, dtype=np.int32)
-        mt_names = np.asarray(table.mod_type).astype(str)
-        mt = np.full(len(table), 255, dtype=np.uint8)
-        for i, name in enumerate(self.mod_types):
-            mt[mt_names == str(name)] = i
-        self.mod_type_id = mt
-        self.table = table
-        self.pileup = DevicePileup.from_columns(self.assembly, self.contig_id, table.position,
-                                                strand_codes(table.strand), table.fraction_mod, low_meth_threshold,
-                                                high_meth_threshold, mt, n_modtypes=len(self.mod_types))
+        d = self.assembly.device
+        if isinstance(pileup, DeviceRows) or hasattr(pileup, "columns") or hasattr(pileup, "column_names") \
+                or isinstance(pileup, PileupTable) or (isinstance(pileup, dict) and "position" in pileup):
+            tables = [pileup]
+        elif isinstance(pileup, dict):
+            tables = list(pileup.values())  # the reference's partitioned_pileup: {(bin, mod_type): frame}
+        else:
+            tables = list(pileup)
+        self.pileup = DevicePileup(self.assembly, len(self.mod_types), low_meth_threshold, high_meth_threshold).clear()
+        self.rows, cache = [], {}
+        for t in tables:
+            rows = t if isinstance(t, DeviceRows) else rows_from_table(t, self.assembly.names, self.mod_types, d, cache)
+            cid, mt = rows.contig_id, rows.mod_type
+            if isinstance(t, DeviceRows) and (list(t.contig_names) != self.assembly.names or
+                                              [str(m) for m in t.mod_types] != [str(m) for m in self.mod_types]):
+                with torch.cuda.device(d):  # ids of the rows' contig / mod-type tables -> ids of this assembly / list
+                    c_lut = np.fromiter((self.assembly.index.get(n, -1) for n in t.contig_names), dtype=np.int32,
+                                        count=len(t.contig_names))
+                    names = [str(m) for m in self.mod_types]
+                    m_lut = np.full(256, 255, dtype=np.uint8)
+                    for i, name in enumerate(t.mod_types):
+                        if str(name) in names:
+                            m_lut[i] = names.index(str(name))
+                    cid = torch.from_numpy(np.append(c_lut, np.int32(-1))).to(d)[rows.contig_id.long()]  # -1 -> -1
+                    mt = torch.from_numpy(m_lut).to(d)[rows.mod_type.long()]
+            self.pileup.add_columns(cid, rows.position, rows.strand, rows.fraction_mod, mt, sync=False)
+            if keep_rows:  # device columns for the window step (growth.WindowPool) -- ids of THIS assembly
+                self.rows.append(DeviceRows(self.assembly.names, self.mod_types, d, contig_id=cid, position=rows.position,
+                                            strand=rows.strand, mod_type=mt, fraction_mod=rows.fraction_mod,
+                                            Nvalid_cov=rows.Nvalid_cov))
+        torch.cuda.current_stream(d).synchronize()
+        self.pileup.check_unique()
+        first = self.rows[0] if self.rows else None
+        self.contig_id = first.contig_id if first is not None else None
+        self.mod_type_id = first.mod_type if first is not None else None
+        self.table = tables[0] if len(tables) == 1 and isinstance(tables[0], PileupTable) else None
+
+    @classmethod
+    def from_device(cls, assembly: DeviceAssembly, pileup: DevicePileup, ranges: dict, mod_types) -> "MultiBinScorer":
+        """Scorer over state that already lives on the device: ranges = {bin name: (contig_begin, contig_end)}."""
+        self = cls.__new__(cls)
+        self.assembly, self.pileup, self._ranges, self.mod_types = assembly, pileup, dict(ranges), list(mod_types)
+        self.rows, self.contig_id, self.mod_type_id, self.table = [], None, None, None
+        return self
 
     def context(self, bin_name, mod_type) -> BinContext:
         begin, end = self._ranges[bin_name]
         return BinContext(self, bin_name, mod_type, begin, end, self.mod_types.index(mod_type))
 
+    def score_batch_device(self, requests, out: torch.Tensor | None = None) -> torch.Tensor:
+        """requests: [(BinContext or None, motifs)] -> int64 device tensor [total motifs, 4] (n_mod '+', n_nomod '+',
+        n_mod '-', n_nomod '-') in request order; ONE scan launch, nothing synchronised.  Rows of requests whose
+        context is None (bins that live on another rank, sharding.ShardedMultiBinScorer) stay zero.  `out` is
+        accumulated into when given."""
+        requests = [(ctx, list(motifs)) for ctx, motifs in requests]
+        total = sum(len(ms) for _, ms in requests)
+        d = self.assembly.device
+        if out is None:
+            with torch.cuda.device(d):
+                out = torch.zeros((total, 4), dtype=torch.int64, device=d)
+        live, base = [], 0
+        for ctx, ms in requests:
+            if ctx is not None and ms and ctx.tile_count > 0:
+                live.append((ctx, ms, base))
+            base += len(ms)
+        if not live:
+            return out
+        progs = MotifPrograms([m for _, ms, _ in live for m in ms], d, strip=True)
+        jobs = make_jobs(len(live))
+        at = 0
+        for j, (ctx, ms, row) in enumerate(live):
+            jobs[j]["motif_begin"], jobs[j]["motif_count"], jobs[j]["modtype"] = at, len(ms), ctx.modtype_index
+            jobs[j]["tile_begin"], jobs[j]["tile_count"] = ctx.tile_begin, ctx.tile_count
+            jobs[j]["contig_begin"], jobs[j]["contig_end"] = ctx.contig_begin, ctx.contig_end
+            jobs[j]["group_mode"], jobs[j]["n_groups"], jobs[j]["out_base"] = 0, 1, row
+            at += len(ms)
+        return scan_count(self.assembly, self.pileup, progs, jobs, total, out=out)
+
     def score_batch(self, requests) -> list:
         """requests: [(BinContext, motifs)] -> [int64 array [n_motifs, 2] = (n_mod, n_nomod)] per request."""
         requests = [(ctx, list(motifs)) for ctx, motifs in requests]
-        all_motifs = [m for _, ms in requests for m in ms]
-        if not all_motifs:
+        if not any(ms for _, ms in requests):
             return [np.zeros((0, 2), dtype=np.int64) for _ in requests]
-        progs = MotifPrograms(all_motifs, self.assembly.device, strip=True)
-        live = [(ctx, ms) for ctx, ms in requests if ms]
-        jobs = make_jobs(len(live))
-        base = 0
-        for j, (ctx, ms) in enumerate(live):
-            jobs[j]["motif_begin"], jobs[j]["motif_count"], jobs[j]["modtype"] = base, len(ms), ctx.modtype_index
-            jobs[j]["tile_begin"], jobs[j]["tile_count"] = ctx.tile_begin, ctx.tile_count
-            jobs[j]["contig_begin"], jobs[j]["contig_end"] = ctx.contig_begin, ctx.contig_end
-            jobs[j]["group_mode"], jobs[j]["n_groups"], jobs[j]["out_base"] = 0, 1, base
-            base += len(ms)
-        c = scan_count(self.assembly, self.pileup, progs, jobs, base).cpu().numpy()
-        counts = np.stack([c[:, 0] + c[:, 2], c[:, 1] + c[:, 3]], axis=1)
-        out, at = [], 0
-        for _, ms in requests:
-            out.append(counts[at:at + len(ms)])
-            at += len(ms)
-        return out
+        return split_counts(self.score_batch_device(requests).cpu().numpy(), requests)
+
+
+def split_counts(c: np.ndarray, requests) -> list:
+    """[total motifs, 4] strand-wise counts -> per request [n_motifs, 2] = (n_mod, n_nomod)."""
+    counts = np.stack([c[:, 0] + c[:, 2], c[:, 1] + c[:, 3]], axis=1)
+    out, at = [], 0
+    for _, ms in requests:
+        out.append(counts[at:at + len(ms)])
+        at += len(ms)
+    return out
 
 
 def _scorer_for(pileup, contigs, low, high) -> BinScorer:

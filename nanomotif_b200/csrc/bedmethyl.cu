@@ -262,6 +262,25 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const T *__restrict__ 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[index[i]];
 }
 
+
+// ---- string columns of a table (Arrow utf8 / large_utf8 layout) -> ids -----------------------------
+// Row r's string is data[off[r] .. off[r+1]); offsets are 32- or 64-bit.  One thread per row: FNV-1a of the
+// bytes, binary search in the name table, byte compare.  Consecutive rows of a pileup mostly carry the same
+// contig name, so the table probes hit the same cache lines across a warp.
+template <typename OffT, typename OutT>
+__global__ void __launch_bounds__(256) lookup_strings_kernel(const uint8_t *__restrict__ data,
+                                                             const OffT *__restrict__ off, int64_t n_rows,
+                                                             NameTable table, int missing,
+                                                             OutT *__restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int64_t b = off[r], e = off[r + 1];
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (int64_t i = b; i < e; ++i) h = (h ^ data[i]) * 0x100000001b3ull;
+    const int id = lookup_name(table, h, data + b, (int)(e - b));
+    out[r] = (OutT)(id < 0 ? missing : id);
+}
+
 }  // namespace nmb
 
 extern "C" {
@@ -362,6 +381,31 @@ int nmb_gather_rows(const void *src, int32_t elem_bytes, const int64_t *index, i
         case 8: nmb::gather_rows_kernel<uint64_t><<<(unsigned)blocks, 256, 0, s>>>((const uint64_t *)src, index, n, (uint64_t *)dst); break;
         default: NMB_FAIL(NMB_ERR_INVALID, "nmb_gather_rows: elem_bytes=%d not in {1,2,4,8}", elem_bytes);
     }
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_lookup_strings(const uint8_t *data, const void *offsets, int32_t offset_bytes, int64_t n_rows,
+                       const uint64_t *name_hash, const int32_t *name_ids, const int64_t *name_off,
+                       const uint8_t *names, int32_t n_names, int32_t missing, void *out, int32_t out_bytes,
+                       void *stream) {
+    NMB_REQUIRE(n_rows >= 0 && n_names >= 0, "nmb_lookup_strings: bad sizes");
+    NMB_REQUIRE((offset_bytes == 4 || offset_bytes == 8) && (out_bytes == 1 || out_bytes == 4),
+                "nmb_lookup_strings: offsets must be 4 or 8 bytes wide, outputs 1 or 4");
+    if (n_rows == 0) return NMB_OK;
+    NMB_REQUIRE(offsets && out && (n_names == 0 || (name_hash && name_ids && name_off && names)),
+                "nmb_lookup_strings: null argument");
+    nmb::NameTable t = {name_hash, name_ids, name_off, names, n_names};
+    const unsigned blocks = (unsigned)((n_rows + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (offset_bytes == 4 && out_bytes == 4)
+        nmb::lookup_strings_kernel<int32_t, int32_t><<<blocks, 256, 0, s>>>(data, (const int32_t *)offsets, n_rows, t, missing, (int32_t *)out);
+    else if (offset_bytes == 4)
+        nmb::lookup_strings_kernel<int32_t, uint8_t><<<blocks, 256, 0, s>>>(data, (const int32_t *)offsets, n_rows, t, missing, (uint8_t *)out);
+    else if (out_bytes == 4)
+        nmb::lookup_strings_kernel<int64_t, int32_t><<<blocks, 256, 0, s>>>(data, (const int64_t *)offsets, n_rows, t, missing, (int32_t *)out);
+    else
+        nmb::lookup_strings_kernel<int64_t, uint8_t><<<blocks, 256, 0, s>>>(data, (const int64_t *)offsets, n_rows, t, missing, (uint8_t *)out);
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;
 }

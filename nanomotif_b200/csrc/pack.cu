@@ -6,7 +6,7 @@
 
 namespace nmb {
 
-// One warp per 256-bp chunk.  Lane l reads base l of each of the chunk's 8 words (coalesced
+// One warp per 512-bp chunk.  Lane l reads base l of each of the chunk's 16 words (coalesced
 // 32-byte reads) and three ballots build the word of each plane.
 __global__ void __launch_bounds__(256) pack_sequence_kernel(
     const uint8_t *__restrict__ ascii, const int64_t *__restrict__ ascii_off,
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) class_planes_kernel(
     const uint8_t *__restrict__ strand, const uint8_t *__restrict__ modtype,
     const double *__restrict__ fraction, int64_t n_rows, double low, double high,
     const int64_t *__restrict__ contig_start, const int64_t *__restrict__ contig_len, int n_contigs,
-    int n_tiles, int n_modtypes, uint32_t *__restrict__ cls) {
+    int n_tiles, int n_modtypes, uint32_t *__restrict__ cls, unsigned long long *__restrict__ dup_count) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
         const int c = contig_id[r];
@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(256) class_planes_kernel(
         if (p < 0 || p >= __ldg(contig_len + c)) continue;
         const int mt = modtype ? modtype[r] : 0;
         if (mt >= n_modtypes) continue;
+        const int st = strand[r];
+        if (st > 1) continue;  // modkit's '.' (--combine-strands): the reference's strand == "+" / "-" filters drop it
         const double f = fraction[r];
         const bool is_mod = f >= high;   // find_motifs_bin.py:1308
         const bool is_non = f <= low;    // find_motifs_bin.py:1309
@@ -154,9 +156,11 @@ __global__ void __launch_bounds__(256) class_planes_kernel(
         const int w = word_slot((int)((g >> 5) & (kTileWords - 1)));
         const uint32_t bit = 1u << (g & 31);
         uint32_t *rec = cls + ((int64_t)mt * n_tiles + tile) * kClsRecWords +
-                        (strand[r] ? 2 : 0) * kTileWords + w;
-        if (is_mod) atomicOr(rec, bit);
-        if (is_non) atomicOr(rec + kTileWords, bit);
+                        (st ? 2 : 0) * kTileWords + w;
+        uint32_t old = 0;
+        if (is_mod) old |= atomicOr(rec, bit);
+        if (is_non) old |= atomicOr(rec + kTileWords, bit);
+        if ((old & bit) && dup_count) atomicAdd(dup_count, 1ull);  // a repeated (contig, pos, strand, mod type)
     }
 }
 
@@ -221,17 +225,24 @@ int nmb_build_class_planes(const int32_t *contig_id, const int64_t *pos, const u
                            const uint8_t *modtype, const double *fraction_mod, int64_t n_rows,
                            double low, double high, const nmb_assembly *a, int32_t n_modtypes,
                            uint32_t *class_records, void *stream) {
-    NMB_REQUIRE(a && class_records, "nmb_build_class_planes: null argument");
-    NMB_REQUIRE(n_rows >= 0 && n_modtypes > 0 && a->n_tiles > 0, "nmb_build_class_planes: bad sizes");
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t bytes = (size_t)n_modtypes * a->n_tiles * nmb::kClsRecBytes;
-    NMB_CUDA(cudaMemsetAsync(class_records, 0, bytes, s));
+    const int rc = nmb_clear_class_planes(a, n_modtypes, class_records, stream);
+    if (rc != NMB_OK) return rc;
+    return nmb_add_class_planes(contig_id, pos, strand, modtype, fraction_mod, n_rows, low, high, a, n_modtypes,
+                                class_records, nullptr, stream);
+}
+
+int nmb_add_class_planes(const int32_t *contig_id, const int64_t *pos, const uint8_t *strand, const uint8_t *modtype,
+                         const double *fraction_mod, int64_t n_rows, double low, double high, const nmb_assembly *a,
+                         int32_t n_modtypes, uint32_t *class_records, int64_t *dup_count, void *stream) {
+    NMB_REQUIRE(a && class_records, "nmb_add_class_planes: null argument");
+    NMB_REQUIRE(n_rows >= 0 && n_modtypes > 0 && a->n_tiles > 0, "nmb_add_class_planes: bad sizes");
     if (n_rows == 0) return NMB_OK;
+    NMB_REQUIRE(contig_id && pos && strand && fraction_mod, "nmb_add_class_planes: null column");
     int64_t blocks = (n_rows + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    nmb::class_planes_kernel<<<(unsigned)blocks, 256, 0, s>>>(
-        contig_id, pos, strand, modtype, fraction_mod, n_rows, low, high, a->contig_start,
-        a->contig_len, a->n_contigs, a->n_tiles, n_modtypes, class_records);
+    nmb::class_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        contig_id, pos, strand, modtype, fraction_mod, n_rows, low, high, a->contig_start, a->contig_len,
+        a->n_contigs, a->n_tiles, n_modtypes, class_records, (unsigned long long *)dup_count);
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;
 }

@@ -68,7 +68,9 @@ def load_fasta(path: str, trim_names: bool = False, trim_character: str = " ") -
                 if name is not None:
                     out[name] = "".join(parts).upper()
                 name = line[1:].strip()
-                name = name.split(trim_character)[0] if trim_names else name.split()[0]
+                name = name.split(trim_character)[0] if trim_names else (name.split() or [""])[0]
+                if name in out:
+                    raise ValueError(f"duplicate contig name {name!r} in {path}")
                 parts = []
             else:
                 parts.append(line.strip())
@@ -287,6 +289,154 @@ class DeviceRows:
                 rows = self.take_mask((self.strand < 2).to(torch.uint8))
         return DevicePileup.from_columns(assembly, rows.contig_id, rows.position, rows.strand, rows.fraction_mod, low, high,
                                          rows.mod_type, n_modtypes=max(1, len(self.mod_types)))
+
+
+
+# ---------------------------------------------------------------------------------------------
+# host TABLE -> device rows: the frames nanomotif hands to its workers (find_motifs_bin.py:399-427) are
+# polars frames = Arrow buffers.  The numeric columns go to the device as they are, the three string
+# columns (contig, strand, mod_type) as their raw offsets + bytes buffers and are resolved to ids by
+# nmb_lookup_strings -- no per-row host work, no Python strings.
+# ---------------------------------------------------------------------------------------------
+def _frame_column(frame, name):
+    """Column `name` of a pyarrow Table / polars / pandas frame / PileupTable / mapping, or None."""
+    if isinstance(frame, PileupTable):
+        return getattr(frame, name, None)
+    if isinstance(frame, dict):
+        return frame.get(name)
+    cols = getattr(frame, "column_names", None) or getattr(frame, "columns", None)
+    if cols is not None and name not in list(cols):
+        return None
+    if hasattr(frame, "get_column"):  # polars
+        return frame.get_column(name)
+    if hasattr(frame, "column") and hasattr(frame, "num_rows"):  # pyarrow.Table
+        return frame.column(name)
+    return frame[name]  # pandas
+
+
+def _string_column(col, ints_are_codes: bool = True):
+    """A string column as ("utf8", offsets int32/int64 [n + 1], bytes uint8) -- zero-copy views of Arrow buffers --
+    or ("dict", codes int32 [n], [values]) for dictionary / categorical columns and for plain numpy / pandas object
+    columns when pyarrow is not installed."""
+    try:
+        import pyarrow as pa
+    except ImportError:  # pragma: no cover - pyarrow is in the image
+        pa = None
+    if pa is not None:
+        if hasattr(col, "to_arrow"):  # polars Series
+            col = col.to_arrow()
+        if isinstance(col, pa.ChunkedArray):
+            col = col.chunk(0) if col.num_chunks == 1 else col.combine_chunks()
+        if not isinstance(col, pa.Array):
+            a = col.to_numpy() if hasattr(col, "to_numpy") and not isinstance(col, np.ndarray) else np.asarray(col)
+            if a.dtype.kind in "iub":
+                if ints_are_codes:
+                    return "codes", a, None
+                uniq, inv = np.unique(a, return_inverse=True)
+                return "dict", inv.astype(np.int32), [str(u) for u in uniq]
+            try:
+                col = pa.array(a, type=pa.large_string())
+            except (pa.ArrowInvalid, pa.ArrowTypeError, pa.ArrowNotImplementedError):
+                col = pa.array(a.astype(str).astype(object), type=pa.large_string())
+        t = col.type
+        if pa.types.is_dictionary(t):
+            return "dict", col.indices.to_numpy(zero_copy_only=False).astype(np.int32), [str(v) for v in col.dictionary.to_pylist()]
+        if not (pa.types.is_string(t) or pa.types.is_large_string(t)):
+            col = col.cast(pa.large_string())  # string_view, ...
+            t = col.type
+        n = len(col)
+        bufs = col.buffers()
+        odt = np.int64 if pa.types.is_large_string(t) else np.int32
+        off = np.frombuffer(bufs[1], dtype=odt)[col.offset:col.offset + n + 1] if n else np.zeros(1, odt)
+        data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None and bufs[2].size else np.zeros(1, np.uint8)
+        lo, hi = int(off[0]), int(off[-1])
+        if lo:  # a sliced array: rebase, ship only the bytes in use
+            off = off - lo
+        return "utf8", off, data[lo:max(hi, lo + 1)]
+    a = np.asarray(col)
+    if a.dtype.kind in "iub" and ints_are_codes:
+        return "codes", a, None
+    uniq, inv = np.unique(a.astype(str), return_inverse=True)
+    return "dict", inv.astype(np.int32), [str(u) for u in uniq]
+
+
+def _numeric_column(col, dtype):
+    if hasattr(col, "to_arrow"):
+        col = col.to_arrow()
+    if hasattr(col, "combine_chunks") and hasattr(col, "num_chunks"):
+        col = col.chunk(0) if col.num_chunks == 1 else col.combine_chunks()
+    if hasattr(col, "to_numpy") and not isinstance(col, np.ndarray):
+        try:
+            col = col.to_numpy(zero_copy_only=False)
+        except TypeError:
+            col = col.to_numpy()
+    return np.ascontiguousarray(np.asarray(col), dtype=dtype)
+
+
+def _lookup_ids(kind, a, b, names, missing, out_dtype, device, table_cache=None):
+    """Device ids of a string column (see _string_column) against `names`."""
+    n_names = len(names)
+    if kind == "codes":  # already integer codes (strand 0/1, mod type index)
+        return _to_device(np.asarray(a).astype({torch.int32: np.int32, torch.uint8: np.uint8}[out_dtype], copy=False), device)
+    if kind == "dict":
+        index = {str(v): i for i, v in enumerate(names)}
+        lut = np.array([index.get(v, missing) for v in b] + [missing], dtype=np.int64)
+        codes = _to_device(a, device).long()
+        codes = torch.where(codes < 0, torch.full_like(codes, len(b)), codes)  # null -> missing
+        return torch.from_numpy(lut).to(device)[codes].to(out_dtype)
+    key = ("names", tuple(names)) if table_cache is not None else None
+    tab = table_cache.get(key) if table_cache is not None else None
+    if tab is None:
+        tab = _name_table(names, device)
+        if table_cache is not None:
+            table_cache[key] = tab
+    h, ids, noff, blob = tab
+    n = len(a) - 1
+    off_d, data_d = _to_device(a, device), _to_device(b, device)
+    out = torch.empty(n, dtype=out_dtype, device=device)
+    check(lib.nmb_lookup_strings(ptr(data_d), ptr(off_d), a.dtype.itemsize, n, ptr(h), ptr(ids), ptr(noff), ptr(blob),
+                                 n_names, missing, ptr(out), out.element_size(), _stream()), "nmb_lookup_strings")
+    return out
+
+
+def rows_from_table(frame, contig_names, mod_types=("a", "m", "21839"), device=None, table_cache=None) -> "DeviceRows":
+    """A reference-shaped pileup table (columns contig: str, position: i64, strand: '+'/'-', mod_type: str,
+    fraction_mod: f64 [, Nvalid_cov: i64]; pyarrow Table, polars / pandas frame, PileupTable or dict of arrays) ->
+    DeviceRows.  contig_id = index into contig_names (-1 unknown), strand 0 '+' / 1 '-' / 2 anything else (modkit's
+    '.'), mod_type = index into mod_types (255 unknown; a table without the column is all type 0)."""
+    d = _require_cuda(device)
+    contig_names = list(contig_names)
+    with torch.cuda.device(d):
+        pos_c, frac_c, strand_c = (_frame_column(frame, k) for k in ("position", "fraction_mod", "strand"))
+        if pos_c is None:
+            raise KeyError("pileup has no 'position' column")
+        if strand_c is None or frac_c is None:
+            raise KeyError("pileup needs 'strand' and 'fraction_mod' columns")
+        pos = _to_device(_numeric_column(pos_c, np.int64), d)
+        frac = _to_device(_numeric_column(frac_c, np.float64), d)
+        n = int(pos.numel())
+        strand = _lookup_ids(*_string_column(strand_c), ["+", "-"], 2, torch.uint8, d, table_cache)
+        contig_c = _frame_column(frame, "contig")
+        if contig_c is None:
+            if len(contig_names) != 1:
+                raise KeyError("pileup has no 'contig' column but several contigs were given")
+            cid = torch.zeros(n, dtype=torch.int32, device=d)
+        else:
+            cid = _lookup_ids(*_string_column(contig_c), contig_names, -1, torch.int32, d, table_cache)
+        mt_c = _frame_column(frame, "mod_type")
+        if mt_c is None:
+            mt = torch.zeros(n, dtype=torch.uint8, device=d)
+        else:
+            # integer mod-type columns hold modkit codes such as 21839, not indices
+            mt = _lookup_ids(*_string_column(mt_c, ints_are_codes=False), [str(m) for m in mod_types], 255, torch.uint8,
+                             d, table_cache)
+        cov_c = _frame_column(frame, "Nvalid_cov")
+        cov = None if cov_c is None else _to_device(_numeric_column(cov_c, np.int64), d)
+        for t in (frac, strand, cid, mt):
+            if int(t.numel()) != n:
+                raise ValueError("pileup columns differ in length")
+    return DeviceRows(contig_names, mod_types, d, contig_id=cid, position=pos, strand=strand, mod_type=mt,
+                      fraction_mod=frac, Nvalid_cov=cov)
 
 
 def parse_bedmethyl(data, contig_names, mod_types=("a", "m", "21839"), with_counts: bool = False, device=None,

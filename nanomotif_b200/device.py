@@ -133,13 +133,19 @@ class DevicePileup:
         self.class_records = torch.empty(self.n_modtypes * assembly.n_tiles * _lib.CLS_REC_WORDS,
                                          dtype=torch.int32, device=assembly.device)
 
-    @classmethod
-    def from_columns(cls, assembly: DeviceAssembly, contig_id, position, strand, fraction_mod, low, high,
-                     mod_type=None, n_modtypes: int = 1) -> "DevicePileup":
-        """contig_id int32 (index into the assembly, negative = ignore), position int64, strand uint8
-        (0 '+', 1 '-'), fraction_mod float64, mod_type uint8 or None.  numpy arrays or device tensors."""
-        self = cls(assembly, n_modtypes, low, high)
-        d = assembly.device
+    def clear(self) -> "DevicePileup":
+        view = self.assembly.view()
+        with torch.cuda.device(self.assembly.device):
+            check(lib.nmb_clear_class_planes(C.byref(view), self.n_modtypes, ptr(self.class_records), _stream()),
+                  "nmb_clear_class_planes")
+        self._dups = None
+        return self
+
+    def add_columns(self, contig_id, position, strand, fraction_mod, mod_type=None, sync: bool = True) -> "DevicePileup":
+        """OR rows into the class records (several tables, e.g. one per (bin, mod_type) as the reference partitions
+        its pileup, find_motifs_bin.py:416).  Same columns as from_columns.  Rows that repeat a (contig, position,
+        strand, mod type) are counted in `duplicate_rows` -- bit-planes collapse them, the reference counts them twice."""
+        assembly, d = self.assembly, self.assembly.device
 
         def dev(a, dt):
             if a is None:
@@ -155,14 +161,43 @@ class DevicePileup:
             for t in (pos, st, fr) + ((mt,) if mt is not None else ()):
                 if int(t.numel()) != n:
                     raise ValueError("pileup columns differ in length")
+            if getattr(self, "_dups", None) is None:
+                self._dups = torch.zeros(1, dtype=torch.int64, device=d)
             view = assembly.view()
             check(
-                lib.nmb_build_class_planes(ptr(cid), ptr(pos), ptr(st), ptr(mt), ptr(fr), n, self.low, self.high,
-                                           C.byref(view), self.n_modtypes, ptr(self.class_records), _stream()),
-                "nmb_build_class_planes",
+                lib.nmb_add_class_planes(ptr(cid), ptr(pos), ptr(st), ptr(mt), ptr(fr), n, self.low, self.high,
+                                         C.byref(view), self.n_modtypes, ptr(self.class_records), ptr(self._dups),
+                                         _stream()),
+                "nmb_add_class_planes",
             )
-            torch.cuda.current_stream().synchronize()
+            if sync:
+                torch.cuda.current_stream().synchronize()
         return self
+
+    @property
+    def duplicate_rows(self) -> int:
+        """Rows seen so far whose class bit was already set (synchronises)."""
+        dups = getattr(self, "_dups", None)
+        return 0 if dups is None else int(dups.item())
+
+    def check_unique(self) -> "DevicePileup":
+        n = self.duplicate_rows
+        if n:
+            import warnings
+
+            warnings.warn(f"pileup holds {n} row(s) that repeat a (contig, position, strand, mod_type): they are counted "
+                          "once here but once per row by the reference (np.isin keeps duplicates)", RuntimeWarning,
+                          stacklevel=3)
+        return self
+
+    @classmethod
+    def from_columns(cls, assembly: DeviceAssembly, contig_id, position, strand, fraction_mod, low, high,
+                     mod_type=None, n_modtypes: int = 1) -> "DevicePileup":
+        """contig_id int32 (index into the assembly, negative = ignore), position int64, strand uint8
+        (0 '+', 1 '-'), fraction_mod float64, mod_type uint8 or None.  numpy arrays or device tensors."""
+        self = cls(assembly, n_modtypes, low, high)
+        self.clear().add_columns(contig_id, position, strand, fraction_mod, mod_type)
+        return self.check_unique()
 
     @classmethod
     def from_compact(cls, assembly: DeviceAssembly, position, flags, percent_x100, contig_row_off, low, high,
@@ -235,8 +270,9 @@ def compact_rows(contig_id, position, strand, fraction_mod, mod_type=None, n_con
     mt = np.zeros(len(position), dtype=np.uint8) if mod_type is None else np.asarray(mod_type, dtype=np.uint8)
     if len(mt) and mt.max() > 127:
         mt = np.where(mt > 127, 127, mt)  # out-of-range types are ignored by the kernel (>= n_modtypes)
-    flags = (np.asarray(strand, dtype=np.uint8) & 1) | (mt << 1)
-    keep = cid >= 0
+    strand = np.asarray(strand, dtype=np.uint8)
+    flags = (strand & 1) | (mt << 1)
+    keep = (cid >= 0) & (strand <= 1)  # strand code 2 = neither '+' nor '-': dropped like the reference does
     if not keep.all():
         cid, position, flags, key = cid[keep], position[keep], flags[keep], key[keep]
     if len(cid) > 1 and np.any(cid[1:] < cid[:-1]):

@@ -30,11 +30,13 @@ def _column(frame, name):
 
 
 def strand_codes(strand) -> np.ndarray:
-    """'+' -> 0, '-' -> 1 (uint8 input is passed through)."""
+    """'+' -> 0, '-' -> 1, anything else (modkit's '.' with --combine-strands) -> 2: such rows take no part, as
+    the reference's strand == "+" / strand == "-" filters drop them (find_motifs_bin.py:1311-1314).  Integer input
+    is passed through."""
     a = np.asarray(strand)
     if a.dtype.kind in "iub":
         return a.astype(np.uint8, copy=False)
-    return (a == "-").astype(np.uint8)
+    return np.where(a == "+", 0, np.where(a == "-", 1, 2)).astype(np.uint8)
 
 
 @dataclass

@@ -93,7 +93,11 @@ class ShardedBinScorer:
         if table.contig is not None and len(mine) < len(names):
             keep = np.isin(np.asarray(table.contig).astype(str), np.array(list(mine.keys()), dtype=str))
             table = table.take(keep)
+        import torch
+
         self.scorer = BinScorer(table, mine, low_meth_threshold, high_meth_threshold, device) if mine else None
+        self.device = self.scorer.assembly.device if mine else torch.device(
+            "cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
     def score(self, motifs) -> np.ndarray:
         import torch
@@ -102,6 +106,113 @@ class ShardedBinScorer:
         if self.scorer is not None:
             c = self.scorer.counts_by_strand(motifs)
         else:  # a rank without contigs still takes part in the collective
-            c = torch.zeros((len(motifs), 4), dtype=torch.int64, device="cuda")
+            c = torch.zeros((len(motifs), 4), dtype=torch.int64, device=self.device)
         c = allreduce_counts(c).cpu().numpy()
         return np.stack([c[:, 0] + c[:, 2], c[:, 1] + c[:, 3]], axis=1)
+
+
+def _contig_length(seq) -> int:
+    """Length of a contig given as str, DNAsequence-like (.sequence) or -- for contigs another rank will own --
+    as a plain int (every rank must know all lengths to derive the same shard plan, not all sequences)."""
+    if isinstance(seq, (int, np.integer)):
+        return int(seq)
+    return len(seq if isinstance(seq, str) else seq.sequence)
+
+
+class ShardedContext:
+    """One (bin, mod_type) of a ShardedMultiBinScorer; `local` is the rank's BinContext or None."""
+
+    def __init__(self, owner, bin_name, mod_type, local):
+        self.owner, self.bin_name, self.mod_type, self.local = owner, bin_name, mod_type, local
+
+    def score(self, motifs) -> np.ndarray:
+        return self.owner.score_batch([(self, motifs)])[0]
+
+
+class PendingScores:
+    """Counts of one submitted batch: the scan is enqueued, the all-reduce runs asynchronously."""
+
+    def __init__(self, requests, tensor, work):
+        self.requests, self.tensor, self.work = requests, tensor, work
+
+    def result(self) -> list:
+        from .api import split_counts
+
+        if self.work is not None:
+            self.work.wait()  # orders the current stream after the collective
+        return split_counts(self.tensor.cpu().numpy(), self.requests)
+
+
+class ShardedMultiBinScorer:
+    """The multi-GPU form of api.MultiBinScorer -- what replaces the reference's process pool over bins
+    (nanomotif/find_motifs_bin.py:330-372) on a box with several GPUs.
+
+    `plan_shards` keeps a bin's contigs on one rank unless the bin alone exceeds 1/world_size of the assembly; every
+    rank packs only its own contigs and ingests only the pileup rows of those contigs.  The (replicated) search
+    driver calls `score_batch` with the SAME requests on every rank: each rank scans the requests whose bin has local
+    contigs in ONE launch and the stacked [total motifs, 4] count tensor is summed over the ranks with ONE all-reduce
+    (NCCL over NVLink) -- that merges split bins and replicates the whole-bin results in the same step.
+    `submit` returns before the collective has run, so the driver can enqueue the next batch while this one's counts
+    are in flight."""
+
+    def __init__(self, pileup, bins: dict, mod_types, low_meth_threshold: float, high_meth_threshold: float,
+                 rank: int, world_size: int, device=None, group=None):
+        import torch
+
+        from .api import MultiBinScorer
+
+        self.rank, self.world_size, self.group = int(rank), int(world_size), group
+        names, lengths, groups = [], [], []
+        for b, (bin_name, cs) in enumerate(bins.items()):
+            for name, seq in cs.items():
+                names.append(name)
+                lengths.append(_contig_length(seq))
+                groups.append(b)
+        self.owner = plan_shards(lengths, world_size, groups)
+        mine, at = {}, 0
+        self.split_bins, self.bin_ranks = set(), {}
+        for bin_name, cs in bins.items():
+            own = self.owner[at:at + len(cs)]
+            self.bin_ranks[bin_name] = sorted(set(own.tolist()))
+            if len(self.bin_ranks[bin_name]) > 1:
+                self.split_bins.add(bin_name)
+            local = {n: s for (n, s), r in zip(cs.items(), own) if r == self.rank}
+            if any(isinstance(v, (int, np.integer)) for v in local.values()):
+                raise ValueError(f"bin {bin_name}: this rank owns a contig that was given by length only")
+            if local:
+                mine[bin_name] = local
+            at += len(cs)
+        self.mod_types = list(mod_types)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        tables = pileup
+        if isinstance(pileup, dict) and "position" not in pileup:  # partitioned {(bin, mod_type): frame}
+            tables = {k: v for k, v in pileup.items() if not (isinstance(k, tuple) and k[0] in bins and k[0] not in mine)}
+        self.local = MultiBinScorer(tables, mine, self.mod_types, low_meth_threshold, high_meth_threshold,
+                                    self.device) if mine else None
+        self._local_bins = set(mine)
+
+    def context(self, bin_name, mod_type) -> ShardedContext:
+        if bin_name not in self.bin_ranks:
+            raise KeyError(bin_name)
+        local = self.local.context(bin_name, mod_type) if bin_name in self._local_bins else None
+        return ShardedContext(self, bin_name, mod_type, local)
+
+    def submit(self, requests) -> PendingScores:
+        import torch
+        import torch.distributed as dist
+
+        requests = [(ctx, list(motifs)) for ctx, motifs in requests]
+        local_requests = [(ctx.local, ms) for ctx, ms in requests]
+        total = sum(len(ms) for _, ms in requests)
+        if self.local is not None:
+            t = self.local.score_batch_device(local_requests)
+        else:  # a rank without contigs still takes part in the collective
+            with torch.cuda.device(self.device):
+                t = torch.zeros((total, 4), dtype=torch.int64, device=self.device)
+        work = None
+        if total and self.world_size > 1 and dist.is_available() and dist.is_initialized():
+            work = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return PendingScores(requests, t, work)
+
+    def score_batch(self, requests) -> list:
+        return self.submit(requests).result()

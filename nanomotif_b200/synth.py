@@ -7,7 +7,25 @@ from __future__ import annotations
 
 import numpy as np
 
-from .motif import tokenize, token_mask
+# This module is loaded BY PATH by `bench.py --impl reference` (which must not import the package: the package
+# dlopens libnmb200.so), so it has no package-relative imports at module level.
+_BITS = {"A": 1, "T": 2, "G": 4, "C": 8}
+
+
+def tokenize(motif_string: str) -> list[str]:
+    """Per-position tokens of a regex-subset motif, bracket classes kept together."""
+    return [t for t in __import__("re").findall(r"\[[^\]]*\]|.", motif_string)]
+
+
+def token_mask(token: str) -> int:
+    """Allowed-set of a token: bit0=A bit1=T bit2=G bit3=C; '.' = 0xF."""
+    if token == ".":
+        return 0xF
+    m = 0
+    for ch in token.strip("[]"):
+        m |= _BITS[ch]
+    return m
+
 
 MOD_TYPES = ("a", "m", "21839")
 CANONICAL = {"a": "A", "m": "C", "21839": "C"}  # nanomotif/constants.py:31-35
@@ -210,3 +228,175 @@ def device_pattern_workload(device, total_bp: int = 1_500_000_000, n_contigs: in
         del idx, cid
     del codes
     return asm, {k: torch.cat(v) for k, v in cols.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# cfg 3 (BASELINE.json configs[2]): metagenome of 300 bins x 5 Mbp, 20-200 contigs per bin,
+# per-bin GC in U(0.3, 0.7), 1-5 planted motifs per bin, depth 30, three mod types.
+# The PLAN (contig lengths, GC, planted motifs of every bin) is pure numpy and cheap, so every rank and
+# the CPU arm derive the same one; a bin's sequence + pileup come either from numpy on the host
+# (cfg3_bin_host: the bins the end-to-end leg and the CPU arm share) or from torch on the device
+# (cfg3_bin_device: 1.5 Gbp would take ~15 minutes of numpy).
+# ---------------------------------------------------------------------------------------------
+PLANT_POOL = {
+    "a": (("GATC", 1), ("GCAC......GTT", 2), ("AAC......GTGC", 1), ("G[AG].GAAG[CT]", 5), ("CTGCAG", 4),
+          ("GAATTC", 2), ("GGA......TCC", 2), ("TCGA", 3), ("GAGG", 1)),
+    "m": (("CC[AT]GG", 1), ("GGCC", 2), ("GC.GC", 1), ("CCGG", 1), ("GATC", 3)),
+    "21839": (("CCGG", 0), ("GCGC", 1), ("CC[AT]GG", 0)),
+}
+
+
+def cfg3_plan(n_bins: int = 300, bin_bp: int = 5_000_000, seed: int = 3) -> dict:
+    """Contig lengths, bin of every contig, per-bin GC and planted motifs.  Contig names are contig_<i>,
+    bins bin_<j>; contigs of a bin are consecutive."""
+    rng = np.random.default_rng(seed)
+    lengths, bin_of, gc, planted, ranges = [], [], [], [], []
+    for b in range(n_bins):
+        n = int(round(20 * 10 ** rng.uniform(0.0, 1.0)))  # 20-200 contigs, log-uniform (~78 on average)
+        w = rng.lognormal(mean=0.0, sigma=1.0, size=n)
+        lens = np.maximum(2500, (w / w.sum() * bin_bp).astype(np.int64))
+        ranges.append((len(lengths), len(lengths) + n))
+        lengths.extend(lens.tolist())
+        bin_of.extend([b] * n)
+        gc.append(float(rng.uniform(0.3, 0.7)))
+        pool = [(m, p, mt) for mt in MOD_TYPES for m, p in PLANT_POOL[mt]]
+        k = int(rng.integers(1, 6))
+        planted.append(tuple(pool[i] for i in sorted(rng.choice(len(pool), size=k, replace=False))))
+    return {"lengths": np.asarray(lengths, dtype=np.int64), "bin_of": np.asarray(bin_of, dtype=np.int32),
+            "gc": gc, "planted": planted, "ranges": ranges, "n_bins": n_bins, "seed": seed, "depth": 30}
+
+
+def cfg3_bin_host(plan: dict, b: int) -> dict:
+    """Bin b generated with numpy: {"ascii": uint8 (contigs concatenated), "lengths", and pileup columns
+    contig (index within the bin, int32), position, strand, mod_type (index into MOD_TYPES), fraction_mod,
+    Nvalid_cov} -- rows sorted by (contig, position) like a modkit pileup."""
+    rng = np.random.default_rng([plan["seed"], 1000 + b])
+    lo, hi = plan["ranges"][b]
+    lens = plan["lengths"][lo:hi]
+    seqs, cols = [], {k: [] for k in ("contig", "position", "strand", "mod_type", "fraction_mod", "Nvalid_cov")}
+    for c, n in enumerate(lens.tolist()):
+        seq = random_sequence(rng, n, plan["gc"][b], 1e-6)
+        p = synth_pileup(seq, rng, planted=plan["planted"][b], depth=plan["depth"])
+        seqs.append(seq)
+        cols["contig"].append(np.full(len(p["position"]), c, dtype=np.int32))
+        for k in ("position", "strand", "mod_type", "fraction_mod", "Nvalid_cov"):
+            cols[k].append(p[k])
+    out = {k: np.concatenate(v) for k, v in cols.items()}
+    out["ascii"] = np.concatenate(seqs)
+    out["lengths"] = lens
+    return out
+
+
+def _planted_truth_device(codes, starts_ok_len, motif: str, mod_pos: int):
+    """Boolean tensor over the bin's concatenated positions: True at the modified base of every occurrence of
+    `motif` that lies inside one contig.  codes: uint8 (0 A, 1 T, 2 G, 3 C, 4 other); starts_ok_len(len) ->
+    bool tensor of the starts whose whole occurrence stays inside its contig."""
+    import torch
+
+    toks = tokenize(motif)
+    n = codes.numel() - len(toks) + 1
+    ok = starts_ok_len(len(toks))[:n].clone()
+    for j, t in enumerate(toks):
+        m = token_mask(t)
+        if m == 0xF:
+            continue
+        allowed = torch.tensor([(m >> c) & 1 for c in range(4)] + [0], dtype=torch.bool, device=codes.device)
+        ok &= allowed[codes[j:j + n].long()]
+    truth = torch.zeros(codes.numel(), dtype=torch.bool, device=codes.device)
+    truth[torch.nonzero(ok).view(-1) + mod_pos] = True
+    return truth
+
+
+def cfg3_bin_device(plan: dict, b: int, device, p_meth: float = 0.95, p_unmeth: float = 0.02,
+                    false_high: float = 0.003, ascii_only: bool = False) -> dict:
+    """Bin b generated with torch on `device` (same distributions as cfg3_bin_host, different draws):
+    {"ascii": uint8 device tensor, "lengths", "contig" int32, "position" int64, "strand" uint8, "mod_type" uint8,
+    "fraction_mod" float64} (device tensors; rows grouped by mod type and strand, positions ascending).
+    ascii_only: just the sequence (the first draw of the bin's generator, so a later full call repeats it)."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(plan["seed"] * 100003 + b)
+    lo, hi = plan["ranges"][b]
+    lens = plan["lengths"][lo:hi]
+    total = int(lens.sum())
+    gc = plan["gc"][b]
+    u = torch.rand(total, device=device, generator=g)
+    at = (1.0 - gc) / 2
+    codes = (u >= at).to(torch.uint8) + (u >= 2 * at).to(torch.uint8) + (u >= 2 * at + gc / 2).to(torch.uint8)
+    del u
+    rng = np.random.default_rng([plan["seed"], 2000 + b])
+    for s in rng.integers(0, max(1, total - 100), size=rng.poisson(1e-6 * total)):
+        codes[int(s):int(s) + int(rng.integers(10, 101))] = 4
+    lut = torch.tensor([65, 84, 71, 67, 78], dtype=torch.uint8, device=device)  # A T G C N
+    ascii_d = lut[codes.long()]
+    if ascii_only:  # the sequence is the generator's first draw: a second call with the same seed repeats it
+        return {"ascii": ascii_d, "lengths": lens}
+    ends = torch.from_numpy(np.cumsum(lens)).to(device)
+    pos_all = torch.arange(total, device=device)
+    cid_all = torch.bucketize(pos_all, ends, right=True)
+    start_of = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)[:-1]])).to(device)
+    local_all = pos_all - start_of[cid_all]
+    remain = ends[cid_all] - pos_all  # positions left in the contig, this one included
+
+    def starts_ok_len(n):
+        return remain >= n
+
+    comp = {0: 1, 1: 0, 2: 3, 3: 2}
+    cols = {k: [] for k in ("contig", "position", "strand", "mod_type", "fraction_mod")}
+    for mt, name in enumerate(MOD_TYPES):
+        base = "ATGC".index(CANONICAL[name])
+        truth_p = torch.zeros(total, dtype=torch.bool, device=device)
+        truth_m = torch.zeros(total, dtype=torch.bool, device=device)
+        for motif, mp, mtype in plan["planted"][b]:
+            if mtype != name:
+                continue
+            truth_p |= _planted_truth_device(codes, starts_ok_len, motif, mp)
+            rc, rmp = reverse_complement_motif(motif, mp)
+            truth_m |= _planted_truth_device(codes, starts_ok_len, rc, rmp)
+        for strand, code, truth in ((0, base, truth_p), (1, comp[base], truth_m)):
+            idx = torch.nonzero(codes == code).view(-1)
+            n = int(idx.numel())
+            cov = torch.poisson(torch.full((n,), float(plan["depth"]), device=device), generator=g).clamp_(min=1.0)
+            is_meth = truth[idx] | (torch.rand(n, device=device, generator=g) < false_high)
+            prob = torch.where(is_meth, torch.full_like(cov, p_meth), torch.full_like(cov, p_unmeth))
+            n_mod = torch.binomial(cov, prob, generator=g)
+            key = torch.round(1e4 * n_mod.double() / cov.double())  # modkit prints the percentage with two decimals
+            cols["contig"].append(cid_all[idx].to(torch.int32))
+            cols["position"].append(local_all[idx])
+            cols["strand"].append(torch.full((n,), strand, dtype=torch.uint8, device=device))
+            cols["mod_type"].append(torch.full((n,), mt, dtype=torch.uint8, device=device))
+            cols["fraction_mod"].append((key / 100.0) / 100.0)  # dataload.py:85
+    out = {k: torch.cat(v) for k, v in cols.items()}
+    out["ascii"] = ascii_d
+    out["lengths"] = lens
+    return out
+
+
+def frontier_worklist(seed: int, canonical: str, rounds: int = 64, width: int = 4, window: int = 20) -> list:
+    """Search-shaped work list of one (bin, mod type): `rounds` expansions, each the <= `width` children of one
+    parent that differ in the base added at ONE new position (find_motifs_bin.py:1116-1145: the children of an
+    expansion share every other position).  A chain grows from the bare canonical base until it has 7-10
+    constrained positions, then a new chain starts.  Returns [[(motif string, mod_pos), ...] per round]."""
+    rng = np.random.default_rng([seed, 77])
+    out = []
+    parent, target = None, 0
+    while len(out) < rounds:
+        if parent is None:
+            parent = {0: canonical}  # offset from the modified base -> base
+            target = int(rng.integers(7, 11))
+        free = [o for o in range(-window // 2, window // 2 + 1) if o not in parent and min(abs(o - k) for k in parent) <= 6]
+        o = int(rng.choice(free))
+        bases = [str(x) for x in rng.permutation(list("ACGT"))[:int(rng.integers(max(1, width - 1), width + 1))]]
+        kids = []
+        for bs in bases:
+            cons = dict(parent)
+            cons[o] = bs
+            lo_, hi_ = min(cons), max(cons)
+            kids.append(("".join(cons.get(i, ".") for i in range(lo_, hi_ + 1)), -lo_))
+        out.append(kids)
+        parent = dict(parent)
+        parent[o] = bases[0]
+        if len(parent) >= target:
+            parent = None
+    return out

@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Generate tests/golden/search_trace.json by running the REAL reference search loop.
 
-    python tests/golden/generate_search_golden.py        (needs /root/reference)
+    python tests/golden/generate_search_golden.py          (needs /root/reference)
+    python tests/golden/generate_search_golden.py --cfg1   -> search_trace_cfg1.json: BASELINE.json configs[0], the
+        bundled geobacillus plasmids (nanomotif/datasets/geobacillus-plasmids.assembly.fasta, copied next to this
+        script as a data fixture) with a synthetic depth-100 pileup planting the shipped golden motifs
+        (nanomotif/datasets/geobacillus-plasmids.bin-motifs.tsv:2-5) -- the real pileup is not in the tree
 
 What is real and what is restated:
   * REAL (imported unchanged through oracle/ref_shim.py): MotifSearcher.run (best-first expansion,
@@ -38,14 +42,34 @@ SPEC = dict(seed=2026, contig_lengths=[180000, 90000], gc=0.5, depth=20, mod_typ
             min_kl=0.05, score_threshold=1.5, random_seed=1)
 
 
+CFG1_SPEC = dict(seed=1, fasta="geobacillus-plasmids.assembly.fasta", depth=100, mod_type="a",
+                 planted=[["ACCCA", 4, "a"], ["CCAAAT", 4, "a"], ["G[AG].GAAG[CT]", 5, "a"], ["GATC", 1, "a"]], padding=20,
+                 low=0.3, high=0.7, min_kl=0.05, score_threshold=1.5, random_seed=1)
+
+
+def read_fasta(path):
+    out, name = {}, None
+    for line in open(path):
+        if line.startswith(">"):
+            name = line[1:].split()[0]
+            out[name] = []
+        else:
+            out[name].append(line.strip().upper())
+    return {k: "".join(v) for k, v in out.items()}
+
+
 def build_inputs(spec):
     from nanomotif_b200 import synth
 
     rng = np.random.default_rng(spec["seed"])
     contigs, cols = {}, {k: [] for k in ("contig", "position", "strand", "fraction_mod")}
-    for i, L in enumerate(spec["contig_lengths"]):
-        seq = synth.random_sequence(rng, L, spec["gc"], 2e-5)
-        name = f"contig_{i}"
+    if "fasta" in spec:
+        named = [(k, np.frombuffer(v.encode(), dtype=np.uint8)) for k, v in
+                 read_fasta(os.path.join(os.path.dirname(os.path.abspath(__file__)), spec["fasta"])).items()]
+    else:
+        # a generator: sequence and pileup draws of one contig interleave on the same rng stream
+        named = ((f"contig_{i}", synth.random_sequence(rng, L, spec["gc"], 2e-5)) for i, L in enumerate(spec["contig_lengths"]))
+    for name, seq in named:
         contigs[name] = seq.tobytes().decode()
         p = synth.synth_pileup(seq, rng, depth=spec["depth"], mod_types=(spec["mod_type"],),
                                planted=[tuple(x) for x in spec["planted"]])
@@ -62,7 +86,8 @@ class Cols(dict):
 
 
 def main():
-    spec = SPEC
+    cfg1 = "--cfg1" in sys.argv
+    spec = CFG1_SPEC if cfg1 else SPEC
     contigs, pile = build_inputs(spec)
     pile = Cols(pile)
     pad, low, high = spec["padding"], spec["low"], spec["high"]
@@ -171,7 +196,7 @@ def main():
                            priority=float(d["priority"]), depth=int(d["depth"]), visited=bool(d["visited"]))
                       for n, d in graph.nodes(data=True)],
                edges=[[u.string, v.string] for u, v in graph.edges()])
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "search_trace.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "search_trace_cfg1.json" if cfg1 else "search_trace.json")
     json.dump(out, open(path, "w"))
     print("wrote", path, os.path.getsize(path), "bytes;", len(out["nodes"]), "nodes,", calls["n"], "scoring calls")
     print("best:", [c.strip(".") for c in out["best_candidates"]], "missed:", [c.strip(".") for c in out["missed"]])

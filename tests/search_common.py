@@ -11,19 +11,27 @@ from oracle import restate as O
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def load_trace():
-    with open(os.path.join(HERE, "golden", "search_trace.json")) as f:
+def load_trace(name="search_trace.json"):
+    with open(os.path.join(HERE, "golden", name)) as f:
         return json.load(f)
 
 
 def build_inputs(spec):
+    """The golden search input, regenerated from its seed; spec["fasta"] names a FASTA fixture under tests/golden
+    (cfg 1: the reference's bundled geobacillus plasmids) instead of random contigs."""
     from nanomotif_b200 import synth
 
     rng = np.random.default_rng(spec["seed"])
     contigs, cols = {}, {k: [] for k in ("contig", "position", "strand", "fraction_mod")}
-    for i, L in enumerate(spec["contig_lengths"]):
-        seq = synth.random_sequence(rng, L, spec["gc"], 2e-5)
-        name = f"contig_{i}"
+    if "fasta" in spec:
+        from nanomotif_b200.dataload import load_fasta
+
+        named = [(k, np.frombuffer(v.encode(), dtype=np.uint8)) for k, v in
+                 load_fasta(os.path.join(HERE, "golden", spec["fasta"])).items()]
+    else:
+        # a generator: sequence and pileup draws of one contig interleave on the same rng stream
+        named = ((f"contig_{i}", synth.random_sequence(rng, L, spec["gc"], 2e-5)) for i, L in enumerate(spec["contig_lengths"]))
+    for name, seq in named:
         contigs[name] = seq.tobytes().decode()
         p = synth.synth_pileup(seq, rng, depth=spec["depth"], mod_types=(spec["mod_type"],),
                                planted=[tuple(x) for x in spec["planted"]])

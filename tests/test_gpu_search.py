@@ -70,6 +70,27 @@ def test_gpu_search_reproduces_reference_trace(nmb):
     check_against_trace(trace, search.run(co, backend), rounds)
 
 
+def test_cfg1_bundled_assembly_on_gpu(nmb):
+    """BASELINE.json configs[0] on the GPU operators: the bundled geobacillus plasmids with the shipped golden motifs
+    planted; every node's counts / scores equal the trace recorded from the REAL reference search (whose scoring calls
+    were answered by the oracle), i.e. every visited motif's counts equal the oracle's."""
+    from nanomotif_b200 import search
+
+    trace = load_trace("search_trace_cfg1.json")
+    spec = trace["spec"]
+    contigs, pile = build_inputs(spec)
+    scorer = nmb.BinScorer(pile, contigs, spec["low"], spec["high"])
+    backend, bin_pssm, total = _setup(nmb, contigs, pile, spec, scorer)
+    assert total == trace["total_windows"]
+    np.testing.assert_array_equal(bin_pssm, np.array(trace["bin_pssm"]))
+    rounds = []
+    co = search.find_candidates(spec["mod_type"], spec["padding"], bin_pssm, total, min_kl=spec["min_kl"],
+                                score_threshold=spec["score_threshold"], trace=rounds)
+    graph, best = search.run(co, backend)
+    check_against_trace(trace, (graph, best), rounds)
+    assert [m.new_stripped_motif().string for m in best[:3]] == ["GATC", "ACCCA", "CCAAAT"]
+
+
 def test_lockstep_multibin_search(nmb):
     from nanomotif_b200 import search
 

@@ -21,6 +21,31 @@ def test_search_reproduces_reference_trace():
     assert backend.calls == trace["scoring_calls"]  # the same motif_model_bin evaluations, batched differently
 
 
+def test_cfg1_bundled_assembly_recovers_golden_motifs():
+    """BASELINE.json configs[0]: the reference's bundled geobacillus plasmids (tests/golden/*.fasta) with the shipped
+    golden motifs planted (nanomotif/datasets/geobacillus-plasmids.bin-motifs.tsv:2-5).  The trace was recorded from
+    the REAL MotifSearcher (tests/golden/generate_search_golden.py --cfg1)."""
+    trace = load_trace("search_trace_cfg1.json")
+    spec = trace["spec"]
+    contigs, pile = build_inputs(spec)
+    assert {k: len(v) for k, v in contigs.items()} == {"contig_3": 82915, "contig_2": 93311}
+    backend = OracleBackend(contigs, pile, spec)
+    assert backend.arr.shape[0] == trace["total_windows"]
+    rounds = []
+    co = search.find_candidates(spec["mod_type"], spec["padding"], backend.bin_pssm, backend.arr.shape[0],
+                                min_kl=spec["min_kl"], score_threshold=spec["score_threshold"], trace=rounds)
+    graph, best = search.run(co, backend)
+    check_against_trace(trace, (graph, best), rounds)
+    found = [m.new_stripped_motif() for m in best]
+    for want in (search.Motif("GATC", 1), search.Motif("ACCCA", 4), search.Motif("CCAAAT", 4)):
+        assert want in found
+    grn = search.Motif("G[AG].GAAG[CT]", 5)  # GRNGAAGY comes out as its concrete variants (merged later, motif.py:470-560)
+    rest = [m for m in found if m.string not in ("GATC", "ACCCA", "CCAAAT")]
+    assert rest and all(m.mod_position == 5 and m.length() == grn.length() for m in rest)
+    for m in rest:  # every constrained position agrees with GRNGAAGY
+        assert all(t == "." or set(t.strip("[]")) <= set(g.strip("[]")) for t, g in zip(m.split(), grn.split())), m
+
+
 def test_lockstep_driver_matches_sequential():
     trace = load_trace()
     spec = trace["spec"]
