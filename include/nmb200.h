@@ -304,6 +304,14 @@ NMB_API int nmb_match_plane(const nmb_assembly *assembly_h, const void *programs
                     int32_t strand, int32_t motif_len, int32_t tile_begin, int32_t tile_count,
                     uint32_t *match_plane, void *stream);
 
+/* Literal non-ACGT letters in a motif string (regex-literal semantics of utils.subseq_indices, utils.py:61-66: an 'N'
+ * in the motif matches the contig letter N and nothing else).  plane[p] &= (upper(ascii[p + shift]) == letter) for
+ * the n_words words of a flat match plane over ONE contig of n letters starting at global position 0; positions whose
+ * p + shift falls outside [0, n) are cleared.  The caller matches the motif with such positions as wildcards
+ * (nmb_match_plane) and ANDs one letter plane per literal. */
+NMB_API int nmb_letter_plane(const uint8_t *ascii, int64_t n, int32_t letter, int64_t shift, uint32_t *plane,
+                             int64_t n_words, void *stream);
+
 /* Ascending positions of the set bits of plane & (mask or all-ones) within the global position
  * range [pos_begin, pos_end).  Two passes on the same stream: tile_counts is scratch of
  * ceil((pos_end-pos_begin)/NMB_TILE_BP)+2 int64.  Positions are written relative to pos_begin.
@@ -450,6 +458,18 @@ NMB_API int nmb_sweep_expand(const uint32_t *src, uint32_t *dst, int64_t outer, 
  * = number of hits, of which at most `capacity` are written. */
 NMB_API int nmb_sweep_filter(const uint32_t *n_mod, const uint32_t *n_nomod, int64_t n, double min_mean,
                              int64_t min_mod, int64_t *out_index, int64_t capacity, int64_t *n_out, void *stream);
+
+/* ---- host -> device staging of PAGEABLE host buffers (the Arrow buffers of the frames nanomotif hands to its
+ *      workers, find_motifs_bin.py:399-427).  n_threads host threads each own a CUDA stream and two pinned slots of
+ *      slot_bytes (allocated by nmb_stager_create -- the one allocation this library makes -- and freed by
+ *      nmb_stager_destroy); a copy is split into slot-sized chunks, memcpy()ed into the slots in parallel and sent by
+ *      DMA, ordered after the work already on `stream`, with `stream` ordered after it.  nmb_stager_copy returns when
+ *      the source has been READ (it may be freed), not when the DMA has finished.  src_host/dst_dev: host and device
+ *      pointers.  Not re-entrant per stager: one copy at a time. ---- */
+typedef struct nmb_stager nmb_stager;
+NMB_API int nmb_stager_create(int64_t slot_bytes, int32_t n_threads, nmb_stager **out);
+NMB_API int nmb_stager_copy(nmb_stager *stager, void *dst_dev, const void *src_host, int64_t bytes, void *stream);
+NMB_API int nmb_stager_destroy(nmb_stager *stager);
 
 #ifdef __cplusplus
 }

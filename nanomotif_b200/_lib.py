@@ -110,6 +110,7 @@ SIGNATURES = {
     "nmb_compile_motifs": (C.c_int, [_P, _I32, _P, _P]),
     "nmb_scan_count": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
     "nmb_match_plane": (C.c_int, [C.POINTER(NmbAssembly), _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "nmb_letter_plane": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _P]),
     "nmb_compact_positions": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P, _P]),
     "nmb_test_positions": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P]),
     "nmb_extract_windows": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _I64, _I32, _P, _P]),
@@ -121,6 +122,9 @@ SIGNATURES = {
     "nmb_pattern_scan": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P]),
     "nmb_segment_offsets": (C.c_int, [_P, _I64, _P, _P, _P]),
     "nmb_segment_median": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "nmb_stager_create": (C.c_int, [_I64, _I32, C.POINTER(_P)]),
+    "nmb_stager_copy": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "nmb_stager_destroy": (C.c_int, [_P]),
     "nmb_pssm_kl": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P]),
 }
 

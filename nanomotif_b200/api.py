@@ -35,18 +35,25 @@ from .pileup import PileupTable, strand_codes
 
 
 class _IdCache:
+    """LRU of device state keyed by the identity of the caller's objects PLUS a cheap content fingerprint (the
+    reference functions are pure: a caller may mutate a dict of contigs or filter a pileup in place between calls),
+    bounded by entry count and by device bytes (NMB_CACHE_BYTES, default 16 GiB)."""
+
     def __init__(self, capacity: int):
+        import os
+
         self.capacity = capacity
+        self.byte_budget = int(os.environ.get("NMB_CACHE_BYTES", 16 << 30))
         self._d: OrderedDict = OrderedDict()
 
-    def get(self, key, refs, build):
+    def get(self, key, refs, build, nbytes=lambda v: 0):
         hit = self._d.get(key)
         if hit is not None and all(a is b for a, b in zip(hit[0], refs)):
             self._d.move_to_end(key)
             return hit[1]
         val = build()
-        self._d[key] = (refs, val)  # holding refs keeps the ids stable while cached
-        while len(self._d) > self.capacity:
+        self._d[key] = (refs, val, int(nbytes(val)))  # holding refs keeps the ids stable while cached
+        while len(self._d) > 1 and (len(self._d) > self.capacity or sum(e[2] for e in self._d.values()) > self.byte_budget):
             self._d.popitem(last=False)
         return val
 
@@ -54,17 +61,55 @@ class _IdCache:
         self._d.clear()
 
 
+def _sample(a, k: int = 64) -> tuple:
+    """k evenly spaced elements of a column (O(k)): part of the cache fingerprint."""
+    n = len(a)
+    if n == 0:
+        return ()
+    idx = np.linspace(0, n - 1, num=min(k, n)).astype(np.int64)
+    try:
+        return tuple(np.asarray(a)[idx].tolist())
+    except Exception:
+        return tuple(a[int(i)] for i in idx)
+
+
+def _pileup_fingerprint(pileup) -> tuple:
+    """(rows, samples of position and fraction_mod): catches in-place filtering / edits of a cached pileup."""
+    from .pileup import _column
+
+    try:
+        pos, frac = _column(pileup, "position"), _column(pileup, "fraction_mod")
+    except Exception:
+        return (id(pileup),)
+    if pos is None or frac is None:
+        return (id(pileup),)
+    return (len(pos), _sample(pos), _sample(frac))
+
+
+def _contigs_fingerprint(contigs) -> tuple:
+    if isinstance(contigs, str):
+        return (len(contigs),)
+    return (len(contigs), sum(len(sequence_of(c)) for c in contigs.values()), tuple(contigs.keys())[:4])
+
+
+def _scorer_bytes(scorer) -> int:
+    t = [scorer.assembly.seq_records, scorer.assembly.nonacgt, scorer.pileup.class_records]
+    return sum(x.numel() * x.element_size() for x in t)
+
+
 _seq_cache = _IdCache(8)
 _bin_cache = _IdCache(8)
 
 
 def clear_caches() -> None:
+    """Drop the device state cached for the drop-in functions (packed assemblies, class planes)."""
     _seq_cache.clear()
     _bin_cache.clear()
 
 
 def _single_contig_assembly(seq: str) -> DeviceAssembly:
-    return _seq_cache.get(("seq", id(seq), len(seq)), (seq,), lambda: DeviceAssembly.from_sequences({"_": seq}))
+    return _seq_cache.get(("seq", id(seq), len(seq)), (seq,), lambda: DeviceAssembly.from_sequences({"_": seq}),
+                          lambda a: a.seq_records.numel() * 4 + a.nonacgt.numel() * 4)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -72,19 +117,52 @@ def _single_contig_assembly(seq: str) -> DeviceAssembly:
 # ---------------------------------------------------------------------------------------------
 
 
-def _match_plane(asm: DeviceAssembly, motif: Motif, align: int, strand: int = 0) -> tuple[torch.Tensor, int, int]:
+def _split_literals(toks: list[str]) -> tuple[list[str], dict[int, str]]:
+    """Motif tokens with literal non-ACGT letters (e.g. an 'N' typed into a motif string) replaced by '.', and
+    {token index: letter} of those literals.  Under the reference's regex semantics (utils.py:61-66) such a letter
+    matches the same contig letter and nothing else; it is applied as a letter plane on top of the matcher."""
+    lit = {j: t for j, t in enumerate(toks) if len(t) == 1 and t not in "ACGT."}
+    for t in lit.values():
+        if not ("A" <= t <= "Z"):
+            raise ValueError(f"motif token {t!r}: only letters, '.' and [..] classes are supported")
+    return ["." if j in lit else t for j, t in enumerate(toks)], lit
+
+
+def _apply_literals(plane: torch.Tensor, seq: str, literals: dict[int, str], t0: int) -> None:
+    """plane (bit p <-> motif token t0 at contig position p) &= 'token j is the literal letter' for every literal."""
+    if not literals:
+        return
+    from .device import _to_device
+
+    d = plane.device
+    with torch.cuda.device(d):
+        ascii_d = _to_device(np.frombuffer(seq.encode("ascii"), dtype=np.uint8), d)
+        for j, letter in literals.items():
+            check(lib.nmb_letter_plane(ptr(ascii_d), len(seq), ord(letter), j - t0, ptr(plane), int(plane.numel()),
+                                       _stream()), "nmb_letter_plane")
+
+
+def _match_plane(asm: DeviceAssembly, motif: Motif, align: int, strand: int = 0, seq: str | None = None
+                 ) -> tuple[torch.Tensor, int, int]:
     """Device bit-plane of the occurrences of `motif` (regex as given, flanking wildcards allowed).
 
-    Returns (plane, delta, length): bit p of `plane` is set iff the stripped motif occurs with motif
+    Returns (plane, delta, length): bit p of `plane` is set iff the motif occurs with motif
     position `align - delta` at p.  delta is 0 unless `align` points into the flanking wildcards.
-    The caller restores the whole-motif-inside-contig rule with `length`.
+    The caller restores the whole-motif-inside-contig rule with `length`.  Literal non-ACGT letters in the motif
+    need `seq` (the contig text, single-contig assemblies only).
     """
-    toks = tokenize(motif.string)
+    toks, literals = _split_literals(tokenize(motif.string))
     length = len(toks)
+    if literals and seq is None:
+        raise ValueError("a motif with literal non-ACGT letters needs the contig text")
     lead = 0
     while lead < length and toks[lead] == ".":
         lead += 1
-    core = Motif(motif.string.strip("."), 0)
+    if lead == length:  # nothing but literals and wildcards: every position is a candidate
+        plane = torch.full((asm.n_words,), -1, dtype=torch.int32, device=asm.device)
+        _apply_literals(plane, seq, literals, align)
+        return plane, 0, length
+    core = Motif("".join(toks).strip("."), 0)
     core_len = len(tokenize(core.string))
     a = min(max(align - lead, 0), core_len - 1)
     delta = (align - lead) - a
@@ -93,13 +171,15 @@ def _match_plane(asm: DeviceAssembly, motif: Motif, align: int, strand: int = 0)
     view = asm.view()
     check(lib.nmb_match_plane(C.byref(view), ptr(progs.programs), 0, strand, progs.max_len, 0, asm.n_tiles,
                               ptr(plane), _stream()), "nmb_match_plane")
+    _apply_literals(plane, seq, literals, align - delta)
     return plane, delta, length
 
 
 def subseq_indices(subseq: str, seq: str) -> np.ndarray:
     """All (overlapping) 0-based start positions of the regex motif `subseq` in `seq`, ascending int64.
 
-    Supports the motif alphabet the reference generates: A C G T, '.', and bracket classes.
+    Supports A C G T, '.', bracket classes, and literal non-ACGT letters (an 'N' matches the contig letter N only --
+    regex-literal semantics, utils.py:61-66).
     """
     seq = sequence_of(seq)
     toks = tokenize(subseq)
@@ -109,9 +189,10 @@ def subseq_indices(subseq: str, seq: str) -> np.ndarray:
     if all(t == "." for t in toks):  # closed form: every start where the motif fits
         return np.arange(0, max(0, L - length + 1), dtype=np.int64)
     asm = _single_contig_assembly(seq)
-    lead = next(i for i, t in enumerate(toks) if t != ".")
-    # align at the first constrained position: the stripped motif's position 0
-    plane, _, length = _match_plane(asm, Motif(subseq, 0), align=lead)
+    plain, _ = _split_literals(toks)
+    lead = next((i for i, t in enumerate(plain) if t != "."), 0)
+    # align at the first constrained position (position 0 for motifs made of literals and wildcards only)
+    plane, _, length = _match_plane(asm, Motif(subseq, 0), align=lead, seq=seq)
     pos = _compact(plane, 0, L)
     # whole (unstripped) motif inside the contig: 0 <= start and start + length <= L
     pos = pos - lead
@@ -164,7 +245,7 @@ def methylated_motif_occourances(motif, sequence, methylated_positions, non_meth
         ok = lambda p: (p - mp >= 0) & (p - mp <= L - length)
         return meth[ok(meth)] if meth.size else meth, nonmeth[ok(nonmeth)] if nonmeth.size else nonmeth
     asm = _single_contig_assembly(sequence)
-    plane, delta, length = _match_plane(asm, m, align=mp)
+    plane, delta, length = _match_plane(asm, m, align=mp, seq=sequence)
 
     def pick(p):
         if p.size == 0:
@@ -288,7 +369,8 @@ class MultiBinScorer:
         self.pileup = DevicePileup(self.assembly, len(self.mod_types), low_meth_threshold, high_meth_threshold).clear()
         self.rows, cache = [], {}
         for t in tables:
-            rows = t if isinstance(t, DeviceRows) else rows_from_table(t, self.assembly.names, self.mod_types, d, cache)
+            rows = t if isinstance(t, DeviceRows) else rows_from_table(t, self.assembly.names, self.mod_types, d, cache,
+                                                                             with_coverage=False)
             cid, mt = rows.contig_id, rows.mod_type
             if isinstance(t, DeviceRows) and (list(t.contig_names) != self.assembly.names or
                                               [str(m) for m in t.mod_types] != [str(m) for m in self.mod_types]):
@@ -374,8 +456,8 @@ def split_counts(c: np.ndarray, requests) -> list:
 
 
 def _scorer_for(pileup, contigs, low, high) -> BinScorer:
-    key = ("bin", id(pileup), id(contigs), float(low), float(high))
-    return _bin_cache.get(key, (pileup, contigs), lambda: BinScorer(pileup, contigs, low, high))
+    key = ("bin", id(pileup), id(contigs), float(low), float(high), _pileup_fingerprint(pileup), _contigs_fingerprint(contigs))
+    return _bin_cache.get(key, (pileup, contigs), lambda: BinScorer(pileup, contigs, low, high), _scorer_bytes)
 
 
 def motif_model_bin(pileup, contigs, motif, model, low_meth_threshold, high_meth_threshold):
@@ -409,13 +491,14 @@ def motif_model_contig(pileup, contig: str, prior, motif, low_meth_threshold=0.3
     contig = sequence_of(contig)
     table = PileupTable.from_frame(pileup)
     m = as_motif(motif).new_stripped_motif()
-    key = ("contig", id(pileup), id(contig), float(low_meth_threshold), float(high_meth_threshold))
+    key = ("contig", id(pileup), id(contig), float(low_meth_threshold), float(high_meth_threshold),
+           _pileup_fingerprint(pileup), len(contig))
 
     def build():
         t = PileupTable(None, table.position, table.strand, table.fraction_mod)
         return BinScorer(t, {"_": contig}, low_meth_threshold, high_meth_threshold)
 
-    scorer = _bin_cache.get(key, (pileup, contig), build)
+    scorer = _bin_cache.get(key, (pileup, contig), build, _scorer_bytes)
     c = scorer.counts_by_strand([m]).cpu().numpy()[0]
     prior.update(int(c[0] + c[2]), int(c[1] + c[3]))
     if not save_motif_positions:

@@ -135,6 +135,26 @@ __global__ void __launch_bounds__(256) test_positions_kernel(const uint32_t *__r
     }
 }
 
+
+// plane[p] &= (upper(ascii[p + shift]) == letter), false outside [0, n): one warp per 32-bit word, lane = bit.
+// Serves motif positions that are LITERAL non-ACGT letters (an 'N' in a motif string is the regex literal N,
+// nanomotif/utils.py:61-66 -- it matches the contig letter N and nothing else).
+__global__ void __launch_bounds__(256) letter_plane_kernel(const uint8_t *__restrict__ ascii, int64_t n, int letter,
+                                                           int64_t shift, uint32_t *__restrict__ plane,
+                                                           int64_t n_words) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_words) return;
+    const int64_t q = w * 32 + (threadIdx.x & 31) + shift;
+    bool ok = false;
+    if (q >= 0 && q < n) {
+        int c = ascii[q];
+        if (c >= 'a' && c <= 'z') c -= 32;  // the packer upper-cases, like seq.py:55
+        ok = c == letter;
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+    if ((threadIdx.x & 31) == 0) plane[w] &= m;
+}
+
 }  // namespace nmb
 
 extern "C" {
@@ -199,6 +219,17 @@ int nmb_test_positions(const uint32_t *plane, int64_t base, int64_t limit, const
     if (blocks > 148 * 32) blocks = 148 * 32;
     nmb::test_positions_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(plane, base, limit,
                                                                                  pos, n, flag);
+    NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_letter_plane(const uint8_t *ascii, int64_t n, int32_t letter, int64_t shift, uint32_t *plane, int64_t n_words,
+                     void *stream) {
+    NMB_REQUIRE(ascii && plane && n >= 0 && n_words >= 0 && letter >= 0 && letter < 256, "nmb_letter_plane: bad arguments");
+    if (n_words == 0) return NMB_OK;
+    const int64_t threads = n_words * 32;
+    nmb::letter_plane_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ascii, n, letter, shift,
+                                                                                               plane, n_words);
     NMB_CUDA(cudaGetLastError());
     return NMB_OK;
 }

@@ -399,7 +399,8 @@ def _lookup_ids(kind, a, b, names, missing, out_dtype, device, table_cache=None)
     return out
 
 
-def rows_from_table(frame, contig_names, mod_types=("a", "m", "21839"), device=None, table_cache=None) -> "DeviceRows":
+def rows_from_table(frame, contig_names, mod_types=("a", "m", "21839"), device=None, table_cache=None,
+                    with_coverage: bool = True) -> "DeviceRows":
     """A reference-shaped pileup table (columns contig: str, position: i64, strand: '+'/'-', mod_type: str,
     fraction_mod: f64 [, Nvalid_cov: i64]; pyarrow Table, polars / pandas frame, PileupTable or dict of arrays) ->
     DeviceRows.  contig_id = index into contig_names (-1 unknown), strand 0 '+' / 1 '-' / 2 anything else (modkit's
@@ -430,7 +431,7 @@ def rows_from_table(frame, contig_names, mod_types=("a", "m", "21839"), device=N
             # integer mod-type columns hold modkit codes such as 21839, not indices
             mt = _lookup_ids(*_string_column(mt_c, ints_are_codes=False), [str(m) for m in mod_types], 255, torch.uint8,
                              d, table_cache)
-        cov_c = _frame_column(frame, "Nvalid_cov")
+        cov_c = _frame_column(frame, "Nvalid_cov") if with_coverage else None
         cov = None if cov_c is None else _to_device(_numeric_column(cov_c, np.int64), d)
         for t in (frac, strand, cid, mt):
             if int(t.numel()) != n:

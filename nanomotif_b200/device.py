@@ -33,8 +33,52 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_TORCH_OF = {np.dtype(k): v for k, v in ((np.int32, torch.int32), (np.int64, torch.int64), (np.uint8, torch.uint8),
+                                         (np.int8, torch.int8), (np.float64, torch.float64), (np.uint16, torch.uint16),
+                                         (np.int16, torch.int16), (np.float32, torch.float32), (np.bool_, torch.bool))}
+_STAGERS: dict[int, int] = {}
+STAGE_MIN_BYTES = 4 << 20   # smaller copies go through cudaMemcpy directly
+STAGE_SLOT_BYTES = 4 << 20
+
+
+def stager_threads() -> int:
+    """Host threads of the staging copies: NMB_STAGE_THREADS, else the cores this process may run on (at most 16)."""
+    import os
+
+    env = os.environ.get("NMB_STAGE_THREADS")
+    if env:
+        return max(0, int(env))
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    return max(1, min(16, n))
+
+
+def _stager(device: torch.device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _STAGERS:
+        n = stager_threads()
+        handle = C.c_void_p()
+        if n > 0:
+            with torch.cuda.device(idx):
+                check(lib.nmb_stager_create(STAGE_SLOT_BYTES, n, C.byref(handle)), "nmb_stager_create")
+        _STAGERS[idx] = handle.value or 0
+    return _STAGERS[idx]
+
+
 def _to_device(arr: np.ndarray, device: torch.device) -> torch.Tensor:
+    """Host array -> device tensor on the current stream.  Large pageable arrays (the Arrow buffers of a pileup table)
+    go through the multi-threaded pinned stager (csrc/stage.cu); the source is never modified."""
     arr = np.ascontiguousarray(arr)
+    tdt = _TORCH_OF.get(arr.dtype)
+    if arr.nbytes >= STAGE_MIN_BYTES and tdt is not None:
+        st = _stager(device)
+        if st:
+            with torch.cuda.device(device):
+                out = torch.empty(arr.shape, dtype=tdt, device=device)
+                check(lib.nmb_stager_copy(st, ptr(out), arr.ctypes.data, arr.nbytes, _stream()), "nmb_stager_copy")
+            return out
     if not arr.flags.writeable:  # e.g. np.frombuffer over a bytes object; torch wants writable memory
         arr = arr.copy()
     return torch.from_numpy(arr).to(device, non_blocking=True)

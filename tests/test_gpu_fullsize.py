@@ -162,3 +162,43 @@ def test_pattern_table_at_cfg4_size():
     for c in (0, 17, 4242, nc - 1):
         sel = ok & (rows["contig_id"] == c)
         assert med[1, c] == float(np.median(fr[sel].cpu().numpy()))
+
+
+def test_cfg2_size_counts_equal_oracle():
+    """BASELINE.json configs[1] at full size against the ORACLE (not another kernel): one 4.6 Mbp contig, a depth-100
+    pileup of three mod types, 36 motifs (the planted ones, short dense ones, gapped and degenerate ones, seeded random
+    ones) -- every (n_mod, n_nomod) pair equals oracle.restate.motif_model_bin."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import nanomotif_b200 as nmb
+    from nanomotif_b200 import synth
+    from oracle import restate as O
+
+    rng = np.random.default_rng(2)
+    seq = synth.random_sequence(rng, 4_600_000, 0.508, 1e-6)
+    pile = synth.synth_pileup(seq, rng, depth=100)
+    text = seq.tobytes().decode()
+    contigs = {"contig_0": text}
+    fixed = {"a": [("GATC", 1), ("A", 0), ("GCAC......GTT", 2), ("AAC......GTGC", 1), ("G[AG].GAAG[CT]", 5), ("CA", 1),
+                   ("T.A", 2), ("A" + "." * 40 + "C", 0)],
+             "m": [("CC[AT]GG", 1), ("C", 0), ("GC.GC", 1), ("[AG]C[CT]", 1)],
+             "21839": [("CCGG", 0), ("C.G", 0), ("GCGC", 1)]}
+    mrng = np.random.default_rng(99)
+    names = np.array(synth.MOD_TYPES, dtype=object)
+    table = {"contig": np.full(len(pile["position"]), "contig_0", dtype=object), "position": pile["position"],
+             "strand": np.where(pile["strand"] == 0, "+", "-").astype(object), "mod_type": names[pile["mod_type"]],
+             "fraction_mod": pile["fraction_mod"]}
+    scorer = nmb.MultiBinScorer(table, {"bin": contigs}, synth.MOD_TYPES, 0.3, 0.7)
+    n = 0
+    for mt, name in enumerate(synth.MOD_TYPES):
+        motifs = fixed[name] + synth.random_motifs(mrng, 7, synth.CANONICAL[name])
+        got = scorer.context("bin", name).score([nmb.Motif(m, p) for m, p in motifs])
+        sel = pile["mod_type"] == mt
+        for (m, p), g in zip(motifs, got.tolist()):
+            want = O.motif_model_bin(table["contig"][sel], table["position"][sel], table["strand"][sel],
+                                     table["fraction_mod"][sel], contigs, m, p, fast=True)
+            assert tuple(g) == tuple(want), (name, m, p)
+            n += 1
+    assert n >= 30

@@ -23,12 +23,32 @@ def G():
 def test_subseq_indices_golden(G):
     import nanomotif_b200 as nmb
 
-    for c in G["subseq_indices"]:
-        if "N" in c["motif"]:  # a literal N in a motif is outside the motif alphabet of the device path
-            with pytest.raises(ValueError):
-                nmb.subseq_indices(c["motif"], c["seq"])
-            continue
+    seen_literal = False
+    for c in G["subseq_indices"]:  # includes the literal 'N' motif: regex-literal semantics (N matches N only)
+        seen_literal |= "N" in c["motif"]
         assert nmb.subseq_indices(c["motif"], c["seq"]).tolist() == c["result"], c["motif"]
+    assert seen_literal
+
+
+def test_literal_letters_in_motifs_match_like_the_regex(G):
+    """A non-ACGT letter typed into a motif is a regex literal (utils.py:61-66): it matches the same contig letter and
+    nothing else; '.' matches everything.  Against the oracle's regex on contigs with N / R / Y runs."""
+    import nanomotif_b200 as nmb
+    from oracle import restate as O
+
+    rng = np.random.default_rng(5)
+    letters = np.frombuffer(b"ACGTNRY", dtype=np.uint8)
+    for L in (50, 3000, 70000):
+        seq = letters[rng.choice(7, size=L, p=[0.22, 0.22, 0.22, 0.22, 0.06, 0.03, 0.03])].tobytes().decode()
+        for motif in ("N", "NN", "AN", "N.A", "A.N.C", "GNNT", "R", "[AC]N", ".N", "N.", "TNA[GT].N"):
+            np.testing.assert_array_equal(nmb.subseq_indices(motif, seq), O.subseq_indices(motif, seq), err_msg=motif)
+        meth = np.sort(rng.choice(L, size=L // 3, replace=False)).astype(np.int64)
+        non = np.setdiff1d(np.arange(L), meth)[: L // 3].astype(np.int64)
+        for motif, mp in (("AN", 0), ("N.A", 2), ("GNNT", 3), ("N", 0), (".NA.", 2)):
+            got = nmb.methylated_motif_occourances(nmb.Motif(motif, mp), seq, meth, non)
+            want = O.methylated_motif_occourances(motif, mp, seq, meth, non)
+            np.testing.assert_array_equal(got[0], want[0], err_msg=motif)
+            np.testing.assert_array_equal(got[1], want[1], err_msg=motif)
 
 
 def test_methylated_motif_occourances_golden(G):

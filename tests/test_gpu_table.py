@@ -164,3 +164,31 @@ def test_duplicate_rows_are_reported(nmb, data):
     with warnings.catch_warnings():
         warnings.simplefilter("error")
         nmb.MultiBinScorer(pile, bins, MOD_TYPES, 0.3, 0.7)
+
+
+def test_drop_in_cache_sees_mutated_inputs(nmb, data):
+    """The reference functions are pure; the cached device state behind the drop-in names must not go stale when the
+    caller mutates the SAME objects between calls (contigs dict edited, pileup filtered in place)."""
+    bins, pile = data
+    contigs = dict(bins["bin_A"])
+    sel = (pile["mod_type"] == "a") & np.isin(pile["contig"], list(contigs))
+    p = {k: v[sel] for k, v in pile.items()}
+    m = nmb.Motif("GATC", 1)
+
+    def got():
+        mdl = nmb.motif_model_bin(p, contigs, m, nmb.BetaBernoulliModel(), 0.3, 0.7)
+        return mdl._alpha - 5, mdl._beta - 5
+
+    def want():
+        return tuple(O.motif_model_bin(p["contig"], p["position"], p["strand"], p["fraction_mod"], contigs, "GATC", 1, fast=True))
+
+    first = got()
+    assert first == want() and got() == first  # second call: cache hit
+    del contigs[next(iter(contigs))]           # same dict object, one contig fewer
+    assert got() == want() != first
+    keep = p["position"] % 2 == 0              # same dict-of-arrays pileup, filtered in place
+    for k in p:
+        p[k] = p[k][keep]
+    assert got() == want()
+    nmb.clear_caches()
+    assert got() == want()

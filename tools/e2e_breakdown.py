@@ -1,74 +1,71 @@
 #!/usr/bin/env python
-"""Where the end-to-end step of bench.py spends its time (development tool)."""
+"""Where the end-to-end step of bench.py goes (development tool): host table -> device, name resolution, class planes,
+packing, 64 frontier rounds.  python tools/e2e_breakdown.py [--bins 8]"""
+import argparse
 import os
 import sys
 import time
 
 import numpy as np
-import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from nanomotif_b200.device import DeviceAssembly, DevicePileup, MotifPrograms, scan_count  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--bins", type=int, default=8)
+args = ap.parse_args()
+synth = bench.load_synth()
+plan = synth.cfg3_plan(400, 5_000_000)
+bins = list(range(args.bins))
+hb = bench.host_bins(synth, plan, bins)
+
+import torch  # noqa: E402
+
+import nanomotif_b200 as nmb  # noqa: E402
+from nanomotif_b200 import dataload, device as D  # noqa: E402
 
 dev = torch.device("cuda", 0)
-seq, pile, work = bench.build_cfg2(1)
-state = bench.Cfg2Device(seq, pile, work, dev)
-n = len(pile["position"])
-host = {"ascii": torch.from_numpy(seq.copy()).pin_memory(), "contig_id": torch.zeros(n, dtype=torch.int32).pin_memory(),
-        "position": torch.from_numpy(pile["position"]).pin_memory(), "strand": torch.from_numpy(pile["strand"]).pin_memory(),
-        "mod_type": torch.from_numpy(pile["mod_type"]).pin_memory(), "fraction_mod": torch.from_numpy(pile["fraction_mod"]).pin_memory()}
+torch.cuda.set_device(dev)
+table = bench.arrow_table(plan, hb)
+bins_arg = {f"bin_{b}": bench.contig_strings(plan, b, hb[b]) for b in bins}
+names = [n for cs in bins_arg.values() for n in cs]
+print(f"{table.num_rows} rows, {bench.table_bytes(table) / 1e9:.2f} GB of table, {sum(map(len, bins_arg.values()))} contigs")
 
 
-def t(fn, reps=10):
+def t(label, fn, reps=3, nbytes=None):
     fn()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(reps):
-        r = fn()
+        out = fn()
     torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / reps * 1e3, r
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    extra = f"  {nbytes / ms / 1e6:.1f} GB/s" if nbytes else ""
+    print(f"{label:48s} {ms:9.2f} ms{extra}")
+    return out
 
 
-ms, asm = t(lambda: DeviceAssembly(["c"], [len(seq)], host["ascii"], [0], dev))
-print(f"DeviceAssembly (H2D 4.6 MB + pack + sync)      {ms:7.3f} ms")
-ms, _ = t(lambda: [host[k].to(dev, non_blocking=True) for k in ("contig_id", "position", "strand", "mod_type", "fraction_mod")])
-print(f"H2D of pileup columns (152 MB pinned)           {ms:7.3f} ms")
-cols = [host[k].to(dev) for k in ("contig_id", "position", "strand", "fraction_mod", "mod_type")]
-ms, dp = t(lambda: DevicePileup.from_columns(asm, cols[0], cols[1], cols[2], cols[3], 0.3, 0.7, cols[4], n_modtypes=3))
-print(f"DevicePileup from device columns (memset+kernel) {ms:7.3f} ms")
-ms, dp = t(lambda: DevicePileup.from_columns(asm, host["contig_id"], host["position"], host["strand"], host["fraction_mod"], 0.3, 0.7, host["mod_type"], n_modtypes=3))
-print(f"DevicePileup from pinned host columns            {ms:7.3f} ms")
-ms, progs = t(lambda: MotifPrograms(state.packed, dev))
-print(f"MotifPrograms (H2D 192 KB + compile)             {ms:7.3f} ms")
-ms, out = t(lambda: scan_count(asm, dp, progs, state.jobs, len(state.packed)))
-print(f"scan_count (jobs upload + launch)                {ms:7.3f} ms")
-ms, _ = t(lambda: out.cpu())
-print(f"D2H counts                                       {ms:7.3f} ms")
-hostd = dict(host, length=len(seq), packed=state.packed, jobs=state.jobs)
-ms, _ = t(lambda: bench.e2e_step(hostd, dev))
-print(f"e2e_step total                                   {ms:7.3f} ms")
-
-# ---- streamed path (pipeline.score_host_blocks): host-side timeline of one step, ms since the call ----
-from nanomotif_b200.device import compact_rows  # noqa: E402
-from nanomotif_b200.pipeline import HostBlock, blocks_by_modtype, blocks_by_position, score_host_blocks  # noqa: E402
-
-rows = compact_rows(np.zeros(n, np.int32), pile["position"], pile["strand"], pile["fraction_mod"], pile["mod_type"], 1)
-pin = lambda bs: [HostBlock(*(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in b[:4]), b.modtypes, b.tiles) for b in bs]
-args4 = (rows["position"], rows["flags"], rows["percent_x100"], rows["contig_row_off"])
-styles = {"one block per mod type": pin(blocks_by_modtype(*args4, 3)),
-          "tile ranges 1/8 + 3 x 7/24": pin(blocks_by_position(*args4, [len(seq)], 3)),
-          "tile ranges 1/4 x 4": pin(blocks_by_position(*args4, [len(seq)], 3, (0.25, 0.25, 0.25, 0.25))),
-          "tile ranges 1/6 + 5/12 x 2": pin(blocks_by_position(*args4, [len(seq)], 3, (1 / 6, 5 / 12, 5 / 12)))}
-jobs0 = state.jobs.copy()
-jobs0["tile_count"] = 0
-out_host = torch.empty((len(state.packed), 4), dtype=torch.int64).pin_memory()
-for name, blocks in styles.items():
-    done = []
-    for rep in range(8):
-        tl = {}
-        torch.cuda.synchronize()
-        score_host_blocks(["c"], [len(seq)], host["ascii"], [0], blocks, state.packed, jobs0, len(state.packed), n_modtypes=3,
-                          device=dev, out_host=out_host, timeline=tl)
-        done.append(tl["done"])
-    print(f"streamed step, {name}: median {np.median(done[2:]):.3f} ms; last timeline", {k: round(v, 3) for k, v in tl.items()})
+pos = table.column("position").chunk(0).to_numpy()
+print("--- raw copies of the position column (%.0f MB) ---" % (pos.nbytes / 1e6))
+t("torch pageable .to()", lambda: torch.from_numpy(pos).to(dev), nbytes=pos.nbytes)
+pinned = torch.from_numpy(pos).pin_memory()
+t("torch pinned .to(non_blocking)", lambda: pinned.to(dev, non_blocking=True), nbytes=pos.nbytes)
+for n in (1, 2, 4, 8, 16):
+    os.environ["NMB_STAGE_THREADS"] = str(n)
+    D._STAGERS.clear()
+    t(f"stager, {n} threads", lambda: D._to_device(pos, dev), nbytes=pos.nbytes)
+del os.environ["NMB_STAGE_THREADS"]
+D._STAGERS.clear()
+print("--- stages ---")
+rows = t("rows_from_table (H2D + 3 name lookups)", lambda: dataload.rows_from_table(table, names, bench.MOD_TYPES, dev, {}, with_coverage=False),
+         nbytes=bench.table_bytes(table))
+asm = t("DeviceAssembly.from_sequences (join + H2D + pack)", lambda: D.DeviceAssembly.from_sequences({n: s for cs in bins_arg.values() for n, s in cs.items()}, dev))
+pile = D.DevicePileup(asm, 3, 0.3, 0.7)
+t("class planes (clear + add)", lambda: pile.clear().add_columns(rows.contig_id, rows.position, rows.strand, rows.fraction_mod, rows.mod_type))
+scorer = t("MultiBinScorer(table, bins) whole constructor", lambda: nmb.MultiBinScorer(table, bins_arg, bench.MOD_TYPES, 0.3, 0.7, dev), reps=2)
+wl = bench.job_worklists(synth, bins)
+keys = sorted(wl)
+motifs = {k: [[nmb.Motif(m, p) for m, p in kids] for kids in wl[k]] for k in keys}
+ctx = {k: scorer.context(f"bin_{k[0]}", bench.MOD_TYPES[k[1]]) for k in keys}
+t("64 score_batch rounds (counts to the host each)", lambda: [scorer.score_batch([(ctx[k], motifs[k][r]) for k in keys]) for r in range(64)], reps=2)
