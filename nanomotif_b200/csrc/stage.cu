@@ -66,10 +66,46 @@ int nmb_stager_destroy(nmb_stager *s) {
     return NMB_OK;
 }
 
+// Copy bytes [off, off + n) of the logical concatenation of the pieces into dst.
+static void gather_bytes(uint8_t *dst, const void *const *srcs, const int64_t *piece_off, int64_t n_src, int64_t off,
+                         int64_t n) {
+    int64_t lo = 0, hi = n_src;  // largest piece with piece_off[piece] <= off
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (piece_off[mid] <= off) lo = mid; else hi = mid;
+    }
+    for (int64_t p = lo; n > 0 && p < n_src; ++p) {
+        const int64_t within = off - piece_off[p];
+        int64_t take = piece_off[p + 1] - off;
+        if (take > n) take = n;
+        if (take > 0) memcpy(dst, (const uint8_t *)srcs[p] + within, (size_t)take);
+        dst += take; off += take; n -= take;
+    }
+}
+
+static int stager_run(nmb_stager *s, void *dst_dev, const void *src_host, const void *const *srcs,
+                      const int64_t *piece_off, int64_t n_src, int64_t bytes, void *stream);
+
 int nmb_stager_copy(nmb_stager *s, void *dst_dev, const void *src_host, int64_t bytes, void *stream) {
     NMB_REQUIRE(s && bytes >= 0, "nmb_stager_copy: bad arguments");
     if (bytes == 0) return NMB_OK;
     NMB_REQUIRE(dst_dev && src_host, "nmb_stager_copy: null buffer");
+    return stager_run(s, dst_dev, src_host, nullptr, nullptr, 0, bytes, stream);
+}
+
+int nmb_stager_gather(nmb_stager *s, void *dst_dev, const void *const *srcs_h, const int64_t *piece_off_h,
+                      int64_t n_src, void *stream) {
+    NMB_REQUIRE(s && n_src >= 0, "nmb_stager_gather: bad arguments");
+    if (n_src == 0) return NMB_OK;
+    NMB_REQUIRE(dst_dev && srcs_h && piece_off_h, "nmb_stager_gather: null argument");
+    const int64_t bytes = piece_off_h[n_src];
+    NMB_REQUIRE(piece_off_h[0] == 0 && bytes >= 0, "nmb_stager_gather: piece offsets must start at 0 and ascend");
+    if (bytes == 0) return NMB_OK;
+    return stager_run(s, dst_dev, nullptr, srcs_h, piece_off_h, n_src, bytes, stream);
+}
+
+static int stager_run(nmb_stager *s, void *dst_dev, const void *src_host, const void *const *srcs,
+                      const int64_t *piece_off, int64_t n_src, int64_t bytes, void *stream) {
     cudaStream_t caller = (cudaStream_t)stream;
     NMB_CUDA(cudaSetDevice(s->device));
     NMB_CUDA(cudaEventRecord(s->begin, caller));  // dst may still be in use by work enqueued before this call
@@ -87,7 +123,8 @@ int nmb_stager_copy(nmb_stager *s, void *dst_dev, const void *src_host, int64_t 
             const int64_t n = bytes - off < s->slot_bytes ? bytes - off : s->slot_bytes;
             if (k >= 2) e = cudaEventSynchronize(s->slot_done[slot]);  // the DMA that last read this slot
             if (e != cudaSuccess) break;
-            memcpy(s->slots[slot], (const uint8_t *)src_host + off, (size_t)n);
+            if (src_host) memcpy(s->slots[slot], (const uint8_t *)src_host + off, (size_t)n);
+            else gather_bytes(s->slots[slot], srcs, piece_off, n_src, off, n);
             e = cudaMemcpyAsync((uint8_t *)dst_dev + off, s->slots[slot], (size_t)n, cudaMemcpyHostToDevice, st);
             if (e == cudaSuccess) e = cudaEventRecord(s->slot_done[slot], st);
         }
@@ -105,7 +142,7 @@ int nmb_stager_copy(nmb_stager *s, void *dst_dev, const void *src_host, int64_t 
     for (auto &th : threads) th.join();
     for (int t = 0; t < T; ++t) {
         if (err[t] != cudaSuccess)
-            NMB_FAIL(NMB_ERR_CUDA, "nmb_stager_copy: %s", cudaGetErrorString(err[t]));
+            NMB_FAIL(NMB_ERR_CUDA, "nmb_stager: %s", cudaGetErrorString(err[t]));
         NMB_CUDA(cudaStreamWaitEvent(caller, s->done[t], 0));
     }
     return NMB_OK;

@@ -67,6 +67,24 @@ def _stager(device: torch.device):
     return _STAGERS[idx]
 
 
+_AsUTF8AndSize = C.pythonapi.PyUnicode_AsUTF8AndSize
+_AsUTF8AndSize.restype = C.c_void_p
+_AsUTF8AndSize.argtypes = [C.py_object, C.POINTER(C.c_ssize_t)]
+
+
+def _ascii_pointers(strings) -> np.ndarray | None:
+    """Addresses of the character data of ASCII str objects (valid while the strings live), or None when one of
+    them is not pure ASCII."""
+    out = np.empty(len(strings), dtype=np.uint64)
+    size = C.c_ssize_t()
+    for i, s in enumerate(strings):
+        p = _AsUTF8AndSize(s, C.byref(size))
+        if not p or size.value != len(s):
+            return None
+        out[i] = p
+    return out
+
+
 def _to_device(arr: np.ndarray, device: torch.device) -> torch.Tensor:
     """Host array -> device tensor on the current stream.  Large pageable arrays (the Arrow buffers of a pileup table)
     go through the multi-threaded pinned stager (csrc/stage.cu); the source is never modified."""
@@ -145,6 +163,21 @@ class DeviceAssembly:
         off = np.zeros(len(seqs), dtype=np.int64)
         if len(seqs):
             off[1:] = np.cumsum(lengths)[:-1]
+        total = int(lengths.sum())
+        if total >= STAGE_MIN_BYTES:
+            # large assemblies: the contig strings' own buffers are gathered straight into the pinned staging slots
+            # (no "".join, no .encode copy): CPython keeps ASCII text as one byte per character
+            dev = _require_cuda(device)
+            st = _stager(dev)
+            ptrs = _ascii_pointers(seqs) if st else None
+            if ptrs is not None:
+                piece_off = np.zeros(len(seqs) + 1, dtype=np.int64)
+                np.cumsum(lengths, out=piece_off[1:])
+                with torch.cuda.device(dev):
+                    ascii_d = torch.empty(total, dtype=torch.uint8, device=dev)
+                    check(lib.nmb_stager_gather(st, ptr(ascii_d), ptrs.ctypes.data, piece_off.ctypes.data, len(seqs),
+                                                _stream()), "nmb_stager_gather")
+                return cls(names, lengths, ascii_d, off, dev)
         buf = np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8) if len(seqs) else np.zeros(0, np.uint8)
         if buf.size == 0:
             buf = np.zeros(1, dtype=np.uint8)

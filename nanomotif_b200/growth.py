@@ -182,6 +182,19 @@ class WindowPool:
             if a.alive is not None:
                 self.alive[b:e] = a.alive
 
+    @classmethod
+    def from_ranges(cls, windows: torch.Tensor, width: int, begin, end) -> "WindowPool":
+        """Pool over windows that are already one device array: search `slot` owns rows [begin[slot], end[slot])."""
+        self = cls.__new__(cls)
+        self.width = int(width)
+        self.windows = windows.contiguous()
+        self.n_total = int(windows.shape[0])
+        self.alive = torch.ones(self.n_total, dtype=torch.uint8, device=windows.device)
+        self.begin = np.asarray(begin, dtype=np.int64).copy()
+        self.end = np.asarray(end, dtype=np.int64).copy()
+        self.n_alive = (self.end - self.begin).astype(np.int64)
+        return self
+
     def _launch(self, slots, motifs, keep_rows):
         d = self.windows.device
         masks = window_masks(motifs, self.width)
@@ -276,6 +289,104 @@ def background_pssm(assembly: DeviceAssembly, contigs, mod_base: str, padding: i
     arr = DeviceDNAarray.from_positions(assembly, np.concatenate(ci), np.concatenate(pos),
                                         np.zeros(sum(len(p) for p in pos), dtype=np.uint8), padding)
     return arr.exact_pssm()
+
+
+def prepare_searches(scorer, mod_type, padding: int, high: float, bin_names=None, sampling_frequency: float = 0.01,
+                     seeds=None):
+    """Everything find_best_candidates builds before its search loop (find_motifs_bin.py:625-686), for EVERY bin of a
+    MultiBinScorer at once and on the device: the methylation windows of all bins as one WindowPool and each bin's
+    background PSSM.  Returns (pool, bin_pssms, totals): search slot i belongs to bin_names[i].
+
+    Windows: the confidently methylated rows (fraction_mod >= high) of `mod_type` that satisfy the strict bound
+    padding < position < len - padding (seq.py:186), in the reference's order -- per contig '+' sites then '-' sites,
+    each in row order -- selected and ordered by ONE stable device sort over the rows the scorer already holds, then
+    ONE nmb_extract_windows launch.
+    Background (seq.py:202-225 + 391-422): per contig max(ceil(0.01 L), 50) windows centred on the canonical base.  The
+    reference draws them with random.sample(valid_starts, n); its picks depend only on len(valid_starts) and n, so the
+    host draws random.sample(range(N), n) from the SAME global `random` stream (bins and contigs in order; `seeds[i]`
+    re-seeds before bin i) while the valid starts themselves are enumerated on the device: the canonical base's match
+    plane (K3) compacted once for the whole assembly, per-contig ranges by binary search."""
+    from .api import _match_plane, _compact
+    from .motif import Motif as _Motif
+
+    asm = scorer.assembly
+    d = asm.device
+    names = list(scorer._ranges) if bin_names is None else list(bin_names)
+    mti = scorer.mod_types.index(mod_type)
+    width = 2 * padding + 1
+    if not scorer.rows:
+        raise ValueError("the scorer keeps no pileup rows (built with keep_rows=False or from_device)")
+    from .search import CANONICAL
+
+    base = CANONICAL[str(mod_type)]
+    with torch.cuda.device(d):
+        cat = lambda k: torch.cat([getattr(r, k) for r in scorer.rows]) if len(scorer.rows) > 1 else getattr(scorer.rows[0], k)
+        cid, pos, strand, frac, mt = cat("contig_id"), cat("position"), cat("strand"), cat("fraction_mod"), cat("mod_type")
+        safe = cid.clamp(min=0).long()
+        keep = (mt == mti) & (frac >= high) & (strand <= 1) & (cid >= 0)
+        keep &= (pos > padding) & (pos < asm.contig_len[safe] - padding)
+        idx = torch.nonzero(keep).view(-1)
+        key = cid[idx].long() * 2 + strand[idx].long()
+        key, perm = torch.sort(key, stable=True)  # row order survives inside (contig, strand)
+        idx = idx[perm]
+        gpos = (asm.contig_start[cid[idx].long()] + pos[idx]).contiguous()
+        st = strand[idx].contiguous()
+        n = int(idx.numel())
+        win = torch.empty((n, 3), dtype=torch.int64, device=d)
+        view = asm.view()
+        if n:
+            check(lib.nmb_extract_windows(C.byref(view), ptr(gpos), ptr(st), n, int(padding), ptr(win), _stream()),
+                  "nmb_extract_windows")
+        bounds = np.array([[2 * scorer._ranges[b][0], 2 * scorer._ranges[b][1]] for b in names], dtype=np.int64)
+        edges = torch.searchsorted(key, torch.from_numpy(bounds.reshape(-1)).to(d)).cpu().numpy().reshape(-1, 2)
+        pool = WindowPool.from_ranges(win, width, edges[:, 0], edges[:, 1])
+
+        # ---- background: valid window centres = positions of the canonical base, enumerated on the device ----
+        plane, _, _ = _match_plane(asm, _Motif(base, 0), align=0)
+        P = _compact(plane, 0, asm.n_tiles * _lib.TILE_BP)  # every position holding `base`, ascending (global)
+        contigs = [c for b in names for c in range(*scorer._ranges[b])]
+        L = asm.lengths[contigs]
+        max_start = L - width + 1
+        lo_pos = asm.starts[contigs] + padding
+        q = torch.from_numpy(np.stack([lo_pos, lo_pos + np.maximum(max_start, 0)], axis=1).reshape(-1)).to(d)
+        lohi = torch.searchsorted(P, q).cpu().numpy().reshape(-1, 2)
+        n_valid = lohi[:, 1] - lohi[:, 0]
+        picks, at, bg_begin, bg_end = [], 0, [], []
+        ci = 0
+        for i, b in enumerate(names):
+            if seeds is not None:
+                random.seed(seeds[i])
+            bg_begin.append(at)
+            for _ in range(*scorer._ranges[b]):
+                k = int(max(math.ceil(int(L[ci]) * sampling_frequency), 50))  # find_motifs_bin.py:633
+                if k > max_start[ci]:
+                    raise ValueError("Too many samples requested for unique subsequences")  # seq.py:210
+                if n_valid[ci] < k:
+                    raise ValueError(f"Not enough subsequences with 'C' in the middle (found {int(n_valid[ci])}, need {k})")
+                picks.append(np.asarray(random.sample(range(int(n_valid[ci])), k), dtype=np.int64) + lohi[ci, 0])
+                at += k
+                ci += 1
+            bg_end.append(at)
+        centre = P[_to_device(np.concatenate(picks), d)].contiguous()  # start + padding = the base's own position
+        nb = int(centre.numel())
+        bgw = torch.empty((nb, 3), dtype=torch.int64, device=d)
+        zeros = torch.zeros(nb, dtype=torch.uint8, device=d)
+        check(lib.nmb_extract_windows(C.byref(view), ptr(centre), ptr(zeros), nb, int(padding), ptr(bgw), _stream()),
+              "nmb_extract_windows")
+        wild = np.zeros(len(names), dtype=_lib.MOTIF_DTYPE)
+        wild["allowed"][:, :width] = 0xF
+        wild["len"][:] = width
+        masks_d = _to_device(wild.view(np.uint8).reshape(-1), d)
+        rb, re = np.asarray(bg_begin, dtype=np.int64), np.asarray(bg_end, dtype=np.int64)
+        rb_d, re_d = _to_device(rb, d), _to_device(re, d)
+        hist = torch.empty((len(names), width, 4), dtype=torch.int32, device=d)
+        n_active = torch.empty(len(names), dtype=torch.int64, device=d)
+        check(lib.nmb_window_hist_ranges(ptr(bgw), None, nb, width, ptr(masks_d), len(names), ptr(rb_d), ptr(re_d),
+                                         int((re - rb).max()), 0, ptr(hist), ptr(n_active), None, _stream()),
+              "nmb_window_hist_ranges")
+        hist = hist.cpu().numpy().astype(np.int64)
+    pssms = [h.transpose() / float(e - b) for h, b, e in zip(hist, bg_begin, bg_end)]  # exact-letter frequencies
+    return pool, pssms, [int(x) for x in (edges[:, 1] - edges[:, 0])]
 
 
 def column_kl(pk: np.ndarray, qk: np.ndarray) -> np.ndarray:

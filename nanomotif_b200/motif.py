@@ -205,33 +205,81 @@ def motif_masks(motif) -> tuple[np.ndarray, int]:
     return np.fromiter((token_mask(t) for t in toks), dtype=np.uint8, count=len(toks)), int(m.mod_position)
 
 
+_PLAIN_LUT = np.full(256, 0xFF, dtype=np.uint8)  # byte -> allowed-set; 0xFF = not a plain motif character
+for _ch, _m in _BIT.items():
+    _PLAIN_LUT[ord(_ch)] = _m
+_PLAIN_LUT[ord(".")] = _WILD
+_PLAIN_LUT[0] = 0  # padding
+
+
+def _pack_one(out, i, m, strip, mod_pos_override):
+    if strip:
+        m = m.new_stripped_motif()
+    masks, mp = motif_masks(m)
+    n = len(masks)
+    if n == 0:
+        raise ValueError("Motif is empty")
+    if n > _lib.MAX_MOTIF_LEN:
+        raise ValueError(f"motif {m!r}: stripped length {n} exceeds {_lib.MAX_MOTIF_LEN}")
+    if int(masks.min()) == _WILD:
+        raise ValueError(f"motif {m!r} has no constrained position")
+    if mod_pos_override is not None:
+        mp = mod_pos_override
+    if not (0 <= mp < n):
+        raise ValueError(f"motif {m!r}: mod_position {mp} outside the stripped motif")
+    out["allowed"][i, :n] = masks
+    out["len"][i] = n
+    out["mod_pos"][i] = mp
+
+
 def pack_motifs(motifs, strip: bool = True, mod_pos_override: int | None = None) -> np.ndarray:
     """Compile motifs to an array of ``nmb_motif`` records (include/nmb200.h).
 
     strip=True applies new_stripped_motif first, as motif_model_contig does
     (find_motifs_bin.py:1307).  Raises ValueError for motifs the device path cannot represent.
+    Motifs without bracket classes (everything the search generates) are packed together: one bytes join and one
+    table lookup for the whole batch (~0.5 us per motif instead of ~6 us -- a frontier round of a lock-step search
+    over hundreds of bins packs thousands of motifs).
     """
-    out = np.zeros(len(motifs), dtype=_lib.MOTIF_DTYPE)
-    allowed, lens, mod_pos = out["allowed"], out["len"], out["mod_pos"]  # field views, taken once
+    n_motifs = len(motifs)
+    out = np.zeros(n_motifs, dtype=_lib.MOTIF_DTYPE)
+    W = _lib.MAX_MOTIF_LEN
+    plain_idx, parts, mods, slow = [], [], [], []
     for i, mo in enumerate(motifs):
-        m = as_motif(mo)
+        st = str.__str__(mo)
+        if "[" in st:
+            slow.append(i)
+            continue
+        mp = mo.mod_position if hasattr(mo, "mod_position") else None
+        if mp is None:
+            raise TypeError("Motif is not a Motif type")
         if strip:
-            m = m.new_stripped_motif()
-        masks, mp = motif_masks(m)
-        n = len(masks)
-        if n == 0:
-            raise ValueError("Motif is empty")
-        if n > _lib.MAX_MOTIF_LEN:
-            raise ValueError(f"motif {m!r}: stripped length {n} exceeds {_lib.MAX_MOTIF_LEN}")
-        if int(masks.min()) == _WILD:
-            raise ValueError(f"motif {m!r} has no constrained position")
-        if mod_pos_override is not None:
-            mp = mod_pos_override
-        if not (0 <= mp < n):
-            raise ValueError(f"motif {m!r}: mod_position {mp} outside the stripped motif")
-        allowed[i, :n] = masks
-        lens[i] = n
-        mod_pos[i] = mp
+            core = st.lstrip(".")
+            lead = len(st) - len(core)
+            if core:  # an all-wildcard motif is returned unchanged by new_stripped_motif (and rejected below)
+                st, mp = core.rstrip("."), mp - lead
+        if len(st) > W or not st.isascii():
+            slow.append(i)  # raises the precise error
+            continue
+        plain_idx.append(i)
+        parts.append(st.ljust(W, "\0"))
+        mods.append(mp)
+    if plain_idx:
+        idx = np.asarray(plain_idx, dtype=np.int64)
+        codes = np.frombuffer("".join(parts).encode("latin-1"), dtype=np.uint8).reshape(len(parts), W)
+        masks = _PLAIN_LUT[codes]
+        lens = (codes != 0).sum(axis=1)
+        mp = np.asarray(mods, dtype=np.int64) if mod_pos_override is None else np.full(len(parts), mod_pos_override, dtype=np.int64)
+        ok = (masks != 0xFF).all(axis=1) & (lens > 0) & (mp >= 0) & (mp < lens)
+        ok &= ((masks != _WILD) & (masks != 0)).any(axis=1)
+        if not ok.all():
+            slow.extend(idx[~ok].tolist())  # the slow path raises the precise error
+            idx, masks, lens, mp = idx[ok], masks[ok], lens[ok], mp[ok]
+        out["allowed"][idx] = masks
+        out["len"][idx] = lens
+        out["mod_pos"][idx] = mp
+    for i in slow:
+        _pack_one(out, i, as_motif(motifs[i]), strip, mod_pos_override)
     return out
 
 

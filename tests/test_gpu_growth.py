@@ -114,3 +114,52 @@ def test_empty_filter_returns_none(env):
     impossible = np.zeros((41, 4), dtype=int)
     with pytest.warns(UserWarning):
         assert arr.filter_sequence_matches(impossible) is None
+
+
+def test_prepare_searches_equals_the_per_bin_setup(env):
+    """growth.prepare_searches (all bins at once, rows selected and ordered on the device, valid background starts
+    enumerated on the device, the reference's random.sample stream kept on the host) gives the same windows and the
+    same background PSSM as the per-bin host-driven setup -- and as the oracle's restatement of find_motifs_bin.py:625-686."""
+    import torch
+
+    nmb, g = env["nmb"], env["growth"]
+    from nanomotif_b200 import synth
+
+    rng = np.random.default_rng(17)
+    bins, cols = {}, {k: [] for k in ("contig", "position", "strand", "mod_type", "fraction_mod")}
+    for b, lens in (("b0", (60000, 9000)), ("b1", (30000,)), ("b2", (12000, 45000, 8000))):
+        bins[b] = {}
+        for i, L in enumerate(lens):
+            name = f"{b}_{i}"
+            seq = synth.random_sequence(rng, L, 0.5, 3e-5)
+            bins[b][name] = seq.tobytes().decode()
+            p = synth.synth_pileup(seq, rng, depth=20, mod_types=("a", "m"), planted=(("GATC", 1, "a"), ("CC[AT]GG", 1, "m")))
+            n = len(p["position"])
+            cols["contig"].append(np.full(n, name, dtype=object))
+            cols["position"].append(p["position"])
+            cols["strand"].append(np.where(p["strand"] == 0, "+", "-").astype(object))
+            cols["mod_type"].append(np.array(["a", "m"], dtype=object)[p["mod_type"]])
+            cols["fraction_mod"].append(p["fraction_mod"])
+    pile = {k: np.concatenate(v) for k, v in cols.items()}
+    multi = nmb.MultiBinScorer(pile, bins, ["a", "m"], 0.3, 0.7)
+    asm = multi.assembly
+    for mod_type, base in (("a", "A"), ("m", "C")):
+        for pad in (20, 7):
+            pool, pssms, totals = g.prepare_searches(multi, mod_type, pad, 0.7, seeds=[11, 12, 13])
+            sel_mt = pile["mod_type"] == mod_type
+            for slot, (b, contigs) in enumerate(bins.items()):
+                sel = sel_mt & np.isin(pile["contig"], list(contigs))
+                cid = np.array([asm.index[c] for c in pile["contig"][sel]], dtype=np.int32)
+                want = g.methylation_windows(asm, cid, pile["position"][sel], (pile["strand"][sel] == "-").astype(np.uint8),
+                                             pile["fraction_mod"][sel], 0.7, pad)
+                got = pool.windows[pool.begin[slot]:pool.end[slot]]
+                assert totals[slot] == want.n_total == int(got.shape[0])
+                assert torch.equal(got, want.windows)
+                random.seed(11 + slot)
+                np.testing.assert_array_equal(pssms[slot], g.background_pssm(asm, contigs, base, pad))
+                # and the oracle: windows around the same sites, background from the same random stream
+                rng_o = random.Random(11 + slot)
+                bg = []
+                for seq in contigs.values():
+                    bg += O.sample_background(seq, 2 * pad + 1, O.n_background_samples(len(seq)), base, rng_o)
+                np.testing.assert_array_equal(pssms[slot], O.background_pssm(bg))

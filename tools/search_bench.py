@@ -61,6 +61,7 @@ def main():
     ap.add_argument("--bin-bp", type=int, default=1_000_000)
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--cpu-bins", type=int, default=1, help="bins also searched with the CPU oracle backend (slow)")
+    ap.add_argument("--check-setup", action="store_true", help="compare the batched setup with the per-bin host-driven one")
     args = ap.parse_args()
     pad, low, high, min_kl, thr = 20, 0.3, 0.7, 0.05, 1.5
     rng = np.random.default_rng(5)
@@ -72,19 +73,32 @@ def main():
         bins[f"bin{b}"], truth[f"bin{b}"] = contigs, planted
         piles.append(pile)
     pile = {k: np.concatenate([p[k] for p in piles]) for k in piles[0]}
+    import pyarrow as pa
+
+    # the input a polars frame would hold: Arrow columns (built here, outside the timed setup: it is the INPUT)
+    table = pa.table({"contig": pa.array(pile["contig"], type=pa.large_string()), "position": pa.array(pile["position"]),
+                      "strand": pa.array(pile["strand"], type=pa.large_string()),
+                      "mod_type": pa.array(pile["mod_type"], type=pa.large_string()),
+                      "fraction_mod": pa.array(pile["fraction_mod"])})
     t_gen = time.perf_counter() - t0
+    nmb.MultiBinScorer(table.slice(0, 1000), {"w": {"w": "ACGT" * 100}}, ["a"], low, high)  # CUDA context, stager, caches
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    multi = nmb.MultiBinScorer(pile, bins, ["a"], low, high)
-    asm = multi.assembly
-    setups = []
-    for b in range(args.bins):
-        random.seed(1 + b)
-        w = windows_for(asm, bins[f"bin{b}"], piles[b], pad, high)
-        bg = growth.background_pssm(asm, bins[f"bin{b}"], "A", pad)
-        setups.append((w, bg))
-    pool = growth.WindowPool([w for w, _ in setups])
+    multi = nmb.MultiBinScorer(table, bins, ["a"], low, high)
+    torch.cuda.synchronize()
+    t_ingest = time.perf_counter() - t0
+    # windows of every bin + every bin's background PSSM, batched on the device (growth.prepare_searches)
+    pool, pssms, totals = growth.prepare_searches(multi, "a", pad, high, seeds=[1 + b for b in range(args.bins)])
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
+    if args.check_setup:  # the old per-bin host-driven setup must give the same windows and backgrounds
+        asm = multi.assembly
+        for b in range(args.bins):
+            random.seed(1 + b)
+            w = windows_for(asm, bins[f"bin{b}"], piles[b], pad, high)
+            bg = growth.background_pssm(asm, bins[f"bin{b}"], "A", pad)
+            assert torch.equal(pool.windows[pool.begin[b]:pool.end[b]], w.windows) and np.array_equal(bg, pssms[b])
+    setups = list(zip(totals, pssms))
     counts = {"score": 0, "expand": 0, "remove": 0, "motifs": 0}
 
     def counting(kind, fn):
@@ -96,8 +110,8 @@ def main():
         return hook
 
     searches = []
-    for b, (w, bg) in enumerate(setups):
-        co = search.find_candidates("a", pad, bg, w.shape[0], min_kl=min_kl, score_threshold=thr)
+    for b, (total, bg) in enumerate(setups):
+        co = search.find_candidates("a", pad, bg, total, min_kl=min_kl, score_threshold=thr)
         searches.append((co, search.PoolBackend(multi.context(f"bin{b}", "a"), pool, b)))
     t0 = time.perf_counter()
     results = search.run_lockstep(searches, counting("score", search.gpu_batch_score), counting("expand", search.gpu_batch_expand),
@@ -116,7 +130,7 @@ def main():
         found += all(p[0] in best or all(e in best for e in expansions(p[0])) for p in truth[f"bin{b}"])
     total_bp = sum(len(s) for cs in bins.values() for s in cs.values())
     print(f"{args.bins} bins, {total_bp / 1e6:.1f} Mbp, {len(pile['position']) / 1e6:.1f} M pileup rows (host generation {t_gen:.1f} s)")
-    print(f"device setup (pack, class planes, windows, background)  {t_setup:7.2f} s")
+    print(f"device setup from the Arrow table (ingest {t_ingest:.3f} s + windows / backgrounds of all bins) {t_setup:7.3f} s")
     print(f"lock-step search of {args.bins} (bin, mod type) pairs          {t_search:7.2f} s   rounds: score {counts['score']} "
           f"({counts['motifs']} motifs), expand {counts['expand']}, remove {counts['remove']}")
     print(f"bins whose planted motifs were all recovered: {found} / {args.bins}")
