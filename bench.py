@@ -58,6 +58,18 @@ ROUNDS, WIDTH = 64, 4
 LOW, HIGH = 0.3, 0.7
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def load_synth():
     """nanomotif_b200/synth.py loaded BY PATH: the generators are plain numpy / torch, and the reference arm must
     not import the package (which dlopens libnmb200.so)."""
@@ -297,7 +309,7 @@ def run_reference(args):
                              "sample": f"{per_step} (bin, motif, mod type) tasks per step from bins {bins} of the cfg3 "
                                        "work list, each one motif over a ~5 Mbp bin, both strands"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -483,7 +495,7 @@ def sweep_leg(res: Resident, world, reps: int = 2):
         torch.cuda.synchronize()
         for k, a, b in (("hist", 0, 1), ("bipartite", 1, 2), ("allreduce", 2, 3)):
             ms[k].append(ev[a].elapsed_time(ev[b]))
-        n_inc = int(index.hist.long().sum().item())
+        n_inc = int(index.raw.long().sum().item())
         del index
     t = torch.tensor([min(ms["hist"]), min(ms["bipartite"]), min(ms["allreduce"])], dtype=torch.float64, device=res.device)
     if world > 1:
@@ -552,6 +564,11 @@ def main():
     ap.add_argument("--ref-tasks-per-core", type=int, default=1, help="--impl reference: tasks per core and step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (e.g. "NCCL version ...") goes to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference(args)
@@ -738,7 +755,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "scan_count_kernel<1,1>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-                         "traffic": recorded_traffic("cfg3_frontier4"), "launch_ms": scan_ms,
+                         "traffic": recorded_traffic("cfg3_frontier4") if world == 1 else None, "launch_ms": scan_ms,
                          "alg_bytes_per_launch": alg_bytes,
                          "motifs_per_job_and_launch": round(
                              float(np.mean([L["n_motifs"] / max(1, L["n_jobs"]) for L in head])), 2),
@@ -779,7 +796,7 @@ def main():
     if rank == 0:
         if cpu_on and e2e_counts:
             line["cpu_baseline"] = cpu_leg(hb, worklists, plan, args.cpu_seconds, e2e_counts)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -432,6 +432,12 @@ NMB_API int nmb_segment_median(const double *fractions, const int64_t *offsets, 
 NMB_API int64_t nmb_sweep_hist_size(void);
 NMB_API int nmb_sweep_hist(const nmb_assembly *assembly_h, const uint32_t *class_records_of_modtype, int32_t tile_begin,
                            int32_t tile_count, int32_t contig_begin, int32_t contig_end, uint32_t *hist, void *stream);
+/* nmb_sweep_hist leaves the histogram RAW: only the k = 8 block is counted row by row (8 atomic adds per pileup row
+ * instead of 30); the blocks of k < 8 hold just the windows at contig ends that have no one-letter extension inside
+ * the contig.  nmb_sweep_finalize completes them in place, hist[k] += marginal of hist[k+1] over the trailing letter,
+ * k = 7 .. 4.  Call it ONCE, after every nmb_sweep_hist call (and after the histograms of several GPUs have been
+ * summed: raw histograms add, finalized ones must not be finalized again). */
+NMB_API int nmb_sweep_finalize(uint32_t *hist, void *stream);
 
 /* The bipartite half of the sweep: shapes X{a} N{g} Y{b}, a, b in {3, 4}, g in 4..8, concrete letters only.
  * hist: nmb_sweep_bipartite_size() uint32 counters (zeroed by the caller, counters add); shapes are stored g major,
@@ -442,6 +448,12 @@ NMB_API int64_t nmb_sweep_bipartite_size(void);
 NMB_API int nmb_sweep_bipartite(const nmb_assembly *assembly_h, const uint32_t *class_records_of_modtype,
                                 int32_t tile_begin, int32_t tile_count, int32_t contig_begin, int32_t contig_end,
                                 uint32_t *hist, void *stream);
+
+/* Like nmb_sweep_hist, nmb_sweep_bipartite leaves a RAW histogram: only the shapes (4, g, 4) are counted row by row
+ * (40 atomic adds per pileup row instead of 140); (4,g,3), (3,g,4) and (3,g,3) hold just the windows whose extending
+ * letter is not a concrete letter of the same contig.  nmb_sweep_bipartite_finalize completes them in place by summing
+ * the longer shapes over the dropped letter.  Call it ONCE after all passes / after summing the GPUs' raw histograms. */
+NMB_API int nmb_sweep_bipartite_finalize(uint32_t *hist, void *stream);
 
 /* dst[hi][lo] = src[hi][digit][lo] with lo < axis_stride: fixes one base-5 axis (the modified position's own
  * letter) and drops it.  n_out = elements of dst. */

@@ -98,8 +98,10 @@ SIGNATURES = {
     "nmb_bgzf_inflate": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _P, _P]),
     "nmb_sweep_hist_size": (C.c_int64, []),
     "nmb_sweep_hist": (C.c_int, [C.POINTER(NmbAssembly), _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "nmb_sweep_finalize": (C.c_int, [_P, _P]),
     "nmb_sweep_bipartite_size": (C.c_int64, []),
     "nmb_sweep_bipartite": (C.c_int, [C.POINTER(NmbAssembly), _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "nmb_sweep_bipartite_finalize": (C.c_int, [_P, _P]),
     "nmb_sweep_slice": (C.c_int, [_P, _P, _I64, _I64, _I32, _P]),
     "nmb_sweep_expand": (C.c_int, [_P, _P, _I64, _I64, _P]),
     "nmb_sweep_filter": (C.c_int, [_P, _P, _I64, _F64, _I64, _P, _I64, _P, _P]),

@@ -5,12 +5,21 @@
 // counts that motif_model_bin returns (find_motifs_bin.py:1265-1331: pileup rows classified methylated /
 // unmethylated whose position is the modified base of an occurrence, both strands) are additive over the
 // CONCRETE sequence contexts of the rows, so one pass over the assembly suffices:
-//   sweep_hist_kernel    for every window of k = 4..8 letters inside a contig and every classified row under
-//                        it: hist[k][o][class][window] += 1, o = offset of the row in the window ('+' rows use
+//   sweep_hist_kernel    for every window of 8 letters inside a contig and every classified row under it:
+//                        hist[8][o][class][window] += 1, o = offset of the row in the window ('+' rows use
 //                        the window, '-' rows its reverse complement with the offset mirrored -- the reference
 //                        scans the reverse-complement motif on the forward text, find_motifs_bin.py:1317).
 //                        Letters have FIVE states: A, T, G, C and "other" (non-ACGT), because the regex
 //                        wildcard matches any character while sets do not.
+//                        Only k = 8 is counted row by row (8 REDs per row instead of 4+5+6+7+8 = 30): a motif of
+//                        k < 8 letters is the PREFIX of the (k+1)-letter motifs that extend it by one letter, so
+//                            hist[k][o][c][w] = sum_j hist[k+1][o][c][5 w + j]  +  the k-windows that have no
+//                                                                                  (k+1)-extension inside the contig
+//                        ('+' rows: the one window that ends at the contig end; '-' rows, whose motif is the
+//                        reverse complement and therefore extends to the LEFT in contig coordinates: the one window
+//                        that starts at the contig start).  The kernel adds those edge windows directly (a handful
+//                        per contig) and sweep_marginalise_kernel folds the levels 8 -> 7 -> ... -> 4 afterwards
+//                        (nmb_sweep_finalize).
 //   sweep_expand_kernel  subset-sum (zeta) transform, one axis at a time: 5 letter states -> 15 IUPAC letters
 //                        (N includes "other").  After all axes, table[L_0 .. L_{k-1}] is the count of motif L.
 //   sweep_filter_kernel  posterior-mean / support filter over a finished table -> candidate list.
@@ -78,14 +87,14 @@ __device__ __forceinline__ unsigned rev_bits(unsigned v, int n) { return __brev(
 // under its reverse complement, whose shape is (B, G, A).
 template <int A, int G, int B>
 __device__ __forceinline__ void bip_add(uint32_t *hist, uint64_t X, uint64_t Y, uint64_t N, uint64_t plus, uint64_t minus,
-                                        int s, int cls, int rem) {
+                                        int s, int cls, int rem, bool do_plus = true, bool do_minus = true) {
     constexpr int span = A + G + B;
     if (rem < span) return;
     constexpr unsigned ma = (1u << A) - 1u, mb = (1u << B) - 1u;
     const unsigned nl = (unsigned)(N >> s) & ma, nr = (unsigned)(N >> (s + A + G)) & mb;
     if (nl | nr) return;  // a concrete letter cannot match a non-ACGT letter
-    const unsigned pl = (unsigned)(plus >> s) & ma, pr = (unsigned)(plus >> (s + A + G)) & mb;
-    const unsigned ql = (unsigned)(minus >> s) & ma, qr = (unsigned)(minus >> (s + A + G)) & mb;
+    const unsigned pl = do_plus ? (unsigned)(plus >> s) & ma : 0u, pr = do_plus ? (unsigned)(plus >> (s + A + G)) & mb : 0u;
+    const unsigned ql = do_minus ? (unsigned)(minus >> s) & ma : 0u, qr = do_minus ? (unsigned)(minus >> (s + A + G)) & mb : 0u;
     if (!(pl | pr | ql | qr)) return;
     const unsigned xl = (unsigned)(X >> s) & ma, yl = (unsigned)(Y >> s) & ma;
     const unsigned xr = (unsigned)(X >> (s + A + G)) & mb, yr = (unsigned)(Y >> (s + A + G)) & mb;
@@ -113,13 +122,26 @@ __device__ __forceinline__ void bip_add(uint32_t *hist, uint64_t X, uint64_t Y, 
     }
 }
 
+// Only the shape (4, G, 4) is counted row by row.  The three shorter shapes are prefixes / suffixes of it at the MOTIF
+// level -- (4,G,3) drops the motif's last letter, (3,G,4) its first, (3,G,3) then the last letter of (3,G,4) -- so
+// nmb_sweep_bipartite_finalize gets them by summing over the dropped letter (4 concrete letters).  A window is counted
+// directly only when the letter that would extend it is not a concrete letter of the same contig (non-ACGT, or past
+// the contig's edge: inter-contig padding is flagged in the non-ACGT plane), because then no longer window covers it.
+// '+' rows: motif = window, so "last letter" extends to the right and "first" to the left; '-' rows: motif = reverse
+// complement, so the directions swap.  left_n = the letter left of the window start is not concrete.
 template <int G>
 __device__ __forceinline__ void bip_add_gap(uint32_t *hist, uint64_t X, uint64_t Y, uint64_t N, uint64_t plus,
-                                            uint64_t minus, int s, int cls, int rem) {
-    bip_add<3, G, 3>(hist, X, Y, N, plus, minus, s, cls, rem);
-    bip_add<3, G, 4>(hist, X, Y, N, plus, minus, s, cls, rem);
-    bip_add<4, G, 3>(hist, X, Y, N, plus, minus, s, cls, rem);
+                                            uint64_t minus, int s, int cls, int rem, bool left_n) {
     bip_add<4, G, 4>(hist, X, Y, N, plus, minus, s, cls, rem);
+    const bool right4_n = (N >> (s + 7 + G)) & 1;  // the letter after a (4,G,3) window
+    const bool right3_n = (N >> (s + 6 + G)) & 1;  // the letter after a (3,G,3) / before-last of (3,G,4)
+    // fwd (4,G,3): '+' motif (4,G,3) and '-' motif (3,G,4) both extend to the right
+    if (right4_n) bip_add<4, G, 3>(hist, X, Y, N, plus, minus, s, cls, rem);
+    // fwd (3,G,4): '+' motif (3,G,4) and '-' motif (4,G,3) both extend to the left
+    if (left_n) bip_add<3, G, 4>(hist, X, Y, N, plus, minus, s, cls, rem);
+    // fwd (3,G,3): '+' motif comes from (3,G,4) at the same start (right extension), '-' motif from the reverse
+    // complement of fwd (4,G,3) one letter to the left
+    if (right3_n | left_n) bip_add<3, G, 3>(hist, X, Y, N, plus, minus, s, cls, rem, right3_n, left_n);
 }
 
 // One CTA per tile, one lane per 512-bp chunk, positions in order: the 8-letter window code slides by one letter
@@ -140,7 +162,8 @@ __global__ void __launch_bounds__(kTileChunks) sweep_hist_kernel(const SweepPara
     if (contig < p.contig_begin || contig >= p.contig_end) return;
     const uint32_t *scls = p.cls + (size_t)tile * kClsRecWords;
     const int64_t chunk_pos = ((int64_t)tile * kTileChunks + tid) * NMB_CHUNK_BP;
-    const int64_t contig_end_pos = __ldg(p.contig_start + contig) + __ldg(p.contig_len + contig);
+    const int64_t contig_start_pos = __ldg(p.contig_start + contig);
+    const int64_t contig_end_pos = contig_start_pos + __ldg(p.contig_len + contig);
     const int n_here = (int)min((int64_t)NMB_CHUNK_BP, contig_end_pos - chunk_pos);  // window starts in this chunk
     // word 16 of every plane: the record halo / the next tile's class record for the last chunk
     const bool last_chunk = tid + 1 == kTileChunks;
@@ -173,6 +196,7 @@ __global__ void __launch_bounds__(kTileChunks) sweep_hist_kernel(const SweepPara
     auto comp = [](int d) -> int { return d < 4 ? (d ^ 1) : 4; };  // A<->T, G<->C
 
     load_pair(0);
+    bool left_n = (__ldg(gn - 1) >> 31) & 1;  // the letter before the chunk (padding and pad words are flagged)
     int code8 = 0, rc8 = 0, first = 0;  // first = the window's leading letter (leaves on the next slide)
     for (int i = 0; i < kSweepMaxK; ++i) {
         const int d = letter(i);
@@ -186,37 +210,43 @@ __global__ void __launch_bounds__(kTileChunks) sweep_hist_kernel(const SweepPara
         if (BIPARTITE) {  // spans of 10..16 letters: bits b .. b + 15 of the pairs
             const int rem16 = (int)min((int64_t)16, contig_end_pos - (chunk_pos + s));
             if ((C0 | C2) >> b & 0xFFFF) {
-                bip_add_gap<4>(p.hist, X, Y, N, C0, C2, b, 0, rem16);
-                bip_add_gap<5>(p.hist, X, Y, N, C0, C2, b, 0, rem16);
-                bip_add_gap<6>(p.hist, X, Y, N, C0, C2, b, 0, rem16);
-                bip_add_gap<7>(p.hist, X, Y, N, C0, C2, b, 0, rem16);
-                bip_add_gap<8>(p.hist, X, Y, N, C0, C2, b, 0, rem16);
+                bip_add_gap<4>(p.hist, X, Y, N, C0, C2, b, 0, rem16, left_n);
+                bip_add_gap<5>(p.hist, X, Y, N, C0, C2, b, 0, rem16, left_n);
+                bip_add_gap<6>(p.hist, X, Y, N, C0, C2, b, 0, rem16, left_n);
+                bip_add_gap<7>(p.hist, X, Y, N, C0, C2, b, 0, rem16, left_n);
+                bip_add_gap<8>(p.hist, X, Y, N, C0, C2, b, 0, rem16, left_n);
             }
             if ((C1 | C3) >> b & 0xFFFF) {
-                bip_add_gap<4>(p.hist, X, Y, N, C1, C3, b, 1, rem16);
-                bip_add_gap<5>(p.hist, X, Y, N, C1, C3, b, 1, rem16);
-                bip_add_gap<6>(p.hist, X, Y, N, C1, C3, b, 1, rem16);
-                bip_add_gap<7>(p.hist, X, Y, N, C1, C3, b, 1, rem16);
-                bip_add_gap<8>(p.hist, X, Y, N, C1, C3, b, 1, rem16);
+                bip_add_gap<4>(p.hist, X, Y, N, C1, C3, b, 1, rem16, left_n);
+                bip_add_gap<5>(p.hist, X, Y, N, C1, C3, b, 1, rem16, left_n);
+                bip_add_gap<6>(p.hist, X, Y, N, C1, C3, b, 1, rem16, left_n);
+                bip_add_gap<7>(p.hist, X, Y, N, C1, C3, b, 1, rem16, left_n);
+                bip_add_gap<8>(p.hist, X, Y, N, C1, C3, b, 1, rem16, left_n);
             }
+            left_n = (N >> b) & 1;
             continue;
         }
         const int rem = (int)min((int64_t)kSweepMaxK, contig_end_pos - (chunk_pos + s));
         const unsigned mp = (unsigned)(C0 >> b) & 0xFF, np = (unsigned)(C1 >> b) & 0xFF;  // rows under the window, '+'
         const unsigned mm = (unsigned)(C2 >> b) & 0xFF, nm = (unsigned)(C3 >> b) & 0xFF;  // '-'
-        if (mp | mm) {
-            sweep_add<4>(p.hist, code8, rc8, mp, mm, 0, rem);
-            sweep_add<5>(p.hist, code8, rc8, mp, mm, 0, rem);
-            sweep_add<6>(p.hist, code8, rc8, mp, mm, 0, rem);
-            sweep_add<7>(p.hist, code8, rc8, mp, mm, 0, rem);
-            sweep_add<8>(p.hist, code8, rc8, mp, mm, 0, rem);
+        if (rem >= kSweepMaxK) {  // the common case: the 8-window lies inside the contig
+            if (mp | mm) sweep_add<8>(p.hist, code8, rc8, mp, mm, 0, rem);
+            if (np | nm) sweep_add<8>(p.hist, code8, rc8, np, nm, 1, rem);
         }
-        if (np | nm) {
-            sweep_add<4>(p.hist, code8, rc8, np, nm, 1, rem);
-            sweep_add<5>(p.hist, code8, rc8, np, nm, 1, rem);
-            sweep_add<6>(p.hist, code8, rc8, np, nm, 1, rem);
-            sweep_add<7>(p.hist, code8, rc8, np, nm, 1, rem);
-            sweep_add<8>(p.hist, code8, rc8, np, nm, 1, rem);
+        // k < 8 comes from marginalising k + 1 (nmb_sweep_finalize) except for the windows without an extension inside
+        // the contig: '+' rows under the k-window that ENDS at the contig end (rem == k), '-' rows under the k-window
+        // that STARTS at the contig start
+        const bool at_start = s == 0 && chunk_pos == contig_start_pos;
+        if (rem < kSweepMaxK || at_start) {
+#define NMB_EDGE(K)                                                                                              \
+            {                                                                                                    \
+                const unsigned pm = rem == K ? mp : 0u, pn = rem == K ? np : 0u;                                 \
+                const unsigned qm = at_start ? mm : 0u, qn = at_start ? nm : 0u;                                 \
+                if (pm | qm) sweep_add<K>(p.hist, code8, rc8, pm, qm, 0, rem);                                   \
+                if (pn | qn) sweep_add<K>(p.hist, code8, rc8, pn, qn, 1, rem);                                   \
+            }
+            NMB_EDGE(4) NMB_EDGE(5) NMB_EDGE(6) NMB_EDGE(7)
+#undef NMB_EDGE
         }
         // slide: drop the leading letter, append the letter at s + 8
         const int d_new = letter(b + kSweepMaxK);
@@ -224,6 +254,48 @@ __global__ void __launch_bounds__(kTileChunks) sweep_hist_kernel(const SweepPara
         rc8 = (rc8 - comp(first)) / 5 + comp(d_new) * pow5(kSweepMaxK - 1);
         first = letter(b + 1);
     }
+}
+
+// hist[k][o][c][w] += sum_{j < 5} hist[k + 1][o][c][5 w + j] for o < k: a k-letter motif is the prefix of its five
+// one-letter extensions (the trailing letter is the least significant base-5 digit).
+__global__ void __launch_bounds__(256) sweep_marginalise_kernel(uint32_t *__restrict__ hist, int k) {
+    int n5 = 1;
+    for (int i = 0; i < k; ++i) n5 *= 5;
+    const int64_t n = (int64_t)k * 2 * n5;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t oc = i / n5, w = i - oc * n5;  // oc = o * 2 + class, the same index in both levels (o < k)
+    int64_t off_k = 0, off_k1 = 0;               // sweep_hist_offset(k), sweep_hist_offset(k + 1)
+    for (int j = kSweepMinK, p5 = pow5(kSweepMinK); j <= k; ++j, p5 *= 5) {
+        if (j < k) off_k += (int64_t)j * 2 * p5;
+        off_k1 += (int64_t)j * 2 * p5;
+    }
+    const uint32_t *src = hist + off_k1 + oc * (int64_t)n5 * 5 + w * 5;
+    hist[off_k + i] += src[0] + src[1] + src[2] + src[3] + src[4];
+}
+
+// Bipartite marginals (see bip_add_gap).  mode 0: shape (a, b) += sum over the LAST right letter of shape (a, b + 1),
+// same offsets; mode 1: shape (a, b) += sum over the FIRST left letter of shape (a + 1, b), offset o <- o + 1.
+__global__ void __launch_bounds__(256) bip_marginalise_kernel(uint32_t *__restrict__ hist, int g, int a, int b, int mode) {
+    const int n_code = 1 << (2 * (a + b));
+    const int64_t n = (int64_t)(a + b) * 2 * n_code;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int oc = (int)(i / n_code), code = (int)(i - (int64_t)oc * n_code);
+    const int o = oc >> 1, cls = oc & 1;
+    const unsigned xl = code & ((1u << a) - 1), yl = (code >> a) & ((1u << a) - 1);
+    const unsigned xr = (code >> (2 * a)) & ((1u << b) - 1), yr = (code >> (2 * a + b)) & ((1u << b) - 1);
+    const int sa = mode ? a + 1 : a, sb = mode ? b : b + 1;
+    const uint32_t *src = hist + bip_offset(sa, g, sb) + (size_t)(((mode ? o + 1 : o) * 2 + cls)) * (1u << (2 * (sa + sb)));
+    uint32_t sum = 0;
+    for (unsigned t = 0; t < 4; ++t) {
+        const unsigned tx = t >> 1, ty = t & 1;
+        unsigned sxl = xl, syl = yl, sxr = xr, syr = yr;
+        if (mode) { sxl = (xl << 1) | tx; syl = (yl << 1) | ty; }
+        else { sxr = xr | (tx << b); syr = yr | (ty << b); }
+        sum += src[sxl | (syl << sa) | (sxr << (2 * sa)) | (syr << (2 * sa + sb))];
+    }
+    hist[bip_offset(a, g, b) + i] += sum;
 }
 
 // dst[outer][15][inner] = subset sums of src[outer][5][inner] over the letters of each IUPAC code.
@@ -314,6 +386,31 @@ static int sweep_launch(bool bipartite, const nmb_assembly *a, const uint32_t *c
     else
         nmb::sweep_hist_kernel<false><<<tile_count, nmb::kTileChunks, 0, (cudaStream_t)stream>>>(p);
     NMB_CUDA(cudaGetLastError());
+    return NMB_OK;
+}
+
+int nmb_sweep_finalize(uint32_t *hist, void *stream) {
+    NMB_REQUIRE(hist, "nmb_sweep_finalize: null argument");
+    for (int k = nmb::kSweepMaxK - 1; k >= nmb::kSweepMinK; --k) {  // 8 -> 7, then 7 -> 6, ... each level complete first
+        const int64_t n = (int64_t)k * 2 * nmb::pow5(k);
+        nmb::sweep_marginalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hist, k);
+        NMB_CUDA(cudaGetLastError());
+    }
+    return NMB_OK;
+}
+
+int nmb_sweep_bipartite_finalize(uint32_t *hist, void *stream) {
+    NMB_REQUIRE(hist, "nmb_sweep_bipartite_finalize: null argument");
+    auto run = [&](int g, int a, int b, int mode) {
+        const int64_t n = (int64_t)(a + b) * 2 * (1ll << (2 * (a + b)));
+        nmb::bip_marginalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hist, g, a, b, mode);
+    };
+    for (int g = nmb::kBipMinGap; g <= nmb::kBipMaxGap; ++g) {
+        run(g, 4, 3, 0);  // (4,g,3) from (4,g,4): last letter
+        run(g, 3, 4, 1);  // (3,g,4) from (4,g,4): first letter
+        run(g, 3, 3, 0);  // (3,g,3) from the now complete (3,g,4): last letter
+        NMB_CUDA(cudaGetLastError());
+    }
     return NMB_OK;
 }
 

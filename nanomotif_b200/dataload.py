@@ -562,6 +562,29 @@ def load_pileup_device(path: str, contig_names, mod_types=("a", "m", "21839"), w
     return parse_bedmethyl(data, contig_names, mod_types, with_counts, device, keep_unknown_contigs)
 
 
+def load_contigs_pileup_bgzip(path: str, contigs, mod_types=("a", "m", "21839"), with_counts: bool = False,
+                              device=None) -> DeviceRows:
+    """dataload.load_contigs_pileup_bgzip (dataload.py:102-152) = epymetheus.query_pileup_records on a bgzip + tabix
+    pileup: ONLY the BGZF members that hold the requested contigs are read from disk (virtual offsets of the .tbi),
+    inflated (K7) and parsed (K6) on the device.  Rows come back with contig_id indexing `contigs`; contigs that are
+    not in the index contribute nothing (the reference logs a warning and returns an empty frame when nothing is found).
+    A bin's pileup therefore costs its own share of the file, not the whole file (cfg 3: > 100 GB of text)."""
+    from .bgzf import TabixIndex, fetch_contigs_device
+
+    contigs = list(contigs)
+    d = _require_cuda(device)
+    index = TabixIndex.read(path + ".tbi")
+    text, _ = fetch_contigs_device(path, contigs, d, index)
+    if int(text.numel()) == 0:
+        new = lambda dt: torch.empty(0, dtype=dt, device=d)
+        return DeviceRows(contigs, mod_types, d, contig_id=new(torch.int32), position=new(torch.int64), strand=new(torch.uint8),
+                          mod_type=new(torch.uint8), Nvalid_cov=new(torch.int64), fraction_mod=new(torch.float64),
+                          percent_x100=new(torch.uint16))
+    # merged block ranges may carry neighbouring contigs (two requested contigs with others between them never do:
+    # ranges are per contig span); rows of unknown contigs are dropped by the parser
+    return parse_bedmethyl(text, contigs, mod_types, with_counts, d)
+
+
 def parse_fasta_device(data, trim_names: bool = False, trim_character: str = " ", device=None):
     """FASTA TEXT (bytes / uint8 array / tensor, host or device) -> DeviceAssembly, parsed on the GPU: the sequence lines
     of every record are concatenated on the device and packed (nmb_fasta_lines / nmb_fasta_copy / nmb_pack_sequence);

@@ -40,9 +40,23 @@ class SweepIndex:
         if not 0 <= self.modtype < pileup.n_modtypes:
             raise ValueError("mod type index outside the pileup's class records")
         with torch.cuda.device(assembly.device):
-            self.hist = torch.zeros(int(lib.nmb_sweep_hist_size()), dtype=torch.int32, device=assembly.device)
-        self.bip = None
+            # RAW histogram (nmb_sweep_hist): k = 8 counted row by row, k < 8 only the contig-end windows; raw
+            # histograms add (more contig ranges, other GPUs).  `hist` is the finalized copy, made on demand.
+            self.raw = torch.zeros(int(lib.nmb_sweep_hist_size()), dtype=torch.int32, device=assembly.device)
+        self._hist = None
+        self.bip_raw = None
+        self._bip = None
         self._tables: dict = {}
+
+    @property
+    def hist(self) -> torch.Tensor:
+        """The finished histogram of every k = 4..8 (nmb_sweep_finalize applied to a copy of the raw one)."""
+        if self._hist is None:
+            with torch.cuda.device(self.asm.device):
+                h = self.raw.clone()
+                check(lib.nmb_sweep_finalize(ptr(h), _stream()), "nmb_sweep_finalize")
+            self._hist = h
+        return self._hist
 
     def add(self, contig_begin: int = 0, contig_end: int | None = None) -> "SweepIndex":
         asm = self.asm
@@ -52,9 +66,10 @@ class SweepIndex:
         view = asm.view()
         with torch.cuda.device(asm.device):
             base = ptr(cls) + self.modtype * asm.n_tiles * _lib.CLS_REC_WORDS * 4
-            check(lib.nmb_sweep_hist(C.byref(view), base, tile_begin, tile_count, contig_begin, contig_end, ptr(self.hist),
+            check(lib.nmb_sweep_hist(C.byref(view), base, tile_begin, tile_count, contig_begin, contig_end, ptr(self.raw),
                                      _stream()), "nmb_sweep_hist")
         self._tables.clear()
+        self._hist = None
         return self
 
     # ---- bipartite shapes X{3,4} N{4..8} Y{3,4} over ACGT ----
@@ -64,12 +79,25 @@ class SweepIndex:
         tile_begin, tile_count = asm.tile_span(contig_begin, contig_end)
         view = asm.view()
         with torch.cuda.device(asm.device):
-            if getattr(self, "bip", None) is None:
-                self.bip = torch.zeros(int(lib.nmb_sweep_bipartite_size()), dtype=torch.int32, device=asm.device)
+            if self.bip_raw is None:
+                self.bip_raw = torch.zeros(int(lib.nmb_sweep_bipartite_size()), dtype=torch.int32, device=asm.device)
             base = ptr(self.pileup.class_records) + self.modtype * asm.n_tiles * _lib.CLS_REC_WORDS * 4
             check(lib.nmb_sweep_bipartite(C.byref(view), base, tile_begin, tile_count, contig_begin, contig_end,
-                                          ptr(self.bip), _stream()), "nmb_sweep_bipartite")
+                                          ptr(self.bip_raw), _stream()), "nmb_sweep_bipartite")
+        self._bip = None
         return self
+
+    @property
+    def bip(self):
+        """The finished bipartite histogram (nmb_sweep_bipartite_finalize applied to a copy of the raw one), or None."""
+        if self.bip_raw is None:
+            return None
+        if self._bip is None:
+            with torch.cuda.device(self.asm.device):
+                h = self.bip_raw.clone()
+                check(lib.nmb_sweep_bipartite_finalize(ptr(h), _stream()), "nmb_sweep_bipartite_finalize")
+            self._bip = h
+        return self._bip
 
     @staticmethod
     def bipartite_block(a: int, g: int, b: int) -> tuple[int, int]:
@@ -109,10 +137,11 @@ class SweepIndex:
         """Sum the histograms over the ranks of the default process group (contig-sharded assemblies)."""
         import torch.distributed as dist
 
-        dist.all_reduce(self.hist)
-        if getattr(self, "bip", None) is not None:
-            dist.all_reduce(self.bip)
+        dist.all_reduce(self.raw)  # raw histograms add; the marginalisation runs once, on the sum
+        if self.bip_raw is not None:
+            dist.all_reduce(self.bip_raw)
         self._tables.clear()
+        self._hist = self._bip = None
         return self
 
     def table(self, k: int, mod_pos: int, canonical: str = "A", keep: bool = False):

@@ -147,6 +147,25 @@ def test_exhaustive_tables_equal_per_motif_counts():
     np.testing.assert_array_equal(got[:, 0], bip_mod[sel].cpu().numpy())
     np.testing.assert_array_equal(got[:, 1], bip_nomod[sel].cpu().numpy())
     assert int(got.sum()) > 1000
+    # whole tables of the other shapes (they come from marginalising (4, g, 4) + edge windows) against K2: every motif
+    # with an A at the modified position, in the left part and in the right part
+    import itertools
+
+    for a, g, b, mp in ((4, 4, 3, 2), (3, 8, 4, 3 + 8 + 1), (4, 5, 4, 0), (3, 4, 3, 3 + 4 + 2)):
+        t_mod, t_nomod = index.bipartite_table(a, g, b, mp)
+        motifs, idx = [], []
+        for letters in itertools.product("ACGT", repeat=a + b - 1):
+            concrete = list(letters)
+            k = mp if mp < a else mp - g
+            concrete.insert(k, "A")
+            left, right = "".join(concrete[:a]), "".join(concrete[a:])
+            motifs.append(nmb.Motif(left + "N" * g + right, mp).from_iupac())
+            idx.append(SweepIndex.bipartite_index(left, right))
+        got = scorer.score(motifs)
+        sel = torch.tensor(idx, device=t_mod.device)
+        np.testing.assert_array_equal(got[:, 0], t_mod[sel].cpu().numpy(), err_msg=str((a, g, b, mp)))
+        np.testing.assert_array_equal(got[:, 1], t_nomod[sel].cpu().numpy(), err_msg=str((a, g, b, mp)))
+        assert int(got.sum()) > 100
     # candidates: the planted GATC stands out among all 4-mers
     cand = index.candidates(4, 1, "A", min_mean=0.8, min_mod=100)
     assert ("GATC", int(n_mod[SweepIndex.motif_index("GATC", 1)]), int(n_nomod[SweepIndex.motif_index("GATC", 1)])) in cand

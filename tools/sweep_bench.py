@@ -33,7 +33,7 @@ def main():
     torch.cuda.synchronize()
     t_hist = time.perf_counter() - t0
     print(f"assembly {asm.total_bp / 1e9:.2f} Gbp, {asm.n_contigs} contigs; histogram pass {t_hist * 1e3:.1f} ms "
-          f"({asm.total_bp / t_hist / 1e9:.1f} Gbp/s), {int(index.hist.long().sum().item()) / 1e9:.2f} G increments")
+          f"({asm.total_bp / t_hist / 1e9:.1f} Gbp/s), {int(index.raw.long().sum().item()) / 1e9:.2f} G increments")
     n_motifs, t_tab, t_filt, n_cand = 0, 0.0, 0.0, 0
     for k in range(4, 9):
         for o in range(k):
@@ -61,7 +61,7 @@ def main():
     t_bip = time.perf_counter() - t0
     n_bip = sum(4 ** (a + b) * (a + b) for a in (3, 4) for b in (3, 4)) * 5
     print(f"bipartite X{{3,4}} N{{4..8}} Y{{3,4}}: {n_bip / 1e6:.2f} M (motif, position) pairs in {t_bip * 1e3:.0f} ms, "
-          f"{int(index.bip.long().sum().item()) / 1e9:.1f} G increments (K2 brute force: {n_bip * asm.total_bp / 1e13:.0f} s)")
+          f"{int(index.bip_raw.long().sum().item()) / 1e9:.1f} G increments (K2 brute force: {n_bip * asm.total_bp / 1e13:.0f} s)")
     # cross-check against K2
     rng = np.random.default_rng(3)
     motifs, want = [], []
