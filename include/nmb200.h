@@ -421,6 +421,24 @@ NMB_API int nmb_segment_offsets(const int64_t *stats, int64_t n_segments, int64_
 NMB_API int nmb_segment_median(const double *fractions, const int64_t *offsets, int64_t n_segments, double *median,
                                void *stream);
 
+/* ---- K9: binnary feature matrix from the K5 arrays on the device (replaces the polars pipeline of
+ *      nanomotif/main.py:192-205 + binnary/data_processing.py:174-213,255-269: threshold filter, add_bin, per-bin
+ *      weighted mean, within-bin imputation, pivot) ----
+ * stats [n_motifs][n_contigs][3] and value [n_motifs][n_contigs] are nmb_pattern_scan / nmb_segment_median outputs
+ * (value NULL = weighted mean, sum n_mod / sum n_valid_cov).  Binned contigs are given grouped by bin (CSR: bin_off
+ * [n_bins + 1], bin_contigs ascending inside a bin).  nmb_bin_means: keep[m][c] = the cell passes n_motif_obs *
+ * mean_read_cov >= threshold and its contig is binned; bin_mean / bin_has [n_motifs][n_bins] = sum(value * n_obs) /
+ * sum(n_obs) over the kept cells of the bin (summed in ascending contig order, deterministic) and whether any cell
+ * was kept; contig_has[c] = the contig has a kept cell.  nmb_bin_matrix: matrix[r][f] for contig rows[r] and motif
+ * feats[f] = own value if kept, else the bin mean if the bin has one, else 0 (contig_bin[c] = bin of contig c). */
+NMB_API int nmb_bin_means(const int64_t *stats, const double *value, int32_t n_motifs, int32_t n_contigs,
+                          const int64_t *bin_off, const int32_t *bin_contigs, int32_t n_bins, double threshold, uint8_t *keep,
+                          double *bin_mean, uint8_t *bin_has, uint8_t *contig_has, void *stream);
+NMB_API int nmb_bin_matrix(const int64_t *stats, const double *value, const uint8_t *keep, const double *bin_mean,
+                           const uint8_t *bin_has, const int32_t *contig_bin, int32_t n_contigs, int32_t n_bins,
+                           const int32_t *rows, int64_t n_rows, const int32_t *feats, int32_t n_feat, double *matrix,
+                           void *stream);
+
 /* ---- K8: exhaustive candidate sweep (BASELINE.json configs[4]): counts of EVERY IUPAC motif of length 4..8
  *      at every modified position from one pass over the assembly (csrc/sweep.cu) ----
  * hist: nmb_sweep_hist_size() uint32 counters, zeroed by the caller; counters ADD, so several calls (contig

@@ -128,6 +128,8 @@ SIGNATURES = {
     "nmb_stager_copy": (C.c_int, [_P, _P, _P, _I64, _P]),
     "nmb_stager_gather": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
     "nmb_stager_destroy": (C.c_int, [_P]),
+    "nmb_bin_means": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _I32, _F64, _P, _P, _P, _P, _P]),
+    "nmb_bin_matrix": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P, _I32, _P, _P]),
     "nmb_pssm_kl": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P]),
 }
 

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnmb200.so")
-SOURCES = ["api.cu", "pack.cu", "filters.cu", "scan.cu", "positions.cu", "windows.cu", "pattern.cu", "pattern_scan.cu", "bedmethyl.cu", "bgzf.cu", "sweep.cu", "stage.cu"]
+SOURCES = ["api.cu", "pack.cu", "filters.cu", "scan.cu", "positions.cu", "windows.cu", "pattern.cu", "pattern_scan.cu", "bedmethyl.cu", "bgzf.cu", "sweep.cu", "stage.cu", "binnary.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

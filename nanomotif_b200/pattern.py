@@ -81,18 +81,48 @@ class PatternIndex:
             self.n_valid_rows = int(n_valid.item())
 
 
-def pattern_table(index: PatternIndex, motifs, median: bool = True, batch: int = 64, motifs_per_item: int | None = None):
+def pattern_table(index: PatternIndex, motifs, median: bool = True, batch: int = 64, motifs_per_item: int | None = None,
+                  on_device: bool = False):
     """(stats int64 [n_motifs, n_contigs, 3] = n_motif_obs / sum n_mod / sum n_valid_cov, value float64
     [n_motifs, n_contigs] = median of the per-occurrence fractions, or None) on the host, for regex `Motif`s
     scored against one mod type's index.  Two tile-driven passes per batch of motifs (count, then write +
-    exact medians); a batch's results travel to pinned host memory while the next batch is scanned."""
+    exact medians); a batch's results travel to pinned host memory while the next batch is scanned.
+    on_device=True keeps both arrays on the GPU (device tensors) for consumers that stay there
+    (tables.bin_feature_matrix_device)."""
     asm = index.asm
     d, nc = asm.device, asm.n_contigs
     motifs = list(motifs)
-    stats_out = np.zeros((len(motifs), nc, 3), dtype=np.int64)
-    value_out = np.full((len(motifs), nc), np.nan) if median else None
     view = asm.view()
     batch = max(1, min(batch, len(motifs)))
+    if on_device:
+        with torch.cuda.device(d):
+            stats_all = torch.zeros((len(motifs), nc, 3), dtype=torch.int64, device=d)
+            value_all = torch.full((len(motifs), nc), float("nan"), dtype=torch.float64, device=d) if median else None
+            for b0 in range(0, len(motifs), batch):
+                chunk = motifs[b0:b0 + batch]
+                progs = MotifPrograms(chunk, d, strip=False)
+                nb = len(chunk)
+                mpi = motifs_per_item or int(min(_lib.MAX_MOTIFS_PER_ITEM, max(1, nb * asm.n_tiles // (16 * sm_count(d)))))
+                stats = stats_all[b0:b0 + nb].view(nb * nc, 3)  # contiguous slice: the scan adds into it in place
+
+                def scan_d(phase, offsets=None, cursor=None, fractions=None):
+                    check(lib.nmb_pattern_scan(C.byref(view), ptr(index.valid), ptr(index.rank_dir), ptr(index.payload),
+                                               ptr(progs.programs), nb, mpi, progs.max_len, phase, ptr(stats), ptr(offsets),
+                                               ptr(cursor), ptr(fractions), 0, _stream()), "nmb_pattern_scan")
+
+                scan_d(0)
+                if median:
+                    offsets = torch.empty(nb * nc + 1, dtype=torch.int64, device=d)
+                    cursor = torch.empty(nb * nc, dtype=torch.int32, device=d)
+                    check(lib.nmb_segment_offsets(ptr(stats), nb * nc, ptr(offsets), ptr(cursor), _stream()), "nmb_segment_offsets")
+                    total = int(offsets[-1].item())
+                    fractions = torch.empty(max(1, total), dtype=torch.float64, device=d)
+                    scan_d(1, offsets, cursor, fractions)
+                    med = value_all[b0:b0 + nb].view(nb * nc)
+                    check(lib.nmb_segment_median(ptr(fractions), ptr(offsets), nb * nc, ptr(med), _stream()), "nmb_segment_median")
+        return stats_all, value_all
+    stats_out = np.zeros((len(motifs), nc, 3), dtype=np.int64)
+    value_out = np.full((len(motifs), nc), np.nan) if median else None
     with torch.cuda.device(d):
         host = [(torch.empty((batch * nc, 3), dtype=torch.int64, pin_memory=True),
                  torch.empty(batch * nc, dtype=torch.float64, pin_memory=True) if median else None) for _ in range(2)]

@@ -111,3 +111,52 @@ def bin_feature_matrix(stats: np.ndarray, value: np.ndarray, contig_names, motif
     own = keep[:, rows]
     cell = np.where(own, value[:, rows], np.where(bin_has[:, b], bin_mean[:, b], 0.0))
     return names[rows], np.ascontiguousarray(cell[feat_used].T), motif_mods[feat_used]
+
+
+def bin_feature_matrix_device(stats, value, contig_names, motif_mods, contig_bin: dict, methylation_threshold: float = 24.0):
+    """bin_feature_matrix on the DEVICE (K9: nmb_bin_means + nmb_bin_matrix), straight from the K5 outputs as device
+    tensors -- stats int64 [n_motifs, n_contigs, 3], value float64 [n_motifs, n_contigs] or None (weighted mean) --
+    as pattern.pattern_table(..., on_device=True) returns them.  Returns (contig names, matrix as a device tensor
+    [n_rows, n_features] float64, feature names); same cells, bit for bit, as bin_feature_matrix.  Only the two string
+    sorts (rows by (bin, contig name), features by motif_mod) run on the host, on two small flag arrays."""
+    import torch
+
+    from ._lib import check, lib, ptr
+    from .device import _stream, _to_device
+
+    d = stats.device
+    names = np.asarray(contig_names, dtype=object)
+    motif_mods = np.asarray(motif_mods, dtype=object)
+    nm, nc = int(stats.shape[0]), int(stats.shape[1])
+    bins = np.array([contig_bin.get(n) for n in names], dtype=object)
+    binned = np.array([b is not None for b in bins], dtype=bool)
+    bin_names, bin_of = np.unique(bins[binned].astype(str), return_inverse=True)
+    bin_idx = np.full(nc, -1, dtype=np.int32)
+    bin_idx[binned] = bin_of
+    nb = len(bin_names)
+    order = np.flatnonzero(binned)
+    order = order[np.argsort(bin_idx[order], kind="stable")].astype(np.int32)  # grouped by bin, contigs ascending inside
+    bin_off = np.zeros(nb + 1, dtype=np.int64)
+    np.cumsum(np.bincount(bin_idx[binned], minlength=nb), out=bin_off[1:])
+    with torch.cuda.device(d):
+        stats = stats.contiguous()
+        value = None if value is None else value.contiguous()
+        keep = torch.empty((nm, nc), dtype=torch.uint8, device=d)
+        bin_mean = torch.empty((nm, max(nb, 1)), dtype=torch.float64, device=d)
+        bin_has = torch.zeros((nm, max(nb, 1)), dtype=torch.uint8, device=d)
+        contig_has = torch.empty(nc, dtype=torch.uint8, device=d)
+        off_d, ord_d, bidx_d = _to_device(bin_off, d), _to_device(order if len(order) else np.zeros(1, np.int32), d), _to_device(bin_idx, d)
+        check(lib.nmb_bin_means(ptr(stats), ptr(value), nm, nc, ptr(off_d), ptr(ord_d), nb, float(methylation_threshold),
+                                ptr(keep), ptr(bin_mean), ptr(bin_has), ptr(contig_has), _stream()), "nmb_bin_means")
+        rows = np.flatnonzero(contig_has.cpu().numpy())
+        rows = rows[np.lexsort((names[rows].astype(str), bins[rows].astype(str)))].astype(np.int32)
+        feat_order = np.argsort(motif_mods.astype(str), kind="stable")
+        has_any = bin_has[:, :nb].any(dim=1).cpu().numpy() if nb else np.zeros(nm, dtype=bool)
+        feats = feat_order[has_any[feat_order]].astype(np.int32)
+        matrix = torch.empty((len(rows), len(feats)), dtype=torch.float64, device=d)
+        if len(rows) and len(feats):
+            rows_d, feats_d = _to_device(rows, d), _to_device(feats, d)
+            check(lib.nmb_bin_matrix(ptr(stats), ptr(value), ptr(keep), ptr(bin_mean), ptr(bin_has), ptr(bidx_d), nc, max(nb, 1),
+                                     ptr(rows_d), len(rows), ptr(feats_d), len(feats), ptr(matrix), _stream()),
+                  "nmb_bin_matrix")
+    return names[rows], matrix, motif_mods[feats]

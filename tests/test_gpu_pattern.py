@@ -113,3 +113,62 @@ def test_tile_driven_equals_row_driven_and_file_input(tmp_path):
     out = tmp_path / "table.tsv"
     df2 = methylation_pattern(str(path), str(fa), specs, output=str(out))
     assert df2.equals(df) and out.read_text().startswith("contig\tmotif\tmod_type")
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_binnary_matrix_on_device_from_k5_arrays(weighted):
+    """SURVEY 8f rank 3 on the GPU: the feature matrix of detect_contamination / include_contigs built by K9
+    (nmb_bin_means + nmb_bin_matrix) straight from the K5 device arrays -- bit-identical to the host restatement
+    (tables.bin_feature_matrix) and equal to the oracle's pandas pipeline (main.py:192-205,
+    binnary/data_processing.py:174-213,255-269) run on the methylation_pattern frame."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pandas as pd
+
+    from nanomotif_b200 import synth, tables
+    from nanomotif_b200.device import DeviceAssembly, _to_device
+    from nanomotif_b200.motif import Motif
+    from nanomotif_b200.pattern import PatternIndex, pattern_table
+
+    rng = np.random.default_rng(31)
+    contigs, cols = {}, {k: [] for k in ("contig_id", "position", "strand", "Nvalid_cov", "n_mod", "n_diff")}
+    for i in range(26):
+        seq = synth.random_sequence(rng, int(rng.integers(1500, 30000)), 0.5, 1e-4)
+        contigs[f"contig_{i}"] = seq.tobytes().decode()
+        p = synth.synth_pileup(seq, rng, depth=int(rng.integers(2, 12)), mod_types=("a",), with_counts=True)
+        cols["contig_id"].append(np.full(len(p["position"]), i, dtype=np.int32))
+        for k in ("position", "strand", "Nvalid_cov", "n_mod", "n_diff"):
+            cols[k].append(p[k])
+    c = {k: np.concatenate(v) for k, v in cols.items()}
+    asm = DeviceAssembly.from_sequences(contigs)
+    d = asm.device
+    rows = {k: _to_device(v, d) for k, v in c.items()}
+    index = PatternIndex(asm, rows, 0)
+    specs = [("GATC", 1), ("A", 0), ("GRNGAAGY", 5), ("TTAA", 3), ("CAYNNNNRTG", 1), ("ACGTACGTACGT", 0), ("AC", 0)]
+    motifs = [Motif(s, p).from_iupac() for s, p in specs]
+    motif_mods = [f"{s}_a_{p}" for s, p in specs]
+    st_h, val_h = pattern_table(index, motifs, median=not weighted)
+    st_d, val_d = pattern_table(index, motifs, median=not weighted, on_device=True, batch=3)
+    np.testing.assert_array_equal(st_d.cpu().numpy(), st_h)
+    if not weighted:
+        np.testing.assert_array_equal(val_d.cpu().numpy(), val_h)
+    names = list(contigs)
+    contig_bin = {n: f"bin{(i * 5) % 4}" for i, n in enumerate(names) if i % 7 != 3}  # some contigs stay unbinned
+    if weighted:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            val_h = st_h[:, :, 1] / st_h[:, :, 2]
+    mi, ci = np.nonzero(st_h[:, :, 0] > 0)
+    frame = pd.DataFrame({"contig": np.array(names, dtype=object)[ci], "motif": [specs[m][0] for m in mi], "mod_type": "a",
+                          "mod_position": [specs[m][1] for m in mi], "methylation_value": val_h[mi, ci],
+                          "mean_read_cov": st_h[mi, ci, 2] / st_h[mi, ci, 0], "n_motif_obs": st_h[mi, ci, 0].astype(np.int32)})
+    for thr in (24.0, 0.0, 400.0):
+        got_c, got_m, got_f = tables.bin_feature_matrix_device(st_d, val_d, names, motif_mods, contig_bin, thr)
+        host_c, host_m, host_f = tables.bin_feature_matrix(st_h, val_h, names, motif_mods, contig_bin, thr)
+        assert got_m.is_cuda and got_c.tolist() == host_c.tolist() and got_f.tolist() == host_f.tolist()
+        np.testing.assert_array_equal(got_m.cpu().numpy(), host_m)  # same sums in the same order: bit-identical
+        want_c, want_m, want_f = O.binnary_matrix(frame, contig_bin, thr)
+        assert got_c.tolist() == want_c.tolist() and got_f.tolist() == want_f.tolist()
+        np.testing.assert_allclose(got_m.cpu().numpy(), want_m, rtol=1e-13, atol=0)
+    assert got_m.shape[0] >= 1
