@@ -151,7 +151,7 @@ def bin_feature_matrix_device(stats, value, contig_names, motif_mods, contig_bin
         rows = np.flatnonzero(contig_has.cpu().numpy())
         rows = rows[np.lexsort((names[rows].astype(str), bins[rows].astype(str)))].astype(np.int32)
         feat_order = np.argsort(motif_mods.astype(str), kind="stable")
-        has_any = bin_has[:, :nb].any(dim=1).cpu().numpy() if nb else np.zeros(nm, dtype=bool)
+        has_any = (bin_has[:, :nb] != 0).any(dim=1).cpu().numpy().astype(bool) if nb else np.zeros(nm, dtype=bool)
         feats = feat_order[has_any[feat_order]].astype(np.int32)
         matrix = torch.empty((len(rows), len(feats)), dtype=torch.float64, device=d)
         if len(rows) and len(feats):

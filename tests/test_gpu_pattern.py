@@ -163,7 +163,7 @@ def test_binnary_matrix_on_device_from_k5_arrays(weighted):
     frame = pd.DataFrame({"contig": np.array(names, dtype=object)[ci], "motif": [specs[m][0] for m in mi], "mod_type": "a",
                           "mod_position": [specs[m][1] for m in mi], "methylation_value": val_h[mi, ci],
                           "mean_read_cov": st_h[mi, ci, 2] / st_h[mi, ci, 0], "n_motif_obs": st_h[mi, ci, 0].astype(np.int32)})
-    for thr in (24.0, 0.0, 400.0):
+    for thr in (24.0, 0.0, 60.0):
         got_c, got_m, got_f = tables.bin_feature_matrix_device(st_d, val_d, names, motif_mods, contig_bin, thr)
         host_c, host_m, host_f = tables.bin_feature_matrix(st_h, val_h, names, motif_mods, contig_bin, thr)
         assert got_m.is_cuda and got_c.tolist() == host_c.tolist() and got_f.tolist() == host_f.tolist()
