@@ -292,6 +292,18 @@ NMB_API int nmb_scan_count(const nmb_assembly *assembly_h, const uint32_t *class
                    int32_t motifs_per_item, int32_t max_motif_len, const int32_t *contig_group,
                    int64_t *out, int32_t grid_ctas /* 0 = auto */, void *stream);
 
+/* nmb_scan_count with FAMILY sharing: inside every work item's block of motifs_per_item motifs, runs of consecutive
+ * motifs that share all constrained positions but one -- the children of one search expansion,
+ * find_motifs_bin.py:1116-1145 -- are found on the device (from the raw motif records the programs were compiled
+ * from) and evaluated as ONE parent chain plus one shifted indicator plane per member.  Same counts as nmb_scan_count,
+ * bit for bit.  motifs: the n_motifs records in the order of `programs`; family_scratch: nmb_family_scratch_bytes(
+ * n_motifs) bytes of device memory, overwritten. */
+NMB_API int64_t nmb_family_scratch_bytes(int32_t n_motifs);
+NMB_API int nmb_scan_count_families(const nmb_assembly *assembly_h, const uint32_t *class_records, const void *programs,
+                                    const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
+                                    int32_t max_motif_len, const int32_t *contig_group, int64_t *out, int32_t grid_ctas,
+                                    const nmb_motif *motifs, int32_t n_motifs, void *family_scratch, void *stream);
+
 /* ---- K3: occurrence positions (subseq_indices output and the save_motif_positions=True lists
  *      of motif_model_contig, find_motifs_bin.py:1322-1329) ---- */
 

@@ -21,6 +21,19 @@ namespace nmb {
 constexpr int kScanThreads = kTileChunks;                                       // 128
 constexpr int kMaxMpi = NMB_MAX_MOTIFS_PER_ITEM;
 
+// A FAMILY is a run of consecutive motifs of one work item that share all constrained positions but one -- the children
+// of one search expansion (find_motifs_bin.py:1116-1145 adds one base at one position to the same parent).  The parent's
+// two chains are evaluated once; a child is then one indicator plane, shifted to the modified base's alignment, ANDed
+// with the parent's aligned planes: ~6 logic ops per word and strand instead of 4 per word, strand and constrained
+// position.  Offsets are relative to the modified base, which all members share.
+struct FamInfo {
+    uint8_t n;      // at the first member (leader): members in the run (>= 2); 0 elsewhere / for single motifs
+    uint8_t set;    // allowed-set of the member's extra position
+    int8_t delta;   // its offset from the modified base, |delta| <= 31
+    uint8_t pad;
+};
+static_assert(sizeof(FamInfo) == 4, "FamInfo is 4 bytes");
+
 struct ScanParams {
     const uint32_t *seq_records;
     const uint32_t *nonacgt;
@@ -30,6 +43,8 @@ struct ScanParams {
     const int32_t *contig_group;
     const int64_t *contig_start, *contig_len;
     unsigned long long *out;
+    const FamInfo *fam;       // per motif: family run length at a leader, the member's extra (set, offset); or null
+    const Program *parents;   // per motif: the family's parent program (valid at leaders)
     int n_jobs, n_items, mpi, n_tiles;
 };
 
@@ -69,35 +84,9 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
                                              uint32_t (*acc)[4]) {
     const int m_begin = job.motif_begin + meta.mblk * p.mpi;
     const int m_count = min(p.mpi, job.motif_count - meta.mblk * p.mpi);
-#pragma unroll 1
-    for (int mi = 0; mi < m_count; ++mi) {
-        // ONE program per motif serves both strands (scan.cuh: run_chain_pair)
-        const ProgramView pv = load_program(p.programs + (size_t)(m_begin + mi) * 2);
-        uint32_t c[NW + 2 * H], d[NW + 2 * H];
-        if (!run_chain_pair<H, PLANES>(pv, q, c, d, edge)) continue;  // no occurrence in this warp's chunk
-        const bool far = pv.mod_pos >= 32;  // only possible when H == 2
-        const int sh = pv.mod_pos & 31;
-        uint32_t cnt[4] = {0, 0, 0, 0};  // n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'
-#pragma unroll
-        for (int h = 0; h < NW; h += 4) {
-            uint4 pl[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                pl[k] = *reinterpret_cast<const uint4 *>(cl + k * kTileWords + (h >> 2) * kSlotStride);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t mf = aligned_word<H>(c, h + k, sh, far);
-                const uint32_t mr = aligned_word_rc<H>(d, h + k, sh, far);
-                const uint32_t w0 = k == 0 ? pl[0].x : k == 1 ? pl[0].y : k == 2 ? pl[0].z : pl[0].w;
-                const uint32_t w1 = k == 0 ? pl[1].x : k == 1 ? pl[1].y : k == 2 ? pl[1].z : pl[1].w;
-                const uint32_t w2 = k == 0 ? pl[2].x : k == 1 ? pl[2].y : k == 2 ? pl[2].z : pl[2].w;
-                const uint32_t w3 = k == 0 ? pl[3].x : k == 1 ? pl[3].y : k == 2 ? pl[3].z : pl[3].w;
-                cnt[0] += __popc(mf & w0);  // occurrences whose modified base is methylated, '+'
-                cnt[1] += __popc(mf & w1);  // ... unmethylated, '+'
-                cnt[2] += __popc(mr & w2);  // reverse-complement occurrences, '-' strand rows
-                cnt[3] += __popc(mr & w3);
-            }
-        }
+
+    // per-lane counts of one motif -> warp sums -> the CTA's accumulators / the output
+    auto flush = [&](int mi, const uint32_t (&cnt)[4]) {
         // n_mod | n_nomod << 16 per strand (per-lane counts are <= 512)
         uint32_t pk_f = valid ? (cnt[0] | (cnt[1] << 16)) : 0u;
         uint32_t pk_r = valid ? (cnt[2] | (cnt[3] << 16)) : 0u;
@@ -122,6 +111,107 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
                     if (v[c]) atomicAdd(p.out + (row + g) * 4 + c, (unsigned long long)v[c]);
             }
         }
+    };
+    // popcounts of (match & class plane) over the lane's 16 words; mf / mr give word k of the two aligned match planes
+    auto count_planes = [&](auto mf_of, auto mr_of, uint32_t (&cnt)[4]) {
+#pragma unroll
+        for (int h = 0; h < NW; h += 4) {
+            uint4 pl[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                pl[k] = *reinterpret_cast<const uint4 *>(cl + k * kTileWords + (h >> 2) * kSlotStride);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t mf = mf_of(h + k);
+                const uint32_t mr = mr_of(h + k);
+                const uint32_t w0 = k == 0 ? pl[0].x : k == 1 ? pl[0].y : k == 2 ? pl[0].z : pl[0].w;
+                const uint32_t w1 = k == 0 ? pl[1].x : k == 1 ? pl[1].y : k == 2 ? pl[1].z : pl[1].w;
+                const uint32_t w2 = k == 0 ? pl[2].x : k == 1 ? pl[2].y : k == 2 ? pl[2].z : pl[2].w;
+                const uint32_t w3 = k == 0 ? pl[3].x : k == 1 ? pl[3].y : k == 2 ? pl[3].z : pl[3].w;
+                cnt[0] += __popc(mf & w0);  // occurrences whose modified base is methylated, '+'
+                cnt[1] += __popc(mf & w1);  // ... unmethylated, '+'
+                cnt[2] += __popc(mr & w2);  // reverse-complement occurrences, '-' strand rows
+                cnt[3] += __popc(mr & w3);
+            }
+        }
+    };
+
+    int mi = 0;
+#pragma unroll 1
+    while (mi < m_count) {
+        // ---- a family (see FamInfo): warps without non-ACGT letters or contig edges in reach only; the others take
+        //      the members one by one through the general path below (every member keeps its own program) ----
+        if (!PLANES && p.fam != nullptr && !edge.edge) {  // warp-uniform
+            const int run = __ldg(reinterpret_cast<const uint32_t *>(p.fam + m_begin + mi)) & 0xFF;
+            if (run >= 2) {
+                const ProgramView pv = load_program(p.parents + (m_begin + mi));
+                uint32_t c[NW + 2 * H], d[NW + 2 * H];
+                bool alive = run_chain_pair<H, PLANES>(pv, q, c, d, edge);
+                uint32_t mf[NW], mr[NW];
+                if (alive) {
+                    const bool far = pv.mod_pos >= 32;
+                    const int sh = pv.mod_pos & 31;
+                    uint32_t any = 0;
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) {
+                        mf[k] = aligned_word<H>(c, k, sh, far);
+                        mr[k] = aligned_word_rc<H>(d, k, sh, far);
+                        any |= mf[k] | mr[k];
+                    }
+                    alive = __any_sync(0xFFFFFFFFu, any != 0);
+                }
+                if (alive) {  // else: no occurrence of the parent in the warp's positions -> every member counts 0
+#pragma unroll 1
+                    for (int k = 0; k < run; ++k) {
+                        const uint32_t fi = __ldg(reinterpret_cast<const uint32_t *>(p.fam + m_begin + mi + k));
+                        const int code = (fi >> 8) & 0xFF;
+                        const int delta = (int)(int8_t)((fi >> 16) & 0xFF);
+                        // c <- indicator of the extra position's set, d <- indicator of the complementary set (reversed
+                        // word order, as init_pair stores the reverse-complement chain)
+                        switch (code) {
+#define NMB_CASE(m) case m: init_pair<m, H, PLANES>(c, d, q); break;
+                            NMB_CASE(1) NMB_CASE(2) NMB_CASE(3) NMB_CASE(4) NMB_CASE(5) NMB_CASE(6) NMB_CASE(7)
+                            NMB_CASE(8) NMB_CASE(9) NMB_CASE(10) NMB_CASE(11) NMB_CASE(12) NMB_CASE(13) NMB_CASE(14)
+#undef NMB_CASE
+                            default:
+#pragma unroll
+                                for (int i = 0; i < NW + 2 * H; ++i) c[i] = d[i] = 0u;
+                                break;
+                        }
+                        constexpr int CW = NW + 2 * H;
+                        uint32_t cnt[4] = {0, 0, 0, 0};
+                        // forward: the member matches at p iff the parent does and base[p + delta] is in the set;
+                        // reverse complement (aligned at ITS modified base q): base[q - delta] in the complementary set
+                        if (delta >= 0) {
+                            count_planes(
+                                [&](int w) { return mf[w] & __funnelshift_r(c[w + H], c[w + H + 1], delta); },
+                                [&](int w) { return mr[w] & __funnelshift_l(d[CW - 1 - (w + H - 1)], d[CW - 1 - (w + H)], delta); },
+                                cnt);
+                        } else {
+                            count_planes(
+                                [&](int w) { return mf[w] & __funnelshift_l(c[w + H - 1], c[w + H], -delta); },
+                                [&](int w) { return mr[w] & __funnelshift_r(d[CW - 1 - (w + H)], d[CW - 1 - (w + H + 1)], -delta); },
+                                cnt);
+                        }
+                        flush(mi + k, cnt);
+                    }
+                }
+                mi += run;
+                continue;
+            }
+        }
+        // ---- one motif: ONE program serves both strands (scan.cuh: run_chain_pair) ----
+        const ProgramView pv = load_program(p.programs + (size_t)(m_begin + mi) * 2);
+        uint32_t c[NW + 2 * H], d[NW + 2 * H];
+        if (run_chain_pair<H, PLANES>(pv, q, c, d, edge)) {  // else: no occurrence in this warp's chunks
+            const bool far = pv.mod_pos >= 32;  // only possible when H == 2
+            const int sh = pv.mod_pos & 31;
+            uint32_t cnt[4] = {0, 0, 0, 0};  // n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'
+            count_planes([&](int w) { return aligned_word<H>(c, w, sh, far); },
+                         [&](int w) { return aligned_word_rc<H>(d, w, sh, far); }, cnt);
+            flush(mi, cnt);
+        }
+        ++mi;
     }
 }
 
@@ -242,29 +332,16 @@ __global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(co
 // ---------------------------------------------------------------------------------------------
 // motif compiler: nmb_motif -> forward and reverse-complement Programs
 // ---------------------------------------------------------------------------------------------
-__global__ void compile_motifs_kernel(const nmb_motif *__restrict__ motifs, int n_motifs,
-                                      Program *__restrict__ programs) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * n_motifs) return;
-    const nmb_motif mt = motifs[t >> 1];
-    const bool rc = t & 1;
-    Program pr;
+// Program of a motif strand given as allowed-sets per position (0xF = wildcard) in reading order.
+// Gaps of 32 or more positions become "shift one word" pseudo entries so that every real entry carries a shift < 32.
+// The first processed entry is the last motif position (shift 0); a stripped motif starts with a constrained position,
+// so the chain ends aligned at position 0.
+__device__ void build_program(const uint8_t *allowed, int len, int mp, Program &pr) {
     for (int i = 0; i < kMaxLen; ++i) pr.ent[i] = 0;
-    int len = mt.len, mp = mt.mod_pos;
     pr.reserved = 0;
-    if (len < 1 || len > kMaxLen || mp >= len) {  // invalid: compile to "never matches"
-        pr.n = 1; pr.mod_pos = 0; pr.len = 1;
-        programs[t] = pr;
-        return;
-    }
-    if (rc) mp = len - 1 - mp;  // motif.py:264
-    // Gaps of 32 or more positions become "shift one word" pseudo entries so that every real entry
-    // carries a shift < 32.  The first processed entry is the last motif position (shift 0); a
-    // stripped motif starts with a constrained position, so the chain ends aligned at position 0.
     int n = 0, prev = -1;
     for (int j = len - 1; j >= 0; --j) {
-        int a = mt.allowed[rc ? (len - 1 - j) : j] & 0xF;
-        if (rc) a = ((a & 5) << 1) | ((a & 10) >> 1);  // A<->T, G<->C (constants.py:14-20)
+        const int a = allowed[j] & 0xF;
         if (a == 0xF && j != 0) continue;
         int d = prev < 0 ? 0 : prev - j;
         for (; d >= 32 && n < kMaxLen - 1; d -= 32) pr.ent[n++] = kEntShift32;
@@ -272,7 +349,115 @@ __global__ void compile_motifs_kernel(const nmb_motif *__restrict__ motifs, int 
         prev = j;
     }
     pr.n = (uint8_t)n; pr.mod_pos = (uint8_t)mp; pr.len = (uint8_t)len;
+}
+
+__global__ void compile_motifs_kernel(const nmb_motif *__restrict__ motifs, int n_motifs,
+                                      Program *__restrict__ programs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n_motifs) return;
+    const nmb_motif mt = motifs[t >> 1];
+    const bool rc = t & 1;
+    Program pr;
+    int len = mt.len, mp = mt.mod_pos;
+    if (len < 1 || len > kMaxLen || mp >= len) {  // invalid: compile to "never matches"
+        for (int i = 0; i < kMaxLen; ++i) pr.ent[i] = 0;
+        pr.reserved = 0;
+        pr.n = 1; pr.mod_pos = 0; pr.len = 1;
+        programs[t] = pr;
+        return;
+    }
+    uint8_t allowed[kMaxLen];
+    for (int j = 0; j < len; ++j) {
+        int a = mt.allowed[rc ? (len - 1 - j) : j] & 0xF;
+        if (rc) a = ((a & 5) << 1) | ((a & 10) >> 1);  // A<->T, G<->C (constants.py:14-20)
+        allowed[j] = (uint8_t)a;
+    }
+    if (rc) mp = len - 1 - mp;  // motif.py:264
+    build_program(allowed, len, mp, pr);
     programs[t] = pr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// family finder: runs of consecutive motifs inside one work item's motif block that share a parent
+// ---------------------------------------------------------------------------------------------
+constexpr int kFamSpan = 2 * kMaxLen - 1;  // offsets -61 .. 61 from the modified base
+
+// constraints of a motif by offset from its modified base: 0 = unconstrained, else the allowed-set (1..14)
+__device__ int motif_constraints(const nmb_motif &m, uint8_t (&cons)[kFamSpan]) {
+    for (int i = 0; i < kFamSpan; ++i) cons[i] = 0;
+    if (m.len < 1 || m.len > kMaxLen || m.mod_pos >= m.len) return -1;
+    int k = 0;
+    for (int j = 0; j < m.len; ++j) {
+        const int a = m.allowed[j] & 0xF;
+        if (a == 0) return -1;  // an empty set never matches: leave such motifs to the general path
+        if (a != 0xF) {
+            cons[j - m.mod_pos + kMaxLen - 1] = (uint8_t)a;
+            ++k;
+        }
+    }
+    return k;
+}
+
+__global__ void __launch_bounds__(64) find_families_kernel(const nmb_motif *__restrict__ motifs,
+                                                           const nmb_job *__restrict__ jobs, int mpi,
+                                                           FamInfo *__restrict__ fam, Program *__restrict__ parents) {
+    const nmb_job job = jobs[blockIdx.x];
+    const int n_blocks = (job.motif_count + mpi - 1) / mpi;
+    for (int blk = threadIdx.x; blk < n_blocks; blk += blockDim.x) {
+        const int m0 = job.motif_begin + blk * mpi;
+        const int cnt = min(mpi, job.motif_count - blk * mpi);
+        int i = 0;
+        while (i < cnt) {
+            FamInfo single = {0, 0, 0, 0};
+            fam[m0 + i] = single;
+            int run = 1;
+            uint8_t a[kFamSpan], b[kFamSpan], par[kFamSpan];
+            const int ka = motif_constraints(motifs[m0 + i], a);
+            if (i + 1 < cnt && ka >= 2 && a[kMaxLen - 1] != 0) {
+                const int kb = motif_constraints(motifs[m0 + i + 1], b);
+                int common = 0, lo = kFamSpan, hi = -1;
+                for (int o = 0; o < kFamSpan; ++o) {
+                    par[o] = (a[o] != 0 && a[o] == b[o]) ? a[o] : 0;
+                    if (par[o]) { ++common; lo = min(lo, o); hi = max(hi, o); }
+                }
+                // the parent holds all but one position of both, includes the modified base and spans <= 32 positions
+                if (kb == ka && common == ka - 1 && par[kMaxLen - 1] != 0 && hi - lo + 1 <= 32) {
+                    FamInfo info[kMaxMpi];
+                    auto extra_of = [&](const uint8_t (&c)[kFamSpan], FamInfo &out) -> bool {
+                        for (int o = 0; o < kFamSpan; ++o) {
+                            if (c[o] != 0 && par[o] != c[o]) {
+                                const int delta = o - (kMaxLen - 1);
+                                if (par[o] != 0 || delta < -31 || delta > 31) return false;
+                                out.set = c[o]; out.delta = (int8_t)delta; out.n = 0; out.pad = 0;
+                                return true;
+                            }
+                        }
+                        return false;
+                    };
+                    if (extra_of(a, info[0]) && extra_of(b, info[1])) {
+                        run = 2;
+                        while (i + run < cnt) {
+                            const int kc = motif_constraints(motifs[m0 + i + run], b);
+                            bool ok = kc == ka;
+                            for (int o = 0; o < kFamSpan && ok; ++o) ok = par[o] == 0 || par[o] == b[o];
+                            if (!ok || !extra_of(b, info[run])) break;
+                            ++run;
+                        }
+                        info[0].n = (uint8_t)run;
+                        for (int k = 0; k < run; ++k) fam[m0 + i + k] = info[k];
+                        uint8_t allowed[kMaxLen];
+                        const int len = hi - lo + 1;
+                        for (int j = 0; j < len; ++j) allowed[j] = par[lo + j] ? par[lo + j] : 0xF;
+                        Program pr;
+                        build_program(allowed, len, kMaxLen - 1 - lo, pr);
+                        parents[m0 + i] = pr;
+                    }
+                }
+            }
+            for (int k = 1; k < run; ++k) {}  // members were written above
+            i += run;
+        }
+    }
 }
 
 }  // namespace nmb
@@ -289,10 +474,37 @@ int nmb_compile_motifs(const nmb_motif *motifs, int32_t n_motifs, void *programs
     return NMB_OK;
 }
 
+int64_t nmb_family_scratch_bytes(int32_t n_motifs) {
+    const int64_t n = n_motifs > 0 ? n_motifs : 0;
+    return ((n * (int64_t)sizeof(nmb::FamInfo) + 127) / 128) * 128 + n * (int64_t)sizeof(nmb::Program);
+}
+
+static int scan_count_impl(const nmb_assembly *a, const uint32_t *class_records, const void *programs,
+                           const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
+                           int32_t max_motif_len, const int32_t *contig_group, int64_t *out, int32_t grid_ctas,
+                           const nmb_motif *motifs, int32_t n_motifs, void *family_scratch, void *stream);
+
 int nmb_scan_count(const nmb_assembly *a, const uint32_t *class_records, const void *programs,
                    const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
                    int32_t max_motif_len, const int32_t *contig_group, int64_t *out,
                    int32_t grid_ctas, void *stream) {
+    return scan_count_impl(a, class_records, programs, jobs, n_jobs, n_items, motifs_per_item, max_motif_len,
+                           contig_group, out, grid_ctas, nullptr, 0, nullptr, stream);
+}
+
+int nmb_scan_count_families(const nmb_assembly *a, const uint32_t *class_records, const void *programs,
+                            const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
+                            int32_t max_motif_len, const int32_t *contig_group, int64_t *out, int32_t grid_ctas,
+                            const nmb_motif *motifs, int32_t n_motifs, void *family_scratch, void *stream) {
+    NMB_REQUIRE(motifs && family_scratch && n_motifs > 0, "nmb_scan_count_families: null argument");
+    return scan_count_impl(a, class_records, programs, jobs, n_jobs, n_items, motifs_per_item, max_motif_len,
+                           contig_group, out, grid_ctas, motifs, n_motifs, family_scratch, stream);
+}
+
+static int scan_count_impl(const nmb_assembly *a, const uint32_t *class_records, const void *programs,
+                           const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
+                           int32_t max_motif_len, const int32_t *contig_group, int64_t *out, int32_t grid_ctas,
+                           const nmb_motif *motifs, int32_t n_motifs, void *family_scratch, void *stream) {
     NMB_REQUIRE(a && class_records && programs && jobs && out, "nmb_scan_count: null argument");
     NMB_REQUIRE(n_jobs > 0 && n_items >= 0, "nmb_scan_count: n_jobs=%d n_items=%d", n_jobs, n_items);
     NMB_REQUIRE(motifs_per_item >= 1 && motifs_per_item <= NMB_MAX_MOTIFS_PER_ITEM,
@@ -315,6 +527,16 @@ int nmb_scan_count(const nmb_assembly *a, const uint32_t *class_records, const v
     p.n_items = n_items;
     p.mpi = motifs_per_item;
     p.n_tiles = a->n_tiles;
+    p.fam = nullptr;
+    p.parents = nullptr;
+    if (family_scratch && motifs_per_item >= 2) {  // group the motif blocks into families (device, one block per job)
+        p.fam = (const nmb::FamInfo *)family_scratch;
+        p.parents = (const nmb::Program *)((uint8_t *)family_scratch +
+                                           ((n_motifs * (int64_t)sizeof(nmb::FamInfo) + 127) / 128) * 128);
+        nmb::find_families_kernel<<<n_jobs, 64, 0, (cudaStream_t)stream>>>(motifs, jobs, motifs_per_item,
+                                                                          (nmb::FamInfo *)p.fam, (nmb::Program *)p.parents);
+        NMB_CUDA(cudaGetLastError());
+    }
 
     // One buffer x four CTAs per SM everywhere.  The double-buffered variant (two buffers x two CTAs) is kept for
     // experiments only: with conflict-free shared memory it is still SLOWER in the streaming regime it was meant for

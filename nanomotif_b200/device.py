@@ -360,6 +360,11 @@ def compact_rows(contig_id, position, strand, fraction_mod, mod_type=None, n_con
     return dict(position=position.astype(np.int32), flags=flags, percent_x100=key, contig_row_off=off)
 
 
+import os as _os
+
+FAMILIES = _os.environ.get("NMB_FAMILIES", "1") != "0"  # family sharing in K2 (device.scan_count); 0 = general path only
+
+
 def make_jobs(n: int) -> np.ndarray:
     return np.zeros(n, dtype=_lib.JOB_DTYPE)
 
@@ -461,6 +466,18 @@ def scan_count(assembly: DeviceAssembly, pileup: DevicePileup, programs: MotifPr
         if out is None:
             out = torch.zeros((n_out_rows, 4), dtype=torch.int64, device=d)
         view = assembly.view()
+        if FAMILIES and prepared.mpi >= 2 and programs.n >= 2:
+            # motifs that share all positions but one (the children of a search expansion) are evaluated as one parent
+            # chain + one indicator plane each; the grouping runs on the device inside the call
+            scratch = torch.empty(int(lib.nmb_family_scratch_bytes(programs.n)), dtype=torch.uint8, device=d)
+            check(
+                lib.nmb_scan_count_families(C.byref(view), ptr(pileup.class_records), ptr(programs.programs),
+                                            ptr(prepared.jobs_d), prepared.n_jobs, prepared.n_items, prepared.mpi,
+                                            programs.max_len, ptr(contig_group), ptr(out), grid_ctas, ptr(programs.motifs_d),
+                                            programs.n, ptr(scratch), _stream()),
+                "nmb_scan_count_families",
+            )
+            return out
         check(
             lib.nmb_scan_count(C.byref(view), ptr(pileup.class_records), ptr(programs.programs), ptr(prepared.jobs_d),
                                prepared.n_jobs, prepared.n_items, prepared.mpi, programs.max_len, ptr(contig_group),

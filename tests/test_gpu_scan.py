@@ -304,3 +304,57 @@ def test_random_layouts_against_oracle(nmb, seed):
     models = nmb.motif_model_bin_many(pile, contigs, motifs, 0.3, 0.7)
     for mi, mdl in enumerate(models):
         assert (mdl._alpha - 5, mdl._beta - 5) == (int(per[mi, :, [0, 2]].sum()), int(per[mi, :, [1, 3]].sum()))
+
+
+def test_family_sharing_equals_general_path_and_oracle(nmb):
+    """K2's family path (children of one search expansion share the parent's chains) against the general path and the
+    oracle: search-shaped work lists (synth.frontier_worklist) plus hand-made families -- extra position left / right of
+    the parent, same position with different bases, bracket classes, members beyond 31 positions (no family), short
+    contigs and non-ACGT letters (those warps take the general path) -- for several motifs-per-item block sizes."""
+    import torch
+
+    from nanomotif_b200 import device as D, synth
+
+    rng = np.random.default_rng(23)
+    contigs, cols = {}, {k: [] for k in ("contig", "position", "strand", "fraction_mod")}
+    for i, L in enumerate((150000, 700, 66000, 40, 9000, 131072 - 64)):
+        seq = synth.random_sequence(rng, L, 0.45, 3e-5 if L > 1000 else 0.0)
+        contigs[f"c{i}"] = seq.tobytes().decode()
+        p = synth.synth_pileup(seq, rng, depth=15, mod_types=("a",))
+        cols["contig"].append(np.full(len(p["position"]), f"c{i}", dtype=object))
+        cols["position"].append(p["position"])
+        cols["strand"].append(_strand_str(p["strand"]))
+        cols["fraction_mod"].append(p["fraction_mod"])
+    pile = {k: np.concatenate(v) for k, v in cols.items()}
+    lists = []
+    for seed in (1, 2, 3):
+        for kids in synth.frontier_worklist(seed, "A", rounds=24, width=4):
+            lists.append(kids)
+    lists += [
+        [("GA", 1), ("CA", 1), ("TA", 1), ("AA", 1)],                       # parent = the modified base alone
+        [("A.G", 0), ("A.C", 0), ("A..T", 0), ("T.A", 2)],                   # extras on both sides
+        [("GA.C", 1), ("GA[CT]C", 1), ("GA[AG]C", 1)],                       # a class as the extra; 'GA.C' is the parent itself
+        [("GATC", 1), ("GATG", 1), ("CATC", 1), ("GAT.C", 1)],               # mixed: runs break and restart
+        [("A" + "." * 30 + "C", 0), ("A" + "." * 30 + "G", 0)],              # extra at offset 31: still a family
+        [("A" + "." * 31 + "C", 0), ("A" + "." * 31 + "G", 0)],              # offset 32: general path
+        [("C" + "." * 30 + "AG", 31), ("T" + "." * 30 + "AG", 31)],          # extra 31 to the left
+        [("G" + "." * 28 + "A.C", 29), ("G" + "." * 28 + "A.T", 29)],        # parent spans 30 positions
+        [("GATC", 1)], [("GATC", 1), ("GATC", 1)],                           # single; duplicates (no extra position)
+    ]
+    scorer = nmb.BinScorer(pile, contigs, 0.3, 0.7)
+    flat = [nmb.Motif(m, p) for kids in lists for m, p in kids]
+    want = np.array([O.motif_model_bin(pile["contig"], pile["position"], pile["strand"], pile["fraction_mod"], contigs,
+                                       m.string, m.mod_position, fast=True) for m in flat])
+    old = D.FAMILIES
+    try:
+        for families in (True, False):
+            D.FAMILIES = families
+            for mpi in (None, 4, 3, 32):
+                got = scorer.counts_by_strand(flat, motifs_per_item=mpi).cpu().numpy()
+                np.testing.assert_array_equal(np.stack([got[:, 0] + got[:, 2], got[:, 1] + got[:, 3]], axis=1), want,
+                                              err_msg=f"families={families} mpi={mpi}")
+            per = scorer.counts_by_strand(flat[:40], per_contig=True).cpu().numpy()  # group mode 1 through the same path
+            assert per.sum() == scorer.counts_by_strand(flat[:40]).cpu().numpy().sum()
+    finally:
+        D.FAMILIES = old
+    assert int(want.sum()) > 10000
