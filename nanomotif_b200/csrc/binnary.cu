@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(128) bin_means_kernel(const int64_t *__restric
         keep[i] = kept;
         if (kept) {
             const double w = (double)st[0];
-            num += cell_value(st, value, i) * w;
-            den += w;
+            num = __dadd_rn(num, __dmul_rn(cell_value(st, value, i), w));  // no FMA contraction: the host restatement
+            den = __dadd_rn(den, w);                                        // (numpy) rounds the product, then the sum
             contig_has[c] = 1;  // benign race: every writer stores 1
         }
     }

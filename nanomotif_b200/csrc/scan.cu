@@ -75,8 +75,54 @@ __device__ __forceinline__ int group_of(const nmb_job &job, int contig, const in
     return __ldg(contig_group + contig);
 }
 
+// Indicator plane of allowed-set `code` over the lane's words [-H, NW + H) (all fourteen sets; 0 for anything else).
+template <int H, bool HASN>
+__device__ __forceinline__ void set_indicator(const LaneSeq<H, HASN> &q, int code, uint32_t (&ind)[NW + 2 * H]) {
+    switch (code) {
+#define NMB_CASE(m)                                                                            \
+    case m:                                                                                    \
+        _Pragma("unroll") for (int i = 0; i < NW + 2 * H; ++i) ind[i] = q.template and_code<m>(i, 0xFFFFFFFFu); \
+        break;
+        NMB_CASE(1) NMB_CASE(2) NMB_CASE(3) NMB_CASE(4) NMB_CASE(5) NMB_CASE(6) NMB_CASE(7)
+        NMB_CASE(8) NMB_CASE(9) NMB_CASE(10) NMB_CASE(11) NMB_CASE(12) NMB_CASE(13) NMB_CASE(14)
+#undef NMB_CASE
+        default:
+#pragma unroll
+            for (int i = 0; i < NW + 2 * H; ++i) ind[i] = 0u;
+            break;
+    }
+}
+
+// One strand of one family member: the parent's aligned match words m[0..NW) ANDed with the indicator of the extra
+// position's set seen `shift` positions to the right (negative: to the left), popcounted against two class planes.
+template <int H, bool HASN>
+__device__ __forceinline__ void count_member_strand(const LaneSeq<H, HASN> &q, const uint32_t (&m)[NW], int code, int shift,
+                                                    const uint32_t *cl_a, const uint32_t *cl_b, uint32_t &cnt_a,
+                                                    uint32_t &cnt_b) {
+    constexpr int CW = NW + 2 * H;
+    uint32_t ind[CW];
+    set_indicator<H, HASN>(q, code, ind);
+    if (shift < 0) {  // warp-uniform: look one word to the left, then shift right by 32 - |shift|
+#pragma unroll
+        for (int i = CW - 1; i > 0; --i) ind[i] = ind[i - 1];
+        ind[0] = 0u;
+    }
+    const int s = shift & 31;
+#pragma unroll
+    for (int h = 0; h < NW; h += 4) {
+        const uint4 pa = *reinterpret_cast<const uint4 *>(cl_a + (h >> 2) * kSlotStride);
+        const uint4 pb = *reinterpret_cast<const uint4 *>(cl_b + (h >> 2) * kSlotStride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t w = m[h + k] & __funnelshift_r(ind[h + k + H], ind[h + k + H + 1], s);
+            cnt_a += __popc(w & (k == 0 ? pa.x : k == 1 ? pa.y : k == 2 ? pa.z : pa.w));
+            cnt_b += __popc(w & (k == 0 ? pb.x : k == 1 ? pb.y : k == 2 ? pb.z : pb.w));
+        }
+    }
+}
+
 // Evaluate the item's motifs on this lane's chunk and accumulate the four counters.
-template <int H, bool PLANES>
+template <int H, bool PLANES, bool FAM>
 __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job &job, const ItemMeta &meta,
                                              const LaneSeq<H, PLANES> &q, const LaneEdge &edge, const uint32_t *cl,
                                              bool valid,
@@ -86,10 +132,10 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
     const int m_count = min(p.mpi, job.motif_count - meta.mblk * p.mpi);
 
     // per-lane counts of one motif -> warp sums -> the CTA's accumulators / the output
-    auto flush = [&](int mi, const uint32_t (&cnt)[4]) {
+    auto flush = [&](int mi, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
         // n_mod | n_nomod << 16 per strand (per-lane counts are <= 512)
-        uint32_t pk_f = valid ? (cnt[0] | (cnt[1] << 16)) : 0u;
-        uint32_t pk_r = valid ? (cnt[2] | (cnt[3] << 16)) : 0u;
+        uint32_t pk_f = valid ? (c0 | (c1 << 16)) : 0u;
+        uint32_t pk_r = valid ? (c2 | (c3 << 16)) : 0u;
         const long long row = job.out_base + (long long)(meta.mblk * p.mpi + mi) * job.n_groups;
         // two 16-bit fields per word survive a 32-lane sum (<= 8192)
         if (uniform) {  // all counted lanes of the warp feed the same output row (the common case)
@@ -112,106 +158,77 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
             }
         }
     };
-    // popcounts of (match & class plane) over the lane's 16 words; mf / mr give word k of the two aligned match planes
-    auto count_planes = [&](auto mf_of, auto mr_of, uint32_t (&cnt)[4]) {
-#pragma unroll
-        for (int h = 0; h < NW; h += 4) {
-            uint4 pl[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                pl[k] = *reinterpret_cast<const uint4 *>(cl + k * kTileWords + (h >> 2) * kSlotStride);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t mf = mf_of(h + k);
-                const uint32_t mr = mr_of(h + k);
-                const uint32_t w0 = k == 0 ? pl[0].x : k == 1 ? pl[0].y : k == 2 ? pl[0].z : pl[0].w;
-                const uint32_t w1 = k == 0 ? pl[1].x : k == 1 ? pl[1].y : k == 2 ? pl[1].z : pl[1].w;
-                const uint32_t w2 = k == 0 ? pl[2].x : k == 1 ? pl[2].y : k == 2 ? pl[2].z : pl[2].w;
-                const uint32_t w3 = k == 0 ? pl[3].x : k == 1 ? pl[3].y : k == 2 ? pl[3].z : pl[3].w;
-                cnt[0] += __popc(mf & w0);  // occurrences whose modified base is methylated, '+'
-                cnt[1] += __popc(mf & w1);  // ... unmethylated, '+'
-                cnt[2] += __popc(mr & w2);  // reverse-complement occurrences, '-' strand rows
-                cnt[3] += __popc(mr & w3);
-            }
-        }
-    };
 
     int mi = 0;
 #pragma unroll 1
     while (mi < m_count) {
-        // ---- a family (see FamInfo): warps without non-ACGT letters or contig edges in reach only; the others take
-        //      the members one by one through the general path below (every member keeps its own program) ----
-        if (!PLANES && p.fam != nullptr && !edge.edge) {  // warp-uniform
-            const int run = __ldg(reinterpret_cast<const uint32_t *>(p.fam + m_begin + mi)) & 0xFF;
-            if (run >= 2) {
-                const ProgramView pv = load_program(p.parents + (m_begin + mi));
-                uint32_t c[NW + 2 * H], d[NW + 2 * H];
-                bool alive = run_chain_pair<H, PLANES>(pv, q, c, d, edge);
-                uint32_t mf[NW], mr[NW];
-                if (alive) {
-                    const bool far = pv.mod_pos >= 32;
-                    const int sh = pv.mod_pos & 31;
-                    uint32_t any = 0;
-#pragma unroll
-                    for (int k = 0; k < NW; ++k) {
-                        mf[k] = aligned_word<H>(c, k, sh, far);
-                        mr[k] = aligned_word_rc<H>(d, k, sh, far);
-                        any |= mf[k] | mr[k];
-                    }
-                    alive = __any_sync(0xFFFFFFFFu, any != 0);
-                }
-                if (alive) {  // else: no occurrence of the parent in the warp's positions -> every member counts 0
-#pragma unroll 1
-                    for (int k = 0; k < run; ++k) {
-                        const uint32_t fi = __ldg(reinterpret_cast<const uint32_t *>(p.fam + m_begin + mi + k));
-                        const int code = (fi >> 8) & 0xFF;
-                        const int delta = (int)(int8_t)((fi >> 16) & 0xFF);
-                        // c <- indicator of the extra position's set, d <- indicator of the complementary set (reversed
-                        // word order, as init_pair stores the reverse-complement chain)
-                        switch (code) {
-#define NMB_CASE(m) case m: init_pair<m, H, PLANES>(c, d, q); break;
-                            NMB_CASE(1) NMB_CASE(2) NMB_CASE(3) NMB_CASE(4) NMB_CASE(5) NMB_CASE(6) NMB_CASE(7)
-                            NMB_CASE(8) NMB_CASE(9) NMB_CASE(10) NMB_CASE(11) NMB_CASE(12) NMB_CASE(13) NMB_CASE(14)
-#undef NMB_CASE
-                            default:
-#pragma unroll
-                                for (int i = 0; i < NW + 2 * H; ++i) c[i] = d[i] = 0u;
-                                break;
-                        }
-                        constexpr int CW = NW + 2 * H;
-                        uint32_t cnt[4] = {0, 0, 0, 0};
-                        // forward: the member matches at p iff the parent does and base[p + delta] is in the set;
-                        // reverse complement (aligned at ITS modified base q): base[q - delta] in the complementary set
-                        if (delta >= 0) {
-                            count_planes(
-                                [&](int w) { return mf[w] & __funnelshift_r(c[w + H], c[w + H + 1], delta); },
-                                [&](int w) { return mr[w] & __funnelshift_l(d[CW - 1 - (w + H - 1)], d[CW - 1 - (w + H)], delta); },
-                                cnt);
-                        } else {
-                            count_planes(
-                                [&](int w) { return mf[w] & __funnelshift_l(c[w + H - 1], c[w + H], -delta); },
-                                [&](int w) { return mr[w] & __funnelshift_r(d[CW - 1 - (w + H)], d[CW - 1 - (w + H + 1)], -delta); },
-                                cnt);
-                        }
-                        flush(mi + k, cnt);
-                    }
-                }
-                mi += run;
-                continue;
+        // A family (see FamInfo) is taken as one parent + members only by warps without non-ACGT letters or contig
+        // edges in reach; the other warps take the members one by one (every member keeps its own program).
+        int run = 1;
+        const Program *prog = p.programs + (size_t)(m_begin + mi) * 2;
+        if (FAM && !PLANES && !edge.edge) {  // warp-uniform
+            const int n = __ldg(reinterpret_cast<const uint32_t *>(p.fam + m_begin + mi)) & 0xFF;
+            if (n >= 2) {
+                run = n;
+                prog = p.parents + (m_begin + mi);
             }
         }
-        // ---- one motif: ONE program serves both strands (scan.cuh: run_chain_pair) ----
-        const ProgramView pv = load_program(p.programs + (size_t)(m_begin + mi) * 2);
+        // ONE program serves both strands (scan.cuh: run_chain_pair) -- the motif's own, or the family's parent
+        const ProgramView pv = load_program(prog);
         uint32_t c[NW + 2 * H], d[NW + 2 * H];
         if (run_chain_pair<H, PLANES>(pv, q, c, d, edge)) {  // else: no occurrence in this warp's chunks
             const bool far = pv.mod_pos >= 32;  // only possible when H == 2
             const int sh = pv.mod_pos & 31;
-            uint32_t cnt[4] = {0, 0, 0, 0};  // n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'
-            count_planes([&](int w) { return aligned_word<H>(c, w, sh, far); },
-                         [&](int w) { return aligned_word_rc<H>(d, w, sh, far); }, cnt);
-            flush(mi, cnt);
+            if (!FAM || run == 1) {
+                uint32_t cnt[4] = {0, 0, 0, 0};  // n_mod '+', n_nomod '+', n_mod '-', n_nomod '-'
+#pragma unroll
+                for (int h = 0; h < NW; h += 4) {
+                    uint4 pl[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        pl[k] = *reinterpret_cast<const uint4 *>(cl + k * kTileWords + (h >> 2) * kSlotStride);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t mf = aligned_word<H>(c, h + k, sh, far);
+                        const uint32_t mr = aligned_word_rc<H>(d, h + k, sh, far);
+                        const uint32_t w0 = k == 0 ? pl[0].x : k == 1 ? pl[0].y : k == 2 ? pl[0].z : pl[0].w;
+                        const uint32_t w1 = k == 0 ? pl[1].x : k == 1 ? pl[1].y : k == 2 ? pl[1].z : pl[1].w;
+                        const uint32_t w2 = k == 0 ? pl[2].x : k == 1 ? pl[2].y : k == 2 ? pl[2].z : pl[2].w;
+                        const uint32_t w3 = k == 0 ? pl[3].x : k == 1 ? pl[3].y : k == 2 ? pl[3].z : pl[3].w;
+                        cnt[0] += __popc(mf & w0);  // occurrences whose modified base is methylated, '+'
+                        cnt[1] += __popc(mf & w1);  // ... unmethylated, '+'
+                        cnt[2] += __popc(mr & w2);  // reverse-complement occurrences, '-' strand rows
+                        cnt[3] += __popc(mr & w3);
+                    }
+                }
+                flush(mi, cnt[0], cnt[1], cnt[2], cnt[3]);
+            } else {
+                // the parent's two match planes aligned at the modified base; the chains are dead after this
+                uint32_t mf[NW], mr[NW], any = 0;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) {
+                    mf[k] = aligned_word<H>(c, k, sh, far);
+                    mr[k] = aligned_word_rc<H>(d, k, sh, far);
+                    any |= mf[k] | mr[k];
+                }
+                if (__any_sync(0xFFFFFFFFu, any != 0)) {  // else every member counts 0 in this warp
+#pragma unroll 1
+                    for (int k = 0; k < run; ++k) {
+                        const uint32_t fi = __ldg(reinterpret_cast<const uint32_t *>(p.fam + m_begin + mi + k));
+                        const int code = (fi >> 8) & 0xF;
+                        const int delta = (int)(int8_t)((fi >> 16) & 0xFF);
+                        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                        // forward: the member occurs at p iff the parent does and base[p + delta] is in the set;
+                        // reverse complement (aligned at ITS modified base q): base[q - delta] in the complementary set
+                        count_member_strand<H, PLANES>(q, mf, code, delta, cl, cl + kTileWords, c0, c1);
+                        count_member_strand<H, PLANES>(q, mr, comp_set(code), -delta, cl + 2 * kTileWords,
+                                                       cl + 3 * kTileWords, c2, c3);
+                        flush(mi + k, c0, c1, c2, c3);
+                    }
+                }
+            }
         }
-        ++mi;
+        mi += run;
     }
 }
 
@@ -224,7 +241,7 @@ constexpr int kScanSmemBytes = kSeqRecBytes + kClsRecBytes;
 // STAGES = 1 (the product configuration): one tile buffer per CTA, four CTAs per SM; sixteen resident warps hide
 // each other's latencies and the copy latency.  STAGES = 2 (experiment, NMB_SCAN_STAGES=2): two buffers per CTA, two
 // CTAs per SM, the next tile in flight while this one is evaluated -- measured slower, see nmb_scan_count.
-template <int H, int STAGES>
+template <int H, int STAGES, bool FAM>
 __global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(const ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_all[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -306,13 +323,13 @@ __global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(co
                 LaneSeq<H, true> q;
                 load_xyn<H>(sx, sy, tid, p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H, q);
                 const LaneEdge edge = {0, false, false};
-                score_motifs<H, true>(p, job, meta, q, edge, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
+                score_motifs<H, true, FAM>(p, job, meta, q, edge, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
             } else {
                 LaneSeq<H, false> q;
                 load_xy<H>(sx, sy, tid, q);
                 const LaneEdge edge = lane_edge(warp_edge, info, (int64_t)meta.tile * kTileChunks + tid,
                                                 p.contig_start, p.contig_len);
-                score_motifs<H, false>(p, job, meta, q, edge, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
+                score_motifs<H, false, FAM>(p, job, meta, q, edge, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
             }
         }
         __syncthreads();  // everyone is done with the tile and with s_acc[par]
@@ -554,16 +571,18 @@ static int scan_count_impl(const nmb_assembly *a, const uint32_t *class_records,
     if (grid > n_items) grid = n_items;
     cudaStream_t s = (cudaStream_t)stream;
     const int smem_bytes = stages * nmb::kScanSmemBytes;
-#define NMB_LAUNCH_SCAN(H, S)                                                                                         \
+#define NMB_LAUNCH_SCAN(H, S, F)                                                                                      \
     do {                                                                                                              \
-        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<H, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+        NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<H, S, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                       smem_bytes));                                                                   \
-        nmb::scan_count_kernel<H, S><<<grid, nmb::kScanThreads, smem_bytes, s>>>(p);                                   \
+        nmb::scan_count_kernel<H, S, F><<<grid, nmb::kScanThreads, smem_bytes, s>>>(p);                                \
     } while (0)
+    if (stages == 2) p.fam = nullptr;  // the experimental double-buffered variant has no family path
+    const bool fam = p.fam != nullptr;
     if (max_motif_len <= 32) {  // one halo word covers a total shift (and a mod_pos) of at most 31
-        if (stages == 2) NMB_LAUNCH_SCAN(1, 2); else NMB_LAUNCH_SCAN(1, 1);
+        if (stages == 2) NMB_LAUNCH_SCAN(1, 2, false); else if (fam) NMB_LAUNCH_SCAN(1, 1, true); else NMB_LAUNCH_SCAN(1, 1, false);
     } else {
-        if (stages == 2) NMB_LAUNCH_SCAN(2, 2); else NMB_LAUNCH_SCAN(2, 1);
+        if (stages == 2) NMB_LAUNCH_SCAN(2, 2, false); else if (fam) NMB_LAUNCH_SCAN(2, 1, true); else NMB_LAUNCH_SCAN(2, 1, false);
     }
 #undef NMB_LAUNCH_SCAN
     NMB_CUDA(cudaGetLastError());
