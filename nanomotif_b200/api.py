@@ -428,13 +428,14 @@ class MultiBinScorer:
             return out
         progs = MotifPrograms([m for _, ms, _ in live for m in ms], d, strip=True)
         jobs = make_jobs(len(live))
-        at = 0
-        for j, (ctx, ms, row) in enumerate(live):
-            jobs[j]["motif_begin"], jobs[j]["motif_count"], jobs[j]["modtype"] = at, len(ms), ctx.modtype_index
-            jobs[j]["tile_begin"], jobs[j]["tile_count"] = ctx.tile_begin, ctx.tile_count
-            jobs[j]["contig_begin"], jobs[j]["contig_end"] = ctx.contig_begin, ctx.contig_end
-            jobs[j]["group_mode"], jobs[j]["n_groups"], jobs[j]["out_base"] = 0, 1, row
-            at += len(ms)
+        counts = np.fromiter((len(ms) for _, ms, _ in live), dtype=np.int64, count=len(live))
+        jobs["motif_count"] = counts
+        jobs["motif_begin"] = np.cumsum(counts) - counts
+        jobs["out_base"] = np.fromiter((row for _, _, row in live), dtype=np.int64, count=len(live))
+        for field in ("modtype_index", "tile_begin", "tile_count", "contig_begin", "contig_end"):  # whole columns at once
+            jobs["modtype" if field == "modtype_index" else field] = np.fromiter(
+                (getattr(ctx, field) for ctx, _, _ in live), dtype=np.int64, count=len(live))
+        jobs["n_groups"] = 1  # group_mode 0: one posterior per motif
         return scan_count(self.assembly, self.pileup, progs, jobs, total, out=out)
 
     def score_batch(self, requests) -> list:

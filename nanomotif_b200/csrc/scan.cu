@@ -33,6 +33,7 @@ struct FamInfo {
     uint8_t pad;
 };
 static_assert(sizeof(FamInfo) == 4, "FamInfo is 4 bytes");
+static_assert(NMB_MAX_MOTIFS_PER_ITEM == 32, "one lane per motif of a block holds its family word");
 
 struct ScanParams {
     const uint32_t *seq_records;
@@ -130,6 +131,11 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
                                              uint32_t (*acc)[4]) {
     const int m_begin = job.motif_begin + meta.mblk * p.mpi;
     const int m_count = min(p.mpi, job.motif_count - meta.mblk * p.mpi);
+    // family table of the whole block in ONE coalesced load (lane l holds motif l's word; kMaxMpi == 32): looked up
+    // with shuffles below, so no motif waits for a dependent global load before its program can be fetched
+    uint32_t fam_w = 0;
+    if (FAM && !PLANES && !edge.edge && (int)(threadIdx.x & 31) < m_count)
+        fam_w = __ldg(reinterpret_cast<const uint32_t *>(p.fam + m_begin) + (threadIdx.x & 31));
 
     // per-lane counts of one motif -> warp sums -> the CTA's accumulators / the output
     auto flush = [&](int mi, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
@@ -167,7 +173,7 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
         int run = 1;
         const Program *prog = p.programs + (size_t)(m_begin + mi) * 2;
         if (FAM && !PLANES && !edge.edge) {  // warp-uniform
-            const int n = __ldg(reinterpret_cast<const uint32_t *>(p.fam + m_begin + mi)) & 0xFF;
+            const int n = __shfl_sync(0xFFFFFFFFu, fam_w, mi) & 0xFF;
             if (n >= 2) {
                 run = n;
                 prog = p.parents + (m_begin + mi);
@@ -214,7 +220,7 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
                 if (__any_sync(0xFFFFFFFFu, any != 0)) {  // else every member counts 0 in this warp
 #pragma unroll 1
                     for (int k = 0; k < run; ++k) {
-                        const uint32_t fi = __ldg(reinterpret_cast<const uint32_t *>(p.fam + m_begin + mi + k));
+                        const uint32_t fi = __shfl_sync(0xFFFFFFFFu, fam_w, mi + k);
                         const int code = (fi >> 8) & 0xF;
                         const int delta = (int)(int8_t)((fi >> 16) & 0xFF);
                         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
