@@ -403,83 +403,109 @@ __global__ void compile_motifs_kernel(const nmb_motif *__restrict__ motifs, int 
 // ---------------------------------------------------------------------------------------------
 // family finder: runs of consecutive motifs inside one work item's motif block that share a parent
 // ---------------------------------------------------------------------------------------------
-constexpr int kFamSpan = 2 * kMaxLen - 1;  // offsets -61 .. 61 from the modified base
+// One WARP per motif block, lane l = motif l of the block (<= 32).  Offsets are relative to the modified base and
+// limited to [-31, 31] (a member's extra position must be reachable with one halo word and the parent must fit one
+// word span); motifs reaching further are never family members.  Pass 1: every lane tests whether it and its right
+// neighbour are siblings (same number of constrained positions, all but one shared).  Then leaders are walked left
+// to right: without a sibling to the right a motif is single; otherwise every lane to the right tests itself
+// against the parent P = (leader AND leader + 1) and the run extends while consecutive lanes pass.
+constexpr int kFamReach = 31;
 
-// constraints of a motif by offset from its modified base: 0 = unconstrained, else the allowed-set (1..14)
-__device__ int motif_constraints(const nmb_motif &m, uint8_t (&cons)[kFamSpan]) {
-    for (int i = 0; i < kFamSpan; ++i) cons[i] = 0;
-    if (m.len < 1 || m.len > kMaxLen || m.mod_pos >= m.len) return -1;
-    int k = 0;
-    for (int j = 0; j < m.len; ++j) {
-        const int a = m.allowed[j] & 0xF;
-        if (a == 0) return -1;  // an empty set never matches: leave such motifs to the general path
-        if (a != 0xF) {
-            cons[j - m.mod_pos + kMaxLen - 1] = (uint8_t)a;
-            ++k;
-        }
-    }
-    return k;
+__device__ __forceinline__ int fam_set_at(const nmb_motif *m, int len, int mod, int o) {  // 0xF outside / wildcard
+    const int j = o + mod;
+    return (j >= 0 && j < len) ? (__ldg(&m->allowed[j]) & 0xF) : 0xF;
 }
 
-__global__ void __launch_bounds__(64) find_families_kernel(const nmb_motif *__restrict__ motifs,
-                                                           const nmb_job *__restrict__ jobs, int mpi,
-                                                           FamInfo *__restrict__ fam, Program *__restrict__ parents) {
-    const nmb_job job = jobs[blockIdx.x];
-    const int n_blocks = (job.motif_count + mpi - 1) / mpi;
-    for (int blk = threadIdx.x; blk < n_blocks; blk += blockDim.x) {
-        const int m0 = job.motif_begin + blk * mpi;
-        const int cnt = min(mpi, job.motif_count - blk * mpi);
-        int i = 0;
-        while (i < cnt) {
-            FamInfo single = {0, 0, 0, 0};
-            fam[m0 + i] = single;
-            int run = 1;
-            uint8_t a[kFamSpan], b[kFamSpan], par[kFamSpan];
-            const int ka = motif_constraints(motifs[m0 + i], a);
-            if (i + 1 < cnt && ka >= 2 && a[kMaxLen - 1] != 0) {
-                const int kb = motif_constraints(motifs[m0 + i + 1], b);
-                int common = 0, lo = kFamSpan, hi = -1;
-                for (int o = 0; o < kFamSpan; ++o) {
-                    par[o] = (a[o] != 0 && a[o] == b[o]) ? a[o] : 0;
-                    if (par[o]) { ++common; lo = min(lo, o); hi = max(hi, o); }
+__global__ void __launch_bounds__(256) find_families_kernel(const nmb_motif *__restrict__ motifs,
+                                                            const nmb_job *__restrict__ jobs, int mpi,
+                                                            FamInfo *__restrict__ fam, Program *__restrict__ parents) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int motif_begin = __ldg(&jobs[blockIdx.x].motif_begin), motif_count = __ldg(&jobs[blockIdx.x].motif_count);
+    const int n_blocks = (motif_count + mpi - 1) / mpi;
+    for (int blk = blockIdx.y * wpc + warp; blk < n_blocks; blk += gridDim.y * wpc) {
+        const int m0 = motif_begin + blk * mpi;
+        const int cnt = min(mpi, motif_count - blk * mpi);
+        const bool have = lane < cnt;
+        const nmb_motif *me = motifs + m0 + (have ? lane : 0);
+        const int len = have ? __ldg(&me->len) : 0, mod = have ? __ldg(&me->mod_pos) : 0;
+        // eligible: valid record whose positions all lie within [-31, 31] of the modified base
+        const bool elig = have && len >= 1 && len <= kMaxLen && mod < len && mod <= kFamReach && len - 1 - mod <= kFamReach;
+        FamInfo mine = {0, 0, 0, 0};
+        // ---- pass 1: sibling of the right neighbour? ----
+        bool sib = false;
+        {
+            const nmb_motif *nb = me + 1;
+            const bool nb_have = lane + 1 < cnt;
+            const int nlen = nb_have ? __ldg(&nb->len) : 0, nmod = nb_have ? __ldg(&nb->mod_pos) : 0;
+            const bool nelig = nb_have && nlen >= 1 && nlen <= kMaxLen && nmod < nlen && nmod <= kFamReach &&
+                               nlen - 1 - nmod <= kFamReach;
+            if (elig && nelig) {
+                int ka = 0, kb = 0, common = 0, lo = 99, hi = -99;
+                bool bad = false;
+                for (int o = -kFamReach; o <= kFamReach; ++o) {
+                    const int a = fam_set_at(me, len, mod, o), b = fam_set_at(nb, nlen, nmod, o);
+                    bad |= a == 0 || b == 0;  // an empty set never matches: leave such motifs to the general path
+                    ka += a != 0xF;
+                    kb += b != 0xF;
+                    if (a != 0xF && a == b) { ++common; lo = min(lo, o); hi = max(hi, o); }
                 }
-                // the parent holds all but one position of both, includes the modified base and spans <= 32 positions
-                if (kb == ka && common == ka - 1 && par[kMaxLen - 1] != 0 && hi - lo + 1 <= 32) {
-                    FamInfo info[kMaxMpi];
-                    auto extra_of = [&](const uint8_t (&c)[kFamSpan], FamInfo &out) -> bool {
-                        for (int o = 0; o < kFamSpan; ++o) {
-                            if (c[o] != 0 && par[o] != c[o]) {
-                                const int delta = o - (kMaxLen - 1);
-                                if (par[o] != 0 || delta < -31 || delta > 31) return false;
-                                out.set = c[o]; out.delta = (int8_t)delta; out.n = 0; out.pad = 0;
-                                return true;
-                            }
+                sib = !bad && ka == kb && ka >= 2 && common == ka - 1 && lo <= 0 && hi >= 0 && hi - lo + 1 <= 32 &&
+                      fam_set_at(me, len, mod, 0) != 0xF && fam_set_at(me, len, mod, 0) == fam_set_at(nb, nlen, nmod, 0);
+            }
+        }
+        const unsigned adj = __ballot_sync(0xFFFFFFFFu, sib);
+        // ---- walk the leaders ----
+        int leader = 0;
+        while (leader < cnt) {  // warp-uniform
+            int run = 1;
+            if ((adj >> leader) & 1u) {
+                const nmb_motif *A = motifs + m0 + leader, *B = A + 1;
+                const int alen = __ldg(&A->len), amod = __ldg(&A->mod_pos), blen = __ldg(&B->len), bmod = __ldg(&B->mod_pos);
+                // does this lane's motif hold every position of P = A & B, plus exactly one more?
+                bool ok = elig && lane >= leader;
+                int extra_set = 0, extra_o = 0, n_extra = 0, k_me = 0, k_par = 0;
+                if (ok) {
+                    for (int o = -kFamReach; o <= kFamReach; ++o) {
+                        const int a = fam_set_at(A, alen, amod, o), b = fam_set_at(B, blen, bmod, o);
+                        const int c = fam_set_at(me, len, mod, o);
+                        const bool in_par = a != 0xF && a == b;
+                        k_par += in_par;
+                        k_me += c != 0xF;
+                        if (in_par) ok &= c == a;
+                        else if (c != 0xF) { ++n_extra; extra_set = c; extra_o = o; }
+                        ok &= c != 0;
+                    }
+                    ok &= n_extra == 1 && k_me == k_par + 1;
+                }
+                const unsigned pass = __ballot_sync(0xFFFFFFFFu, ok) >> leader;  // bit 0 = the leader itself
+                run = pass == 0xFFFFFFFFu ? 32 : __ffs(~pass) - 1;                // consecutive members from the leader on
+                if (run < 2) run = 1;
+                else {
+                    if (lane >= leader && lane < leader + run) {
+                        mine.n = lane == leader ? (uint8_t)run : 0;
+                        mine.set = (uint8_t)extra_set;
+                        mine.delta = (int8_t)extra_o;
+                    }
+                    if (lane == leader) {  // the parent's program: positions of P over its span, modified base inside
+                        uint8_t allowed[32];
+                        int lo = 99, hi = -99;
+                        for (int o = -kFamReach; o <= kFamReach; ++o) {
+                            const int a = fam_set_at(A, alen, amod, o), b = fam_set_at(B, blen, bmod, o);
+                            if (a != 0xF && a == b) { lo = min(lo, o); hi = max(hi, o); }
                         }
-                        return false;
-                    };
-                    if (extra_of(a, info[0]) && extra_of(b, info[1])) {
-                        run = 2;
-                        while (i + run < cnt) {
-                            const int kc = motif_constraints(motifs[m0 + i + run], b);
-                            bool ok = kc == ka;
-                            for (int o = 0; o < kFamSpan && ok; ++o) ok = par[o] == 0 || par[o] == b[o];
-                            if (!ok || !extra_of(b, info[run])) break;
-                            ++run;
+                        for (int o = lo; o <= hi; ++o) {
+                            const int a = fam_set_at(A, alen, amod, o), b = fam_set_at(B, blen, bmod, o);
+                            allowed[o - lo] = (uint8_t)((a != 0xF && a == b) ? a : 0xF);
                         }
-                        info[0].n = (uint8_t)run;
-                        for (int k = 0; k < run; ++k) fam[m0 + i + k] = info[k];
-                        uint8_t allowed[kMaxLen];
-                        const int len = hi - lo + 1;
-                        for (int j = 0; j < len; ++j) allowed[j] = par[lo + j] ? par[lo + j] : 0xF;
                         Program pr;
-                        build_program(allowed, len, kMaxLen - 1 - lo, pr);
-                        parents[m0 + i] = pr;
+                        build_program(allowed, hi - lo + 1, -lo, pr);
+                        parents[m0 + leader] = pr;
                     }
                 }
             }
-            for (int k = 1; k < run; ++k) {}  // members were written above
-            i += run;
+            leader += run;
         }
+        if (have) fam[m0 + lane] = mine;
     }
 }
 
@@ -556,8 +582,8 @@ static int scan_count_impl(const nmb_assembly *a, const uint32_t *class_records,
         p.fam = (const nmb::FamInfo *)family_scratch;
         p.parents = (const nmb::Program *)((uint8_t *)family_scratch +
                                            ((n_motifs * (int64_t)sizeof(nmb::FamInfo) + 127) / 128) * 128);
-        nmb::find_families_kernel<<<n_jobs, 64, 0, (cudaStream_t)stream>>>(motifs, jobs, motifs_per_item,
-                                                                          (nmb::FamInfo *)p.fam, (nmb::Program *)p.parents);
+        nmb::find_families_kernel<<<dim3(n_jobs, 4), 256, 0, (cudaStream_t)stream>>>(
+            motifs, jobs, motifs_per_item, (nmb::FamInfo *)p.fam, (nmb::Program *)p.parents);
         NMB_CUDA(cudaGetLastError());
     }
 
