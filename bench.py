@@ -577,6 +577,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    affinity = None
+    if world > 1:  # one slice of the host cores per rank (contiguous: GPU i and core slice i share a NUMA node on HGX
+        try:       # boards), so that the staging threads and pinned slots of a rank stay local to its GPU
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            affinity = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, affinity)
+        except (AttributeError, OSError):
+            affinity = None
     synth = load_synth()
     n_bins = args.bins
     extra = SWEEP_EXTRA_BINS if (n_bins == N_BINS and not args.no_extras) else 0
@@ -762,7 +771,7 @@ def main():
                          "note": "3-4 motifs per tile visit: DRAM traffic (one 49.7 KB tile record per job and tile) is "
                                  "below the algorithmic bytes; `stream` is the M = 1 HBM-bound pass of the same kernel"},
             "clocks": clocks,
-            "wall_s": t_wall, "setup_s": setup_s,
+            "wall_s": t_wall, "setup_s": setup_s, "host_cores_per_rank": len(affinity) if affinity else os.cpu_count(),
             "resident": {"bins": len(my_bins), "contigs": res.asm.n_contigs, "bp": res.asm.total_bp,
                          "pileup_rows": res.n_rows, "tiles": res.asm.n_tiles},
         }
