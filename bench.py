@@ -608,11 +608,9 @@ def main():
     e2e_lengths = [int(n) for b in e2e_bins for n in plan["lengths"][plan["ranges"][b][0]:plan["ranges"][b][1]]]
     e2e_groups = [b for b in e2e_bins for _ in range(*plan["ranges"][b])]
     e2e_owner = sharding.plan_shards(e2e_lengths, world, e2e_groups) if e2e_bins else np.zeros(0, np.int32)
-    e2e_bin_owner = {}
-    for b, o in zip(e2e_groups, e2e_owner.tolist()):
-        e2e_bin_owner.setdefault(b, o)
     cpu_on = not args.no_cpu_baseline and world == 1 and rank == 0
-    host_needed = [b for b in e2e_bins if e2e_bin_owner[b] == rank]
+    # host data of every sample bin with a contig on this rank (a bin above 1.25 / world of the sample is split)
+    host_needed = sorted({b for b, o in zip(e2e_groups, e2e_owner.tolist()) if o == rank})
     t_setup = time.perf_counter()
     hb = host_bins(synth, plan, host_needed, workers=max(1, (os.cpu_count() or 1) // max(1, world)))
 

@@ -397,11 +397,13 @@ class MultiBinScorer:
         self.table = tables[0] if len(tables) == 1 and isinstance(tables[0], PileupTable) else None
 
     @classmethod
-    def from_device(cls, assembly: DeviceAssembly, pileup: DevicePileup, ranges: dict, mod_types) -> "MultiBinScorer":
-        """Scorer over state that already lives on the device: ranges = {bin name: (contig_begin, contig_end)}."""
+    def from_device(cls, assembly: DeviceAssembly, pileup: DevicePileup, ranges: dict, mod_types, rows=None) -> "MultiBinScorer":
+        """Scorer over state that already lives on the device: ranges = {bin name: (contig_begin, contig_end)};
+        rows = optional list of dataload.DeviceRows (contig ids of `assembly`, mod types of `mod_types`) for the
+        window step (growth.prepare_searches)."""
         self = cls.__new__(cls)
         self.assembly, self.pileup, self._ranges, self.mod_types = assembly, pileup, dict(ranges), list(mod_types)
-        self.rows, self.contig_id, self.mod_type_id, self.table = [], None, None, None
+        self.rows, self.contig_id, self.mod_type_id, self.table = list(rows or []), None, None, None
         return self
 
     def context(self, bin_name, mod_type) -> BinContext:

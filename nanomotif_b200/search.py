@@ -369,13 +369,29 @@ class PoolBackend:
         return self.pool.remove_batch([(self.slot, arg)])[0]
 
 
+def _per_pool(requests, call):
+    """Serve window requests pool by pool (one WindowPool per mod type): one launch per pool and round."""
+    pools = []
+    for b, _ in requests:
+        if not any(b.pool is p for p in pools):
+            pools.append(b.pool)
+    if len(pools) == 1:
+        return call(pools[0], [(b.slot, motif) for b, motif in requests])
+    out = [None] * len(requests)
+    for pool in pools:
+        idx = [i for i, (b, _) in enumerate(requests) if b.pool is pool]
+        for i, r in zip(idx, call(pool, [(requests[i][0].slot, requests[i][1]) for i in idx])):
+            out[i] = r
+    return out
+
+
 def gpu_batch_expand(requests):
-    """`batch_expand` for run_lockstep over PoolBackends of one WindowPool."""
-    return requests[0][0].pool.expand_batch([(b.slot, motif) for b, motif in requests])
+    """`batch_expand` for run_lockstep over PoolBackends (one launch per WindowPool)."""
+    return _per_pool(requests, lambda pool, reqs: pool.expand_batch(reqs))
 
 
 def gpu_batch_remove(requests):
-    return requests[0][0].pool.remove_batch([(b.slot, motif) for b, motif in requests])
+    return _per_pool(requests, lambda pool, reqs: pool.remove_batch(reqs))
 
 
 def gpu_batch_score(requests):

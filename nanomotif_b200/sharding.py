@@ -17,8 +17,9 @@ import numpy as np
 
 def plan_shards(lengths: Sequence[int], world_size: int, groups: Sequence[int] | None = None) -> np.ndarray:
     """Rank of every contig.  Longest-first greedy packing balances total bp per rank.  With `groups`
-    (bin id per contig) a bin's contigs stay together unless the bin alone exceeds 1/world_size of the
-    total, in which case its contigs are spread individually (then the all-reduce merges the bin)."""
+    (bin id per contig) a bin's contigs stay together unless the bin alone exceeds 1.25 x 1/world_size of
+    the total, in which case its contigs are spread individually (then the all-reduce merges the bin).  The
+    margin keeps bins whole when there are about as many equal-sized bins as ranks."""
     lengths = np.asarray(lengths, dtype=np.int64)
     n = len(lengths)
     owner = np.zeros(n, dtype=np.int32)
@@ -28,7 +29,7 @@ def plan_shards(lengths: Sequence[int], world_size: int, groups: Sequence[int] |
         units = [(int(lengths[i]), [i]) for i in range(n)]
     else:
         groups = np.asarray(groups)
-        limit = lengths.sum() / world_size
+        limit = 1.25 * lengths.sum() / world_size
         units = []
         for g in np.unique(groups):
             idx = np.flatnonzero(groups == g).tolist()

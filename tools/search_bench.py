@@ -55,14 +55,104 @@ def windows_for(asm, contigs, pile, pad, high):
     return growth.DeviceDNAarray.from_positions(asm, np.concatenate(ci), np.concatenate(pos), np.concatenate(st), pad)
 
 
+def cfg3_main(args):
+    """--cfg3: the lock-step search of EVERY (bin, mod type) of the cfg3 metagenome (bench.py's generator: 300 bins x
+    5 Mbp, three mod types, planted motifs per bin), all on one GPU."""
+    import bench
+    from nanomotif_b200.dataload import DeviceRows
+    from nanomotif_b200.device import DeviceAssembly, DevicePileup
+
+    synth_m = bench.load_synth()
+    plan = synth_m.cfg3_plan(bench.N_BINS + bench.SWEEP_EXTRA_BINS, bench.BIN_BP)
+    dev = torch.device("cuda", 0)
+    pad, low, high, min_kl, thr = 20, 0.3, 0.7, 0.05, 1.5
+    bins = list(range(args.bins))
+    t0 = time.perf_counter()
+    names, lens, ranges, parts = [], [], {}, []
+    for b in bins:
+        d = synth_m.cfg3_bin_device(plan, b, dev, ascii_only=True)
+        lo, hi = plan["ranges"][b]
+        ranges[f"bin_{b}"] = (len(names), len(names) + hi - lo)
+        names += [f"contig_{i}" for i in range(lo, hi)]
+        lens.append(d["lengths"])
+        parts.append(d["ascii"])
+    lens = np.concatenate(lens)
+    off = np.zeros(len(lens), dtype=np.int64)
+    off[1:] = np.cumsum(lens)[:-1]
+    asm = DeviceAssembly(names, lens, torch.cat(parts), off, dev)
+    del parts
+    pile = DevicePileup(asm, 3, low, high).clear()
+    rows = []
+    for b in bins:
+        d = synth_m.cfg3_bin_device(plan, b, dev)
+        cid = (d["contig"] + ranges[f"bin_{b}"][0]).to(torch.int32)
+        pile.add_columns(cid, d["position"], d["strand"], d["fraction_mod"], d["mod_type"], sync=False)
+        rows.append(DeviceRows(names, bench.MOD_TYPES, dev, contig_id=cid, position=d["position"], strand=d["strand"],
+                               mod_type=d["mod_type"], fraction_mod=d["fraction_mod"]))
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    multi = nmb.MultiBinScorer.from_device(asm, pile, ranges, bench.MOD_TYPES, rows)
+    n_rows = sum(len(r) for r in rows)
+    print(f"cfg3: {len(bins)} bins, {asm.total_bp / 1e9:.2f} Gbp, {asm.n_contigs} contigs, {n_rows / 1e9:.2f} G pileup rows "
+          f"(device generation + packing + class planes {t_gen:.1f} s)")
+    searches, t_prep = [], 0.0
+    pools = {}
+    for mt in bench.MOD_TYPES:
+        t0 = time.perf_counter()
+        pool, pssms, totals = growth.prepare_searches(multi, mt, pad, high, seeds=[1 + b for b in bins])
+        torch.cuda.synchronize()
+        t_prep += time.perf_counter() - t0
+        pools[mt] = pool
+        for slot, b in enumerate(bins):
+            co = search.find_candidates(mt, pad, pssms[slot], totals[slot], min_kl=min_kl, score_threshold=thr)
+            searches.append((co, search.PoolBackend(multi.context(f"bin_{b}", mt), pool, slot), b, mt))
+    print(f"windows + background PSSMs of all {len(searches)} searches (growth.prepare_searches, host random.sample stream kept) "
+          f"{t_prep:.1f} s; windows: {sum(int(p.n_total) for p in pools.values())}")
+    counts = {"score": 0, "expand": 0, "remove": 0, "motifs": 0}
+
+    def counting(kind, fn):
+        def hook(reqs):
+            counts[kind] += 1
+            if kind == "score":
+                counts["motifs"] += sum(len(m) for _, m in reqs)
+            return fn(reqs)
+        return hook
+
+    t0 = time.perf_counter()
+    results = search.run_lockstep([(co, be) for co, be, _, _ in searches], counting("score", search.gpu_batch_score),
+                                  counting("expand", search.gpu_batch_expand),
+                                  counting("remove", search.gpu_batch_remove))
+    torch.cuda.synchronize()
+    t_search = time.perf_counter() - t0
+    found = total = 0
+    for (co, be, b, mt), res in zip(searches, results):
+        best = set() if res is None else {m.string.strip(".") for m in res[1]}
+        for motif, _, mtype in plan["planted"][b]:
+            if mtype != mt:
+                continue
+            total += 1
+            out = [""]
+            for t in nmb.motif.tokenize(motif):
+                out = [o + c for o in out for c in (t[1:-1] if t.startswith("[") else t)]
+            found += motif in best or all(e in best for e in out)
+    print(f"lock-step search of {len(searches)} (bin, mod type) pairs: {t_search:.1f} s; rounds: score {counts['score']} "
+          f"({counts['motifs']} motifs), expand {counts['expand']}, remove {counts['remove']}")
+    print(f"planted motifs recovered: {found} / {total}")
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--cfg3", action="store_true", help="the whole cfg3 metagenome (device-generated), all mod types")
     ap.add_argument("--bins", type=int, default=16)
     ap.add_argument("--bin-bp", type=int, default=1_000_000)
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--cpu-bins", type=int, default=1, help="bins also searched with the CPU oracle backend (slow)")
     ap.add_argument("--check-setup", action="store_true", help="compare the batched setup with the per-bin host-driven one")
     args = ap.parse_args()
+    if args.cfg3:
+        if args.bins == 16:
+            args.bins = 300
+        return cfg3_main(args)
     pad, low, high, min_kl, thr = 20, 0.3, 0.7, 0.05, 1.5
     rng = np.random.default_rng(5)
     t0 = time.perf_counter()
