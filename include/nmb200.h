@@ -292,6 +292,15 @@ NMB_API int nmb_scan_count(const nmb_assembly *assembly_h, const uint32_t *class
                    int32_t motifs_per_item, int32_t max_motif_len, const int32_t *contig_group,
                    int64_t *out, int32_t grid_ctas /* 0 = auto */, void *stream);
 
+/* nmb_scan_count with DYNAMIC item scheduling: the persistent CTAs draw work items from work_counter (two device
+ * int32, {next item, finished CTAs}: zero before the FIRST launch; the kernel leaves them zero, so the same pair
+ * serves every later launch on the stream) instead of a static round-robin.  Same counts; launches whose items differ
+ * in cost (3 vs 4 motifs per job, dead chains) end without the static split's tail. */
+NMB_API int nmb_scan_count_balanced(const nmb_assembly *assembly_h, const uint32_t *class_records, const void *programs,
+                                    const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
+                                    int32_t max_motif_len, const int32_t *contig_group, int64_t *out, int32_t grid_ctas,
+                                    int32_t *work_counter, void *stream);
+
 /* nmb_scan_count with FAMILY sharing: inside every work item's block of motifs_per_item motifs, runs of consecutive
  * motifs that share all constrained positions but one -- the children of one search expansion,
  * find_motifs_bin.py:1116-1145 -- are found on the device (from the raw motif records the programs were compiled

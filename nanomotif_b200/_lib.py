@@ -111,6 +111,7 @@ SIGNATURES = {
     "nmb_filter_adjacency": (C.c_int, [_P, _P, _P, _P, _I64, _F64, _I32, _P, _P, _P]),
     "nmb_compile_motifs": (C.c_int, [_P, _I32, _P, _P]),
     "nmb_scan_count": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
+    "nmb_scan_count_balanced": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I32, _P, _P]),
     "nmb_family_scratch_bytes": (C.c_int64, [_I32]),
     "nmb_scan_count_families": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I32, _P, _I32, _P, _P]),
     "nmb_match_plane": (C.c_int, [C.POINTER(NmbAssembly), _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),

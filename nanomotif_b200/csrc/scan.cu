@@ -44,6 +44,7 @@ struct ScanParams {
     const int32_t *contig_group;
     const int64_t *contig_start, *contig_len;
     unsigned long long *out;
+    int *counter;             // dynamic item scheduling: {next item, finished CTAs}, zero at launch and at exit; or null
     const FamInfo *fam;       // per motif: family run length at a leader, the member's extra (set, offset); or null
     const Program *parents;   // per motif: the family's parent program (valid at leaders)
     int n_jobs, n_items, mpi, n_tiles;
@@ -266,9 +267,20 @@ __global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(co
     __syncthreads();
 
     // two bulk copies (TMA) bring the self-contained tile of item k into buffer k % STAGES; completion on its mbarrier
+    // Items are handed out through a global counter when the caller provides one (STAGES == 1): a CTA that drew
+    // cheap items (3 instead of 4 motifs, dead chains) simply takes more of them, so the launch ends when the WORK
+    // runs out, not when the unluckiest CTA of a static round-robin finishes (8 800 items over 592 CTAs on a 1/8
+    // shard: the static split left ~10 % of the launch as tail).  Items still start in tile-major order.
+    const bool dynamic = STAGES == 1 && p.counter != nullptr;
     auto issue = [&](int k) {
         const int st = k % STAGES;
-        const ItemMeta m = decode_item(p, (int)blockIdx.x + k * (int)gridDim.x);
+        const int item = dynamic ? atomicAdd(p.counter, 1) : (int)blockIdx.x + k * (int)gridDim.x;
+        if (item >= p.n_items) {  // dynamic only: nothing left -- wake the CTA with an empty phase
+            s_meta_st[st].job = -1;
+            mbar_arrive(&full_bar[st]);
+            return;
+        }
+        const ItemMeta m = decode_item(p, item);
         s_meta_st[st] = m;
         const int modtype = __ldg(&p.jobs[m.job].modtype);
         uint8_t *buf = smem_all + (size_t)st * kScanSmemBytes;
@@ -280,13 +292,14 @@ __global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(co
     };
     if (STAGES > 1 && tid == 0 && n_my > 0) issue(0);
 
-    for (int k = 0; k < n_my; ++k) {
+    for (int k = 0; dynamic || k < n_my; ++k) {
         if (tid == 0) {
             if (STAGES == 1) issue(k);
             else if (k + 1 < n_my) issue(k + 1);  // its buffer was released by the barrier that ended item k - 1
         }
         const int st = k % STAGES;
         mbar_wait(&full_bar[st], (uint32_t)((k / STAGES) & 1));
+        if (dynamic && s_meta_st[st].job < 0) break;  // CTA-uniform: every thread reads the same word
         const uint8_t *smem = smem_all + (size_t)st * kScanSmemBytes;
         const ItemMeta &s_meta = s_meta_st[st];
 
@@ -349,6 +362,11 @@ __global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(co
                 atomicAdd(p.out + row * 4 + c, (unsigned long long)v);
             }
         }
+    }
+    // every CTA has drawn its last (empty) item before it gets here: the last one to leave re-arms the counter
+    if (dynamic && tid == 0 && atomicAdd(p.counter + 1, 1) == (int)gridDim.x - 1) {
+        p.counter[0] = 0;
+        p.counter[1] = 0;
     }
 }
 
@@ -531,14 +549,24 @@ int64_t nmb_family_scratch_bytes(int32_t n_motifs) {
 static int scan_count_impl(const nmb_assembly *a, const uint32_t *class_records, const void *programs,
                            const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
                            int32_t max_motif_len, const int32_t *contig_group, int64_t *out, int32_t grid_ctas,
-                           const nmb_motif *motifs, int32_t n_motifs, void *family_scratch, void *stream);
+                           const nmb_motif *motifs, int32_t n_motifs, void *family_scratch, int32_t *work_counter,
+                           void *stream);
 
 int nmb_scan_count(const nmb_assembly *a, const uint32_t *class_records, const void *programs,
                    const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
                    int32_t max_motif_len, const int32_t *contig_group, int64_t *out,
                    int32_t grid_ctas, void *stream) {
     return scan_count_impl(a, class_records, programs, jobs, n_jobs, n_items, motifs_per_item, max_motif_len,
-                           contig_group, out, grid_ctas, nullptr, 0, nullptr, stream);
+                           contig_group, out, grid_ctas, nullptr, 0, nullptr, nullptr, stream);
+}
+
+int nmb_scan_count_balanced(const nmb_assembly *a, const uint32_t *class_records, const void *programs,
+                            const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
+                            int32_t max_motif_len, const int32_t *contig_group, int64_t *out, int32_t grid_ctas,
+                            int32_t *work_counter, void *stream) {
+    NMB_REQUIRE(work_counter, "nmb_scan_count_balanced: null work counter");
+    return scan_count_impl(a, class_records, programs, jobs, n_jobs, n_items, motifs_per_item, max_motif_len,
+                           contig_group, out, grid_ctas, nullptr, 0, nullptr, work_counter, stream);
 }
 
 int nmb_scan_count_families(const nmb_assembly *a, const uint32_t *class_records, const void *programs,
@@ -547,13 +575,14 @@ int nmb_scan_count_families(const nmb_assembly *a, const uint32_t *class_records
                             const nmb_motif *motifs, int32_t n_motifs, void *family_scratch, void *stream) {
     NMB_REQUIRE(motifs && family_scratch && n_motifs > 0, "nmb_scan_count_families: null argument");
     return scan_count_impl(a, class_records, programs, jobs, n_jobs, n_items, motifs_per_item, max_motif_len,
-                           contig_group, out, grid_ctas, motifs, n_motifs, family_scratch, stream);
+                           contig_group, out, grid_ctas, motifs, n_motifs, family_scratch, nullptr, stream);
 }
 
 static int scan_count_impl(const nmb_assembly *a, const uint32_t *class_records, const void *programs,
                            const nmb_job *jobs, int32_t n_jobs, int32_t n_items, int32_t motifs_per_item,
                            int32_t max_motif_len, const int32_t *contig_group, int64_t *out, int32_t grid_ctas,
-                           const nmb_motif *motifs, int32_t n_motifs, void *family_scratch, void *stream) {
+                           const nmb_motif *motifs, int32_t n_motifs, void *family_scratch, int32_t *work_counter,
+                           void *stream) {
     NMB_REQUIRE(a && class_records && programs && jobs && out, "nmb_scan_count: null argument");
     NMB_REQUIRE(n_jobs > 0 && n_items >= 0, "nmb_scan_count: n_jobs=%d n_items=%d", n_jobs, n_items);
     NMB_REQUIRE(motifs_per_item >= 1 && motifs_per_item <= NMB_MAX_MOTIFS_PER_ITEM,
@@ -576,6 +605,7 @@ static int scan_count_impl(const nmb_assembly *a, const uint32_t *class_records,
     p.n_items = n_items;
     p.mpi = motifs_per_item;
     p.n_tiles = a->n_tiles;
+    p.counter = work_counter;
     p.fam = nullptr;
     p.parents = nullptr;
     if (family_scratch && motifs_per_item >= 2) {  // group the motif blocks into families (device, one block per job)

@@ -370,6 +370,20 @@ import os as _os
 FAMILIES = _os.environ.get("NMB_FAMILIES", "0") == "1"
 
 
+BALANCED = _os.environ.get("NMB_BALANCED", "1") != "0"  # dynamic item scheduling in K2 (nmb_scan_count_balanced)
+_COUNTERS: dict = {}
+
+
+def _work_counter(device: torch.device) -> torch.Tensor:
+    """The {next item, finished CTAs} pair of nmb_scan_count_balanced for the current stream of `device`: zeroed once,
+    left at zero by every launch, so launches that are ordered on one stream share it."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    t = _COUNTERS.get(key)
+    if t is None:
+        t = _COUNTERS[key] = torch.zeros(2, dtype=torch.int32, device=device)
+    return t
+
+
 def make_jobs(n: int) -> np.ndarray:
     return np.zeros(n, dtype=_lib.JOB_DTYPE)
 
@@ -481,6 +495,15 @@ def scan_count(assembly: DeviceAssembly, pileup: DevicePileup, programs: MotifPr
                                             programs.max_len, ptr(contig_group), ptr(out), grid_ctas, ptr(programs.motifs_d),
                                             programs.n, ptr(scratch), _stream()),
                 "nmb_scan_count_families",
+            )
+            return out
+        if BALANCED:  # items drawn from a device counter (one pair per device and stream, re-armed by the kernel)
+            check(
+                lib.nmb_scan_count_balanced(C.byref(view), ptr(pileup.class_records), ptr(programs.programs),
+                                            ptr(prepared.jobs_d), prepared.n_jobs, prepared.n_items, prepared.mpi,
+                                            programs.max_len, ptr(contig_group), ptr(out), grid_ctas,
+                                            ptr(_work_counter(d)), _stream()),
+                "nmb_scan_count_balanced",
             )
             return out
         check(
