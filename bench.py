@@ -557,6 +557,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the regimes / stream / sweep / cfg2 sub-objects")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--only-stream", action="store_true", help="just the M = 1 streaming pass over cfg3 (profiling)")
+    ap.add_argument("--only-sweep", action="store_true", help="just the cfg5 sweep passes (profiling)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-bins", type=int, default=8, help="bins of the end-to-end sample (host tables)")
     ap.add_argument("--bins", type=int, default=N_BINS, help="cfg3 bins (debug: smaller assemblies)")
@@ -636,6 +638,11 @@ def main():
         return float(t.item())
 
     res = Resident(synth, plan, my_bins, device)
+    if args.only_stream or args.only_sweep:
+        out = stream_leg(res) if args.only_stream else dict(zip(("ms", "increments"), sweep_leg(res, world)))
+        if rank == 0:
+            emit(out)
+        return
     all_jobs = [(b, mt) for b in range(n_bins) for mt in range(len(MOD_TYPES))]
     worklists = job_worklists(synth, range(n_bins))
     sched = res.schedules(worklists, set(b for b in my_bins if b < N_BINS), all_jobs)
