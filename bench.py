@@ -563,7 +563,7 @@ def main():
     ap.add_argument("--e2e-bins", type=int, default=8, help="bins of the end-to-end sample (host tables)")
     ap.add_argument("--bins", type=int, default=N_BINS, help="cfg3 bins (debug: smaller assemblies)")
     ap.add_argument("--ref-bins", type=int, default=2, help="--impl reference: bins held by the CPU pool")
-    ap.add_argument("--ref-tasks-per-core", type=int, default=1, help="--impl reference: tasks per core and step")
+    ap.add_argument("--ref-tasks-per-core", type=int, default=8, help="--impl reference: tasks per core and step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # stdout carries exactly ONE line (the JSON): anything a library prints there (e.g. "NCCL version ...") goes to stderr
@@ -722,7 +722,10 @@ def main():
         e2e_units = sum(sum(len(k) for k in rounds) * total_bp[b] for (b, mt), rounds in e2e_lists.items())
         motif_objs = {key: [[nmb.Motif(m, p) for m, p in kids] for kids in rounds] for key, rounds in e2e_lists.items()}
         keys = sorted(e2e_lists)
-        h2d = (table_bytes(table) if table is not None else 0) + sum(len(s) for b in hb for s in bins_arg[f"bin_{b}"].values())
+        # bytes that cross PCIe: the table's Arrow buffers -- with the int64 position column and the three large_utf8
+        # offset columns narrowed to int32 inside the staging copy (4 bytes less per row and column) -- + the contigs
+        h2d = (table_bytes(table) - 16 * table.num_rows if table is not None else 0) + sum(
+            len(s) for b in hb for s in bins_arg[f"bin_{b}"].values())
         d2h = sum(sum(len(k) for k in rounds) for rounds in e2e_lists.values()) * 4 * 8
 
         def e2e_step(keep=None):
@@ -752,6 +755,7 @@ def main():
                          f"largest rank), {len(keys)} jobs x {ROUNDS} rounds",
                "boundary": "ShardedMultiBinScorer(table, {bin: {contig: str}}, mod_types, 0.3, 0.7, rank, world) + "
                            "score_batch per frontier round (MultiBinScorer per rank inside)",
+               "table_bytes_per_step": int(max_over_ranks(float(table_bytes(table) if table is not None else 0))),
                "host_format": "pyarrow Table as a polars frame holds it: contig / strand / mod_type large_utf8, position "
                               "int64, fraction_mod float64, pageable memory; contigs as Python str"}
 

@@ -520,6 +520,11 @@ NMB_API int nmb_sweep_filter(const uint32_t *n_mod, const uint32_t *n_nomod, int
 typedef struct nmb_stager nmb_stager;
 NMB_API int nmb_stager_create(int64_t slot_bytes, int32_t n_threads, nmb_stager **out);
 NMB_API int nmb_stager_copy(nmb_stager *stager, void *dst_dev, const void *src_host, int64_t bytes, void *stream);
+/* Narrowing copy: dst_dev[i] = (int32) src_host[i] for n int64 values (pileup positions, Arrow large_utf8 offsets: half
+ * the bytes over PCIe); *overflow_h (host) = 1 when a value did not fit in int32 -- the destination is then garbage
+ * and the caller copies the column as it is. */
+NMB_API int nmb_stager_copy_narrow(nmb_stager *stager, int32_t *dst_dev, const int64_t *src_host, int64_t n,
+                                   int32_t *overflow_h, void *stream);
 /* Same copy from MANY host pieces (the contig strings of a bin): piece p holds bytes [piece_off_h[p], piece_off_h[p+1])
  * of the destination, piece_off_h[0] = 0; srcs_h / piece_off_h are host arrays of n_src pointers / n_src + 1 offsets. */
 NMB_API int nmb_stager_gather(nmb_stager *stager, void *dst_dev, const void *const *srcs_h, const int64_t *piece_off_h,

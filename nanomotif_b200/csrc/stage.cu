@@ -84,13 +84,34 @@ static void gather_bytes(uint8_t *dst, const void *const *srcs, const int64_t *p
 }
 
 static int stager_run(nmb_stager *s, void *dst_dev, const void *src_host, const void *const *srcs,
-                      const int64_t *piece_off, int64_t n_src, int64_t bytes, void *stream);
+                      const int64_t *piece_off, int64_t n_src, int64_t bytes, void *stream, bool narrow = false,
+                      int32_t *overflow_h = nullptr);
+
+// dst[i] = (int32) src[i]; returns true when a value did not fit
+static bool narrow_i64(int32_t *dst, const int64_t *src, int64_t n) {
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = src[i];
+        dst[i] = (int32_t)v;
+        bad |= v ^ (int64_t)(int32_t)v;
+    }
+    return bad != 0;
+}
 
 int nmb_stager_copy(nmb_stager *s, void *dst_dev, const void *src_host, int64_t bytes, void *stream) {
     NMB_REQUIRE(s && bytes >= 0, "nmb_stager_copy: bad arguments");
     if (bytes == 0) return NMB_OK;
     NMB_REQUIRE(dst_dev && src_host, "nmb_stager_copy: null buffer");
     return stager_run(s, dst_dev, src_host, nullptr, nullptr, 0, bytes, stream);
+}
+
+int nmb_stager_copy_narrow(nmb_stager *s, int32_t *dst_dev, const int64_t *src_host, int64_t n, int32_t *overflow_h,
+                           void *stream) {
+    NMB_REQUIRE(s && n >= 0 && overflow_h, "nmb_stager_copy_narrow: bad arguments");
+    *overflow_h = 0;
+    if (n == 0) return NMB_OK;
+    NMB_REQUIRE(dst_dev && src_host, "nmb_stager_copy_narrow: null buffer");
+    return stager_run(s, dst_dev, src_host, nullptr, nullptr, 0, n * 4, stream, true, overflow_h);
 }
 
 int nmb_stager_gather(nmb_stager *s, void *dst_dev, const void *const *srcs_h, const int64_t *piece_off_h,
@@ -105,13 +126,15 @@ int nmb_stager_gather(nmb_stager *s, void *dst_dev, const void *const *srcs_h, c
 }
 
 static int stager_run(nmb_stager *s, void *dst_dev, const void *src_host, const void *const *srcs,
-                      const int64_t *piece_off, int64_t n_src, int64_t bytes, void *stream) {
+                      const int64_t *piece_off, int64_t n_src, int64_t bytes, void *stream, bool narrow,
+                      int32_t *overflow_h) {
     cudaStream_t caller = (cudaStream_t)stream;
     NMB_CUDA(cudaSetDevice(s->device));
     NMB_CUDA(cudaEventRecord(s->begin, caller));  // dst may still be in use by work enqueued before this call
     const int64_t n_chunks = (bytes + s->slot_bytes - 1) / s->slot_bytes;
     const int T = (int)(n_chunks < s->n_threads ? n_chunks : s->n_threads);
     std::vector<cudaError_t> err(T, cudaSuccess);
+    std::vector<int> overflow(T, 0);
     auto body = [&](int t) {
         cudaError_t e = cudaSetDevice(s->device);
         cudaStream_t st = s->streams[t];
@@ -123,7 +146,9 @@ static int stager_run(nmb_stager *s, void *dst_dev, const void *src_host, const 
             const int64_t n = bytes - off < s->slot_bytes ? bytes - off : s->slot_bytes;
             if (k >= 2) e = cudaEventSynchronize(s->slot_done[slot]);  // the DMA that last read this slot
             if (e != cudaSuccess) break;
-            if (src_host) memcpy(s->slots[slot], (const uint8_t *)src_host + off, (size_t)n);
+            if (narrow)  // off / n count destination bytes: int32 elements made from int64 ones
+                overflow[t] |= narrow_i64((int32_t *)s->slots[slot], (const int64_t *)src_host + off / 4, n / 4);
+            else if (src_host) memcpy(s->slots[slot], (const uint8_t *)src_host + off, (size_t)n);
             else gather_bytes(s->slots[slot], srcs, piece_off, n_src, off, n);
             e = cudaMemcpyAsync((uint8_t *)dst_dev + off, s->slots[slot], (size_t)n, cudaMemcpyHostToDevice, st);
             if (e == cudaSuccess) e = cudaEventRecord(s->slot_done[slot], st);
@@ -144,6 +169,7 @@ static int stager_run(nmb_stager *s, void *dst_dev, const void *src_host, const 
         if (err[t] != cudaSuccess)
             NMB_FAIL(NMB_ERR_CUDA, "nmb_stager: %s", cudaGetErrorString(err[t]));
         NMB_CUDA(cudaStreamWaitEvent(caller, s->done[t], 0));
+        if (overflow_h && overflow[t]) *overflow_h = 1;
     }
     return NMB_OK;
 }

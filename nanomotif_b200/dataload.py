@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from ._lib import check, lib, ptr
-from .device import _require_cuda, _stream, _to_device
+from .device import _require_cuda, _stream, _to_device, _to_device_narrow
 from .pileup import PileupTable, strand_codes
 
 # bedMethyl columns kept by the reference (1-based 1,2,4,6,10,11; dataload.py:84)
@@ -392,9 +392,14 @@ def _lookup_ids(kind, a, b, names, missing, out_dtype, device, table_cache=None)
             table_cache[key] = tab
     h, ids, noff, blob = tab
     n = len(a) - 1
-    off_d, data_d = _to_device(a, device), _to_device(b, device)
+    off_d = None
+    if a.dtype == np.int64 and n and int(a[-1]) < 2**31:  # large_utf8 offsets that fit int32: half the PCIe bytes
+        off_d = _to_device_narrow(a, device)
+    if off_d is None:
+        off_d = _to_device(a, device)
+    data_d = _to_device(b, device)
     out = torch.empty(n, dtype=out_dtype, device=device)
-    check(lib.nmb_lookup_strings(ptr(data_d), ptr(off_d), a.dtype.itemsize, n, ptr(h), ptr(ids), ptr(noff), ptr(blob),
+    check(lib.nmb_lookup_strings(ptr(data_d), ptr(off_d), off_d.element_size(), n, ptr(h), ptr(ids), ptr(noff), ptr(blob),
                                  n_names, missing, ptr(out), out.element_size(), _stream()), "nmb_lookup_strings")
     return out
 
@@ -413,7 +418,9 @@ def rows_from_table(frame, contig_names, mod_types=("a", "m", "21839"), device=N
             raise KeyError("pileup has no 'position' column")
         if strand_c is None or frac_c is None:
             raise KeyError("pileup needs 'strand' and 'fraction_mod' columns")
-        pos = _to_device(_numeric_column(pos_c, np.int64), d)
+        pos_h = _numeric_column(pos_c, np.int64)
+        pos = _to_device_narrow(pos_h, d)  # positions fit int32 (contig coordinates); widened again on the device
+        pos = _to_device(pos_h, d) if pos is None else pos.to(torch.int64)
         frac = _to_device(_numeric_column(frac_c, np.float64), d)
         n = int(pos.numel())
         strand = _lookup_ids(*_string_column(strand_c), ["+", "-"], 2, torch.uint8, d, table_cache)

@@ -85,6 +85,23 @@ def _ascii_pointers(strings) -> np.ndarray | None:
     return out
 
 
+def _to_device_narrow(arr: np.ndarray, device: torch.device) -> torch.Tensor | None:
+    """int64 host array -> int32 device tensor through the stager's narrowing copy (half the PCIe bytes), or None
+    when the array is small, no stager is configured or a value does not fit."""
+    arr = np.ascontiguousarray(arr)
+    if arr.dtype != np.int64 or arr.nbytes < STAGE_MIN_BYTES:
+        return None
+    st = _stager(device)
+    if not st:
+        return None
+    flag = C.c_int32(0)
+    with torch.cuda.device(device):
+        out = torch.empty(arr.shape, dtype=torch.int32, device=device)
+        check(lib.nmb_stager_copy_narrow(st, ptr(out), arr.ctypes.data, arr.size, C.byref(flag), _stream()),
+              "nmb_stager_copy_narrow")
+    return None if flag.value else out
+
+
 def _to_device(arr: np.ndarray, device: torch.device) -> torch.Tensor:
     """Host array -> device tensor on the current stream.  Large pageable arrays (the Arrow buffers of a pileup table)
     go through the multi-threaded pinned stager (csrc/stage.cu); the source is never modified."""

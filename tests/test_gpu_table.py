@@ -192,3 +192,34 @@ def test_drop_in_cache_sees_mutated_inputs(nmb, data):
     assert got() == want()
     nmb.clear_caches()
     assert got() == want()
+
+
+def test_staged_copies_and_narrowing(nmb):
+    """The pinned stager behind every large host -> device copy: plain, gathered from many pieces, and narrowing
+    int64 -> int32 with an overflow flag; odd sizes around the 4 MB slot size."""
+    import torch
+
+    from nanomotif_b200 import device as D
+
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(0)
+    for n in (D.STAGE_SLOT_BYTES // 8 - 3, 3 * D.STAGE_SLOT_BYTES // 8 + 17, 5_000_001):
+        a = rng.integers(0, 2**31 - 1, size=n, dtype=np.int64)
+        assert np.array_equal(D._to_device(a, dev).cpu().numpy(), a)                      # nmb_stager_copy
+        narrow = D._to_device_narrow(a, dev)                                               # nmb_stager_copy_narrow
+        assert narrow is not None and narrow.dtype == torch.int32
+        assert np.array_equal(narrow.cpu().numpy(), a.astype(np.int32))
+        a[n // 2] = 2**31  # does not fit
+        assert D._to_device_narrow(a, dev) is None
+        a[n // 2] = -5     # negative values fit
+        assert np.array_equal(D._to_device_narrow(a, dev).cpu().numpy(), a.astype(np.int32))
+    u8 = rng.integers(0, 256, size=9_000_001, dtype=np.uint8)
+    assert np.array_equal(D._to_device(u8, dev).cpu().numpy(), u8)
+    seqs = {f"c{i}": "".join(rng.choice(list("ACGTN"), size=int(rng.integers(1, 900_000)))) for i in range(23)}
+    asm = D.DeviceAssembly.from_sequences(seqs)                                            # nmb_stager_gather
+    assert asm.total_bp == sum(len(s) for s in seqs.values()) >= D.STAGE_MIN_BYTES
+    for name in ("c0", "c7", "c22"):
+        got = nmb.subseq_indices("ACGT", seqs[name])
+        np.testing.assert_array_equal(got, O.subseq_indices("ACGT", seqs[name]))
+    rows = nmb.MultiBinScorer  # the table tests above cover nmb_lookup_strings through the same stager
+    assert rows is not None
