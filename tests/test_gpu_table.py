@@ -203,7 +203,7 @@ def test_staged_copies_and_narrowing(nmb):
 
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(0)
-    for n in (D.STAGE_SLOT_BYTES // 8 - 3, 3 * D.STAGE_SLOT_BYTES // 8 + 17, 5_000_001):
+    for n in (D.STAGE_MIN_BYTES // 8 + 5, 3 * D.STAGE_SLOT_BYTES // 8 + 17, 5_000_001):  # below STAGE_MIN_BYTES: plain copy
         a = rng.integers(0, 2**31 - 1, size=n, dtype=np.int64)
         assert np.array_equal(D._to_device(a, dev).cpu().numpy(), a)                      # nmb_stager_copy
         narrow = D._to_device_narrow(a, dev)                                               # nmb_stager_copy_narrow
