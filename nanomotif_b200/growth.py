@@ -291,6 +291,74 @@ def background_pssm(assembly: DeviceAssembly, contigs, mod_base: str, padding: i
     return arr.exact_pssm()
 
 
+class MTStream:
+    """`random.sample(range(n), k)` on the module-level `random` generator, drawn in bulk.
+
+    The reference samples its background windows with `random.sample(valid_starts, n)` (seq.py:202-225).  CPython's
+    `sample` (set branch, n > 21 + 4^ceil(log4(3k))) draws `randbelow(n)` until k distinct values have come up, and
+    `randbelow(n)` is `getrandbits(n.bit_length())` = one MT19937 output word shifted right, redrawn while >= n.  The
+    picks are therefore a pure function of the generator's 32-bit word stream: numpy's MT19937, loaded with the same
+    624-word state, produces that stream millions of words at a time and the accept / distinct logic becomes three
+    array operations.  `sync()` leaves the Python generator exactly where the loop of `random.sample` calls would
+    have left it.  Small populations (the pool branch) fall back to `random.sample` itself."""
+
+    def __init__(self):
+        self._ver, internal, self._gauss = random.getstate()
+        self._start = {"bit_generator": "MT19937", "state": {"key": np.array(internal[:-1], dtype=np.uint32), "pos": int(internal[-1])}}
+        self._bg = np.random.MT19937()
+        self._bg.state = self._start
+        self._buf = np.zeros(0, dtype=np.uint32)
+        self._cur = 0        # next unread word of _buf
+        self._consumed = 0   # words consumed since _start
+
+    def _words(self, m: int) -> np.ndarray:
+        have = len(self._buf) - self._cur
+        if have < m:
+            more = self._bg.random_raw(max(m - have, 1 << 20)).astype(np.uint32)
+            self._buf = np.concatenate([self._buf[self._cur:], more])
+            self._cur = 0
+        return self._buf[self._cur:self._cur + m]
+
+    def sync(self) -> None:
+        """Put the module-level `random` generator where the equivalent random.sample calls would have left it."""
+        bg = np.random.MT19937()
+        bg.state = self._start
+        if self._consumed:
+            bg.random_raw(self._consumed)
+        st = bg.state["state"]
+        random.setstate((self._ver, tuple(int(x) for x in st["key"]) + (int(st["pos"]),), self._gauss))
+
+    def sample(self, n: int, k: int) -> np.ndarray:
+        if not 0 <= k <= n:
+            raise ValueError("Sample larger than population or is negative")
+        setsize = 21
+        if k > 5:
+            setsize += 4 ** math.ceil(math.log(k * 3, 4))
+        if n <= setsize or k == 0:  # pool branch (partial shuffle): rare here, let CPython do it
+            self.sync()
+            out = np.asarray(random.sample(range(n), k), dtype=np.int64)
+            self.__init__()
+            return out
+        shift = 32 - n.bit_length()
+        if shift < 0:
+            raise ValueError("population too large for the 32-bit fast path")
+        need = int(k * ((1 << n.bit_length()) / n) * 1.1) + 64
+        while True:
+            w = self._words(need)
+            r = w >> np.uint32(shift)
+            acc = np.flatnonzero(r < n)                     # accepted draws, in stream order
+            cand = r[acc]
+            _, first = np.unique(cand, return_index=True)   # first occurrence of every value
+            if len(first) >= k:
+                first.sort()
+                keep = first[:k]
+                used = int(acc[keep[-1]]) + 1               # words up to and including the k-th distinct value
+                self._cur += used
+                self._consumed += used
+                return cand[keep].astype(np.int64)
+            need *= 2
+
+
 def prepare_searches(scorer, mod_type, padding: int, high: float, bin_names=None, sampling_frequency: float = 0.01,
                      seeds=None):
     """Everything find_best_candidates builds before its search loop (find_motifs_bin.py:625-686), for EVERY bin of a
@@ -353,9 +421,11 @@ def prepare_searches(scorer, mod_type, padding: int, high: float, bin_names=None
         n_valid = lohi[:, 1] - lohi[:, 0]
         picks, at, bg_begin, bg_end = [], 0, [], []
         ci = 0
+        stream = MTStream()
         for i, b in enumerate(names):
             if seeds is not None:
                 random.seed(seeds[i])
+                stream = MTStream()
             bg_begin.append(at)
             for _ in range(*scorer._ranges[b]):
                 k = int(max(math.ceil(int(L[ci]) * sampling_frequency), 50))  # find_motifs_bin.py:633
@@ -363,10 +433,11 @@ def prepare_searches(scorer, mod_type, padding: int, high: float, bin_names=None
                     raise ValueError("Too many samples requested for unique subsequences")  # seq.py:210
                 if n_valid[ci] < k:
                     raise ValueError(f"Not enough subsequences with 'C' in the middle (found {int(n_valid[ci])}, need {k})")
-                picks.append(np.asarray(random.sample(range(int(n_valid[ci])), k), dtype=np.int64) + lohi[ci, 0])
+                picks.append(stream.sample(int(n_valid[ci]), k) + lohi[ci, 0])
                 at += k
                 ci += 1
             bg_end.append(at)
+        stream.sync()  # the module-level generator continues where the reference's calls would have left it
         centre = P[_to_device(np.concatenate(picks), d)].contiguous()  # start + padding = the base's own position
         nb = int(centre.numel())
         bgw = torch.empty((nb, 3), dtype=torch.int64, device=d)

@@ -279,3 +279,32 @@ def test_load_fasta_host(tmp_path):
     assert dataload.load_fasta(str(tmp_path / "a.fa")) == want
     assert dataload.load_fasta(str(tmp_path / "a.fa.gz")) == want
     assert list(dataload.load_fasta(str(tmp_path / "a.fa"), trim_names=True, trim_character="1")) == ["c", "c2\tx", "c3"]
+
+
+def test_mtstream_reproduces_random_sample_and_its_state():
+    """growth.MTStream draws random.sample(range(n), k) in bulk from numpy's MT19937 loaded with the Python generator's
+    state: same picks in the same order, and the Python generator continues exactly where the loop of random.sample
+    calls (seq.py:202-225, one per contig) would have left it -- set branch, pool branch and k = 0 alike."""
+    import random
+
+    from nanomotif_b200.growth import MTStream
+
+    rng = np.random.default_rng(0)
+    cases = [(16000, 650), (100, 50), (62000, 2500), (1250000, 50000), (300, 50), (278, 50), (277, 50), (5, 5), (1000, 0),
+             (70000, 50), (2**20, 100), (2**20 + 1, 1000), (4097, 4000)]
+    for _ in range(30):
+        n = int(rng.integers(60, 400000))
+        cases.append((n, int(min(n, max(50, rng.integers(1, n // 20 + 2))))))
+    random.seed(2403)  # the reference's import-time seed (seq.py:6)
+    random.random()
+    state = random.getstate()
+    want = [random.sample(range(n), k) for n, k in cases]
+    tail = [random.random() for _ in range(5)]
+    random.setstate(state)
+    stream = MTStream()
+    got = [stream.sample(n, k) for n, k in cases]
+    stream.sync()
+    assert [g.tolist() for g in got] == want
+    assert [random.random() for _ in range(5)] == tail
+    with pytest.raises(ValueError):
+        MTStream().sample(5, 6)
