@@ -266,6 +266,9 @@ __device__ __forceinline__ void pattern_motifs(const PatParams &p, int mblk, con
         if (!run_chain_pair<H, HASN>(pv, q, c, d, edge)) continue;
         const bool far = pv.mod_pos >= 32;
         const int sh = pv.mod_pos & 31;
+        // occurrences WITH a pileup row, all 16 words of both strands first (the chains are dead after this): most
+        // (warp, motif) pairs of a specific motif have none, and ONE vote then skips the whole push stage
+        uint32_t hit0[NW], hit1[NW], any = 0;
 #pragma unroll
         for (int h = 0; h < NW; h += 4) {
             const uint4 vp = *reinterpret_cast<const uint4 *>(sv + (h >> 2) * kSlotStride);
@@ -274,13 +277,19 @@ __device__ __forceinline__ void pattern_motifs(const PatParams &p, int mblk, con
             for (int k = 0; k < 4; ++k) {
                 const uint32_t v0 = k == 0 ? vp.x : k == 1 ? vp.y : k == 2 ? vp.z : vp.w;
                 const uint32_t v1 = k == 0 ? vm.x : k == 1 ? vm.y : k == 2 ? vm.z : vm.w;
-                uint32_t hit0 = aligned_word<H>(c, h + k, sh, far) & v0;
-                uint32_t hit1 = aligned_word_rc<H>(d, h + k, sh, far) & v1;
-                if (contig < 0) hit0 = hit1 = 0;
-                if (!__any_sync(0xFFFFFFFFu, (hit0 | hit1) != 0)) continue;  // occurrences WITH a pileup row are sparse
-                push_hits(&p, &wq, hit0, v0, rank_p + s_pref[(h + k) * kTileChunks + tid], contig, mi, m_begin, c0);
-                push_hits(&p, &wq, hit1, v1, rank_m + s_pref[(NW + h + k) * kTileChunks + tid], contig, mi, m_begin, c0);
+                hit0[h + k] = contig < 0 ? 0u : aligned_word<H>(c, h + k, sh, far) & v0;
+                hit1[h + k] = contig < 0 ? 0u : aligned_word_rc<H>(d, h + k, sh, far) & v1;
+                any |= hit0[h + k] | hit1[h + k];
             }
+        }
+        if (!__any_sync(0xFFFFFFFFu, any != 0)) continue;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            if (!__any_sync(0xFFFFFFFFu, (hit0[w] | hit1[w]) != 0)) continue;
+            const uint32_t v0 = sv[(w >> 2) * kSlotStride + (w & 3)];
+            const uint32_t v1 = sv[kTileWords + (w >> 2) * kSlotStride + (w & 3)];
+            push_hits(&p, &wq, hit0[w], v0, rank_p + s_pref[w * kTileChunks + tid], contig, mi, m_begin, c0);
+            push_hits(&p, &wq, hit1[w], v1, rank_m + s_pref[(NW + w) * kTileChunks + tid], contig, mi, m_begin, c0);
         }
     }
     if (wq.n) drain_hits(&p, &wq, wq.n, m_begin, c0);
@@ -297,7 +306,7 @@ __device__ __forceinline__ void pattern_motifs(const PatParams &p, int mblk, con
 constexpr int kPrefBytes = 2 * NW * kTileChunks * 2;  // uint16 prefix counts: 8 KB
 
 template <int H>
-__global__ void __launch_bounds__(kPatThreads, 4) pattern_scan_kernel(const PatParams p) {
+__global__ void __launch_bounds__(kPatThreads, 4) pattern_scan_kernel(const __grid_constant__ PatParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar;
     __shared__ WarpQueue s_queue[kPatThreads / 32];
