@@ -433,6 +433,13 @@ NMB_API int nmb_pattern_scan(const nmb_assembly *assembly_h, const uint32_t *val
                              int32_t max_motif_len, int32_t phase, int64_t *stats, const int64_t *offsets,
                              int32_t *cursor, double *fractions, int32_t grid_ctas, void *stream);
 
+/* nmb_pattern_scan with dynamic item scheduling (work_counter as for nmb_scan_count_balanced). */
+NMB_API int nmb_pattern_scan_balanced(const nmb_assembly *assembly_h, const uint32_t *valid_records,
+                                      const uint32_t *rank_dir, const int32_t *payload, const void *programs,
+                                      int32_t n_motifs, int32_t motifs_per_item, int32_t max_motif_len, int32_t phase,
+                                      int64_t *stats, const int64_t *offsets, int32_t *cursor, double *fractions,
+                                      int32_t grid_ctas, int32_t *work_counter, void *stream);
+
 /* offsets[0..n_segments] = exclusive prefix sum of stats[i][0]; cursor[i] = 0. */
 NMB_API int nmb_segment_offsets(const int64_t *stats, int64_t n_segments, int64_t *offsets, int32_t *cursor,
                                 void *stream);

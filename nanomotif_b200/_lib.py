@@ -125,6 +125,7 @@ SIGNATURES = {
     "nmb_pattern_median": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _P]),
     "nmb_pattern_index_build": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _P, _P, _I32, _P, _P, _P, _I64, _I64, _F64, _P, _P, _P, _P, _P, _P]),
     "nmb_pattern_scan": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P]),
+    "nmb_pattern_scan_balanced": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P]),
     "nmb_segment_offsets": (C.c_int, [_P, _I64, _P, _P, _P]),
     "nmb_segment_median": (C.c_int, [_P, _P, _I64, _P, _P]),
     "nmb_stager_create": (C.c_int, [_I64, _I32, C.POINTER(_P)]),

@@ -140,6 +140,7 @@ struct PatParams {
     const long long *offsets;     // [n_motifs * n_contigs + 1]   (phase 1)
     int *cursor;                  // [n_motifs * n_contigs]       (phase 1)
     double *fractions;            //                              (phase 1)
+    int *counter;                 // dynamic item scheduling {next item, finished CTAs} (see scan.cu), or null
     int64_t n_words;
     int n_motifs, mpi, n_mblk, n_tiles, n_contigs, n_items, write;
 };
@@ -311,26 +312,36 @@ __global__ void __launch_bounds__(kPatThreads, 4) pattern_scan_kernel(const __gr
     __shared__ __align__(8) uint64_t full_bar;
     __shared__ WarpQueue s_queue[kPatThreads / 32];
     const int tid = threadIdx.x;
-    const int n_my = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    __shared__ int s_item;
     if (tid == 0) {
         mbar_init(&full_bar, 1);
         fence_barrier_init();
     }
     __syncthreads();
     uint16_t *s_pref = reinterpret_cast<uint16_t *>(smem + kSeqRecBytes + kValidRecBytes);
-    for (int k = 0; k < n_my; ++k) {
-        const int item = (int)blockIdx.x + k * (int)gridDim.x;
-        const int tile = item / p.n_mblk, mblk = item % p.n_mblk;  // tile-major: concurrent CTAs share a tile in L2
+    // items come from a device counter when the caller provides one (tiles differ in rows and hits: a static
+    // round-robin ends with the unluckiest CTA), else blockIdx.x + k * gridDim.x
+    for (int k = 0;; ++k) {
         if (tid == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(&full_bar, kSeqRecBytes + kValidRecBytes);
-            bulk_g2s(smem, p.seq_records + (size_t)tile * kSeqRecWords, kSeqRecBytes, &full_bar);
-            bulk_g2s(smem + kSeqRecBytes, p.valid + (size_t)tile * kValidRecWords, kValidRecBytes, &full_bar);
+            const int item = p.counter ? atomicAdd(p.counter, 1) : (int)blockIdx.x + k * (int)gridDim.x;
+            s_item = item < p.n_items ? item : -1;
+            if (item < p.n_items) {
+                const int tile = item / p.n_mblk;
+                fence_proxy_async();
+                mbar_expect_tx(&full_bar, kSeqRecBytes + kValidRecBytes);
+                bulk_g2s(smem, p.seq_records + (size_t)tile * kSeqRecWords, kSeqRecBytes, &full_bar);
+                bulk_g2s(smem + kSeqRecBytes, p.valid + (size_t)tile * kValidRecWords, kValidRecBytes, &full_bar);
+            } else {
+                mbar_arrive(&full_bar);  // nothing left: wake the CTA with an empty phase
+            }
         }
+        mbar_wait(&full_bar, (uint32_t)(k & 1));
+        const int item = s_item;
+        if (item < 0) break;  // CTA-uniform
+        const int tile = item / p.n_mblk, mblk = item % p.n_mblk;  // tile-major: concurrent CTAs share a tile in L2
         // rows before the lane's chunk on each strand: the only rank-directory reads of the tile
         const int64_t dir0 = (int64_t)tile * kTileWords + tid * NW;
         const uint32_t rank_p = __ldg(p.rank_dir + dir0), rank_m = __ldg(p.rank_dir + p.n_words + dir0);
-        mbar_wait(&full_bar, (uint32_t)(k & 1));
         const uint32_t *sx = reinterpret_cast<const uint32_t *>(smem);
         const uint32_t *sy = sx + kSeqPlaneWords;
         const int32_t *sinfo = reinterpret_cast<const int32_t *>(sy + kSeqPlaneWords);
@@ -366,7 +377,11 @@ __global__ void __launch_bounds__(kPatThreads, 4) pattern_scan_kernel(const __gr
                 pattern_motifs<H, false>(p, mblk, q, edge, sv, s_pref, wq, rank_p, rank_m, contig, c0);
             }
         }
-        __syncthreads();  // everyone is done with the tile
+        __syncthreads();  // everyone is done with the tile (and has read s_item)
+    }
+    if (p.counter && tid == 0 && atomicAdd(p.counter + 1, 1) == (int)gridDim.x - 1) {  // last CTA out re-arms the counter
+        p.counter[0] = 0;
+        p.counter[1] = 0;
     }
 }
 
@@ -439,10 +454,32 @@ int nmb_pattern_index_build(const nmb_assembly *a, const int32_t *contig_id, con
     return NMB_OK;
 }
 
+static int pattern_scan_impl(const nmb_assembly *a, const uint32_t *valid_records, const uint32_t *rank_dir,
+                             const int32_t *payload, const void *programs, int32_t n_motifs, int32_t motifs_per_item,
+                             int32_t max_motif_len, int32_t phase, int64_t *stats, const int64_t *offsets, int32_t *cursor,
+                             double *fractions, int32_t grid_ctas, int32_t *work_counter, void *stream);
+
 int nmb_pattern_scan(const nmb_assembly *a, const uint32_t *valid_records, const uint32_t *rank_dir,
                      const int32_t *payload, const void *programs, int32_t n_motifs, int32_t motifs_per_item,
                      int32_t max_motif_len, int32_t phase, int64_t *stats, const int64_t *offsets, int32_t *cursor,
                      double *fractions, int32_t grid_ctas, void *stream) {
+    return pattern_scan_impl(a, valid_records, rank_dir, payload, programs, n_motifs, motifs_per_item, max_motif_len, phase,
+                             stats, offsets, cursor, fractions, grid_ctas, nullptr, stream);
+}
+
+int nmb_pattern_scan_balanced(const nmb_assembly *a, const uint32_t *valid_records, const uint32_t *rank_dir,
+                              const int32_t *payload, const void *programs, int32_t n_motifs, int32_t motifs_per_item,
+                              int32_t max_motif_len, int32_t phase, int64_t *stats, const int64_t *offsets,
+                              int32_t *cursor, double *fractions, int32_t grid_ctas, int32_t *work_counter, void *stream) {
+    NMB_REQUIRE(work_counter, "nmb_pattern_scan_balanced: null work counter");
+    return pattern_scan_impl(a, valid_records, rank_dir, payload, programs, n_motifs, motifs_per_item, max_motif_len, phase,
+                             stats, offsets, cursor, fractions, grid_ctas, work_counter, stream);
+}
+
+static int pattern_scan_impl(const nmb_assembly *a, const uint32_t *valid_records, const uint32_t *rank_dir,
+                             const int32_t *payload, const void *programs, int32_t n_motifs, int32_t motifs_per_item,
+                             int32_t max_motif_len, int32_t phase, int64_t *stats, const int64_t *offsets, int32_t *cursor,
+                             double *fractions, int32_t grid_ctas, int32_t *work_counter, void *stream) {
     NMB_REQUIRE(a && valid_records && rank_dir && programs && stats, "nmb_pattern_scan: null argument");
     NMB_REQUIRE(n_motifs >= 0 && (phase == 0 || phase == 1), "nmb_pattern_scan: n_motifs=%d phase=%d", n_motifs, phase);
     NMB_REQUIRE(motifs_per_item >= 1 && motifs_per_item <= NMB_MAX_MOTIFS_PER_ITEM, "nmb_pattern_scan: motifs_per_item=%d",
@@ -465,6 +502,7 @@ int nmb_pattern_scan(const nmb_assembly *a, const uint32_t *valid_records, const
     p.offsets = (const long long *)offsets;
     p.cursor = cursor;
     p.fractions = fractions;
+    p.counter = work_counter;
     p.n_words = (int64_t)a->n_tiles * nmb::kTileWords;
     p.n_motifs = n_motifs;
     p.mpi = motifs_per_item;

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib, ptr
-from .device import DeviceAssembly, MotifPrograms, _stream, _to_device, sm_count
+from .device import DeviceAssembly, MotifPrograms, _stream, _to_device, _work_counter, sm_count
 from .motif import Motif
 from .pileup import PileupTable, strand_codes
 
@@ -106,9 +106,10 @@ def pattern_table(index: PatternIndex, motifs, median: bool = True, batch: int =
                 stats = stats_all[b0:b0 + nb].view(nb * nc, 3)  # contiguous slice: the scan adds into it in place
 
                 def scan_d(phase, offsets=None, cursor=None, fractions=None):
-                    check(lib.nmb_pattern_scan(C.byref(view), ptr(index.valid), ptr(index.rank_dir), ptr(index.payload),
-                                               ptr(progs.programs), nb, mpi, progs.max_len, phase, ptr(stats), ptr(offsets),
-                                               ptr(cursor), ptr(fractions), 0, _stream()), "nmb_pattern_scan")
+                    check(lib.nmb_pattern_scan_balanced(C.byref(view), ptr(index.valid), ptr(index.rank_dir), ptr(index.payload),
+                                                        ptr(progs.programs), nb, mpi, progs.max_len, phase, ptr(stats),
+                                                        ptr(offsets), ptr(cursor), ptr(fractions), 0, ptr(_work_counter(d)),
+                                                        _stream()), "nmb_pattern_scan_balanced")
 
                 scan_d(0)
                 if median:
@@ -143,9 +144,10 @@ def pattern_table(index: PatternIndex, motifs, median: bool = True, batch: int =
             stats = torch.zeros((nb * nc, 3), dtype=torch.int64, device=d)
 
             def scan(phase, offsets=None, cursor=None, fractions=None):
-                check(lib.nmb_pattern_scan(C.byref(view), ptr(index.valid), ptr(index.rank_dir), ptr(index.payload),
-                                           ptr(progs.programs), nb, mpi, progs.max_len, phase, ptr(stats), ptr(offsets),
-                                           ptr(cursor), ptr(fractions), 0, _stream()), "nmb_pattern_scan")
+                check(lib.nmb_pattern_scan_balanced(C.byref(view), ptr(index.valid), ptr(index.rank_dir), ptr(index.payload),
+                                                    ptr(progs.programs), nb, mpi, progs.max_len, phase, ptr(stats),
+                                                    ptr(offsets), ptr(cursor), ptr(fractions), 0, ptr(_work_counter(d)),
+                                                    _stream()), "nmb_pattern_scan_balanced")
 
             scan(0)
             med = None

@@ -71,17 +71,26 @@ def main():
     progs = MotifPrograms(chunk, dev, strip=False)
     stats = torch.zeros((len(chunk) * asm.n_contigs, 3), dtype=torch.int64, device=dev)
     view = asm.view()
-    for mpi in (32, 16, 8):
+    from nanomotif_b200.device import _work_counter
+
+    for mpi, balanced in ((32, True), (32, False), (16, True), (8, True)):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         for rep in range(3):
             if rep == 1:
                 ev[0].record()
-            check(lib.nmb_pattern_scan(C.byref(view), ptr(index.valid), ptr(index.rank_dir), ptr(index.payload), ptr(progs.programs),
-                                       len(chunk), mpi, progs.max_len, 0, ptr(stats), None, None, None, 0, _stream()), "scan")
+            if balanced:
+                check(lib.nmb_pattern_scan_balanced(C.byref(view), ptr(index.valid), ptr(index.rank_dir), ptr(index.payload),
+                                                    ptr(progs.programs), len(chunk), mpi, progs.max_len, 0, ptr(stats), None, None,
+                                                    None, 0, ptr(_work_counter(dev)), _stream()), "scan")
+            else:
+                check(lib.nmb_pattern_scan(C.byref(view), ptr(index.valid), ptr(index.rank_dir), ptr(index.payload),
+                                           ptr(progs.programs), len(chunk), mpi, progs.max_len, 0, ptr(stats), None, None, None,
+                                           0, _stream()), "scan")
         ev[1].record()
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / 2
-        print(f"scan kernel, {len(chunk)} motifs, mpi {mpi}: {ms:8.2f} ms  {len(chunk) * asm.total_bp / ms / 1e9:.2f}e12 motif*bp/s")
+        print(f"scan kernel, {len(chunk)} motifs, mpi {mpi}, {'dynamic' if balanced else 'static '} items: {ms:8.2f} ms  "
+              f"{len(chunk) * asm.total_bp / ms / 1e9:.2f}e12 motif*bp/s")
     for median in (False, True):
         pattern_table(index, motifs[:args.batch], median, args.batch)  # warm-up
         torch.cuda.synchronize()
