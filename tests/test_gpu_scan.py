@@ -345,16 +345,16 @@ def test_family_sharing_equals_general_path_and_oracle(nmb):
     flat = [nmb.Motif(m, p) for kids in lists for m, p in kids]
     want = np.array([O.motif_model_bin(pile["contig"], pile["position"], pile["strand"], pile["fraction_mod"], contigs,
                                        m.string, m.mod_position, fast=True) for m in flat])
-    old = D.FAMILIES
+    old, old_bal = D.FAMILIES, D.BALANCED
     try:
-        for families in (True, False):
-            D.FAMILIES = families
+        for families, balanced in ((True, True), (False, True), (False, False)):  # families / dynamic / static item split
+            D.FAMILIES, D.BALANCED = families, balanced
             for mpi in (None, 4, 3, 32):
                 got = scorer.counts_by_strand(flat, motifs_per_item=mpi).cpu().numpy()
                 np.testing.assert_array_equal(np.stack([got[:, 0] + got[:, 2], got[:, 1] + got[:, 3]], axis=1), want,
-                                              err_msg=f"families={families} mpi={mpi}")
+                                              err_msg=f"families={families} balanced={balanced} mpi={mpi}")
             per = scorer.counts_by_strand(flat[:40], per_contig=True).cpu().numpy()  # group mode 1 through the same path
             assert per.sum() == scorer.counts_by_strand(flat[:40]).cpu().numpy().sum()
     finally:
-        D.FAMILIES = old
+        D.FAMILIES, D.BALANCED = old, old_bal
     assert int(want.sum()) > 10000
