@@ -272,9 +272,12 @@ __global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(co
     // runs out, not when the unluckiest CTA of a static round-robin finishes (8 800 items over 592 CTAs on a 1/8
     // shard: the static split left ~10 % of the launch as tail).  Items still start in tile-major order.
     const bool dynamic = STAGES == 1 && p.counter != nullptr;
+    // the index of the NEXT item is drawn right after the current item's copies have been issued, so the atomic's
+    // round trip to L2 is over long before the item ends (it used to sit in front of every bulk copy)
+    int next_item = (dynamic && tid == 0) ? atomicAdd(p.counter, 1) : 0;
     auto issue = [&](int k) {
         const int st = k % STAGES;
-        const int item = dynamic ? atomicAdd(p.counter, 1) : (int)blockIdx.x + k * (int)gridDim.x;
+        const int item = dynamic ? next_item : (int)blockIdx.x + k * (int)gridDim.x;
         if (item >= p.n_items) {  // dynamic only: nothing left -- wake the CTA with an empty phase
             s_meta_st[st].job = -1;
             mbar_arrive(&full_bar[st]);
@@ -289,6 +292,7 @@ __global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(co
         bulk_g2s(buf, p.seq_records + (size_t)m.tile * kSeqRecWords, kSeqRecBytes, &full_bar[st]);
         bulk_g2s(buf + kSeqRecBytes, p.cls + ((size_t)modtype * p.n_tiles + m.tile) * kClsRecWords, kClsRecBytes,
                  &full_bar[st]);
+        if (dynamic) next_item = atomicAdd(p.counter, 1);
     };
     if (STAGES > 1 && tid == 0 && n_my > 0) issue(0);
 
