@@ -239,81 +239,86 @@ __device__ __forceinline__ void score_motifs(const ScanParams &p, const nmb_job 
     }
 }
 
-// One tile (sequence record + class record = 49.7 KB) per CTA in shared memory; four CTAs of four warps
-// are resident per SM, so while one CTA waits for its bulk copies the other three keep the ALUs busy and
-// up to ~200 KB of copies are in flight per SM.  (Measured alternatives on B200: a 2-stage ring with two
-// resident CTAs, and a split ring with three, were both slower -- profiles/r01_notes.md.)
+// One tile (sequence record + class record = 49.7 KB) per CTA in shared memory; four CTAs of four warps are resident
+// per SM, so while one CTA waits for its bulk copies the other three keep the ALUs busy.  (Measured alternatives on
+// B200: a 2-stage ring with two resident CTAs, and a split ring with three, were both slower -- profiles/r01_notes.md.)
 constexpr int kScanSmemBytes = kSeqRecBytes + kClsRecBytes;
 
-// STAGES = 1 (the product configuration): one tile buffer per CTA, four CTAs per SM; sixteen resident warps hide
-// each other's latencies and the copy latency.  STAGES = 2 (experiment, NMB_SCAN_STAGES=2): two buffers per CTA, two
-// CTAs per SM, the next tile in flight while this one is evaluated -- measured slower, see nmb_scan_count.
+__device__ __forceinline__ void bar_sync_1(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
+
+// The two records of a tile arrive on SEPARATE mbarriers.  The lanes copy their sequence words into registers at the
+// start of an item, after which the sequence half of the buffer is dead: the next item's index is decoded and its
+// sequence record is already on its way while this item's motifs are evaluated; only the class record (2/3 of the
+// bytes) has to wait for the end of the item.  ncu's source view had 19 % of all warp samples on the mbarrier spin in
+// front of a tile (profiles/r02_notes.md).
 template <int H, int STAGES, bool FAM>
-__global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(const ScanParams p) {
-    extern __shared__ __align__(128) uint8_t smem_all[];
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ ItemMeta s_meta_st[STAGES];
+__global__ void __launch_bounds__(kScanThreads, 4) scan_count_kernel(const ScanParams p) {
+    static_assert(STAGES == 1, "one tile buffer per CTA");
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t seq_bar, cls_bar;
+    __shared__ ItemMeta s_meta[2];
     __shared__ uint32_t s_acc[2][kMaxMpi][4];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int n_my = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        mbar_init(&seq_bar, 1);
+        mbar_init(&cls_bar, 1);
         fence_barrier_init();
     }
     for (int i = tid; i < 2 * kMaxMpi * 4; i += kScanThreads) (&s_acc[0][0][0])[i] = 0;
     __syncthreads();
 
-    // two bulk copies (TMA) bring the self-contained tile of item k into buffer k % STAGES; completion on its mbarrier
-    // Items are handed out through a global counter when the caller provides one (STAGES == 1): a CTA that drew
-    // cheap items (3 instead of 4 motifs, dead chains) simply takes more of them, so the launch ends when the WORK
-    // runs out, not when the unluckiest CTA of a static round-robin finishes (8 800 items over 592 CTAs on a 1/8
-    // shard: the static split left ~10 % of the launch as tail).  Items still start in tile-major order.
-    const bool dynamic = STAGES == 1 && p.counter != nullptr;
-    // the index of the NEXT item is drawn right after the current item's copies have been issued, so the atomic's
-    // round trip to L2 is over long before the item ends (it used to sit in front of every bulk copy)
-    int next_item = (dynamic && tid == 0) ? atomicAdd(p.counter, 1) : 0;
-    auto issue = [&](int k) {
-        const int st = k % STAGES;
-        const int item = dynamic ? next_item : (int)blockIdx.x + k * (int)gridDim.x;
-        if (item >= p.n_items) {  // dynamic only: nothing left -- wake the CTA with an empty phase
-            s_meta_st[st].job = -1;
-            mbar_arrive(&full_bar[st]);
+    // Items are handed out through a global counter when the caller provides one: a CTA that drew cheap items (3
+    // instead of 4 motifs, dead chains) simply takes more of them, so the launch ends when the WORK runs out, not
+    // when the unluckiest CTA of a static round-robin finishes.  Items still start in tile-major order.  The index
+    // of the next item is drawn as soon as the previous draw has been used, so the atomic's round trip is hidden.
+    const bool dynamic = p.counter != nullptr;
+    int next_item = 0, n_drawn = 0;  // thread 0 only
+    auto draw = [&]() {
+        next_item = dynamic ? atomicAdd(p.counter, 1) : (int)blockIdx.x + n_drawn * (int)gridDim.x;
+        ++n_drawn;
+    };
+    // thread 0: decode the drawn item into s_meta[slot] and start the copy of its sequence record; an exhausted
+    // work list is signalled through an empty phase of the sequence barrier
+    auto issue_seq = [&](int slot) {
+        const int item = next_item;
+        if (item >= p.n_items) {
+            s_meta[slot].job = -1;
+            mbar_arrive(&seq_bar);
             return;
         }
         const ItemMeta m = decode_item(p, item);
-        s_meta_st[st] = m;
-        const int modtype = __ldg(&p.jobs[m.job].modtype);
-        uint8_t *buf = smem_all + (size_t)st * kScanSmemBytes;
+        s_meta[slot] = m;
         fence_proxy_async();  // order the earlier generic reads of this buffer before the async writes
-        mbar_expect_tx(&full_bar[st], kSeqRecBytes + kClsRecBytes);
-        bulk_g2s(buf, p.seq_records + (size_t)m.tile * kSeqRecWords, kSeqRecBytes, &full_bar[st]);
-        bulk_g2s(buf + kSeqRecBytes, p.cls + ((size_t)modtype * p.n_tiles + m.tile) * kClsRecWords, kClsRecBytes,
-                 &full_bar[st]);
-        if (dynamic) next_item = atomicAdd(p.counter, 1);
+        mbar_expect_tx(&seq_bar, kSeqRecBytes);
+        bulk_g2s(smem, p.seq_records + (size_t)m.tile * kSeqRecWords, kSeqRecBytes, &seq_bar);
+        draw();
     };
-    if (STAGES > 1 && tid == 0 && n_my > 0) issue(0);
+    auto issue_cls = [&](int slot) {
+        const ItemMeta m = s_meta[slot];
+        if (m.job < 0) return;
+        const int modtype = __ldg(&p.jobs[m.job].modtype);
+        fence_proxy_async();
+        mbar_expect_tx(&cls_bar, kClsRecBytes);
+        bulk_g2s(smem + kSeqRecBytes, p.cls + ((size_t)modtype * p.n_tiles + m.tile) * kClsRecWords, kClsRecBytes, &cls_bar);
+    };
+    if (tid == 0) {
+        draw();
+        issue_seq(0);
+        issue_cls(0);
+    }
 
-    for (int k = 0; dynamic || k < n_my; ++k) {
-        if (tid == 0) {
-            if (STAGES == 1) issue(k);
-            else if (k + 1 < n_my) issue(k + 1);  // its buffer was released by the barrier that ended item k - 1
-        }
-        const int st = k % STAGES;
-        mbar_wait(&full_bar[st], (uint32_t)((k / STAGES) & 1));
-        if (dynamic && s_meta_st[st].job < 0) break;  // CTA-uniform: every thread reads the same word
-        const uint8_t *smem = smem_all + (size_t)st * kScanSmemBytes;
-        const ItemMeta &s_meta = s_meta_st[st];
-
-        const ItemMeta meta = s_meta;
-        const nmb_job job = p.jobs[meta.job];
-        const uint32_t *sx = reinterpret_cast<const uint32_t *>(smem);
-        const uint32_t *sy = sx + kSeqPlaneWords;
-        const int32_t *sinfo = reinterpret_cast<const int32_t *>(sy + kSeqPlaneWords);
-        const uint32_t *scls = sx + kSeqRecWords;
+    const uint32_t *sx = reinterpret_cast<const uint32_t *>(smem);
+    const uint32_t *sy = sx + kSeqPlaneWords;
+    const int32_t *sinfo = reinterpret_cast<const int32_t *>(sy + kSeqPlaneWords);
+    const uint32_t *scls = sx + kSeqRecWords;
+    for (int k = 0;; ++k) {
         const int par = k & 1;
+        mbar_wait(&seq_bar, (uint32_t)par);
+        const ItemMeta meta = s_meta[par];
+        if (meta.job < 0) break;  // CTA-uniform: every thread reads the same word
+        const nmb_job job = p.jobs[meta.job];
 
         const int info = sinfo[tid];
         const int contig = info < 0 ? -1 : (info & kChunkIdMask);
@@ -324,38 +329,47 @@ __global__ void __launch_bounds__(kScanThreads, 4 / STAGES) scan_count_kernel(co
         const int primary = info0 < 0 ? -1 : group_of(job, info0 & kChunkIdMask, p.contig_group);
 
         const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
-        if (vmask) {
-            // lanes that are not counted (padding, contigs outside the job) contribute zeros, so the warp
-            // is uniform when all COUNTED lanes share one group
-            const int first = __ffs(vmask) - 1;
-            const int g0 = __shfl_sync(0xFFFFFFFFu, g, first);
-            const bool uniform = __all_sync(0xFFFFFFFFu, !valid || g == g0);
-            unsigned peers = 0xFFFFFFFFu;
-            bool leader = lane == first;
-            if (!uniform) {
-                peers = __match_any_sync(0xFFFFFFFFu, g);
-                leader = valid && lane == __ffs(peers) - 1;
-            }
-            // matcher variant (scan.cuh): non-ACGT letters of a contig in reach -> full test at every step
-            // (rare); inter-contig padding in reach -> plain steps, finished chains clipped to the contig
-            const bool warp_n = __any_sync(0xFFFFFFFFu, valid && (info & kChunkFlagN));
-            const bool warp_edge = __any_sync(0xFFFFFFFFu, valid && (info & kChunkFlagEdge));
-
-            const uint32_t *cl = scls + tid * 4;  // lane-interleaved planes: vector v at cl + v * kSlotStride
-            if (warp_n) {
-                LaneSeq<H, true> q;
-                load_xyn<H>(sx, sy, tid, p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H, q);
-                const LaneEdge edge = {0, false, false};
-                score_motifs<H, true, FAM>(p, job, meta, q, edge, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
-            } else {
-                LaneSeq<H, false> q;
-                load_xy<H>(sx, sy, tid, q);
-                const LaneEdge edge = lane_edge(warp_edge, info, (int64_t)meta.tile * kTileChunks + tid,
-                                                p.contig_start, p.contig_len);
-                score_motifs<H, false, FAM>(p, job, meta, q, edge, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
-            }
+        // lanes that are not counted (padding, contigs outside the job) contribute zeros, so the warp
+        // is uniform when all COUNTED lanes share one group
+        const int first = vmask ? __ffs(vmask) - 1 : 0;
+        const int g0 = __shfl_sync(0xFFFFFFFFu, g, first);
+        const bool uniform = __all_sync(0xFFFFFFFFu, !valid || g == g0);
+        unsigned peers = 0xFFFFFFFFu;
+        bool leader = lane == first;
+        if (!uniform) {
+            peers = __match_any_sync(0xFFFFFFFFu, g);
+            leader = valid && lane == __ffs(peers) - 1;
         }
-        __syncthreads();  // everyone is done with the tile and with s_acc[par]
+        // matcher variant (scan.cuh): non-ACGT letters of a contig in reach -> full test at every step
+        // (rare); inter-contig padding in reach -> plain steps, finished chains clipped to the contig
+        const bool warp_n = __any_sync(0xFFFFFFFFu, valid && (info & kChunkFlagN));
+        const bool warp_edge = __any_sync(0xFFFFFFFFu, valid && (info & kChunkFlagEdge));
+        const uint32_t *cl = scls + tid * 4;  // lane-interleaved planes: vector v at cl + v * kSlotStride
+
+        // after this point nobody reads the sequence half of the buffer any more
+        auto seq_done_prefetch_next = [&]() {
+            bar_sync_1(kScanThreads);
+            if (tid == 0) issue_seq(par ^ 1);
+            mbar_wait(&cls_bar, (uint32_t)par);
+        };
+        if (!vmask) {
+            seq_done_prefetch_next();
+        } else if (warp_n) {
+            LaneSeq<H, true> q;
+            load_xyn<H>(sx, sy, tid, p.nonacgt + kHalo + (size_t)meta.tile * kTileWords + tid * NW - H, q);
+            seq_done_prefetch_next();
+            const LaneEdge edge = {0, false, false};
+            score_motifs<H, true, FAM>(p, job, meta, q, edge, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
+        } else {
+            LaneSeq<H, false> q;
+            load_xy<H>(sx, sy, tid, q);
+            seq_done_prefetch_next();
+            const LaneEdge edge = lane_edge(warp_edge, info, (int64_t)meta.tile * kTileChunks + tid,
+                                            p.contig_start, p.contig_len);
+            score_motifs<H, false, FAM>(p, job, meta, q, edge, cl, valid, uniform, peers, leader, g, primary, s_acc[par]);
+        }
+        __syncthreads();  // everyone is done with the class record and with s_acc[par]
+        if (tid == 0) issue_cls(par ^ 1);
         if (tid < kMaxMpi * 4) {
             const int mi = tid >> 2, c = tid & 3;
             const uint32_t v = s_acc[par][mi][c];
@@ -621,34 +635,26 @@ static int scan_count_impl(const nmb_assembly *a, const uint32_t *class_records,
         NMB_CUDA(cudaGetLastError());
     }
 
-    // One buffer x four CTAs per SM everywhere.  The double-buffered variant (two buffers x two CTAs) is kept for
-    // experiments only: with conflict-free shared memory it is still SLOWER in the streaming regime it was meant for
-    // (same box, 1.5 Gbp, M = 1: GATC 0.206 vs 0.195 ms, GRNGAAGY 0.263 vs 0.234, 13-mer 0.258 vs 0.228; A 0.166 vs
-    // 0.168) -- eight resident warps hide the ALU latencies worse than sixteen, which costs more than the guaranteed
-    // copy/compute overlap gains.
-    int stages = 1;
-    if (const char *e = getenv("NMB_SCAN_STAGES")) stages = atoi(e) == 2 ? 2 : 1;
     int grid = grid_ctas;
     if (grid <= 0) {
         int sms = nmb_device_sm_count();
         if (sms < 0) return sms;
-        grid = (4 / stages) * sms;  // resident CTAs per SM (49.7 KB of shared memory per stage, <= 128 registers)
+        grid = 4 * sms;  // resident CTAs per SM (49.7 KB of shared memory, <= 128 registers)
     }
     if (grid > n_items) grid = n_items;
     cudaStream_t s = (cudaStream_t)stream;
-    const int smem_bytes = stages * nmb::kScanSmemBytes;
+    const int smem_bytes = nmb::kScanSmemBytes;
 #define NMB_LAUNCH_SCAN(H, S, F)                                                                                      \
     do {                                                                                                              \
         NMB_CUDA(cudaFuncSetAttribute(nmb::scan_count_kernel<H, S, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                       smem_bytes));                                                                   \
         nmb::scan_count_kernel<H, S, F><<<grid, nmb::kScanThreads, smem_bytes, s>>>(p);                                \
     } while (0)
-    if (stages == 2) p.fam = nullptr;  // the experimental double-buffered variant has no family path
     const bool fam = p.fam != nullptr;
     if (max_motif_len <= 32) {  // one halo word covers a total shift (and a mod_pos) of at most 31
-        if (stages == 2) NMB_LAUNCH_SCAN(1, 2, false); else if (fam) NMB_LAUNCH_SCAN(1, 1, true); else NMB_LAUNCH_SCAN(1, 1, false);
+        if (fam) NMB_LAUNCH_SCAN(1, 1, true); else NMB_LAUNCH_SCAN(1, 1, false);
     } else {
-        if (stages == 2) NMB_LAUNCH_SCAN(2, 2, false); else if (fam) NMB_LAUNCH_SCAN(2, 1, true); else NMB_LAUNCH_SCAN(2, 1, false);
+        if (fam) NMB_LAUNCH_SCAN(2, 1, true); else NMB_LAUNCH_SCAN(2, 1, false);
     }
 #undef NMB_LAUNCH_SCAN
     NMB_CUDA(cudaGetLastError());
