@@ -6,14 +6,13 @@
 //   motif_model_contig (count step)           nanomotif/find_motifs_bin.py:1285-1331
 //   motif_model_bin (sum over contigs)        nanomotif/find_motifs_bin.py:1265-1283
 //
-// Persistent CTAs walk a list of work items (tile, block of <=32 motifs).  A tile is one
+// Persistent CTAs draw work items (tile, block of <=32 motifs) from a device counter.  A tile is one
 // self-contained 17 KB sequence record + one 32 KB class record, brought into shared memory by two
-// cp.async.bulk (TMA) copies that complete on an mbarrier.  Four CTAs of 128 threads are resident per
-// SM, so copy latency is hidden by the other CTAs' bit-parallel evaluation.  Counts are popcounts of
+// cp.async.bulk (TMA) copies, each completing on its own mbarrier; the next item's sequence record is
+// copied while the current item's motifs are evaluated.  Four CTAs of 128 threads are resident per
+// SM, so the remaining copy latency is hidden by the other CTAs' bit-parallel evaluation.  Counts are popcounts of
 // match & class-plane, reduced with warp REDUX, accumulated per CTA in shared memory and flushed
 // with one 64-bit atomic per (motif, counter) per item.
-#include <stdlib.h>
-
 #include "scan.cuh"
 
 namespace nmb {

@@ -154,7 +154,11 @@ class ShardedMultiBinScorer:
     contigs in ONE launch and the stacked [total motifs, 4] count tensor is summed over the ranks with ONE all-reduce
     (NCCL over NVLink) -- that merges split bins and replicates the whole-bin results in the same step.
     `submit` returns before the collective has run, so the driver can enqueue the next batch while this one's counts
-    are in flight."""
+    are in flight.
+
+    Give every rank the pileup rows of ITS bins: the partitioned form {(bin, mod_type): frame} (frames of bins
+    without local contigs are skipped before any copy) or a table that already holds only the rank's rows.  Rows of
+    other ranks' contigs in a shared table are ignored, but they are still copied to the device."""
 
     def __init__(self, pileup, bins: dict, mod_types, low_meth_threshold: float, high_meth_threshold: float,
                  rank: int, world_size: int, device=None, group=None):
