@@ -517,6 +517,17 @@ NMB_API int nmb_sweep_expand(const uint32_t *src, uint32_t *dst, int64_t outer, 
 NMB_API int nmb_sweep_filter(const uint32_t *n_mod, const uint32_t *n_nomod, int64_t n, double min_mean,
                              int64_t min_mod, int64_t *out_index, int64_t capacity, int64_t *n_out, void *stream);
 
+/* ---- host helper: CPython's random.sample(range(n), k) on a transplanted MT19937 state (the reference draws its
+ *      background windows with random.sample, nanomotif/seq.py:202-225; its picks depend only on n, k and the
+ *      generator's word stream).  state = the 624 key words + position of random.getstate(); out receives the k
+ *      picks in draw order and the state advances exactly as CPython's would (set branch and pool branch of
+ *      Lib/random.py).  Host pointers; no device work. ---- */
+typedef struct nmb_mt19937 {
+    uint32_t key[624];
+    int32_t pos;
+} nmb_mt19937;
+NMB_API int nmb_mt_sample(nmb_mt19937 *state_h, int64_t n, int64_t k, int64_t *out_h);
+
 /* ---- host -> device staging of PAGEABLE host buffers (the Arrow buffers of the frames nanomotif hands to its
  *      workers, find_motifs_bin.py:399-427).  n_threads host threads each own a CUDA stream and two pinned slots of
  *      slot_bytes (allocated by nmb_stager_create -- the one allocation this library makes -- and freed by

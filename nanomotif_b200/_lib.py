@@ -51,6 +51,10 @@ class NmbAssembly(C.Structure):
     ]
 
 
+class NmbMT19937(C.Structure):
+    _fields_ = [("key", C.c_uint32 * 624), ("pos", C.c_int32)]
+
+
 MOTIF_DTYPE = np.dtype([("allowed", np.uint8, (MAX_MOTIF_LEN,)), ("len", np.uint8), ("mod_pos", np.uint8)])
 assert MOTIF_DTYPE.itemsize == 64
 
@@ -128,6 +132,7 @@ SIGNATURES = {
     "nmb_pattern_scan_balanced": (C.c_int, [C.POINTER(NmbAssembly), _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P]),
     "nmb_segment_offsets": (C.c_int, [_P, _I64, _P, _P, _P]),
     "nmb_segment_median": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "nmb_mt_sample": (C.c_int, [_P, _I64, _I64, _P]),
     "nmb_stager_create": (C.c_int, [_I64, _I32, C.POINTER(_P)]),
     "nmb_stager_copy": (C.c_int, [_P, _P, _P, _I64, _P]),
     "nmb_stager_copy_narrow": (C.c_int, [_P, _P, _P, _I64, C.POINTER(C.c_int32), _P]),

@@ -1,4 +1,6 @@
 // Misc entry points of libnmb200: version, error string, device query.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nmb {
@@ -22,5 +24,84 @@ int nmb_device_sm_count(void) {
 }
 
 int nmb_program_bytes(void) { return nmb::kProgramBytesPerMotif; }
+
+// ---- host: CPython's random.sample(range(n), k) on a transplanted MT19937 state -------------------------------
+// The reference draws its background windows with random.sample(valid_starts, n) (nanomotif/seq.py:202-225), whose
+// picks depend only on len(valid_starts), n and the generator's 32-bit word stream.  Python spends ~0.5 us per pick;
+// cfg 3 needs 45 M of them.  This is the same algorithm (Lib/random.py: sample, _randbelow_with_getrandbits) on the
+// standard MT19937 recurrence, so the picks and the state afterwards are bit-identical.
+static inline uint32_t mt_next(nmb_mt19937 *s) {
+    constexpr int N = 624, M = 397;
+    if (s->pos >= N) {
+        uint32_t *mt = s->key;
+        int kk = 0;
+        for (; kk < N - M; ++kk) {
+            const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + M] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        for (; kk < N - 1; ++kk) {
+            const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        const uint32_t y = (mt[N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        s->pos = 0;
+    }
+    uint32_t y = s->key[s->pos++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+static inline int64_t mt_randbelow(nmb_mt19937 *s, int64_t n, int shift) {  // getrandbits(n.bit_length()) until < n
+    for (;;) {
+        const int64_t r = (int64_t)(mt_next(s) >> shift);
+        if (r < n) return r;
+    }
+}
+
+int nmb_mt_sample(nmb_mt19937 *state, int64_t n, int64_t k, int64_t *out) {
+    NMB_REQUIRE(state && n >= 0 && k >= 0 && k <= n && n < (1ll << 32), "nmb_mt_sample: need 0 <= k <= n < 2^32");
+    NMB_REQUIRE(state->pos >= 0 && state->pos <= 624, "nmb_mt_sample: bad generator position");
+    if (k == 0) return NMB_OK;
+    NMB_REQUIRE(out, "nmb_mt_sample: null output");
+    // setsize = 21; if k > 5: setsize += 4 ** ceil(log(k * 3, 4))   (Lib/random.py)
+    int64_t setsize = 21;
+    if (k > 5) {
+        int64_t p = 1;
+        while (p < 3 * k) p *= 4;
+        setsize += p;
+    }
+    if (n <= setsize) {  // pool branch: partial shuffle of list(range(n))
+        int64_t *pool = (int64_t *)malloc((size_t)n * sizeof(int64_t));
+        NMB_REQUIRE(pool, "nmb_mt_sample: out of memory");
+        for (int64_t i = 0; i < n; ++i) pool[i] = i;
+        for (int64_t i = 0; i < k; ++i) {
+            const int64_t m = n - i;
+            int bits = 0;
+            while ((m >> bits) != 0) ++bits;
+            const int64_t j = mt_randbelow(state, m, 32 - bits);
+            out[i] = pool[j];
+            pool[j] = pool[m - 1];
+        }
+        free(pool);
+        return NMB_OK;
+    }
+    int bits = 0;
+    while ((n >> bits) != 0) ++bits;
+    const int shift = 32 - bits;
+    uint64_t *seen = (uint64_t *)calloc((size_t)(n / 64 + 1), sizeof(uint64_t));
+    NMB_REQUIRE(seen, "nmb_mt_sample: out of memory");
+    for (int64_t i = 0; i < k; ++i) {
+        int64_t j = mt_randbelow(state, n, shift);
+        while (seen[j >> 6] >> (j & 63) & 1) j = mt_randbelow(state, n, shift);
+        seen[j >> 6] |= 1ull << (j & 63);
+        out[i] = j;
+    }
+    free(seen);
+    return NMB_OK;
+}
 
 }  // extern "C"

@@ -282,9 +282,10 @@ def test_load_fasta_host(tmp_path):
 
 
 def test_mtstream_reproduces_random_sample_and_its_state():
-    """growth.MTStream draws random.sample(range(n), k) in bulk from numpy's MT19937 loaded with the Python generator's
-    state: same picks in the same order, and the Python generator continues exactly where the loop of random.sample
-    calls (seq.py:202-225, one per contig) would have left it -- set branch, pool branch and k = 0 alike."""
+    """growth.MTStream draws random.sample(range(n), k) natively (nmb_mt_sample: MT19937 + the two branches of
+    Lib/random.py on a copy of the Python generator's state): same picks in the same order, and the Python generator
+    continues exactly where the loop of random.sample calls (seq.py:202-225, one per contig) would have left it --
+    set branch, pool branch and k = 0 alike."""
     import random
 
     from nanomotif_b200.growth import MTStream
