@@ -527,6 +527,9 @@ typedef struct nmb_mt19937 {
     int32_t pos;
 } nmb_mt19937;
 NMB_API int nmb_mt_sample(nmb_mt19937 *state_h, int64_t n, int64_t k, int64_t *out_h);
+/* count consecutive samples from the same stream; sample i is written at out_h + sum(k_h[0..i)). */
+NMB_API int nmb_mt_sample_many(nmb_mt19937 *state_h, const int64_t *n_h, const int64_t *k_h, int64_t count,
+                               int64_t *out_h);
 
 /* ---- host -> device staging of PAGEABLE host buffers (the Arrow buffers of the frames nanomotif hands to its
  *      workers, find_motifs_bin.py:399-427).  n_threads host threads each own a CUDA stream and two pinned slots of

@@ -133,6 +133,7 @@ SIGNATURES = {
     "nmb_segment_offsets": (C.c_int, [_P, _I64, _P, _P, _P]),
     "nmb_segment_median": (C.c_int, [_P, _P, _I64, _P, _P]),
     "nmb_mt_sample": (C.c_int, [_P, _I64, _I64, _P]),
+    "nmb_mt_sample_many": (C.c_int, [_P, _P, _P, _I64, _P]),
     "nmb_stager_create": (C.c_int, [_I64, _I32, C.POINTER(_P)]),
     "nmb_stager_copy": (C.c_int, [_P, _P, _P, _I64, _P]),
     "nmb_stager_copy_narrow": (C.c_int, [_P, _P, _P, _I64, C.POINTER(C.c_int32), _P]),

@@ -104,4 +104,17 @@ int nmb_mt_sample(nmb_mt19937 *state, int64_t n, int64_t k, int64_t *out) {
     return NMB_OK;
 }
 
+// `count` consecutive samples from the same stream: sample i = random.sample(range(n[i]), k[i]) written at
+// out + sum(k[0..i)) -- one call per bin instead of one per contig.
+int nmb_mt_sample_many(nmb_mt19937 *state, const int64_t *n, const int64_t *k, int64_t count, int64_t *out) {
+    NMB_REQUIRE(state && count >= 0 && (count == 0 || (n && k)), "nmb_mt_sample_many: bad arguments");
+    int64_t at = 0;
+    for (int64_t i = 0; i < count; ++i) {
+        const int rc = nmb_mt_sample(state, n[i], k[i], out ? out + at : nullptr);
+        if (rc != NMB_OK) return rc;
+        at += k[i];
+    }
+    return NMB_OK;
+}
+
 }  // extern "C"

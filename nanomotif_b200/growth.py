@@ -321,6 +321,17 @@ class MTStream:
         check(lib.nmb_mt_sample(C.byref(self._state), int(n), int(k), out.ctypes.data), "nmb_mt_sample")
         return out
 
+    def sample_many(self, n, k) -> np.ndarray:
+        """The concatenation of random.sample(range(n[i]), k[i]) for consecutive i (one native call)."""
+        n = np.ascontiguousarray(n, dtype=np.int64)
+        k = np.ascontiguousarray(k, dtype=np.int64)
+        if np.any((k < 0) | (k > n)):
+            raise ValueError("Sample larger than population or is negative")
+        out = np.empty(int(k.sum()), dtype=np.int64)
+        check(lib.nmb_mt_sample_many(C.byref(self._state), n.ctypes.data, k.ctypes.data, len(n), out.ctypes.data),
+              "nmb_mt_sample_many")
+        return out
+
 
 def prepare_searches(scorer, mod_type, padding: int, high: float, bin_names=None, sampling_frequency: float = 0.01,
                      seeds=None):
@@ -382,6 +393,14 @@ def prepare_searches(scorer, mod_type, padding: int, high: float, bin_names=None
         q = torch.from_numpy(np.stack([lo_pos, lo_pos + np.maximum(max_start, 0)], axis=1).reshape(-1)).to(d)
         lohi = torch.searchsorted(P, q).cpu().numpy().reshape(-1, 2)
         n_valid = lohi[:, 1] - lohi[:, 0]
+        # samples per contig (find_motifs_bin.py:633) and the reference's two refusals (seq.py:210, :219)
+        k_all = np.maximum(np.ceil(L * sampling_frequency), 50).astype(np.int64)
+        if np.any(k_all > max_start):
+            raise ValueError("Too many samples requested for unique subsequences")
+        short = np.flatnonzero(n_valid < k_all)
+        if len(short):
+            ci = int(short[0])
+            raise ValueError(f"Not enough subsequences with 'C' in the middle (found {int(n_valid[ci])}, need {int(k_all[ci])})")
         picks, at, bg_begin, bg_end = [], 0, [], []
         ci = 0
         stream = MTStream()
@@ -389,17 +408,14 @@ def prepare_searches(scorer, mod_type, padding: int, high: float, bin_names=None
             if seeds is not None:
                 random.seed(seeds[i])
                 stream = MTStream()
+            nc = scorer._ranges[b][1] - scorer._ranges[b][0]
+            k_bin = k_all[ci:ci + nc]
+            got = stream.sample_many(n_valid[ci:ci + nc], k_bin)  # one call per bin, contigs in order
+            picks.append(got + np.repeat(lohi[ci:ci + nc, 0], k_bin))
             bg_begin.append(at)
-            for _ in range(*scorer._ranges[b]):
-                k = int(max(math.ceil(int(L[ci]) * sampling_frequency), 50))  # find_motifs_bin.py:633
-                if k > max_start[ci]:
-                    raise ValueError("Too many samples requested for unique subsequences")  # seq.py:210
-                if n_valid[ci] < k:
-                    raise ValueError(f"Not enough subsequences with 'C' in the middle (found {int(n_valid[ci])}, need {k})")
-                picks.append(stream.sample(int(n_valid[ci]), k) + lohi[ci, 0])
-                at += k
-                ci += 1
+            at += int(k_bin.sum())
             bg_end.append(at)
+            ci += nc
         stream.sync()  # the module-level generator continues where the reference's calls would have left it
         centre = P[_to_device(np.concatenate(picks), d)].contiguous()  # start + padding = the base's own position
         nb = int(centre.numel())

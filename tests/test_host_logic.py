@@ -309,3 +309,9 @@ def test_mtstream_reproduces_random_sample_and_its_state():
     assert [random.random() for _ in range(5)] == tail
     with pytest.raises(ValueError):
         MTStream().sample(5, 6)
+    random.setstate(state)  # one native call for many consecutive samples
+    stream = MTStream()
+    many = stream.sample_many([n for n, _ in cases], [k for _, k in cases])
+    stream.sync()
+    assert many.tolist() == [x for w in want for x in w]
+    assert [random.random() for _ in range(5)] == tail
