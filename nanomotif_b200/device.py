@@ -382,8 +382,8 @@ import os as _os
 # Family sharing in K2 (nmb_scan_count_families: the children of one search expansion evaluated as one parent chain +
 # one indicator plane each).  OFF by default: exact (tests/test_gpu_scan.py) and 17 % fewer instructions on the cfg3
 # search-shaped work list, but the extra code takes the kernel's hot path past the SM's instruction cache
-# (stalled_no_instruction 0.4 -> 4.2 per issue, profiles/r02_scan_families_experiment.txt) and the launch gets 25 %
-# SLOWER (1.59 -> 1.99 ms).  NMB_FAMILIES=1 enables it.
+# (stalled_no_instruction 0.4 -> 4.2 per issue, profiles/r02_scan_families_experiment.txt) and the launch gets
+# SLOWER (1.59 -> 1.99 ms; 1.30 -> 2.23 ms with the final split-barrier kernel).  NMB_FAMILIES=1 enables it.
 FAMILIES = _os.environ.get("NMB_FAMILIES", "0") == "1"
 
 
