@@ -315,3 +315,32 @@ def test_mtstream_reproduces_random_sample_and_its_state():
     stream.sync()
     assert many.tolist() == [x for w in want for x in w]
     assert [random.random() for _ in range(5)] == tail
+
+
+def test_string_columns_of_every_frame_kind_give_the_same_strings():
+    """dataload._string_column: Arrow string / large_string / dictionary / chunked / sliced arrays, numpy object and
+    unicode arrays and pandas Series all come out as offsets + bytes (or codes + dictionary) of the same strings."""
+    import pandas as pd
+    import pyarrow as pa
+
+    from nanomotif_b200.dataload import _string_column
+
+    values = ["contig_1", "contig_10", "", "k141_7 flag", "c", "contig_1"] * 50
+
+    def strings_of(col, **kw):
+        kind, a, b = _string_column(col, **kw)
+        if kind == "utf8":
+            data = bytes(b)
+            return [data[a[i]:a[i + 1]].decode() for i in range(len(a) - 1)]
+        assert kind == "dict"
+        return [b[i] for i in a]
+
+    arr = pa.array(values, type=pa.string())
+    for col in (arr, pa.array(values, type=pa.large_string()), arr.dictionary_encode(), pa.chunked_array([arr[:100], arr[100:]]),
+                np.array(values, dtype=object), np.array(values), pd.Series(values)):
+        assert strings_of(col) == values
+    assert strings_of(arr.slice(7, 120)) == values[7:127]                      # offsets that do not start at 0
+    assert strings_of(pa.array(values, type=pa.large_string()).slice(200, 33)) == values[200:233]
+    kind, codes, _ = _string_column(np.array([0, 1, 1, 0], dtype=np.uint8))    # strand codes pass through
+    assert kind == "codes" and codes.tolist() == [0, 1, 1, 0]
+    assert strings_of(np.array([21839, 21839, 7]), ints_are_codes=False) == ["21839", "21839", "7"]  # modkit codes
