@@ -503,6 +503,12 @@ def sweep_leg(res: Resident, world, reps: int = 2):
     return [float(x) for x in t.tolist()], n_inc
 
 
+def _one_job(make_jobs, asm, modtype, n_motifs):
+    j = make_jobs(1)
+    j["motif_count"], j["modtype"], j["tile_count"], j["contig_end"], j["n_groups"] = n_motifs, modtype, asm.n_tiles, 1, 1
+    return j
+
+
 def cfg2_leg(synth, device, steps: int = 10):
     """Round-1 headline kept for continuity: one 4.6 Mbp contig (BASELINE.json configs[1]), 3 x 1000 random motifs
     in one launch, inputs resident, 256 MiB L2 flush between steps."""
@@ -545,6 +551,50 @@ def cfg2_leg(synth, device, steps: int = 10):
     units = len(work) * len(seq)
     res = {"workload": "cfg2: one 4.6 Mbp contig, 3 x 1000 random motifs in one launch (round-1 headline)",
            "scan_ms": ms, "value": units / (ms * 1e-3), "alg_frac": ALG_BYTES_PER_UNIT * units / (ms * 1e-3) / 1e9}
+    # the motifs the REFERENCE search visited (tests/golden/search_trace*.json, recorded from the real MotifSearcher):
+    # every expansion = the children of one parent (graph edges), scored expansion by expansion as the search does
+    # (SURVEY 8d cfg 2: "the actual motif sequence visited by the reference search")
+    try:
+        rounds_t = []
+        for name in ("search_trace.json", "search_trace_cfg1.json"):
+            with open(os.path.join(ROOT, "tests", "golden", name)) as f:
+                tr = json.load(f)
+            pad = tr["spec"]["padding"]
+            kids = {}
+            for parent, child in tr["edges"]:
+                kids.setdefault(parent, []).append(child)
+            rounds_t += [[nmb.Motif(c, pad) for c in cs] for cs in kids.values()]
+        n_visited = sum(len(r) for r in rounds_t)
+        one = PreparedJobs(_one_job(make_jobs, asm, 0, n_visited), device)
+        all_progs = MotifPrograms(pack_motifs([m for r in rounds_t for m in r]), device)
+        per_round = [(MotifPrograms(pack_motifs(r), device), PreparedJobs(_one_job(make_jobs, asm, 0, len(r)), device), len(r))
+                     for r in rounds_t]
+        out_t = torch.zeros((n_visited, 4), dtype=torch.int64, device=device)
+
+        def timed(fn, reps=5):
+            fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        def as_rounds():
+            for pr, jb, n in per_round:
+                scan_count(asm, dp, pr, jb, n, out=out_t[:n])
+
+        ms_rounds = timed(as_rounds)
+        ms_one = timed(lambda: scan_count(asm, dp, all_progs, one, n_visited, out=out_t))
+        res["reference_search_trace"] = {
+            "motifs": n_visited, "expansions": len(rounds_t),
+            "ms_expansion_by_expansion": ms_rounds, "value_expansion_by_expansion": n_visited * len(seq) / (ms_rounds * 1e-3),
+            "ms_one_launch": ms_one, "value_one_launch": n_visited * len(seq) / (ms_one * 1e-3),
+            "note": "mod type 'a' over the 4.6 Mbp contig; one launch per expansion is launch-latency bound on ONE small bin "
+                    "(~70 tiles): the lock-step driver batches the expansions of all bins instead (headline schedule)"}
+    except (OSError, KeyError, ValueError) as exc:  # the golden traces are test fixtures; the bench does not depend on them
+        res["reference_search_trace"] = {"unavailable": repr(exc)}
     # round-1's end-to-end leg, kept for continuity: the repo's own pre-compacted 7-byte rows (prepared OUTSIDE the
     # timed region, so this is not the boundary number), one pinned block per mod type, copies overlapped with scans
     from nanomotif_b200.device import compact_rows
