@@ -129,7 +129,10 @@ static int stager_run(nmb_stager *s, void *dst_dev, const void *src_host, const 
                       const int64_t *piece_off, int64_t n_src, int64_t bytes, void *stream, bool narrow,
                       int32_t *overflow_h) {
     cudaStream_t caller = (cudaStream_t)stream;
-    NMB_CUDA(cudaSetDevice(s->device));
+    int current = s->device;
+    NMB_CUDA(cudaGetDevice(&current));
+    if (current != s->device) NMB_FAIL(NMB_ERR_INVALID, "nmb_stager: the stager belongs to device %d, the current device is %d",
+                                       s->device, current);
     NMB_CUDA(cudaEventRecord(s->begin, caller));  // dst may still be in use by work enqueued before this call
     const int64_t n_chunks = (bytes + s->slot_bytes - 1) / s->slot_bytes;
     const int T = (int)(n_chunks < s->n_threads ? n_chunks : s->n_threads);
