@@ -167,26 +167,11 @@ class ShardedMultiBinScorer:
         from .api import MultiBinScorer
 
         self.rank, self.world_size, self.group = int(rank), int(world_size), group
-        names, lengths, groups = [], [], []
-        for b, (bin_name, cs) in enumerate(bins.items()):
-            for name, seq in cs.items():
-                names.append(name)
-                lengths.append(_contig_length(seq))
-                groups.append(b)
-        self.owner = plan_shards(lengths, world_size, groups)
-        mine, at = {}, 0
-        self.split_bins, self.bin_ranks = set(), {}
-        for bin_name, cs in bins.items():
-            own = self.owner[at:at + len(cs)]
-            self.bin_ranks[bin_name] = sorted(set(own.tolist()))
-            if len(self.bin_ranks[bin_name]) > 1:
-                self.split_bins.add(bin_name)
-            local = {n: s for (n, s), r in zip(cs.items(), own) if r == self.rank}
+        self.owner, per_rank, self.split_bins, self.bin_ranks = self.plan(bins, world_size)
+        mine = per_rank[self.rank]
+        for bin_name, local in mine.items():
             if any(isinstance(v, (int, np.integer)) for v in local.values()):
                 raise ValueError(f"bin {bin_name}: this rank owns a contig that was given by length only")
-            if local:
-                mine[bin_name] = local
-            at += len(cs)
         self.mod_types = list(mod_types)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         tables = pileup
@@ -195,6 +180,29 @@ class ShardedMultiBinScorer:
         self.local = MultiBinScorer(tables, mine, self.mod_types, low_meth_threshold, high_meth_threshold,
                                     self.device) if mine else None
         self._local_bins = set(mine)
+
+    @staticmethod
+    def plan(bins: dict, world_size: int):
+        """The shard plan every rank derives for itself (pure host logic, no device): (owner rank of every contig in
+        `bins` order, [{bin: {contig: sequence}} per rank], set of bins whose contigs ended up on several ranks,
+        {bin: ranks holding part of it}).  Contigs may be given by length (int) instead of sequence."""
+        lengths, groups = [], []
+        for b, cs in enumerate(bins.values()):
+            for seq in cs.values():
+                lengths.append(_contig_length(seq))
+                groups.append(b)
+        owner = plan_shards(lengths, world_size, groups)
+        per_rank = [dict() for _ in range(max(1, world_size))]
+        split_bins, bin_ranks, at = set(), {}, 0
+        for bin_name, cs in bins.items():
+            own = owner[at:at + len(cs)]
+            bin_ranks[bin_name] = sorted(set(own.tolist()))
+            if len(bin_ranks[bin_name]) > 1:
+                split_bins.add(bin_name)
+            for (name, seq), r in zip(cs.items(), own.tolist()):
+                per_rank[r].setdefault(bin_name, {})[name] = seq
+            at += len(cs)
+        return owner, per_rank, split_bins, bin_ranks
 
     def context(self, bin_name, mod_type) -> ShardedContext:
         if bin_name not in self.bin_ranks:

@@ -93,3 +93,77 @@ def test_allreduce_of_shard_counts_equals_unsharded_counts():
     for rank, counts, rows in results:
         assert counts == want, f"rank {rank}"
         assert [n for n, _ in rows] == sorted(contigs.keys())  # every contig owned by exactly one rank
+
+
+def test_sharded_scorer_plan_is_pure_host_logic():
+    """ShardedMultiBinScorer.plan: what every rank derives for itself before touching a device -- every contig owned
+    once, bins whole unless one exceeds 1.25 / world of the assembly, lengths-only contigs accepted, same plan from
+    sequences and from lengths."""
+    bins = {"big": {f"big_{i}": "A" * n for i, n in enumerate((900, 700, 600, 400))},
+            "s1": {"s1_0": "C" * 300, "s1_1": "C" * 80}, "s2": {"s2_0": "G" * 250}, "s3": {"s3_0": "T" * 90, "s3_1": "T" * 70}}
+    owner, per_rank, split, bin_ranks = sharding.ShardedMultiBinScorer.plan(bins, 2)
+    names = [n for cs in bins.values() for n in cs]
+    assert len(owner) == len(names) and set(owner.tolist()) == {0, 1}
+    got = sorted(n for r in per_rank for cs in r.values() for n in cs)
+    assert got == sorted(names)                                    # every contig on exactly one rank
+    assert split == {"big"} and bin_ranks["big"] == [0, 1]         # 2600 of 3390 bp > 1.25 / 2: split by contig
+    for b in ("s1", "s2", "s3"):
+        assert len(bin_ranks[b]) == 1                              # small bins stay whole
+    loads = [sum(len(s) for cs in r.values() for s in cs.values()) for r in per_rank]
+    assert abs(loads[0] - loads[1]) <= 400
+    by_len = {b: {n: len(s) for n, s in cs.items()} for b, cs in bins.items()}
+    owner2, per_rank2, split2, _ = sharding.ShardedMultiBinScorer.plan(by_len, 2)
+    assert owner2.tolist() == owner.tolist() and split2 == split   # lengths are all a rank needs of foreign contigs
+    assert [{b: list(cs) for b, cs in r.items()} for r in per_rank2] == [{b: list(cs) for b, cs in r.items()} for r in per_rank]
+    # as many equal bins as ranks: the 25 % margin keeps them whole (cfg3's 8-bin sample on 8 GPUs)
+    eight = {f"b{i}": {f"b{i}_c{j}": 1000 + 3 * i + j for j in range(5)} for i in range(8)}
+    _, per8, split8, _ = sharding.ShardedMultiBinScorer.plan(eight, 8)
+    assert not split8 and all(len(r) == 1 for r in per8)
+    assert sharding.ShardedMultiBinScorer.plan(bins, 1)[1][0].keys() == bins.keys()
+
+
+def _plan_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        contigs, pile = _make_bin()
+        bins = {"bin_a": {k: contigs[k] for k in ("c0", "c1")}, "bin_b": {k: contigs[k] for k in ("c2", "c3", "c4")}}
+        _, per_rank, split, _ = sharding.ShardedMultiBinScorer.plan(bins, world)
+        # what submit() does on a device, with the oracle standing in for the scan: rows of requests whose bin is not
+        # local stay zero, ONE all-reduce of the stacked tensor replicates every request's counts on every rank
+        requests = [("bin_a", MOTIFS[:2]), ("bin_b", MOTIFS), ("bin_a", MOTIFS[2:])]
+        rows = []
+        for b, motifs in requests:
+            local = per_rank[rank].get(b, {})
+            for m, p in motifs:
+                rows.append(O.motif_model_bin(pile["contig"], pile["position"], pile["strand"], pile["fraction_mod"], local, m, p,
+                                              fast=True) if local else (0, 0))
+        t = torch.tensor(rows, dtype=torch.int64)
+        sharding.allreduce_counts(t)
+        q.put((rank, t.tolist(), sorted(split)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stacked_request_tensor_all_reduce_replicates_counts():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_plan_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    contigs, pile = _make_bin()
+    bins = {"bin_a": {k: contigs[k] for k in ("c0", "c1")}, "bin_b": {k: contigs[k] for k in ("c2", "c3", "c4")}}
+    want = []
+    for b, motifs in [("bin_a", MOTIFS[:2]), ("bin_b", MOTIFS), ("bin_a", MOTIFS[2:])]:
+        for m, p in motifs:
+            want.append(list(O.motif_model_bin(pile["contig"], pile["position"], pile["strand"], pile["fraction_mod"], bins[b], m, p,
+                                               fast=True)))
+    for rank, got, split in results:
+        assert got == want, f"rank {rank}"
