@@ -339,14 +339,19 @@ class MultiBinScorer:
     the reference's process pool over bins (nanomotif/find_motifs_bin.py:330-372)."""
 
     def __init__(self, pileup, bins: dict, mod_types, low_meth_threshold: float, high_meth_threshold: float,
-                 device=None, keep_rows: bool = True):
+                 device=None, keep_rows: bool = True, pieces=None):
         """bins: {bin name: {contig name: sequence}}.  pileup: what the reference hands to its workers
         (find_motifs_bin.py:399-427) -- ONE table with contig / position / strand / mod_type / fraction_mod columns
         (pyarrow Table, polars or pandas frame, PileupTable, dict of arrays), or the partitioned form
         {(bin, mod_type): table} / a list of tables -- or dataload.DeviceRows (rows already parsed on the device).
         String columns cross PCIe as their Arrow buffers and are resolved to ids on the device
-        (dataload.rows_from_table): no per-row host work."""
+        (dataload.rows_from_table): no per-row host work.
+
+        pieces (sharding.ShardedMultiBinScorer, a contig cut into position ranges over several ranks): [(contig name
+        of the piece in `bins`, contig name the pileup rows carry, a, b, shift)] -- rows of that contig with
+        a <= position < b are joined to the piece at position - shift, its other rows are dropped."""
         from .dataload import DeviceRows, rows_from_table
+        from .sharding import remap_split_rows
 
         contigs, self._ranges = {}, {}
         for b, cs in bins.items():
@@ -384,9 +389,15 @@ class MultiBinScorer:
                             m_lut[i] = names.index(str(name))
                     cid = torch.from_numpy(np.append(c_lut, np.int32(-1))).to(d)[rows.contig_id.long()]  # -1 -> -1
                     mt = torch.from_numpy(m_lut).to(d)[rows.mod_type.long()]
-            self.pileup.add_columns(cid, rows.position, rows.strand, rows.fraction_mod, mt, sync=False)
+            position = rows.position
+            if pieces:
+                index = self.assembly.index
+                with torch.cuda.device(d):
+                    cid, position = remap_split_rows(cid, position, [(index[carried], index[own], a, b, shift)
+                                                                     for own, carried, a, b, shift in pieces])
+            self.pileup.add_columns(cid, position, rows.strand, rows.fraction_mod, mt, sync=False)
             if keep_rows:  # device columns for the window step (growth.WindowPool) -- ids of THIS assembly
-                self.rows.append(DeviceRows(self.assembly.names, self.mod_types, d, contig_id=cid, position=rows.position,
+                self.rows.append(DeviceRows(self.assembly.names, self.mod_types, d, contig_id=cid, position=position,
                                             strand=rows.strand, mod_type=mt, fraction_mod=rows.fraction_mod,
                                             Nvalid_cov=rows.Nvalid_cov))
         torch.cuda.current_stream(d).synchronize()

@@ -6,6 +6,13 @@ assigned to ranks by greedy bin-packing on base pairs, every rank scores the rep
 against its own contigs, and the per-motif bin-level counts are summed with ONE all-reduce
 (int64, sum) per scoring step -- NCCL over NVLink on GPUs, gloo in the CPU tests.  Per-contig outputs
 (the contig x motif table) need no collective: rows are owned by the rank that owns the contig.
+
+A single contig that alone exceeds 1.25 x 1/world_size of the assembly (SURVEY 8d cfg 2: one 4.6 Mbp contig) is cut
+into position ranges: the rank of range [a, b) packs the text [a - 64, b + 64) and ingests the pileup rows with
+a <= position < b, shifted into the coordinates of that text (`split_ranges`, `ContigPiece`, `remap_split_rows`).
+A motif spans at most 62 positions, so an occurrence whose modified base lies in [a, b) lies inside the packed text
+exactly when it lies inside the contig, and every pileup row is joined on exactly one rank: the counts of the pieces
+add up to the counts of the contig, and the same all-reduce merges them.
 """
 from __future__ import annotations
 
@@ -50,6 +57,63 @@ def plan_shards(lengths: Sequence[int], world_size: int, groups: Sequence[int] |
 def local_contigs(contigs: Mapping[str, object], owner: np.ndarray, rank: int) -> dict:
     """The sub-dict of `contigs` (insertion order kept) owned by `rank`."""
     return {name: seq for i, (name, seq) in enumerate(contigs.items()) if owner[i] == rank}
+
+
+HALO_BP = 64  # text kept on both sides of a piece's position range: > the longest motif (62 positions) - 1
+
+
+class ContigPiece:
+    """Position range [a, b) of a contig of `length` bp that one rank scores: the rank packs `text` = the contig's
+    letters [lo, hi) = [max(0, a - HALO_BP), min(length, b + HALO_BP)) and keeps pileup rows with a <= position < b
+    at position - lo.  `seq` is the whole contig (str / DNAsequence-like) or its length (a rank that does not own the
+    piece needs nothing more)."""
+
+    def __init__(self, name: str, a: int, b: int, length: int, seq=None):
+        self.name, self.a, self.b, self.length, self.seq = name, int(a), int(b), int(length), seq
+        self.lo, self.hi = max(0, self.a - HALO_BP), min(self.length, self.b + HALO_BP)
+
+    @property
+    def shift(self) -> int:
+        return self.lo
+
+    @property
+    def text(self) -> str:
+        if self.seq is None or isinstance(self.seq, (int, np.integer)):
+            raise ValueError(f"contig {self.name}: this rank owns positions [{self.a}, {self.b}) of a contig that was "
+                             "given by length only")
+        s = self.seq if isinstance(self.seq, str) else self.seq.sequence
+        return s[self.lo:self.hi]
+
+    def __len__(self) -> int:  # what the rank packs (plan bookkeeping)
+        return self.hi - self.lo
+
+    def __repr__(self) -> str:
+        return f"ContigPiece({self.name!r}, {self.a}, {self.b}, length={self.length})"
+
+
+def split_ranges(length: int, n_pieces: int) -> list:
+    """[a, b) ranges that cut a contig into n_pieces of (almost) equal length, boundaries on multiples of 512 bp (one
+    lane chunk of the packed layout; any boundary would be correct)."""
+    n_pieces = max(1, min(int(n_pieces), max(1, length // 1024)))
+    cuts = [0] + [int(round(length * k / n_pieces / 512)) * 512 for k in range(1, n_pieces)] + [int(length)]
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+
+def remap_split_rows(contig_id, position, pieces):
+    """Rows of split contigs -> rows of the rank's pieces.  contig_id / position: torch tensors (any device) as the
+    name lookup wrote them, where every row of a split contig carries the id its NAME resolved to; pieces: [(that id,
+    the piece's own contig id, a, b, shift)].  Rows with a <= position < b move to the piece (position - shift); rows
+    of a split contig that fall in no local piece get contig id -1 (another rank joins them).  Returns new tensors."""
+    import torch
+
+    cid, pos = contig_id.clone(), position.clone()
+    for lookup in sorted({int(p[0]) for p in pieces}):
+        cid[contig_id == lookup] = -1
+    for lookup, own, a, b, shift in pieces:
+        m = (contig_id == int(lookup)) & (position >= int(a)) & (position < int(b))
+        cid = torch.where(m, torch.full_like(cid, int(own)), cid)
+        pos = torch.where(m, position - int(shift), pos)
+    return cid, pos
 
 
 def allreduce_counts(counts, group=None):
@@ -161,47 +225,86 @@ class ShardedMultiBinScorer:
     other ranks' contigs in a shared table are ignored, but they are still copied to the device."""
 
     def __init__(self, pileup, bins: dict, mod_types, low_meth_threshold: float, high_meth_threshold: float,
-                 rank: int, world_size: int, device=None, group=None):
+                 rank: int, world_size: int, device=None, group=None, split_contigs: bool = True):
         import torch
 
         from .api import MultiBinScorer
 
         self.rank, self.world_size, self.group = int(rank), int(world_size), group
-        self.owner, per_rank, self.split_bins, self.bin_ranks = self.plan(bins, world_size)
-        mine = per_rank[self.rank]
-        for bin_name, local in mine.items():
-            if any(isinstance(v, (int, np.integer)) for v in local.values()):
-                raise ValueError(f"bin {bin_name}: this rank owns a contig that was given by length only")
+        self.owner, per_rank, self.split_bins, self.bin_ranks = self.plan(bins, world_size, split_contigs)
+        mine, self.pieces = {}, []  # {bin: {local contig name: text}}, [(local name, name the rows carry, a, b, shift)]
+        for bin_name, local in per_rank[self.rank].items():
+            mine[bin_name] = {}
+            for name, seq in local.items():
+                if isinstance(seq, ContigPiece):
+                    mine[bin_name][name] = seq.text
+                    self.pieces.append((name, seq.name, seq.a, seq.b, seq.shift))
+                elif isinstance(seq, (int, np.integer)):
+                    raise ValueError(f"bin {bin_name}: this rank owns a contig that was given by length only")
+                else:
+                    mine[bin_name][name] = seq
         self.mod_types = list(mod_types)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         tables = pileup
         if isinstance(pileup, dict) and "position" not in pileup:  # partitioned {(bin, mod_type): frame}
             tables = {k: v for k, v in pileup.items() if not (isinstance(k, tuple) and k[0] in bins and k[0] not in mine)}
         self.local = MultiBinScorer(tables, mine, self.mod_types, low_meth_threshold, high_meth_threshold,
-                                    self.device) if mine else None
+                                    self.device, pieces=self.pieces) if mine else None
         self._local_bins = set(mine)
 
     @staticmethod
-    def plan(bins: dict, world_size: int):
+    def plan(bins: dict, world_size: int, split_contigs: bool = True):
         """The shard plan every rank derives for itself (pure host logic, no device): (owner rank of every contig in
-        `bins` order, [{bin: {contig: sequence}} per rank], set of bins whose contigs ended up on several ranks,
-        {bin: ranks holding part of it}).  Contigs may be given by length (int) instead of sequence."""
-        lengths, groups = [], []
+        `bins` order, -1 for a contig cut into pieces; [{bin: {contig: sequence or ContigPiece}} per rank]; set of bins
+        that ended up on several ranks; {bin: ranks holding part of it}).  Contigs may be given by length (int)
+        instead of sequence.  A contig longer than 1.25 / world_size of the assembly is cut into about
+        length / (assembly / world_size) position ranges (module docstring); ranges that land on the same rank next to
+        each other are merged again.  The first piece of a contig on a rank keeps the contig's name (the name the
+        pileup rows carry), further pieces are named name + chr(31) + str(a)."""
+        world = max(1, int(world_size))
+        names, lengths, seqs, groups = [], [], [], []
         for b, cs in enumerate(bins.values()):
-            for seq in cs.values():
+            for name, seq in cs.items():
+                names.append(name)
+                seqs.append(seq)
                 lengths.append(_contig_length(seq))
                 groups.append(b)
-        owner = plan_shards(lengths, world_size, groups)
-        per_rank = [dict() for _ in range(max(1, world_size))]
-        split_bins, bin_ranks, at = set(), {}, 0
-        for bin_name, cs in bins.items():
-            own = owner[at:at + len(cs)]
-            bin_ranks[bin_name] = sorted(set(own.tolist()))
-            if len(bin_ranks[bin_name]) > 1:
-                split_bins.add(bin_name)
-            for (name, seq), r in zip(cs.items(), own.tolist()):
-                per_rank[r].setdefault(bin_name, {})[name] = seq
-            at += len(cs)
+        total = int(sum(lengths))
+        limit = 1.25 * total / world
+        unit_len, unit_group, unit_src = [], [], []
+        for i, n in enumerate(lengths):
+            ranges = [(0, n)]
+            if split_contigs and world > 1 and n > limit:
+                ranges = split_ranges(n, -(-n * world // max(1, total)))
+            for a, b in ranges:
+                unit_len.append(b - a)
+                unit_group.append(groups[i])
+                unit_src.append((i, a, b))
+        unit_owner = plan_shards(unit_len, world, unit_group)
+        by_contig = [[] for _ in names]
+        for (i, a, b), r in zip(unit_src, unit_owner.tolist()):
+            if by_contig[i] and by_contig[i][-1][0] == r and by_contig[i][-1][2] == a:
+                by_contig[i][-1] = (r, by_contig[i][-1][1], b)  # next to each other on the same rank: one range
+            else:
+                by_contig[i].append((r, a, b))
+        owner = np.full(len(names), -1, dtype=np.int32)
+        per_rank = [dict() for _ in range(world)]
+        bin_names = list(bins.keys())
+        bin_ranks = {b: set() for b in bin_names}
+        for i, parts in enumerate(by_contig):
+            bin_name = bin_names[groups[i]]
+            if len(parts) == 1 and (parts[0][1], parts[0][2]) == (0, lengths[i]):
+                owner[i] = parts[0][0]
+            for r, a, b in parts:
+                bin_ranks[bin_name].add(r)
+                local = per_rank[r].setdefault(bin_name, {})
+                if owner[i] >= 0:
+                    local[names[i]] = seqs[i]
+                else:
+                    local[names[i] if names[i] not in local else f"{names[i]}\x1f{a}"] = ContigPiece(
+                        names[i], a, b, lengths[i], seqs[i])
+        bin_ranks = {b: sorted(r) for b, r in bin_ranks.items()}
+        split_bins = {b for b, r in bin_ranks.items() if len(r) > 1}
         return owner, per_rank, split_bins, bin_ranks
 
     def context(self, bin_name, mod_type) -> ShardedContext:

@@ -20,14 +20,22 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _make(seed=9):
+LAYOUTS = {
+    # bin_big alone exceeds half of the assembly -> its contigs are split over the two ranks (all-reduce merges them)
+    "bins": (("bin_big", (90000, 70000, 60000, 40000)), ("bin_s1", (30000, 8000)), ("bin_s2", (25000,)), ("bin_s3", (9000, 7000, 3000))),
+    # one contig alone exceeds half of the assembly (a monoculture: chromosome + plasmids) -> it is cut into two
+    # position ranges, each rank packs its range + 64 bp of text on both sides and joins the rows of its range
+    "mono": (("mono", (200000, 9000)), ("bin_s1", (12000, 8000))),
+}
+
+
+def _make(layout="bins", seed=9):
     from nanomotif_b200 import synth
 
     rng = np.random.default_rng(seed)
     bins = {}
     cols = {k: [] for k in ("contig", "position", "strand", "mod_type", "fraction_mod")}
-    # bin_big alone exceeds half of the assembly -> its contigs are split over the two ranks (all-reduce merges them)
-    for b, lens in (("bin_big", (90000, 70000, 60000, 40000)), ("bin_s1", (30000, 8000)), ("bin_s2", (25000,)), ("bin_s3", (9000, 7000, 3000))):
+    for b, lens in LAYOUTS[layout]:
         bins[b] = {}
         for i, L in enumerate(lens):
             name = f"{b}_c{i}"
@@ -47,7 +55,7 @@ def _requests(nmb, scorer, bins):
     return [(scorer.context(b, mt), [nmb.Motif(m, p) for m, p in MOTIFS[mt]]) for b in bins for mt in MOD_TYPES]
 
 
-def _worker(rank, world, port, backend, q):
+def _worker(rank, world, port, backend, q, layout="bins"):
     import torch
     import torch.distributed as dist
 
@@ -60,7 +68,7 @@ def _worker(rank, world, port, backend, q):
         import nanomotif_b200 as nmb
         from nanomotif_b200.sharding import ShardedMultiBinScorer
 
-        bins, pile = _make()
+        bins, pile = _make(layout)
         # every rank knows all lengths; sequences only of the contigs it may own -- here simply all of them
         scorer = ShardedMultiBinScorer(pile, bins, MOD_TYPES, 0.3, 0.7, rank, world, dev)
         first = scorer.submit(_requests(nmb, scorer, bins))  # two batches in flight before the first result is read
@@ -73,27 +81,33 @@ def _worker(rank, world, port, backend, q):
         dist.destroy_process_group()
 
 
-def test_sharded_scorer_equals_unsharded_and_oracle():
+def _run_ranks(layout, world=2):
     import torch
     import torch.multiprocessing as mp
 
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
-    import nanomotif_b200 as nmb
-    from oracle import restate as O
-
-    world = 2
-    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, q, layout)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(world)]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    return results
+
+
+def test_sharded_scorer_equals_unsharded_and_oracle():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import nanomotif_b200 as nmb
+    from oracle import restate as O
+
+    results = _run_ranks("bins")
     bins, pile = _make()
     single = nmb.MultiBinScorer(pile, bins, MOD_TYPES, 0.3, 0.7)
     want = [c.tolist() for c in single.score_batch(_requests(nmb, single, bins))]
@@ -113,6 +127,28 @@ def test_sharded_scorer_equals_unsharded_and_oracle():
                                       pile["fraction_mod"][sel], bins[b], m, p, fast=True)
                 assert tuple(want[at][j]) == tuple(w), (b, mt, m)
             at += 1
+
+
+def test_one_huge_contig_is_cut_into_position_ranges():
+    """SURVEY 8e, cfg 2 on several GPUs: a contig that alone exceeds a rank's share is scored piecewise -- every rank
+    packs its position range (+ 64 bp of text on both sides) and joins the pileup rows of its range; the all-reduce
+    adds the pieces up.  Same counts as the unsharded scorer (whose parity with the oracle the test above pins)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import nanomotif_b200 as nmb
+
+    results = _run_ranks("mono")
+    bins, pile = _make("mono")
+    single = nmb.MultiBinScorer(pile, bins, MOD_TYPES, 0.3, 0.7)
+    want = [c.tolist() for c in single.score_batch(_requests(nmb, single, bins))]
+    total_bp = sum(len(s) for cs in bins.values() for s in cs.values())
+    assert sum(r[3] for r in results) == total_bp + 2 * 64  # the two pieces overlap by their halos
+    for rank, got, split, local_bp in results:
+        assert got == want, f"rank {rank}"
+        assert split == ["mono"]
+        assert 0.4 * total_bp < local_bp < 0.6 * total_bp
 
 
 def test_contigs_of_other_ranks_by_length_only():

@@ -167,3 +167,97 @@ def test_stacked_request_tensor_all_reduce_replicates_counts():
                                                fast=True)))
     for rank, got, split in results:
         assert got == want, f"rank {rank}"
+
+
+# ---------------------------------------------------------------------------------------------
+# a contig that alone exceeds a rank's share is cut into position ranges (cfg 2 on several GPUs)
+# ---------------------------------------------------------------------------------------------
+LONG_MOTIFS = MOTIFS + [("A" + "." * 38 + "T", 0), ("T" + "." * 38 + "A", 39), ("G[AG].GAAG[CT]", 5), ("A" + "." * 60 + "C", 0)]
+
+
+def _huge_bin(seed=11, length=6000, extra=(700, 300)):
+    rng = np.random.default_rng(seed)
+    bins, cols = {"mono": {}, "small": {}}, {k: [] for k in ("contig", "position", "strand", "fraction_mod")}
+    for b, name, L in [("mono", "chrom", length)] + [("small", f"s{i}", n) for i, n in enumerate(extra)]:
+        seq = synth.random_sequence(rng, L, 0.5, 2e-3 if name == "chrom" else 0.0)  # N runs in the big contig
+        bins[b][name] = seq.tobytes().decode()
+        p = synth.synth_pileup(seq, rng, depth=15, mod_types=("a",))
+        cols["contig"].append(np.full(len(p["position"]), name, dtype=object))
+        cols["position"].append(p["position"])
+        cols["strand"].append(np.where(p["strand"] == 0, "+", "-"))
+        cols["fraction_mod"].append(p["fraction_mod"])
+    return bins, {k: np.concatenate(v) for k, v in cols.items()}
+
+
+def _rank_counts(per_rank_bins, pile, motifs):
+    """What one rank's MultiBinScorer(pieces=...) computes, with the oracle standing in for the scan: the rank's texts
+    as its contigs, the rows moved to the pieces by sharding.remap_split_rows (torch, here on the CPU)."""
+    texts, pieces = {}, []
+    for cs in per_rank_bins.values():
+        for name, seq in cs.items():
+            if isinstance(seq, sharding.ContigPiece):
+                texts[name] = seq.text
+                pieces.append((name, seq.name, seq.a, seq.b, seq.shift))
+            else:
+                texts[name] = seq
+    index = {n: i for i, n in enumerate(texts)}
+    cid = torch.tensor([index.get(n, -1) for n in pile["contig"]], dtype=torch.int32)
+    pos = torch.from_numpy(np.asarray(pile["position"], dtype=np.int64))
+    if pieces:
+        cid, pos = sharding.remap_split_rows(cid, pos, [(index[c], index[o], a, b, s) for o, c, a, b, s in pieces])
+    names = np.array(list(texts) + ["?"], dtype=object)[cid.numpy()]
+    out = np.zeros((len(motifs), 2), dtype=np.int64)
+    for mi, (m, p) in enumerate(motifs):
+        out[mi] = O.motif_model_bin(names, pos.numpy(), pile["strand"], pile["fraction_mod"], texts, m, p, fast=True)
+    return out
+
+
+@pytest.mark.parametrize("world,length", [(2, 6000), (4, 6000), (8, 20000), (3, 5000)])
+def test_counts_of_contig_pieces_add_up_to_the_contig(world, length):
+    bins, pile = _huge_bin(length=length)
+    owner, per_rank, split, bin_ranks = sharding.ShardedMultiBinScorer.plan(bins, world)
+    assert owner[0] == -1 and "mono" in split and len(bin_ranks["mono"]) == min(world, len(bin_ranks["mono"])) > 1
+    pieces = sorted((p.a, p.b) for r in per_rank for cs in r.values() for p in cs.values() if isinstance(p, sharding.ContigPiece))
+    assert pieces[0][0] == 0 and pieces[-1][1] == length
+    assert all(x[1] == y[0] for x, y in zip(pieces, pieces[1:]))  # the ranges tile the contig
+    for r in per_rank:  # local names are unique, the first piece of a contig on a rank keeps the contig's name
+        mine = [n for cs in r.values() for n, p in cs.items() if isinstance(p, sharding.ContigPiece)]
+        assert len(set(mine)) == len(mine) and (not mine or "chrom" in mine)
+    want = _oracle_counts_motifs(bins, pile, LONG_MOTIFS)
+    got = sum(_rank_counts(r, pile, LONG_MOTIFS) for r in per_rank)
+    assert got.tolist() == want.tolist()
+    assert want[:, 0].sum() > 0 and want[-1].sum() > 0  # the 62-position motif has joined rows
+    # without splitting the big contig sits on one rank
+    owner0, per0, _, _ = sharding.ShardedMultiBinScorer.plan(bins, world, split_contigs=False)
+    assert owner0[0] >= 0 and not any(isinstance(p, sharding.ContigPiece) for r in per0 for cs in r.values() for p in cs.values())
+
+
+def _oracle_counts_motifs(bins, pile, motifs):
+    contigs = {n: s for cs in bins.values() for n, s in cs.items()}
+    out = np.zeros((len(motifs), 2), dtype=np.int64)
+    for mi, (m, p) in enumerate(motifs):
+        out[mi] = O.motif_model_bin(pile["contig"], pile["position"], pile["strand"], pile["fraction_mod"], contigs, m, p, fast=True)
+    return out
+
+
+def test_two_pieces_of_one_contig_on_one_rank_and_lengths_only():
+    """Pieces of a contig that land on one rank without being neighbours get their own local names; a rank needs the
+    text of its own pieces only."""
+    a, b = sharding.ContigPiece("x", 0, 1024, 5000, "ACGT" * 1250), sharding.ContigPiece("x", 2048, 3072, 5000, "ACGT" * 1250)
+    assert (a.lo, a.hi, a.shift, len(a)) == (0, 1024 + 64, 0, 1088) and (b.lo, b.hi, b.shift) == (2048 - 64, 3072 + 64, 1984)
+    assert a.text == ("ACGT" * 1250)[:1088] and b.text == ("ACGT" * 1250)[1984:3136]
+    with pytest.raises(ValueError, match="length only"):
+        sharding.ContigPiece("x", 0, 1024, 5000, 5000).text
+    cid = torch.tensor([0, 0, 0, 0, 1, 0], dtype=torch.int32)
+    pos = torch.tensor([5, 1024, 2048, 3071, 7, 4999])
+    ncid, npos = sharding.remap_split_rows(cid, pos, [(0, 0, 0, 1024, 0), (0, 2, 2048, 3072, 1984)])
+    assert ncid.tolist() == [0, -1, 2, 2, 1, -1] and npos.tolist() == [5, 1024, 64, 1087, 7, 4999]
+    assert cid.tolist() == [0, 0, 0, 0, 1, 0]  # inputs untouched
+    assert sharding.split_ranges(5000, 3) == [(0, 1536), (1536, 3584), (3584, 5000)]
+    assert sharding.split_ranges(1500, 4) == [(0, 1500)]  # too short to cut
+    # contigs of other ranks by length: the same plan as from sequences
+    bins, _ = _huge_bin()
+    by_len = {b: {n: len(s) for n, s in cs.items()} for b, cs in bins.items()}
+    p1, p2 = sharding.ShardedMultiBinScorer.plan(bins, 4), sharding.ShardedMultiBinScorer.plan(by_len, 4)
+    assert p1[0].tolist() == p2[0].tolist() and p1[2] == p2[2] and p1[3] == p2[3]
+    assert [[(b, n) for b, cs in r.items() for n in cs] for r in p1[1]] == [[(b, n) for b, cs in r.items() for n in cs] for r in p2[1]]
