@@ -78,8 +78,8 @@ class Motif(str):
             and self.mod_position == other.mod_position
         )
 
-    def __ne__(self, other):
-        return not self.__eq__(other)
+    # no __ne__: like the reference type (motif.py:26-36 defines __eq__ only), `!=` is str's -- it compares the strings
+    # and ignores mod_position.  Its one use on the path (find_motifs_bin.py:780) compares motifs of equal position.
 
     def __hash__(self):
         return hash((self.string, self.mod_position))

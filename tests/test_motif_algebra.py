@@ -1,0 +1,140 @@
+"""The host-side value types of the path against the REAL reference, method by method (CPU).
+
+nanomotif_b200.motif.Motif mirrors nanomotif.motif.Motif (nanomotif/motif.py:18-359) and nanomotif_b200.model.
+BetaBernoulliModel mirrors nanomotif/model.py:11-126: the search driver's heap order (priority x 10^isolated bases),
+the dedup of candidates (sub_motif_of), the reverse-strand scan (reverse_compliment) and the window filter (one_hot) all
+go through them.  tests/golden/motif_algebra.json was recorded by running the reference types on seeded random motifs
+(tests/golden/generate_motif_golden.py); with /root/reference mounted the same comparison also runs live on fresh motifs."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from nanomotif_b200.model import BetaBernoulliModel
+from nanomotif_b200.motif import Motif, as_motif, motif_masks, token_mask, tokenize, window_masks
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def G():
+    with open(os.path.join(HERE, "golden", "motif_algebra.json")) as f:
+        return json.load(f)
+
+
+def _check_single(m, rec):
+    assert m.split() == rec["split"] and tokenize(m.string) == rec["split"]
+    assert m.length() == rec["length"]
+    st = m.new_stripped_motif()
+    assert [st.string, st.mod_position] == rec["stripped"]
+    rc = m.reverse_compliment()
+    assert [rc.string, rc.mod_position] == rec["reverse_compliment"]
+    assert m.one_hot().tolist() == rec["one_hot"]
+    assert m.iupac() == rec["iupac"]
+    assert [m.count_isolated_bases(isolation_size=k) for k in (1, 2, 3)] == rec["isolated"]
+    assert repr(m) == rec["repr"]
+
+
+def test_motif_methods_equal_the_reference(G):
+    assert len(G["single"]) >= 250
+    for rec in G["single"]:
+        m = Motif(rec["motif"], rec["mod_pos"])
+        _check_single(m, rec)
+        assert hash(m) == hash(Motif(rec["motif"], rec["mod_pos"])) and rec["hash_equal"]
+        assert as_motif(m) is m
+        # the device masks are the one-hot rows as bit sets (bit0 = A, bit1 = T, bit2 = G, bit3 = C: constants.py:21-28)
+        masks, mp = motif_masks(m)
+        assert mp == rec["mod_pos"]
+        assert masks.tolist() == [sum(int(v) << b for b, v in enumerate(row)) for row in rec["one_hot"]]
+        assert window_masks([m], m.length())["allowed"][0, :m.length()].tolist() == masks.tolist()
+
+
+def test_motif_relations_equal_the_reference(G):
+    n_true = 0
+    for rec in G["pairs"]:
+        a, b = Motif(*rec["a"]), Motif(*rec["b"])
+        assert a.sub_motif_of(b) == rec["a_sub_b"], (a, b)
+        assert b.sub_motif_of(a) == rec["b_sub_a"], (a, b)
+        assert (a == b) == rec["eq"] and (a != b) == rec["ne"]
+        n_true += rec["a_sub_b"] + rec["b_sub_a"]
+    assert n_true > 100  # the relation is exercised in both directions, not only on unrelated pairs
+    for rec in G["groups"]:
+        assert Motif(*rec["motif"]).sub_motif_of_any([Motif(*o) for o in rec["others"]]) == rec["sub_motif_of_any"]
+    for rec in G["from_iupac"]:
+        assert Motif(rec["iupac"], 0).from_iupac().string == rec["regex"]
+
+
+def test_motif_is_a_str_with_value_semantics():
+    m = Motif("G[AG].GAAG[CT]", 5)
+    assert isinstance(m, str) and str(m) == "G[AG].GAAG[CT]" and len(m) == 14 and m.length() == 8
+    assert m == Motif("G[AG].GAAG[CT]", 5) and not (m == Motif("G[AG].GAAG[CT]", 4)) and not (m == "G[AG].GAAG[CT]")
+    # `!=` is str's in the reference (only __eq__ is overridden): it ignores mod_position -- mirrored, not "fixed"
+    assert not (m != Motif("G[AG].GAAG[CT]", 4)) and m != Motif("G[AG].GAAG[CA]", 5)
+    assert len({m, Motif("G[AG].GAAG[CT]", 5), Motif("G[AG].GAAG[CT]", 4)}) == 2
+    assert sorted([Motif("GATC", 1), Motif("AATC", 3)]) == [Motif("AATC", 3), Motif("GATC", 1)]  # heap ties: str order
+    r = pickle.loads(pickle.dumps(m))
+    assert r == m and r.mod_position == 5
+    with pytest.raises(ValueError):
+        tokenize("A[CG")
+    with pytest.raises(ValueError):
+        token_mask("N")  # set semantics only through from_iupac(); a literal N is a K3 feature (api._split_literals)
+    with pytest.raises(TypeError, match="Motif is not a Motif type"):
+        as_motif("GATC")
+
+    class Foreign(str):  # e.g. the reference's own Motif
+        mod_position = 1
+
+    assert as_motif(Foreign("GATC")) == Motif("GATC", 1)
+
+
+def test_model_methods_equal_the_reference(G):
+    for rec in G["models"]:
+        m = BetaBernoulliModel()
+        m.update(rec["n_mod"], rec["n_nomod"])
+        assert (m._alpha, m._beta) == (rec["alpha"], rec["beta"]) and isinstance(m._alpha, int)
+        assert list(m.get_raw_counts()) == rec["raw"]
+        assert m.mean() == rec["mean"] and m.variance() == rec["variance"] and m.standard_deviation() == rec["std"]
+        assert m.posterior_predictive(rec["x"], rec["y"]) == pytest.approx(rec["posterior_predictive"], rel=1e-12, abs=0)
+        assert m.posterior_predictive_per_obs(rec["x"], rec["y"]) == pytest.approx(rec["posterior_predictive_per_obs"], rel=1e-12, abs=0)
+        assert m.__getstate__() == rec["state"]
+        r = pickle.loads(pickle.dumps(m))
+        assert (r._alpha, r._beta, r._alpha_prior, r._beta_prior) == (m._alpha, m._beta, 5, 5)
+        m.reset()
+        assert [m._alpha, m._beta] == rec["after_reset"]
+    c = BetaBernoulliModel(2, 7)
+    c.update(3, 4)
+    want = G["custom_prior"]
+    assert (c._alpha, c._beta, list(c.get_raw_counts()), c.mean()) == (want["alpha"], want["beta"], want["raw"], want["mean"])
+
+
+def test_live_against_the_mounted_reference():
+    """Fresh random motifs through both implementations (skipped on a box without /root/reference)."""
+    from oracle import ref_shim
+
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not mounted")
+    nm = ref_shim.load_reference()
+    R = nm.motif.Motif
+    rng = np.random.default_rng()
+    classes = ["[AC]", "[AG]", "[AT]", "[CG]", "[CT]", "[GT]", "[ACG]", "[ACT]", "[AGT]", "[CGT]"]
+
+    def rand():
+        toks = [("." if r < 0.4 else (str(rng.choice(classes)) if r < 0.55 else str(rng.choice(list("ACGT")))))
+                for r in rng.random(int(rng.integers(1, 14)))]
+        toks = ["."] * int(rng.integers(0, 3)) + toks + ["."] * int(rng.integers(0, 3))
+        return "".join(toks), int(rng.integers(0, len(toks)))
+
+    pool = [rand() for _ in range(300)]
+    for s, p in pool:
+        a, b = Motif(s, p), R(s, p)
+        sa, sb = a.new_stripped_motif(), b.new_stripped_motif()
+        assert (sa.string, sa.mod_position) == (sb.string, sb.mod_position)
+        ra, rb = a.reverse_compliment(), b.reverse_compliment()
+        assert (ra.string, ra.mod_position) == (rb.string, rb.mod_position)
+        assert a.one_hot().tolist() == b.one_hot().tolist() and a.iupac() == b.iupac()
+        assert [a.count_isolated_bases(k) for k in (1, 2)] == [b.count_isolated_bases(k) for k in (1, 2)]
+    for _ in range(3000):
+        (s1, p1), (s2, p2) = pool[int(rng.integers(300))], pool[int(rng.integers(300))]
+        assert Motif(s1, p1).sub_motif_of(Motif(s2, p2)) == R(s1, p1).sub_motif_of(R(s2, p2)), ((s1, p1), (s2, p2))
