@@ -33,7 +33,7 @@ def test_motif_type_matches_reference(G):
     for c in G["from_iupac"]:
         assert nmb.Motif(c["iupac"], 0).from_iupac().string == c["regex"]
     a, b = nmb.Motif("GATC", 1), nmb.Motif("GATC", 1)
-    assert a == b and hash(a) == hash(b) and a != nmb.Motif("GATC", 2) and repr(a) == "Motif('GATC', pos=1)"
+    assert a == b and hash(a) == hash(b) and not (a == nmb.Motif("GATC", 2)) and repr(a) == "Motif('GATC', pos=1)"
 
 
 def test_pack_motifs():
