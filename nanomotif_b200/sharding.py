@@ -138,44 +138,6 @@ def gather_rows(rows, group=None):
     return [r for part in out for r in part]
 
 
-class ShardedBinScorer:
-    """BinScorer over the rank's share of a bin's contigs + all-reduce of the counts.
-
-    Every rank must call `score` with the same motif list (the search is replicated; only the scan is
-    sharded).  Requires an initialised torch.distributed process group when world_size > 1."""
-
-    def __init__(self, pileup, contigs, low_meth_threshold, high_meth_threshold, rank: int, world_size: int,
-                 device=None):
-        from .api import BinScorer
-        from .pileup import PileupTable
-
-        names = list(contigs.keys())
-        lengths = [len(c if isinstance(c, str) else c.sequence) for c in contigs.values()]
-        self.owner = plan_shards(lengths, world_size)
-        self.rank, self.world_size = rank, world_size
-        mine = local_contigs(contigs, self.owner, rank)
-        table = PileupTable.from_frame(pileup)
-        if table.contig is not None and len(mine) < len(names):
-            keep = np.isin(np.asarray(table.contig).astype(str), np.array(list(mine.keys()), dtype=str))
-            table = table.take(keep)
-        import torch
-
-        self.scorer = BinScorer(table, mine, low_meth_threshold, high_meth_threshold, device) if mine else None
-        self.device = self.scorer.assembly.device if mine else torch.device(
-            "cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-
-    def score(self, motifs) -> np.ndarray:
-        import torch
-
-        motifs = list(motifs)
-        if self.scorer is not None:
-            c = self.scorer.counts_by_strand(motifs)
-        else:  # a rank without contigs still takes part in the collective
-            c = torch.zeros((len(motifs), 4), dtype=torch.int64, device=self.device)
-        c = allreduce_counts(c).cpu().numpy()
-        return np.stack([c[:, 0] + c[:, 2], c[:, 1] + c[:, 3]], axis=1)
-
-
 def _contig_length(seq) -> int:
     """Length of a contig given as str, DNAsequence-like (.sequence) or -- for contigs another rank will own --
     as a plain int (every rank must know all lengths to derive the same shard plan, not all sequences)."""
