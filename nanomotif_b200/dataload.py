@@ -169,10 +169,28 @@ def _fnv1a64(b: bytes) -> int:
     return h
 
 
+def _fnv1a64_many(enc) -> np.ndarray:
+    """_fnv1a64 of every byte string of a list, one numpy pass per byte position instead of a Python step per byte
+    (an assembly has tens of thousands of contig names; uint64 arithmetic wraps like the & _U64 above)."""
+    n = len(enc)
+    lens = np.fromiter((len(b) for b in enc), dtype=np.int64, count=n)
+    h = np.full(n, _FNV_OFFSET, dtype=np.uint64)
+    if n == 0 or int(lens.max()) == 0:
+        return h
+    start = np.zeros(n, dtype=np.int64)
+    np.cumsum(lens[:-1], out=start[1:])
+    flat = np.frombuffer(b"".join(enc), dtype=np.uint8)
+    prime = np.uint64(_FNV_PRIME)
+    for j in range(int(lens.max())):
+        live = np.flatnonzero(lens > j)
+        h[live] = (h[live] ^ flat[start[live] + j].astype(np.uint64)) * prime
+    return h
+
+
 def _name_table(names, device):
     """Device lookup table of nmb_bed_parse: hashes ascending, ids, name bytes by rank."""
     enc = [str(n).encode() for n in names]
-    hashes = np.array([_fnv1a64(b) for b in enc], dtype=np.uint64)
+    hashes = _fnv1a64_many(enc)
     order = np.argsort(hashes, kind="stable")
     off = np.zeros(len(enc) + 1, dtype=np.int64)
     np.cumsum([len(enc[i]) for i in order], out=off[1:])

@@ -127,11 +127,12 @@ def sequence_of(obj) -> str:
 def plan_layout(lengths: Sequence[int]) -> tuple[np.ndarray, int]:
     """Global start position of every contig (256-bp aligned, >= 64 flagged positions apart) and
     the number of 65536-bp tiles."""
-    starts = np.zeros(len(lengths), dtype=np.int64)
-    cur = 0
-    for i, n in enumerate(lengths):
-        starts[i] = cur
-        cur = -(-(cur + int(n) + _lib.MIN_GAP_BP) // _lib.CHUNK_BP) * _lib.CHUNK_BP
+    # every start is a multiple of CHUNK_BP, so a contig advances the cursor by its length + gap rounded up to chunks
+    lengths = np.asarray(lengths, dtype=np.int64)
+    step = -(-(lengths + _lib.MIN_GAP_BP) // _lib.CHUNK_BP) * _lib.CHUNK_BP
+    ends = np.cumsum(step)
+    starts = ends - step
+    cur = int(ends[-1]) if len(lengths) else 0
     n_tiles = max(1, -(-cur // _lib.TILE_BP))
     return starts, n_tiles
 

@@ -83,7 +83,17 @@ def test_plan_layout():
     lens = np.array([300, 5000, 65536 * 2 + 17, 512, 1])
     assert ((starts[1:] - (starts[:-1] + lens[:-1])) >= _lib.MIN_GAP_BP).all()
     assert n_tiles * _lib.TILE_BP >= starts[-1] + lens[-1] + _lib.MIN_GAP_BP
-    assert plan_layout([])[1] == 1
+    assert plan_layout([])[1] == 1 and len(plan_layout([])[0]) == 0
+    # the closed form equals the contig-by-contig recurrence (cursor rounded up to a chunk after every contig + gap)
+    rng = np.random.default_rng(3)
+    lens = np.concatenate([rng.integers(0, 2000, 300), rng.integers(1, 300000, 50), [0, 448, 449, 511, 512, 513]])
+    rng.shuffle(lens)
+    cur, want = 0, []
+    for n in lens.tolist():
+        want.append(cur)
+        cur = -(-(cur + n + _lib.MIN_GAP_BP) // _lib.CHUNK_BP) * _lib.CHUNK_BP
+    starts, n_tiles = plan_layout(lens)
+    assert starts.tolist() == want and starts.dtype == np.int64 and n_tiles == max(1, -(-cur // _lib.TILE_BP))
 
 
 def test_jobs_and_items():
@@ -344,3 +354,16 @@ def test_string_columns_of_every_frame_kind_give_the_same_strings():
     kind, codes, _ = _string_column(np.array([0, 1, 1, 0], dtype=np.uint8))    # strand codes pass through
     assert kind == "codes" and codes.tolist() == [0, 1, 1, 0]
     assert strings_of(np.array([21839, 21839, 7]), ints_are_codes=False) == ["21839", "21839", "7"]  # modkit codes
+
+
+def test_name_hashes_vectorised_equal_scalar_fnv1a():
+    """The contig-name table of the device parsers (nmb_bed_parse / nmb_lookup_strings) hashes every name with FNV-1a;
+    the vectorised hash must equal the byte-by-byte definition the kernels implement."""
+    from nanomotif_b200 import dataload as D
+
+    names = [f"contig_{i}" for i in range(3000)] + ["", "a", "é", "x" * 70, "bin_1|contig 9", "NODE_1_length_5000_cov_3.2"]
+    enc = [n.encode() for n in names]
+    got = D._fnv1a64_many(enc)
+    assert got.dtype == np.uint64 and got.tolist() == [D._fnv1a64(b) for b in enc]
+    assert D._fnv1a64(b"") == 0xCBF29CE484222325 and D._fnv1a64(b"a") == 0xAF63DC4C8601EC8C  # published FNV-1a vectors
+    assert D._fnv1a64_many([]).shape == (0,) and D._fnv1a64_many([b""]).tolist() == [0xCBF29CE484222325]
