@@ -417,8 +417,6 @@ def binnary_matrix(contig_methylation, contig_bins: dict, methylation_threshold:
     """main.py:192-193 filter, then add_bin (:174-187), impute_contig_methylation_within_bin (:189-213) and
     create_matrix (:255-269) on a pandas frame with the columns of main.py:157-161.  Returns (contig names,
     matrix, feature names)."""
-    import pandas as pd
-
     df = contig_methylation
     df = df[df["n_motif_obs"].astype(np.float64) * df["mean_read_cov"] >= methylation_threshold].copy()
     df["motif_mod"] = df["motif"] + "_" + df["mod_type"] + "_" + df["mod_position"].astype(str)

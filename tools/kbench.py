@@ -14,7 +14,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nanomotif_b200 as nmb  # noqa: E402
 from nanomotif_b200 import _lib  # noqa: E402
-from nanomotif_b200.device import DeviceAssembly, DevicePileup, MotifPrograms, make_jobs, scan_count  # noqa: E402
+from nanomotif_b200.device import MotifPrograms, make_jobs, scan_count  # noqa: E402
 
 MOTIFS = {"A": ("A", 0), "GATC": ("GATC", 1), "CCWGG": ("CC[AT]GG", 1), "GRNGAAGY": ("G[AG].GAAG[CT]", 5),
           "GCACN6GTT": ("GCAC......GTT", 2), "L13": ("ACGTTGCAAGCTA", 3)}
