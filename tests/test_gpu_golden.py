@@ -95,3 +95,49 @@ def test_growth_golden(G):
         assert [[c.string, c.mod_position] for c in children] == step["children"]
         rest = arr.filter_sequence_matches(m.one_hot(), keep_matches=False)
         assert (0 if rest is None else rest.shape[0]) == step["n_removed_rest"]
+
+
+def test_drop_in_bin_model_functions_equal_the_reference_functions():
+    """motif_model_bin / motif_model_contig (with its four position lists) / get_parent_scores on the GPU against
+    tests/golden/binmodel_vectors.json, which tests/golden/generate_binmodel_golden.py recorded by running the reference's
+    OWN functions (find_motifs_bin.py:1265-1331, 1382-1433) on a frame.  Every mismatch is reported, not just the first."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import nanomotif_b200 as nmb
+    from test_binmodel_golden import build_inputs, digest
+
+    with open(os.path.join(HERE, "golden", "binmodel_vectors.json")) as f:
+        V = json.load(f)
+    contigs, pile = build_inputs(V["spec"])
+    assert len(pile["position"]) == V["n_rows"] and int(pile["position"].sum()) == V["checksum"]
+    sub = {mt: {k: v[pile["mod_type"] == mt] for k, v in pile.items()} for mt in V["spec"]["mod_types"]}
+    bad = []
+    for rec in V["bin"]:
+        m = nmb.motif_model_bin(sub[rec["mod_type"]], contigs, nmb.Motif(rec["motif"], rec["mod_pos"]),
+                                nmb.BetaBernoulliModel(), rec["low"], rec["high"])
+        if list(m.get_raw_counts()) != rec["counts"]:
+            bad.append(("bin", rec, list(m.get_raw_counts())))
+    per_contig = {}
+    for rec in V["contig"]:
+        key = (rec["mod_type"], rec["contig"])
+        if key not in per_contig:
+            sel = sub[rec["mod_type"]]["contig"] == rec["contig"]
+            per_contig[key] = {k: v[sel] for k, v in sub[rec["mod_type"]].items()}
+        m, pos = nmb.motif_model_contig(per_contig[key], contigs[rec["contig"]], nmb.BetaBernoulliModel(),
+                                        nmb.Motif(rec["motif"], rec["mod_pos"]), save_motif_positions=True)
+        if list(m.get_raw_counts()) != rec["counts"] or {k: digest(v) for k, v in pos.items()} != rec["positions"]:
+            bad.append(("contig", rec["motif"], rec["contig"], list(m.get_raw_counts()), rec["counts"]))
+    for rec in V["parents"]:
+        res = nmb.get_parent_scores(nmb.Motif(rec["motif"], rec["mod_pos"]), sub[rec["mod_type"]], contigs, 0.3, 0.7)
+        got = [(k.string, int(k.mod_position), int(v["motif_position"]), list(v["parent_model"].get_raw_counts()),
+                list(v["child_model"].get_raw_counts())) for k, v in res.items()]
+        want = [(p["parent"], p["mod_pos"], p["motif_position"], p["parent_counts"], p["child_counts"]) for p in rec["parents"]]
+        if got != want:
+            bad.append(("parents", rec["motif"], got, want))
+        else:
+            for v, p in zip(res.values(), rec["parents"]):
+                if v["score"] != pytest.approx(p["score"], rel=1e-6, abs=1e-9):
+                    bad.append(("score", rec["motif"], p["parent"], float(v["score"]), p["score"]))
+    assert not bad, bad[:6]
