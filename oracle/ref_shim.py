@@ -9,6 +9,10 @@ pyinstrument, snakemake, hdbscan, Bio).  It exists for two purposes only:
 * ``tests/test_oracle_vs_reference.py`` cross-checks ``oracle/restate.py`` against the real
   functions whenever ``/root/reference`` happens to be mounted (skipped otherwise).
 
+``oracle/minipolars.py`` goes one step further for the functions that take a polars FRAME: after
+``load_reference()``, ``minipolars.install(nm)`` makes the few polars calls of the scoring path work on numpy
+columns, so that ``motif_model_bin`` / ``get_parent_scores`` / ``find_best_candidates`` run unmodified too.
+
 Nothing in ``nanomotif_b200/`` may import this module.
 
 Recipe follows SURVEY.md Appendix A.  Placeholders raise ``AttributeError`` for dunder names
