@@ -138,3 +138,37 @@ def test_live_against_the_mounted_reference():
     for _ in range(3000):
         (s1, p1), (s2, p2) = pool[int(rng.integers(300))], pool[int(rng.integers(300))]
         assert Motif(s1, p1).sub_motif_of(Motif(s2, p2)) == R(s1, p1).sub_motif_of(R(s2, p2)), ((s1, p1), (s2, p2))
+
+
+def test_reference_known_answers_for_the_motif_type():
+    """The known-answer vectors of the reference's own tests of the methods mirrored here
+    (tests/test_candidate.py:42-93 reverse_compliment / new_stripped_motif / sub_motif_of, :206-222 iupac)."""
+    rc = [(("ATCG", 0), ("CGAT", 3)), (("AT[CG]G", 0), ("C[CG]AT", 3)), (("ATC.G.", 0), (".C.GAT", 5)), (("ATAC.G.", 2), (".C.GTAT", 4))]
+    for a, b in rc:
+        assert Motif(*a).reverse_compliment() == Motif(*b)
+    for a, b in [(("....ATCG", 4), ("ATCG", 0)), (("ATCG....", 0), ("ATCG", 0)), (("....AT..CG", 4), ("AT..CG", 0))]:
+        assert Motif(*a).new_stripped_motif() == Motif(*b)
+    assert Motif("....AT..CG..", 4).new_stripped_motif().reverse_compliment() == Motif("CG..AT", 5)
+    sub = [(("ATCG", 2), ("ATCG", 2), False), (("ATCG", 0), ("AT", 0), True), (("A[TCG]CG", 0), ("A.C", 0), True),
+           (("ATCG", 2), ("CG", 0), True), (("ATCG", 2), ("CG", 2), False), (("CG", 1), ("ATCG", 2), False)]
+    for a, b, want in sub:
+        assert Motif(*a).sub_motif_of(Motif(*b)) is want, (a, b)
+    iupac = [(("A[TCG]CG", 0), "ABCG"), (("A.C", 0), "ANC"), (("ATCG", 0), "ATCG"), (("ATCG", 2), "ATCG"), (("CG", 0), "CG"),
+             (("C...ATCG", 6), "CNNNATCG"), (("C..CG...G", 3), "CNNCGNNNG"), (("C..CG...[GC]", 3), "CNNCGNNNS")]
+    for a, want in iupac:
+        assert Motif(*a).iupac() == want
+
+
+def test_reference_known_answers_for_motif_type_helper():
+    """tests/test_candidate.py:226-251: has_n_character_stretches_of_length_m, the helper behind utils.motif_type."""
+    from nanomotif_b200.tables import has_n_character_stretches_of_length_m as f
+
+    cases = [("NNA", 1, 2, True), ("NNA", 2, 1, False), ("NNA", 2, 2, False), ("NNANN", 2, 2, True), ("NNANN", 1, 2, True),
+             ("NNANN", 2, 1, True), ("NNANN", 1, 1, True), ("NNANN", 3, 1, False), ("NNANN", 4, 1, False), ("NNANN", 3, 2, False),
+             ("NNANN", 4, 2, False), ("NNANN", 3, 3, False), ("NNANN", 4, 3, False), ("NaNNaNNNaNNNN", 4, 1, True),
+             ("NaNNaNNNaNNNN", 4, 2, False), ("NaNNaNNNaNNNN", 4, 3, False), ("NaNNaNNNaNNNN", 4, 4, False),
+             ("NaNNaNNNaNNNN", 3, 1, True), ("NaNNaNNNaNNNN", 3, 2, True), ("NaNNaNNNaNNNN", 3, 3, False),
+             ("NaNNaNNNaNNNN", 3, 4, False), ("NaNNaNNNaNNNN", 2, 1, True), ("NaNNaNNNaNNNN", 2, 2, True),
+             ("NaNNaNNNaNNNN", 2, 3, True), ("NaNNaNNNaNNNN", 2, 4, False)]
+    for s, n, m, want in cases:
+        assert f(s, n, m, "N") is want, (s, n, m)
