@@ -11,6 +11,9 @@ calls those functions make, so that the UNMODIFIED reference code runs on a `Dat
     filter_pileup / filter_pileup_minimummod_frequency         dataload.py:191-226
         + with_columns([(col + "_" + col).alias(n)]), group_by(c).agg(name=expr), pl.count(), (expr > v).sum(),
           expr / expr, is_in, drop
+    merge_motifs_in_df                                         find_motifs_bin.py:1436-1537
+        + `for key, df in frame.group_by(a, b)`, is_in(...).not_(), DataFrame({column: scalar}), concat
+          (with `pl.DataFrame` bound to this module's DataFrame and the MotifSearchResult wrapper bypassed by the test)
 
 `install(nm)` puts `col`, `count`, `lit` on the stub `polars` module that oracle/ref_shim.py registered (the reference
 modules hold that module as `pl`) and on the names imported with `from polars import col`.  Everything else of polars
@@ -25,10 +28,27 @@ import numpy as np
 
 
 def _arr(v):
-    a = np.asarray(v)
+    if isinstance(v, np.ndarray):
+        a = v
+    elif isinstance(v, (list, tuple)):
+        if v and not isinstance(v[0], (int, float, bool, str, np.generic)):
+            a = np.empty(len(v), dtype=object)  # arbitrary objects (e.g. models): no array coercion
+            a[:] = list(v)
+        else:
+            a = np.asarray(v)
+    else:  # a scalar: a one-row column (pl.DataFrame({"motif": "GATC", "model": model, ...}))
+        a = np.empty(1, dtype=object)
+        a[0] = v
+        if isinstance(v, (int, float, bool, np.generic)) and not isinstance(v, str):
+            a = np.asarray([v])
     if a.dtype.kind in "US":
         a = a.astype(object)
     return a
+
+
+def _plain(v):
+    """str subclasses (the reference's Motif) compare by their text inside a frame, as in polars."""
+    return str.__str__(v) if isinstance(v, str) else v
 
 
 class Series:
@@ -103,9 +123,9 @@ class Expr:
     __hash__ = None
 
     def is_in(self, values):
-        vals = list(values.to_list() if isinstance(values, Series) else values)
-        return Expr(lambda df: np.isin(self.fn(df), np.array(vals, dtype=object) if vals and isinstance(vals[0], str) else vals),
-                    self.name)
+        vals = {_plain(v) for v in (values.to_list() if isinstance(values, Series) else values)}
+        return Expr(lambda df: np.fromiter((_plain(x) in vals for x in np.asarray(self.fn(df)).tolist()), dtype=bool,
+                                           count=len(self.fn(df))), self.name)
 
     def sum(self):
         return Expr(lambda df: np.asarray(self.fn(df)).sum(), self.name)
@@ -130,18 +150,29 @@ class GroupBy:
     def __init__(self, frame, keys):
         self.frame, self.keys = frame, keys
 
-    def agg(self, *exprs, **named):
+    def _groups(self):
         f = self.frame
         key_cols = [f._cols[k] for k in self.keys]
         tags = np.array(["\x1f".join(str(c[i]) for c in key_cols) for i in range(f.height)], dtype=object)
         _, first, inv = np.unique(tags.astype(str), return_index=True, return_inverse=True)
-        order = np.argsort(first)  # groups in first-appearance order
+        for g in np.argsort(first):  # groups in first-appearance order
+            yield np.flatnonzero(inv == g)
+
+    def __iter__(self):
+        """((key values), sub-frame) per group, as `for (a, b), df in frame.group_by("a", "b")`."""
+        f = self.frame
+        for rows in self._groups():
+            key = tuple(_plain(f._cols[k][rows[0]]) if not hasattr(f._cols[k][rows[0]], "item") else f._cols[k][rows[0]].item()
+                        for k in self.keys)
+            yield key, DataFrame({k: v[rows] for k, v in f._cols.items()})
+
+    def agg(self, *exprs, **named):
+        f = self.frame
         out = {k: [] for k in self.keys}
         specs = [(e.name, e) for e in exprs] + list(named.items())
         for name, _ in specs:
             out[name] = []
-        for g in order:
-            rows = np.flatnonzero(inv == g)
+        for rows in self._groups():
             sub = DataFrame({k: v[rows] for k, v in f._cols.items()})
             for k in self.keys:
                 out[k].append(f._cols[k][rows[0]])
@@ -213,13 +244,29 @@ class DataFrame:
         return dict(self._cols)
 
 
+def concat(frames, **_kwargs):
+    """Rows of frames with the same columns, in order (pl.concat with its default vertical strategy)."""
+    frames = list(frames)
+    cols = frames[0].columns
+    for f in frames:
+        if set(f.columns) != set(cols):
+            raise ValueError(f"concat: columns differ: {f.columns} vs {cols}")
+    out = {}
+    for c in cols:
+        parts = [f._cols[c] for f in frames]
+        if any(p.dtype == object for p in parts):
+            parts = [p.astype(object) for p in parts]
+        out[c] = np.concatenate(parts) if parts else np.zeros(0)
+    return DataFrame(out)
+
+
 def install(nm) -> None:
     """Make `pl.col` / `pl.count` / `pl.lit` and the `col` imported by name resolve to this module inside the loaded
     reference package `nm` (oracle/ref_shim.load_reference())."""
     import sys
 
     pl = sys.modules["polars"]
-    for name, obj in (("col", col), ("count", count), ("lit", lit)):
+    for name, obj in (("col", col), ("count", count), ("lit", lit), ("concat", concat)):
         setattr(pl, name, obj)
     for mod in (nm.find_motifs_bin, nm.dataload):
         if hasattr(mod, "col") or "col" in vars(mod):

@@ -197,3 +197,46 @@ def test_unmodified_find_best_candidates_reproduces_the_committed_trace(nm, trac
         assert a[:3] == b[:3] and a[5:] == b[5:] and a[3] == pytest.approx(b[3], rel=1e-12, abs=1e-12) \
             and a[4] == pytest.approx(b[4], rel=1e-12, abs=1e-300), (a, b)
     assert sorted([u.string, v.string] for u, v in graph.edges()) == sorted(trace["edges"])
+
+
+@needs_reference
+def test_unmodified_merge_motifs_in_df_reproduces_the_committed_merge_trace(nm):
+    """tests/golden/merge_trace.json was recorded with the loop body of merge_motifs_in_df restated without its frames.
+    Here the reference function itself (find_motifs_bin.py:1436-1537: group_by, the real merge_motifs clustering, the
+    real motif_model_bin / get_parent_scores on frames, concat) runs and must return the same rows, models and scores.
+    Only the MotifSearchResult wrapper (a polars subclass that is not on the path) is bypassed."""
+    import sys
+
+    from oracle import minipolars as mp
+    from search_common import build_inputs as search_inputs, load_merge_trace, load_trace
+
+    golden, spec = load_merge_trace(), load_trace()["spec"]
+    contigs, pile = search_inputs(spec)
+    n = len(golden["motifs"])
+    B = nm.model.BetaBernoulliModel
+    motif_df = mp.DataFrame({"motif": [s for s, _ in golden["motifs"]], "score": [1.0] * n,
+                             "mod_position": [p for _, p in golden["motifs"]], "reference": ["bin1"] * n, "mod_type": ["a"] * n,
+                             "model": [B() for _ in range(n)]})
+    pileup = mp.DataFrame(dict(pile, mod_type=np.full(len(pile["position"]), "a", dtype=object)))
+    assembly = {k: nm.seq.DNAsequence(v) for k, v in contigs.items()}
+    pl = sys.modules["polars"]
+    saved = (pl.DataFrame, nm.motif.MotifSearchResult)
+    pl.DataFrame, nm.motif.MotifSearchResult = mp.DataFrame, (lambda frame, *a, **k: frame)
+    try:
+        for run in golden["runs"]:
+            res = nm.find_motifs_bin.merge_motifs_in_df(motif_df, pileup, assembly, {"bin1": list(contigs)}, spec["low"],
+                                                        spec["high"], merge_threshold=run["merge_threshold"])
+            # the order of the merged rows follows networkx's clique enumeration over a set of str-hashed nodes, i.e. the
+            # interpreter's hash seed: compare the rows as a set
+            got = {(m, int(p)): (model, score) for m, p, model, score in zip(
+                res["motif"].to_list(), res["mod_position"].to_list(), res["model"].to_list(), res["score"].to_list())}
+            assert len(got) == res.height == len(run["rows"])
+            assert sorted(got) == sorted((r["motif"], r["mod_position"]) for r in run["rows"]), run["merge_threshold"]
+            for want in run["rows"]:
+                model, score = got[(want["motif"], want["mod_position"])]
+                if want["merged"]:
+                    assert [int(model._alpha), int(model._beta)] == want["model"]
+                    assert float(score) == pytest.approx(want["score"], rel=1e-9, abs=1e-12)
+            assert sum(r["merged"] for r in run["rows"]) > 0
+    finally:
+        pl.DataFrame, nm.motif.MotifSearchResult = saved
