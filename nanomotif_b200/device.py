@@ -125,7 +125,7 @@ def sequence_of(obj) -> str:
 
 
 def plan_layout(lengths: Sequence[int]) -> tuple[np.ndarray, int]:
-    """Global start position of every contig (256-bp aligned, >= 64 flagged positions apart) and
+    """Global start position of every contig (aligned to CHUNK_BP = 512 bp, >= 64 flagged positions apart) and
     the number of 65536-bp tiles."""
     # every start is a multiple of CHUNK_BP, so a contig advances the cursor by its length + gap rounded up to chunks
     lengths = np.asarray(lengths, dtype=np.int64)
