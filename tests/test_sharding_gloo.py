@@ -253,6 +253,9 @@ def test_two_pieces_of_one_contig_on_one_rank_and_lengths_only():
     ncid, npos = sharding.remap_split_rows(cid, pos, [(0, 0, 0, 1024, 0), (0, 2, 2048, 3072, 1984)])
     assert ncid.tolist() == [0, -1, 2, 2, 1, -1] and npos.tolist() == [5, 1024, 64, 1087, 7, 4999]
     assert cid.tolist() == [0, 0, 0, 0, 1, 0]  # inputs untouched
+    from nanomotif_b200 import _lib
+
+    assert sharding.HALO_BP >= _lib.MAX_MOTIF_LEN  # an occurrence reaches at most MAX_MOTIF_LEN - 1 bp past its modified base
     assert sharding.split_ranges(5000, 3) == [(0, 1536), (1536, 3584), (3584, 5000)]
     assert sharding.split_ranges(1500, 4) == [(0, 1500)]  # too short to cut
     # contigs of other ranks by length: the same plan as from sequences
