@@ -240,3 +240,44 @@ def test_unmodified_merge_motifs_in_df_reproduces_the_committed_merge_trace(nm):
             assert sum(r["merged"] for r in run["rows"]) > 0
     finally:
         pl.DataFrame, nm.motif.MotifSearchResult = saved
+
+
+@needs_reference
+@pytest.mark.parametrize("seed,mod_type,planted", [
+    (4242, "m", [["CC[AT]GG", 1, "m"], ["GCGC", 1, "m"]]),
+    (977, "a", [["GAGG", 1, "a"], ["CTA....TGC", 2, "a"], ["AC...GT", 0, "a"]]),
+])
+def test_search_driver_equals_the_unmodified_reference_search_on_new_inputs(nm, seed, mod_type, planted):
+    """Beyond the two committed traces: a bin the repo has never seen (other seed, other motifs, 5mC as well as 6mA).
+    Reference side: the unmodified find_best_candidates on a frame.  This side: search.find_candidates (the coroutine the
+    lock-step GPU driver advances) answered by the oracle backend.  Same graph -- posteriors, scores, priorities, depth
+    and visited flag of every node, same edges -- and the same candidates in the same order."""
+    from oracle import minipolars as mp
+    from nanomotif_b200 import search
+    from search_common import OracleBackend, build_inputs as search_inputs, check_against_trace
+
+    spec = dict(seed=seed, contig_lengths=[70000, 40000, 2500], gc=0.5, depth=15, mod_type=mod_type, planted=planted,
+                padding=20, low=0.3, high=0.7, min_kl=0.05, score_threshold=1.5, random_seed=3)
+    contigs, pile = search_inputs(spec)
+    seqs = {k: nm.seq.DNAsequence(v) for k, v in contigs.items()}
+    random.seed(spec["random_seed"])
+    with tempfile.TemporaryDirectory() as out:
+        res = nm.find_motifs_bin.find_best_candidates(
+            mp.DataFrame(dict(pile)), seqs, mod_type, "bin1", out, spec["low"], spec["high"], spec["padding"],
+            min_kl=spec["min_kl"], score_threshold=spec["score_threshold"])
+    assert res is not None
+    graph, best = res
+    trace = dict(best_candidates=[b.string for b in best], missed=[],
+                 nodes=[dict(motif=n.string, alpha=int(d["model"]._alpha), beta=int(d["model"]._beta), score=float(d["score"]),
+                             priority=float(d["priority"]), depth=int(d["depth"]), visited=bool(d["visited"]))
+                        for n, d in graph.nodes(data=True)],
+                 edges=[[u.string, v.string] for u, v in graph.edges()])
+    assert len(trace["nodes"]) > 10 and trace["best_candidates"]
+    backend = OracleBackend(contigs, pile, spec)
+    rounds = []
+    co = search.find_candidates(mod_type, spec["padding"], backend.bin_pssm, backend.arr.shape[0], min_kl=spec["min_kl"],
+                                score_threshold=spec["score_threshold"], trace=rounds)
+    got_graph, got_best = search.run(co, backend)
+    trace["rounds"] = [dict(r, score=r["score"]) for r in rounds]  # the rounds are this side's own; the graph is the pin
+    check_against_trace(trace, (got_graph, got_best), rounds)
+    assert [m.string for m in got_best] == trace["best_candidates"]
