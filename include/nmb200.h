@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define NMB_ABI_VERSION 3 /* 2: lane-interleaved tile records (NMB_WORD_SLOT), chunk_info flag bits 28-30; 3: table ingest */
+#define NMB_ABI_VERSION 4 /* 2: lane-interleaved tile records (NMB_WORD_SLOT), chunk_info flag bits 28-30; 3: table ingest; 4: nmb_pack_motifs */
 
 #if defined(__GNUC__)
 #define NMB_API __attribute__((visibility("default")))
@@ -530,6 +530,18 @@ NMB_API int nmb_mt_sample(nmb_mt19937 *state_h, int64_t n, int64_t k, int64_t *o
 /* count consecutive samples from the same stream; sample i is written at out_h + sum(k_h[0..i)). */
 NMB_API int nmb_mt_sample_many(nmb_mt19937 *state_h, const int64_t *n_h, const int64_t *k_h, int64_t count,
                                int64_t *out_h);
+
+/* ---- host helper: a batch of motif strings -> nmb_motif records, i.e. Motif.new_stripped_motif + Motif.split
+ *      (nanomotif/motif.py:213-245) + the allowed-set bits above, for every motif of a scoring request at once (a
+ *      lock-step search round packs the <= 4 children of every search).  text_h = the motif strings back to back
+ *      (ASCII), motif i = [offset_h[i], offset_h[i+1]); mod_pos_h[i] = its mod_position (may be NULL when
+ *      mod_pos_override >= 0, which replaces every mod position AFTER the strip); strip != 0 drops flanking '.' and
+ *      re-bases the mod position (an all-wildcard motif is left as it is).  status_h[i] = 0 and out_h[i] filled, or
+ *      1 (out_h[i] zeroed) for a motif this path refuses: a character other than A C G T . [ ], an unmatched or empty
+ *      class, more than NMB_MAX_MOTIF_LEN positions, no constrained position, mod position outside the stripped
+ *      motif.  Host pointers; no device work. ---- */
+NMB_API int nmb_pack_motifs(const char *text_h, const int64_t *offset_h, const int32_t *mod_pos_h, int32_t n,
+                            int32_t strip, int32_t mod_pos_override, nmb_motif *out_h, uint8_t *status_h);
 
 /* ---- host -> device staging of PAGEABLE host buffers (the Arrow buffers of the frames nanomotif hands to its
  *      workers, find_motifs_bin.py:399-427).  n_threads host threads each own a CUDA stream and two pinned slots of

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnmb200.so")
 
 # ---- constants mirrored from include/nmb200.h -------------------------------------------------
-ABI_VERSION = 3
+ABI_VERSION = 4
 CHUNK_WORDS = 16
 CHUNK_BP = 512
 TILE_WORDS = 2048
@@ -134,6 +134,7 @@ SIGNATURES = {
     "nmb_segment_median": (C.c_int, [_P, _P, _I64, _P, _P]),
     "nmb_mt_sample": (C.c_int, [_P, _I64, _I64, _P]),
     "nmb_mt_sample_many": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "nmb_pack_motifs": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P]),
     "nmb_stager_create": (C.c_int, [_I64, _I32, C.POINTER(_P)]),
     "nmb_stager_copy": (C.c_int, [_P, _P, _P, _I64, _P]),
     "nmb_stager_copy_narrow": (C.c_int, [_P, _P, _P, _I64, C.POINTER(C.c_int32), _P]),

@@ -1,5 +1,6 @@
 // Misc entry points of libnmb200: version, error string, device query.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -113,6 +114,80 @@ int nmb_mt_sample_many(nmb_mt19937 *state, const int64_t *n, const int64_t *k, i
         const int rc = nmb_mt_sample(state, n[i], k[i], out ? out + at : nullptr);
         if (rc != NMB_OK) return rc;
         at += k[i];
+    }
+    return NMB_OK;
+}
+
+// ---- host: motif strings -> nmb_motif records ----------------------------------------------------------------------
+// What Motif.new_stripped_motif + Motif.split do before a scan (nanomotif/motif.py:213-245), for a whole batch: a
+// lock-step search round packs the <= 4 children of every (bin, mod type) search, and at ~2 us per motif the Python
+// loop was half of the host time of a round.  Tokens: A C G T, '.', and [..] classes of A C G T; allowed-set bits in
+// the order of nanomotif/constants.py:21-28.  Anything else (other letters, unbalanced or empty brackets, no
+// constrained position, too long, mod position outside the stripped motif) sets status 1 and the caller's slow path
+// raises the precise error.
+static inline int base_bit(unsigned char c) {
+    switch (c) {
+        case 'A': return 1;
+        case 'T': return 2;
+        case 'G': return 4;
+        case 'C': return 8;
+        default: return 0;
+    }
+}
+
+int nmb_pack_motifs(const char *text, const int64_t *offset, const int32_t *mod_pos, int32_t n, int32_t strip,
+                    int32_t mod_pos_override, nmb_motif *out, uint8_t *status) {
+    NMB_REQUIRE(n >= 0 && (n == 0 || (text && offset && out && status)), "nmb_pack_motifs: bad arguments");
+    NMB_REQUIRE(n == 0 || mod_pos || mod_pos_override >= 0, "nmb_pack_motifs: no mod positions");
+    for (int32_t i = 0; i < n; ++i) {
+        nmb_motif rec;
+        memset(&rec, 0, sizeof(rec));
+        memset(&out[i], 0, sizeof(rec));
+        status[i] = 1;
+        int64_t a = offset[i], b = offset[i + 1];
+        if (b < a) continue;
+        int64_t mp = mod_pos ? mod_pos[i] : 0;
+        if (strip) {  // flanking '.' characters go, mod_position is re-based; an all-wildcard motif stays as it is
+            int64_t lead = a;
+            while (lead < b && text[lead] == '.') ++lead;
+            if (lead < b) {
+                mp -= lead - a;
+                a = lead;
+                while (b > a && text[b - 1] == '.') --b;
+            }
+        }
+        if (mod_pos_override >= 0) mp = mod_pos_override;
+        int len = 0, constrained = 0;
+        bool ok = true;
+        for (int64_t k = a; k < b; ++k) {
+            const unsigned char c = (unsigned char)text[k];
+            int mask;
+            if (c == '.') {
+                mask = 0xF;
+            } else if (c == '[') {
+                mask = 0;
+                for (++k; k < b && text[k] != ']'; ++k) {
+                    const int bit = base_bit((unsigned char)text[k]);
+                    if (!bit) ok = false;
+                    mask |= bit;
+                }
+                if (k >= b || mask == 0) ok = false;  // unmatched bracket / empty class
+            } else {
+                mask = base_bit(c);
+                if (!mask) ok = false;
+            }
+            if (!ok || len >= NMB_MAX_MOTIF_LEN) {
+                ok = false;
+                break;
+            }
+            constrained += mask != 0xF;
+            rec.allowed[len++] = (uint8_t)mask;
+        }
+        if (!ok || len == 0 || constrained == 0 || mp < 0 || mp >= len) continue;
+        rec.len = (uint8_t)len;
+        rec.mod_pos = (uint8_t)mp;
+        out[i] = rec;
+        status[i] = 0;
     }
     return NMB_OK;
 }

@@ -42,14 +42,36 @@ def test_batched_motif_packing_equals_the_one_by_one_path(specs):
         with pytest.raises(ValueError):
             M.pack_motifs(motifs)
         return
-    got = M.pack_motifs(motifs)
+    got = M.pack_motifs(motifs)  # one native call for the batch (nmb_pack_motifs)
     assert got.tobytes() == np.concatenate(want).tobytes()
+    assert M._pack_motifs_numpy(motifs).tobytes() == got.tobytes()  # the numpy implementation it replaced
+    assert M.pack_motifs(motifs, strip=False, mod_pos_override=0).tobytes() == M._pack_motifs_numpy(motifs, False, 0).tobytes()
     for m, rec in zip(motifs, got):
         s = m.new_stripped_motif()
         oh = s.one_hot()
         assert rec["len"] == len(oh) and rec["mod_pos"] == s.mod_position
         assert rec["allowed"][:len(oh)].tolist() == [int(r[0] + 2 * r[1] + 4 * r[2] + 8 * r[3]) for r in oh]
         assert not rec["allowed"][len(oh):].any()
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.tuples(st.text(alphabet="ACGT.[]N", min_size=0, max_size=70), st.integers(-2, 70)), min_size=1, max_size=6),
+       st.booleans(), st.sampled_from([None, 0, 3]))
+def test_native_packer_refuses_exactly_what_the_python_path_refuses(specs, strip, override):
+    """Arbitrary strings over the motif alphabet plus junk (unbalanced and empty brackets, N, too long, nothing but
+    wildcards, mod positions outside the motif): the native batch packer and the numpy / one-by-one path either return
+    the same records or raise the same kind of error (the same message for a single motif)."""
+    motifs = [M.Motif(s, p) for s, p in specs]
+    results = []
+    for f in (M.pack_motifs, M._pack_motifs_numpy):
+        try:
+            results.append(("ok", f(motifs, strip, override).tobytes()))
+        except (ValueError, TypeError) as exc:
+            results.append((type(exc).__name__, str(exc)))
+    if results[0][0] == "ok" or len(motifs) == 1:
+        assert results[0] == results[1]
+    else:
+        assert results[0][0] == results[1][0]
 
 
 @settings(max_examples=200, deadline=None)
