@@ -110,14 +110,14 @@ def test_model_methods_equal_the_reference(G):
 
 
 def test_live_against_the_mounted_reference():
-    """Fresh random motifs through both implementations (skipped on a box without /root/reference)."""
+    """Motifs that are not in the golden file through both implementations (skipped on a box without /root/reference)."""
     from oracle import ref_shim
 
     if not ref_shim.reference_available():
         pytest.skip("reference tree not mounted")
     nm = ref_shim.load_reference()
     R = nm.motif.Motif
-    rng = np.random.default_rng()
+    rng = np.random.default_rng(20261019)  # fixed: the suite must give the same verdict on every run
     classes = ["[AC]", "[AG]", "[AT]", "[CG]", "[CT]", "[GT]", "[ACG]", "[ACT]", "[AGT]", "[CGT]"]
 
     def rand():
