@@ -11,9 +11,15 @@ known-answer tests (tests/test_fasta.py:95-109, tests/test_motif_find.py:14-39,
 tests/test_dataload.py:37-69, tests/test_candidate.py:42-58) and (b) golden vectors produced by
 running the real reference functions through ``oracle/ref_shim.py``
 (``tests/golden/generate_golden.py`` -> ``tests/golden/*.json``).  The polars-dependent glue
-(motif_model_contig's row split, the three pileup filters) cannot run here (polars is not
-installed), so those restatements follow the cited lines and are pinned only through the pure
-functions they call plus the reference's adjacency-filter known answers.
+(motif_model_contig's row split, motif_model_bin, get_parent_scores, filter_pileup,
+filter_pileup_minimummod_frequency) is pinned too: ``oracle/minipolars.py`` implements the handful of
+polars calls those functions make on numpy columns, the UNMODIFIED reference functions were run through
+it (``tests/golden/generate_binmodel_golden.py`` -> ``binmodel_vectors.json``) and
+``tests/test_binmodel_golden.py`` holds this module against the recorded results (and against the live
+functions where the reference tree is mounted).  The adjacency filter is pinned by the reference's own
+known answers (tests/test_dataload.py:37-69); its polars ``rolling`` call is not emulated.
+``methylation_pattern`` (external Rust package, no source in the tree) is a written spec:
+PARITY UNPINNED for that one function.
 """
 from __future__ import annotations
 
